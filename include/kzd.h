@@ -1,0 +1,141 @@
+/*
+ * kzd.h - C ABI of libkzd: the sm_100a CUDA implementation of the dense-detection hot path of
+ * Kotomiya07/kuzushiji-vision (its vendored Ultralytics 8.3.63 / YOLOv12).
+ *
+ * The reference has no FFI for this path - the boundary is three Python call signatures
+ * (SURVEY.md section 8b). Each entry point below is what a ctypes binding for one of those
+ * signatures binds; the citation names the reference code it replaces. Paths are relative to
+ * /root/reference/yolov12/ultralytics/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_ (host);
+ *   - the caller owns all memory, including the scratch `workspace` (size it with the matching
+ *     *_workspace_bytes call); the library allocates nothing and keeps no state between calls;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work and never synchronise;
+ *   - every call returns 0 on success, a negative KZD_E* code for a bad argument, or a positive
+ *     cudaError_t; kzd_last_error() returns a thread-local message for the last failure;
+ *   - tensors are dense row-major fp32 unless stated otherwise.
+ */
+#ifndef KZD_H
+#define KZD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KZD_VERSION 100 /* 0.1.0 */
+#define KZD_MAX_LEVELS 8
+#define KZD_REG_MAX 16 /* DFL bins per box side: nn/modules/head.py:39 */
+#define KZD_MAX_TOPK 32
+
+#define KZD_EINVAL (-1)   /* bad argument */
+#define KZD_ENOSPACE (-2) /* workspace too small */
+
+/* One pyramid level of the anchor grid (make_anchors, utils/tal.py:333-345): h*w cells, row-major
+ * (y outer), cell centre (x+0.5, y+0.5)*stride, first anchor of the level at `offset`. */
+typedef struct kzd_level {
+    int32_t h, w;
+    int32_t offset;
+    float stride;
+} kzd_level;
+
+int kzd_version(void);
+const char* kzd_last_error(void);
+/* Number of SMs / compute capability of the current device (diagnostics only). */
+int kzd_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * decode
+ * ------------------------------------------------------------------------------------------ */
+
+/* Detect._inference (nn/modules/head.py:100-131) + DFL.forward (nn/modules/block.py:71-74) +
+ * dist2bbox(xywh=True, dim=1) (utils/tal.py:348-357) + cls.sigmoid(), fused.
+ *   h_level_ptrs[l] : device pointer to level l's map (b, 64+nc, h_l, w_l), contiguous NCHW
+ *   y               : (b, 4+nc, A)  [cx, cy, w, h] in pixels, then sigmoid(class logits)
+ * The per-level `cat` copy (head.py:104) is skipped; anchors and strides come from `levels`. */
+int kzd_decode_infer(const float* const* h_level_ptrs, const kzd_level* h_levels, int n_levels,
+                     int b, int nc, float* y, void* stream);
+
+/* v8DetectionLoss.bbox_decode (utils/loss.py:197-204) + dist2bbox(xywh=False).
+ *   pred_dist     : (b, A, 64)  side-major, 16 bins per side
+ *   anchor_points : (A, 2)      grid units
+ *   out_xyxy      : (b, A, 4)   grid units */
+int kzd_decode_train(const float* pred_dist, const float* anchor_points, int b, int A,
+                     float* out_xyxy, void* stream);
+
+/* Backward of kzd_decode_train wrt pred_dist (the CIoU/DFL losses back-propagate through the
+ * decoded boxes, utils/loss.py:252-254): grad_pred_dist (b,A,64) from grad_xyxy (b,A,4). */
+int kzd_decode_train_bwd(const float* pred_dist, const float* grad_xyxy, int b, int A,
+                         float* grad_pred_dist, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * assign
+ * ------------------------------------------------------------------------------------------ */
+
+size_t kzd_assign_workspace_bytes(int b, int A, int G);
+
+/* TaskAlignedAssigner.forward (utils/tal.py:39-118, helpers :120-295; CIoU utils/metrics.py:96-130).
+ *   pd_scores (b,A,nc) sigmoided, pd_bboxes (b,A,4) xyxy px, anc_points (A,2) px,
+ *   gt_labels (b,G) class ids as float, gt_bboxes (b,G,4) xyxy px, mask_gt (b,G) 0/1 as float.
+ *   h_levels/n_levels: the grid the anchors come from. It is only an accelerator: anc_points is
+ *     checked against it on the device and, on any mismatch (or n_levels == 0), candidate
+ *     enumeration falls back to scanning all A anchors per GT - same results, slower.
+ *   zero_fill: how torch.topk's padding with zero-metric entries is reproduced when a GT has fewer
+ *     than topk positive candidates: 0 = padding never lands inside the GT (true whenever anchors
+ *     0..topk-1 are outside every GT); 1 = emulate "lowest anchor indices first".
+ * Outputs (all written for every anchor):
+ *   target_labels int64 (b,A), target_bboxes (b,A,4), target_scores (b,A,nc), fg_mask uint8 (b,A),
+ *   target_gt_idx int64 (b,A); counters double[2] = { sum(target_scores), count(fg_mask) }
+ *   (may be NULL). G must be >= 1 (the G == 0 early-out of tal.py:64-71 is host logic). */
+int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
+                   const float* gt_labels, const float* gt_bboxes, const float* mask_gt,
+                   int b, int A, int G, int nc, int topk, float alpha, float beta, float eps,
+                   const kzd_level* h_levels, int n_levels, int zero_fill,
+                   int64_t* target_labels, float* target_bboxes, float* target_scores,
+                   uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NMS
+ * ------------------------------------------------------------------------------------------ */
+
+/* Stage 1 of ops.non_max_suppression (utils/ops.py:234-286): xywh->xyxy (written back into
+ * `prediction` when in_place, :243-244), confidence filter, best class (:274-275) or multi-label
+ * (:271-272), optional class filter (:278-279). Candidates are appended (unordered) to a
+ * caller-owned pool of `cand_cap` records per image.
+ *   prediction   : (b, 4+nc, A) in/out
+ *   in_place     : 0 = boxes are xywh, leave them; 1 = boxes are xywh, write xyxy back (the
+ *                  reference's default side effect); 2 = boxes are already xyxy (re-run after a
+ *                  pool overflow), leave them
+ *   classes      : device int32[n_classes] or NULL
+ *   cand_keys    : uint64 (b, cand_cap)   score bits << 32 | ~order   (order = anchor, or
+ *                                          anchor*nc+class when multi_label)
+ *   cand_rows    : float  (b, cand_cap, 6) [x1,y1,x2,y2,conf,cls]
+ *   cand_counts  : int32 (b)  number of candidates found (may exceed cand_cap: the excess was
+ *                  dropped and the caller must retry with a larger pool) */
+int kzd_nms_filter(float* prediction, int b, int A, int nc, float conf_thres, int multi_label,
+                   const int32_t* classes, int n_classes, int in_place,
+                   uint64_t* cand_keys, float* cand_rows, int32_t* cand_counts, int cand_cap,
+                   void* stream);
+
+size_t kzd_nms_workspace_bytes(int b, int cand_cap, int n_cap);
+
+/* Stage 2 (utils/ops.py:285-311 + torchvision.ops.nms): per image, order the candidates by
+ * (score desc, order asc) - torchvision's stable descending sort -, keep the first max_nms,
+ * offset boxes by cls*max_wh unless agnostic, build the IoU > iou_thres bitmask, run the greedy
+ * scan and write the first max_det kept rows in score order.
+ *   n_cap     : capacity of the suppression stage per image (>= min(count, max_nms) for every
+ *               image, else that image's out_counts entry is set to -1 and nothing is written)
+ *   out_rows  : float (b, max_det, 6);  out_counts : int32 (b) */
+int kzd_nms_suppress(const uint64_t* cand_keys, const float* cand_rows, const int32_t* cand_counts,
+                     int b, int cand_cap, int n_cap, float iou_thres, int agnostic, int max_det,
+                     int max_nms, float max_wh, float* out_rows, int32_t* out_counts,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KZD_H */

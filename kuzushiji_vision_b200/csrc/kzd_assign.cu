@@ -1,0 +1,475 @@
+// TaskAlignedAssigner (sm_100a), GT-centric and sparse: no dense (b,G,A) tensor is ever formed.
+//
+// reference: utils/tal.py:39-295 (forward/_forward :39-118, get_pos_mask :120-130, get_box_metrics
+// :132-151, select_topk_candidates :157-190, get_targets :192-238, select_candidates_in_gts :241-262,
+// select_highest_overlaps :264-295) and CIoU utils/metrics.py:96-130.
+//
+// Kernels (one stream, no host sync):
+//   assign_verify_kernel      checks anc_points against the level table (grid accelerator is only
+//                             used when every anchor matches bit-for-bit)
+//   assign_candidates_kernel  one warp per (image, GT): enumerate the anchors inside the GT, CIoU +
+//                             alignment metric, per-anchor argmax-overlap via 64-bit atomicMax,
+//                             warp-shuffle streaming top-k, selection counts
+//   assign_resolve_kernel     one thread per anchor: resolve the owner GT, write labels / boxes /
+//                             fg / gt_idx, recompute the owner pair's metric, per-GT maxima
+//   assign_normalize_kernel   foreground anchors: target_scores = align * pos_ov / (pos_align+eps)
+//
+// Bit-exactness: every fp32 operation of the eager reference rounds separately, so the pair
+// arithmetic below uses __fadd_rn/__fmul_rn/__fdiv_rn (never contracted into FMAs) and the same
+// libdevice atanf / powf / sqrtf that aten's CUDA kernels call.
+#include "kzd_common.cuh"
+
+namespace kzd {
+
+typedef unsigned long long u64;
+
+struct AssignWs {
+    u64* key;            // (b*A)  max over in-GT pairs of  overlap_bits<<32 | ~g
+    uint32_t* sel_cnt;   // (b*A)  number of GTs whose top-k selected the anchor
+    uint32_t* sel_g;     // (b*A)  max of ~g over selecting GTs (= smallest g)
+    uint32_t* pos_align; // (b*G)  per-GT max alignment metric (float bits)
+    uint32_t* pos_ov;    // (b*G)  per-GT max overlap (float bits)
+    int32_t* flags;      // [0] != 0: anc_points does not match the level table
+    size_t zero_bytes;   // prefix of the workspace that must be zero before the candidates kernel
+};
+
+struct AssignParams {
+    const float *pd_scores, *pd_bboxes, *anc, *gt_labels, *gt_bboxes, *mask_gt;
+    int b, A, G, nc, topk;
+    float alpha, beta, eps;
+    kzd_level lv[KZD_MAX_LEVELS];
+    int n_levels, zero_fill;
+    long long* target_labels;
+    float* target_bboxes;
+    float* target_scores;
+    uint8_t* fg_mask;
+    long long* target_gt_idx;
+    double* counters;
+    AssignWs ws;
+};
+
+// ---- arithmetic shared by the candidates and resolve kernels (must be one instruction sequence) ----
+
+// aten pow(tensor, scalar) dispatch: 0.5 -> sqrt, 2 -> x*x, 3 -> x*x*x, 1 -> x, 0 -> 1, -0.5 -> rsqrt,
+// -1 -> 1/x, -2 -> 1/(x*x), else ::pow  (ATen/native/cuda/PowKernel.cu)
+__device__ __forceinline__ float pow_scalar(float x, float p) {
+    if (p == 0.5f) return sqrtf(x);
+    if (p == 2.f) return __fmul_rn(x, x);
+    if (p == 1.f) return x;
+    if (p == 3.f) return __fmul_rn(__fmul_rn(x, x), x);
+    if (p == 0.f) return 1.f;
+    if (p == -0.5f) return rsqrtf(x);
+    if (p == -1.f) return __fdiv_rn(1.f, x);
+    if (p == -2.f) return __fdiv_rn(1.f, __fmul_rn(x, x));
+    return powf(x, p);
+}
+
+struct GtBox {
+    float x1, y1, x2, y2;
+    float w, h, at;  // w1, h1 (+eps) and atan(w1/h1) of utils/metrics.py:107,126 - constant per GT
+};
+
+__device__ __forceinline__ GtBox make_gt(float4 g) {
+    GtBox r;
+    r.x1 = g.x, r.y1 = g.y, r.x2 = g.z, r.y2 = g.w;
+    r.w = __fsub_rn(g.z, g.x);
+    r.h = __fadd_rn(__fsub_rn(g.w, g.y), 1e-7f);
+    r.at = atanf(__fdiv_rn(r.w, r.h));
+    return r;
+}
+
+// utils/tal.py:259-262: min of the four signed distances strictly above 1e-9
+__device__ __forceinline__ bool anchor_in_gt(float ax, float ay, const GtBox& g) {
+    const float d = fminf(fminf(__fsub_rn(ax, g.x1), __fsub_rn(ay, g.y1)),
+                          fminf(__fsub_rn(g.x2, ax), __fsub_rn(g.y2, ay)));
+    return d > 1e-9f;
+}
+
+// clamp(CIoU(box1 = GT, box2 = prediction), 0)   (utils/metrics.py:103-130, utils/tal.py:155)
+__device__ __forceinline__ float overlap_ciou(const GtBox& g, const float4 p) {
+    const float e = 1e-7f;
+    const float pw = __fsub_rn(p.z, p.x);
+    const float ph = __fadd_rn(__fsub_rn(p.w, p.y), e);
+    const float iw = fmaxf(__fsub_rn(fminf(g.x2, p.z), fmaxf(g.x1, p.x)), 0.f);
+    const float ih = fmaxf(__fsub_rn(fminf(g.y2, p.w), fmaxf(g.y1, p.y)), 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(g.w, g.h), __fmul_rn(pw, ph)), inter), e);
+    const float iou = __fdiv_rn(inter, uni);
+    const float cw = __fsub_rn(fmaxf(g.x2, p.z), fminf(g.x1, p.x));
+    const float ch = __fsub_rn(fmaxf(g.y2, p.w), fminf(g.y1, p.y));
+    const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(cw, cw), __fmul_rn(ch, ch)), e);
+    const float dx = __fsub_rn(__fsub_rn(__fadd_rn(p.x, p.z), g.x1), g.x2);
+    const float dy = __fsub_rn(__fsub_rn(__fadd_rn(p.y, p.w), g.y1), g.y2);
+    const float rho2 = __fmul_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), 0.25f);
+    const float da = __fsub_rn(atanf(__fdiv_rn(pw, ph)), g.at);
+    const float v = __fmul_rn(0.40528473456935109f, __fmul_rn(da, da));  // float(4 / pi^2)
+    const float al = __fdiv_rn(v, __fadd_rn(__fsub_rn(v, iou), 1.00000011920928955f));  // float(1 + 1e-7)
+    const float ciou = __fsub_rn(iou, __fadd_rn(__fdiv_rn(rho2, c2), __fmul_rn(v, al)));
+    return fmaxf(ciou, 0.f);
+}
+
+__device__ __forceinline__ u64 shfl64(u64 v, int src) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_up64(u64 v, int d) {
+    const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
+    const uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+    return ((u64)hi << 32) | lo;
+}
+
+// ---- verify ----------------------------------------------------------------------------------
+
+__global__ void assign_verify_kernel(const float* __restrict__ anc, int A, AssignParams p) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    int l = 0;
+    for (int k = 1; k < p.n_levels; ++k)
+        if (a >= p.lv[k].offset) l = k;
+    const int q = a - p.lv[l].offset;
+    const float s = p.lv[l].stride;
+    const float ex = __fmul_rn((float)(q % p.lv[l].w) + 0.5f, s);
+    const float ey = __fmul_rn((float)(q / p.lv[l].w) + 0.5f, s);
+    if (anc[2 * a] != ex || anc[2 * a + 1] != ey) atomicOr(p.ws.flags, 1);
+}
+
+// ---- candidates + top-k ----------------------------------------------------------------------
+
+constexpr int CAND_THREADS = 256;
+
+__global__ void __launch_bounds__(CAND_THREADS) assign_candidates_kernel(const AssignParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= (long long)p.b * p.G) return;
+    const int bi = (int)(wid / p.G), g = (int)(wid % p.G);
+    if (lane == 0) p.ws.pos_align[wid] = 0u, p.ws.pos_ov[wid] = 0u;
+    if (wid == 0 && lane == 0 && p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
+    if (p.mask_gt[wid] == 0.f) return;  // padded GT: claims nothing, contributes zero overlap
+
+    const GtBox gt = make_gt(*reinterpret_cast<const float4*>(p.gt_bboxes + wid * 4));
+    int label = (int)p.gt_labels[wid];
+    label = label < 0 ? 0 : (label >= p.nc ? p.nc - 1 : label);
+    const bool grid_ok = p.n_levels > 0 && p.ws.flags[0] == 0;
+    const size_t img = (size_t)bi * p.A;
+    const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
+    const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
+    const float* __restrict__ pds = p.pd_scores + img * p.nc + label;
+    const uint32_t inv_g = 0xffffffffu - (uint32_t)g;
+    const int topk = p.topk;
+
+    u64 tk = 0ull;   // lane i holds the i-th best  metric_bits<<32 | ~anchor  (0 = empty)
+    u64 kth = 0ull;  // entry topk-1: the bar a new candidate has to clear
+
+    const int n_pseudo = grid_ok ? p.n_levels : 1;
+    for (int l = 0; l < n_pseudo; ++l) {
+        int i0 = 0, j0 = 0, nx = p.A, ny = 1, W = 0, off = 0;
+        if (grid_ok) {
+            // superset of the cells whose centre can be inside the GT (one spare cell each side);
+            // the exact fp32 predicate below decides
+            const float s = p.lv[l].stride;
+            W = p.lv[l].w, off = p.lv[l].offset;
+            const int H = p.lv[l].h;
+            int ia = (int)floorf(gt.x1 / s - 0.5f) - 1, ib = (int)ceilf(gt.x2 / s - 0.5f) + 1;
+            int ja = (int)floorf(gt.y1 / s - 0.5f) - 1, jb = (int)ceilf(gt.y2 / s - 0.5f) + 1;
+            ia = max(ia, 0), ja = max(ja, 0), ib = min(ib, W - 1), jb = min(jb, H - 1);
+            if (ia > ib || ja > jb) continue;
+            i0 = ia, j0 = ja, nx = ib - ia + 1, ny = jb - ja + 1;
+        }
+        const int total = nx * ny;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            u64 key = 0ull;
+            if (t < total) {
+                const int jj = t / nx;
+                const int a = off + (j0 + jj) * W + i0 + (t - jj * nx);
+                const float2 ap = __ldg(anc + a);
+                if (anchor_in_gt(ap.x, ap.y, gt)) {
+                    const float4 pb = __ldg(pdb + a);
+                    const float sc = __ldg(pds + (size_t)a * p.nc);
+                    const float o = overlap_ciou(gt, pb);
+                    if (o > 0.f) atomicMax(p.ws.key + img + a, ((u64)__float_as_uint(o) << 32) | inv_g);
+                    const float al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
+                    if (al > 0.f) key = ((u64)__float_as_uint(al) << 32) | (0xffffffffu - (uint32_t)a);
+                }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, key > kth);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const u64 ck = shfl64(key, src);
+                if (ck > kth) {  // kth may have risen since the ballot
+                    const int pos = __popc(__ballot_sync(0xffffffffu, tk > ck));
+                    const u64 up = shfl_up64(tk, 1);
+                    if (lane == pos) tk = ck;
+                    else if (lane > pos) tk = up;
+                    kth = shfl64(tk, topk - 1);
+                }
+            }
+        }
+    }
+    const bool has = lane < topk && tk != 0ull;
+    if (has) {
+        const uint32_t a = 0xffffffffu - (uint32_t)tk;
+        atomicAdd(p.ws.sel_cnt + img + a, 1u);
+        atomicMax(p.ws.sel_g + img + a, inv_g);
+    }
+    if (p.zero_fill) {
+        // torch.topk pads a short list with zero-metric entries, lowest anchor index first; a padded
+        // pick only matters when that anchor lies inside this GT (utils/tal.py:128).
+        int need = topk - __popc(__ballot_sync(0xffffffffu, has));
+        for (int a = 0; need > 0 && a < p.A; ++a) {
+            const bool mine = has && (0xffffffffu - (uint32_t)tk) == (uint32_t)a;
+            if (__any_sync(0xffffffffu, mine)) continue;  // positive pick, already counted
+            --need;
+            const float2 ap = __ldg(anc + a);
+            if (lane == 0 && anchor_in_gt(ap.x, ap.y, gt)) {
+                atomicAdd(p.ws.sel_cnt + img + a, 1u);
+                atomicMax(p.ws.sel_g + img + a, inv_g);
+            }
+        }
+    }
+}
+
+// ---- resolve -----------------------------------------------------------------------------------
+
+constexpr int RES_THREADS = 256;
+constexpr int RES_ITERS = 8;  // anchors per CTA = RES_THREADS * RES_ITERS
+
+// The image's GT table is staged in shared memory: boxes by one TMA bulk copy (always 16 B aligned),
+// labels and mask by plain loads. Each thread then owns RES_ITERS anchors.
+__global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const AssignParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ int fg_block;
+    float4* s_box = reinterpret_cast<float4*>(smem_raw);
+    float* s_lab = reinterpret_cast<float*>(smem_raw + (size_t)p.G * 16);
+    float* s_msk = s_lab + p.G;
+    const int bi = blockIdx.y;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        fg_block = 0;
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)p.G * 16u;
+        mbar_expect_tx(&bar, bytes);
+        tma_load_1d(s_box, p.gt_bboxes + (size_t)bi * p.G * 4, bytes, &bar);
+    }
+    for (int g = tid; g < p.G; g += RES_THREADS) {
+        s_lab[g] = p.gt_labels[(size_t)bi * p.G + g];
+        s_msk[g] = p.mask_gt[(size_t)bi * p.G + g];
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    const size_t img = (size_t)bi * p.A;
+    const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
+    int n_fg = 0;
+#pragma unroll 2
+    for (int it = 0; it < RES_ITERS; ++it) {
+        const int a = (blockIdx.x * RES_ITERS + it) * RES_THREADS + tid;
+        if (a >= p.A) break;
+        const size_t idx = img + a;
+        const uint32_t cnt = p.ws.sel_cnt[idx];
+        uint32_t g = 0;
+        if (cnt == 1u) {
+            g = 0xffffffffu - p.ws.sel_g[idx];
+        } else if (cnt > 1u) {  // contested: first-max argmax of overlaps over ALL GTs (utils/tal.py:286)
+            const u64 k = p.ws.key[idx];
+            g = (k >> 32) ? 0xffffffffu - (uint32_t)k : 0u;
+        }
+        const bool fg = cnt > 0u;
+        const float4 gb = s_box[g];
+        long long lab = (long long)s_lab[g];
+        lab = lab < 0 ? 0 : lab;
+        p.target_gt_idx[idx] = (long long)g;
+        p.target_labels[idx] = lab;
+        p.fg_mask[idx] = fg ? 1 : 0;
+        reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
+        float al = 0.f;
+        if (fg) {
+            ++n_fg;
+            const GtBox gt = make_gt(gb);
+            const float2 ap = __ldg(anc + a);
+            if (s_msk[g] != 0.f && anchor_in_gt(ap.x, ap.y, gt)) {
+                const int li = lab >= p.nc ? p.nc - 1 : (int)lab;
+                const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
+                const float sc = __ldg(p.pd_scores + idx * p.nc + li);
+                const float o = overlap_ciou(gt, pb);
+                al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
+                atomicMax(p.ws.pos_ov + (size_t)bi * p.G + g, __float_as_uint(o));
+                atomicMax(p.ws.pos_align + (size_t)bi * p.G + g, __float_as_uint(al));
+            }
+        }
+        if (p.nc == 1) p.target_scores[idx] = al;
+        else if (fg) p.target_scores[idx * p.nc + (lab >= p.nc ? p.nc - 1 : lab)] = al;  // row pre-zeroed
+    }
+    if (p.counters) {
+        n_fg = __reduce_add_sync(0xffffffffu, n_fg);
+        if ((tid & 31) == 0 && n_fg) atomicAdd(&fg_block, n_fg);
+        __syncthreads();
+        if (tid == 0 && fg_block) atomicAdd(p.counters + 1, (double)fg_block);
+    }
+}
+
+// ---- normalise ---------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) assign_normalize_kernel(const AssignParams p) {
+    __shared__ double s_sum;
+    if (threadIdx.x == 0) s_sum = 0.0;
+    __syncthreads();
+    const long long n = (long long)p.b * p.A;
+    float local = 0.f;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (!p.fg_mask[idx]) continue;
+        const int bi = (int)(idx / p.A);
+        const long long g = p.target_gt_idx[idx];
+        long long lab = p.target_labels[idx];
+        lab = lab >= p.nc ? p.nc - 1 : lab;
+        float* dst = p.target_scores + idx * p.nc + lab;
+        const float ov = __uint_as_float(p.ws.pos_ov[(size_t)bi * p.G + g]);
+        const float pa = __uint_as_float(p.ws.pos_align[(size_t)bi * p.G + g]);
+        const float v = __fdiv_rn(__fmul_rn(*dst, ov), __fadd_rn(pa, p.eps));  // utils/tal.py:115
+        *dst = v;
+        local += v;
+    }
+    if (p.counters) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(&s_sum, (double)local);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_sum != 0.0) atomicAdd(p.counters, s_sum);
+    }
+}
+
+__global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ dst, size_t n4, float* __restrict__ tail,
+                                                        int n_tail) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        __stcs(dst + i, z);
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0.f;
+}
+
+static void split_ws(void* workspace, int b, int A, int G, AssignWs& ws, size_t& total) {
+    unsigned char* p = (unsigned char*)workspace;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        unsigned char* r = p ? p + o : nullptr;
+        o += align_up(bytes, 256);
+        return r;
+    };
+    const size_t n = (size_t)b * A;
+    ws.key = (u64*)take(n * 8);
+    ws.sel_cnt = (uint32_t*)take(n * 4);
+    ws.sel_g = (uint32_t*)take(n * 4);
+    ws.flags = (int32_t*)take(256);
+    ws.zero_bytes = o;
+    ws.pos_align = (uint32_t*)take((size_t)b * G * 4);
+    ws.pos_ov = (uint32_t*)take((size_t)b * G * 4);
+    total = o;
+}
+
+}  // namespace kzd
+
+using namespace kzd;
+
+extern "C" __attribute__((visibility("default"))) size_t kzd_assign_workspace_bytes(int b, int A, int G) {
+    if (b < 0 || A < 0 || G < 0) return 0;
+    AssignWs ws;
+    size_t total = 0;
+    split_ws(nullptr, b, A, G, ws, total);
+    return total;
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
+                              const float* gt_labels, const float* gt_bboxes, const float* mask_gt, int b, int A,
+                              int G, int nc, int topk, float alpha, float beta, float eps, const kzd_level* h_levels,
+                              int n_levels, int zero_fill, int64_t* target_labels, float* target_bboxes,
+                              float* target_scores, uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    KZD_CHECK_ARG(pd_scores && pd_bboxes && anc_points && gt_labels && gt_bboxes && mask_gt,
+                  "kzd_tal_assign: null input");
+    KZD_CHECK_ARG(target_labels && target_bboxes && target_scores && fg_mask && target_gt_idx && workspace,
+                  "kzd_tal_assign: null output/workspace");
+    KZD_CHECK_ARG(b >= 0 && A >= 1 && G >= 1 && nc >= 1, "kzd_tal_assign: bad sizes b=%d A=%d G=%d nc=%d", b, A, G, nc);
+    KZD_CHECK_ARG(topk >= 1 && topk <= KZD_MAX_TOPK, "kzd_tal_assign: topk=%d not in [1,%d]", topk, KZD_MAX_TOPK);
+    KZD_CHECK_ARG(n_levels >= 0 && n_levels <= KZD_MAX_LEVELS && (n_levels == 0 || h_levels),
+                  "kzd_tal_assign: bad level table");
+    KZD_CHECK_ARG(b <= 65535, "kzd_tal_assign: b=%d > 65535", b);
+    KZD_CHECK_ARG((size_t)G * 24 <= 200 * 1024, "kzd_tal_assign: G=%d exceeds the shared-memory GT table (8533)", G);
+    KZD_CHECK_ARG(((uintptr_t)gt_bboxes) % 16 == 0 && ((uintptr_t)pd_bboxes) % 16 == 0 &&
+                      ((uintptr_t)target_bboxes) % 16 == 0 && ((uintptr_t)anc_points) % 8 == 0 &&
+                      ((uintptr_t)workspace) % 256 == 0,
+                  "kzd_tal_assign: misaligned tensor");
+    if (b == 0) return 0;
+    AssignParams p;
+    size_t need = 0;
+    split_ws(workspace, b, A, G, p.ws, need);
+    if (workspace_bytes < need) {
+        set_error("kzd_tal_assign: workspace %zu B < required %zu B", workspace_bytes, need);
+        return KZD_ENOSPACE;
+    }
+    int off = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        KZD_CHECK_ARG(h_levels[l].h > 0 && h_levels[l].w > 0 && h_levels[l].offset == off && h_levels[l].stride > 0.f,
+                      "kzd_tal_assign: level %d inconsistent", l);
+        p.lv[l] = h_levels[l];
+        off += h_levels[l].h * h_levels[l].w;
+    }
+    KZD_CHECK_ARG(n_levels == 0 || off == A, "kzd_tal_assign: levels cover %d anchors, A=%d", off, A);
+    p.pd_scores = pd_scores, p.pd_bboxes = pd_bboxes, p.anc = anc_points;
+    p.gt_labels = gt_labels, p.gt_bboxes = gt_bboxes, p.mask_gt = mask_gt;
+    p.b = b, p.A = A, p.G = G, p.nc = nc, p.topk = topk;
+    p.alpha = alpha, p.beta = beta, p.eps = eps;
+    p.n_levels = n_levels, p.zero_fill = zero_fill;
+    p.target_labels = (long long*)target_labels, p.target_bboxes = target_bboxes, p.target_scores = target_scores;
+    p.fg_mask = fg_mask, p.target_gt_idx = (long long*)target_gt_idx, p.counters = counters;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    KZD_CUDA(cudaMemsetAsync(workspace, 0, p.ws.zero_bytes, st));
+    if (n_levels > 0) {
+        assign_verify_kernel<<<(A + 255) / 256, 256, 0, st>>>(anc_points, A, p);
+        KZD_LAUNCH_CHECK("assign_verify_kernel");
+    }
+    if (nc > 1) {  // dense (b,A,nc) target_scores: zero rows now, the owner's entry is written later
+        const size_t n = (size_t)b * A * nc;
+        const size_t n4 = (((uintptr_t)target_scores) % 16 == 0) ? n / 4 : 0;
+        const int n_tail = (int)(n - n4 * 4);
+        if (n_tail > 256) {  // unaligned buffer: plain memset
+            KZD_CUDA(cudaMemsetAsync(target_scores, 0, n * 4, st));
+        } else {
+            size_t blocks = (n4 + 255) / 256;
+            const size_t cap = (size_t)sm_count() * 32;
+            if (blocks > cap) blocks = cap;
+            if (blocks < 1) blocks = 1;
+            zero_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>((float4*)target_scores, n4, target_scores + n4 * 4,
+                                                               n_tail);
+            KZD_LAUNCH_CHECK("zero_fill_kernel");
+        }
+    }
+    {
+        const long long warps = (long long)b * G;
+        const long long blocks = (warps * 32 + CAND_THREADS - 1) / CAND_THREADS;
+        assign_candidates_kernel<<<(unsigned)blocks, CAND_THREADS, 0, st>>>(p);
+        KZD_LAUNCH_CHECK("assign_candidates_kernel");
+    }
+    {
+        const size_t smem = (size_t)G * 24;
+        KZD_CUDA(cudaFuncSetAttribute(assign_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((A + RES_THREADS * RES_ITERS - 1) / (RES_THREADS * RES_ITERS), b);
+        assign_resolve_kernel<<<grid, RES_THREADS, smem, st>>>(p);
+        KZD_LAUNCH_CHECK("assign_resolve_kernel");
+    }
+    {
+        const long long n = (long long)b * A;
+        long long blocks = (n + 255) / 256;
+        const long long cap = (long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        assign_normalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+        KZD_LAUNCH_CHECK("assign_normalize_kernel");
+    }
+    return 0;
+}

@@ -1,0 +1,354 @@
+// DFL decode kernels (sm_100a).
+//
+//  * decode_infer : Detect._inference + DFL.forward + dist2bbox(xywh) + sigmoid, reading the
+//                   per-level NCHW maps directly (reference: nn/modules/head.py:100-131,
+//                   nn/modules/block.py:71-74, utils/tal.py:348-357).
+//  * decode_train : v8DetectionLoss.bbox_decode + dist2bbox(xyxy) on the anchor-major (b,A,64)
+//                   layout (reference: utils/loss.py:197-204), and its backward.
+//
+// Both are pure streaming kernels bound by HBM bandwidth (272 B per anchor).
+#include "kzd_common.cuh"
+
+namespace kzd {
+
+// ------------------------------------------------------------------------------------------
+// inference decode
+// ------------------------------------------------------------------------------------------
+
+struct InferParams {
+    const float* ptr[KZD_MAX_LEVELS];
+    int hw[KZD_MAX_LEVELS];
+    int w[KZD_MAX_LEVELS];
+    int off[KZD_MAX_LEVELS + 1];
+    float stride[KZD_MAX_LEVELS];
+    int n_levels, b, nc, A;
+};
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+    using T = float4;
+    static __device__ __forceinline__ void load(float (&v)[4], const float* p) {
+        float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    }
+};
+template <>
+struct Vec<1> {
+    static __device__ __forceinline__ void load(float (&v)[1], const float* p) { v[0] = __ldcs(p); }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { __stcs(p, v[0]); }
+};
+
+// One thread decodes VEC consecutive anchors of one image: 4 sides x 16 bins are read as 64
+// coalesced VEC-wide loads (anchors are the fastest dimension of the NCHW maps), the softmax
+// expectation is evaluated in registers, and the 4+nc output rows are written VEC-wide.
+template <int VEC>
+__global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, float* __restrict__ y) {
+    const int bi = blockIdx.y;
+    const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (a0 >= p.A) return;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < KZD_MAX_LEVELS; ++k)
+        if (k < p.n_levels && a0 >= p.off[k]) l = k;
+    const int hw = p.hw[l];
+    const int pos = a0 - p.off[l];
+    const int no = 4 * KZD_REG_MAX + p.nc;
+    const float* __restrict__ src = p.ptr[l] + (size_t)bi * no * hw + pos;
+
+    float d[4][VEC];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        float v[KZD_REG_MAX][VEC];
+#pragma unroll
+        for (int k = 0; k < KZD_REG_MAX; ++k) Vec<VEC>::load(v[k], src + (size_t)(s * KZD_REG_MAX + k) * hw);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float m = v[0][i];
+#pragma unroll
+            for (int k = 1; k < KZD_REG_MAX; ++k) m = fmaxf(m, v[k][i]);
+            float sum = 0.f, wsum = 0.f;
+#pragma unroll
+            for (int k = 0; k < KZD_REG_MAX; ++k) {
+                const float e = __expf(v[k][i] - m);
+                sum += e;
+                wsum = fmaf((float)k, e, wsum);
+            }
+            d[s][i] = wsum / sum;
+        }
+    }
+    const float st = p.stride[l];
+    const int w = p.w[l];
+    float ox[VEC], oy[VEC], ow[VEC], oh[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int q = pos + i;
+        const float ax = (float)(q % w) + 0.5f;
+        const float ay = (float)(q / w) + 0.5f;
+        const float x1 = ax - d[0][i], y1 = ay - d[1][i];
+        const float x2 = ax + d[2][i], y2 = ay + d[3][i];
+        ox[i] = ((x1 + x2) * 0.5f) * st;
+        oy[i] = ((y1 + y2) * 0.5f) * st;
+        ow[i] = (x2 - x1) * st;
+        oh[i] = (y2 - y1) * st;
+    }
+    float* __restrict__ dst = y + (size_t)bi * (4 + p.nc) * p.A + a0;
+    Vec<VEC>::store(dst, ox);
+    Vec<VEC>::store(dst + (size_t)p.A, oy);
+    Vec<VEC>::store(dst + 2 * (size_t)p.A, ow);
+    Vec<VEC>::store(dst + 3 * (size_t)p.A, oh);
+    const float* __restrict__ csrc = src + (size_t)(4 * KZD_REG_MAX) * hw;
+    float* __restrict__ cdst = dst + 4 * (size_t)p.A;
+#pragma unroll 4
+    for (int c = 0; c < p.nc; ++c) {
+        float v[VEC], o[VEC];
+        Vec<VEC>::load(v, csrc + (size_t)c * hw);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = 1.f / (1.f + expf(-v[i]));
+        Vec<VEC>::store(cdst + (size_t)c * p.A, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// training decode: TMA bulk-copy pipeline
+// ------------------------------------------------------------------------------------------
+
+constexpr int TR_ANCH = 64;                     // anchors per tile
+constexpr int TR_FLOATS = TR_ANCH * 64;         // 4096 floats = 16 KB
+constexpr int TR_STAGES = 4;                    // 64 KB of loads in flight per CTA
+constexpr int TR_THREADS = TR_ANCH * 4;         // one thread per (anchor, side)
+constexpr int TR_SMEM = TR_STAGES * TR_FLOATS * 4;
+
+// Softmax expectation of the 16 bins at smem row `row` (16 floats, 64 B). The four 16-byte chunks
+// are visited in a per-thread rotated order so that every quarter-warp hits 8 distinct bank groups.
+__device__ __forceinline__ void side_stats(const float* row, int tid, float& d, float& m_out, float& sum_out) {
+    float v[4][4];
+    int q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        q[j] = (j + (tid >> 1)) & 3;
+        const float4 t = *reinterpret_cast<const float4*>(row + q[j] * 4);
+        v[j][0] = t.x, v[j][1] = t.y, v[j][2] = t.z, v[j][3] = t.w;
+    }
+    float m = v[0][0];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m = fmaxf(m, v[j][k]);
+    float sum = 0.f, wsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float base = (float)(q[j] * 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float e = __expf(v[j][k] - m);
+            sum += e;
+            wsum = fmaf(base + (float)k, e, wsum);
+        }
+    }
+    d = wsum / sum;
+    m_out = m;
+    sum_out = sum;
+}
+
+// Persistent CTAs; thread 0 is the TMA producer (cp.async.bulk of one 16 KB tile per stage, signalled
+// on an mbarrier), all 256 threads consume: thread t owns (anchor t/4, side t%4) of the tile and
+// writes output element t of the tile's 256 contiguous floats.
+__global__ void __launch_bounds__(TR_THREADS) decode_train_kernel(const float* __restrict__ pred,
+                                                                  const float* __restrict__ anc, int A,
+                                                                  long long N, float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* buf = reinterpret_cast<float*>(smem_raw);
+    __shared__ uint64_t full[TR_STAGES];
+    const int tid = threadIdx.x;
+    const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
+
+    if (tid == 0) {
+        for (int s = 0; s < TR_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](long long tile, int stage) {
+        const long long first = tile * TR_ANCH;
+        const long long cnt = (N - first < TR_ANCH) ? (N - first) : TR_ANCH;
+        const uint32_t bytes = (uint32_t)cnt * 256u;
+        mbar_expect_tx(&full[stage], bytes);
+        tma_load_1d(buf + stage * TR_FLOATS, pred + first * 64, bytes, &full[stage]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < TR_STAGES; ++s) {
+            const long long tile = blockIdx.x + (long long)s * gridDim.x;
+            if (tile < n_tiles) issue(tile, s);
+        }
+    }
+    const int a_local = tid >> 2, side = tid & 3;
+    for (long long it = 0;; ++it) {
+        const long long tile = blockIdx.x + it * gridDim.x;
+        if (tile >= n_tiles) break;
+        const int stage = (int)(it % TR_STAGES);
+        mbar_wait(&full[stage], (uint32_t)((it / TR_STAGES) & 1));
+        const long long n = tile * TR_ANCH + a_local;
+        if (n < N) {
+            float d, m, s;
+            side_stats(buf + stage * TR_FLOATS + tid * 16, tid, d, m, s);
+            const int a_img = (int)(n % A);
+            const float ap = __ldg(anc + a_img * 2 + (side & 1));
+            out[n * 4 + side] = (side < 2) ? (ap - d) : (ap + d);
+        }
+        __syncthreads();  // every thread is done with this stage before it is refilled
+        if (tid == 0) {
+            const long long next = tile + (long long)TR_STAGES * gridDim.x;
+            if (next < n_tiles) issue(next, stage);
+        }
+    }
+}
+
+// Backward: d = sum_j j p_j  =>  dd/dx_j = p_j (j - d); x1y1 = a - lt, x2y2 = a + rb.
+__global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const float* __restrict__ pred,
+                                                                      const float* __restrict__ gout,
+                                                                      long long N, float* __restrict__ gin) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* buf = reinterpret_cast<float*>(smem_raw);
+    __shared__ uint64_t full[TR_STAGES];
+    const int tid = threadIdx.x;
+    const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
+    if (tid == 0) {
+        for (int s = 0; s < TR_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](long long tile, int stage) {
+        const long long first = tile * TR_ANCH;
+        const long long cnt = (N - first < TR_ANCH) ? (N - first) : TR_ANCH;
+        const uint32_t bytes = (uint32_t)cnt * 256u;
+        mbar_expect_tx(&full[stage], bytes);
+        tma_load_1d(buf + stage * TR_FLOATS, pred + first * 64, bytes, &full[stage]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < TR_STAGES; ++s) {
+            const long long tile = blockIdx.x + (long long)s * gridDim.x;
+            if (tile < n_tiles) issue(tile, s);
+        }
+    }
+    const int a_local = tid >> 2, side = tid & 3;
+    for (long long it = 0;; ++it) {
+        const long long tile = blockIdx.x + it * gridDim.x;
+        if (tile >= n_tiles) break;
+        const int stage = (int)(it % TR_STAGES);
+        mbar_wait(&full[stage], (uint32_t)((it / TR_STAGES) & 1));
+        const long long n = tile * TR_ANCH + a_local;
+        if (n < N) {
+            const float* row = buf + stage * TR_FLOATS + tid * 16;
+            float d, m, s;
+            side_stats(row, tid, d, m, s);
+            float g = gout[n * 4 + side];
+            g = (side < 2) ? -g : g;
+            const float inv = g / s;
+            float* dst = gin + n * 64 + side * 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int q = (j + (tid >> 1)) & 3;
+                const float4 t = *reinterpret_cast<const float4*>(row + q * 4);
+                float4 o;
+                o.x = inv * __expf(t.x - m) * ((float)(q * 4 + 0) - d);
+                o.y = inv * __expf(t.y - m) * ((float)(q * 4 + 1) - d);
+                o.z = inv * __expf(t.z - m) * ((float)(q * 4 + 2) - d);
+                o.w = inv * __expf(t.w - m) * ((float)(q * 4 + 3) - d);
+                *reinterpret_cast<float4*>(dst + q * 4) = o;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const long long next = tile + (long long)TR_STAGES * gridDim.x;
+            if (next < n_tiles) issue(next, stage);
+        }
+    }
+}
+
+}  // namespace kzd
+
+using namespace kzd;
+
+extern "C" __attribute__((visibility("default"))) int kzd_decode_infer(const float* const* h_level_ptrs, const kzd_level* h_levels, int n_levels, int b,
+                                int nc, float* y, void* stream) {
+    KZD_CHECK_ARG(h_level_ptrs && h_levels && y, "kzd_decode_infer: null pointer");
+    KZD_CHECK_ARG(n_levels >= 1 && n_levels <= KZD_MAX_LEVELS, "kzd_decode_infer: n_levels=%d not in [1,%d]", n_levels,
+                  KZD_MAX_LEVELS);
+    KZD_CHECK_ARG(b >= 0 && nc >= 0, "kzd_decode_infer: negative size");
+    InferParams p;
+    int off = 0;
+    bool vec4 = true;
+    for (int l = 0; l < n_levels; ++l) {
+        KZD_CHECK_ARG(h_levels[l].h > 0 && h_levels[l].w > 0, "kzd_decode_infer: empty level %d", l);
+        KZD_CHECK_ARG(h_levels[l].offset == off, "kzd_decode_infer: level %d offset %d, expected %d", l,
+                      h_levels[l].offset, off);
+        p.ptr[l] = h_level_ptrs[l];
+        p.hw[l] = h_levels[l].h * h_levels[l].w;
+        p.w[l] = h_levels[l].w;
+        p.off[l] = off;
+        p.stride[l] = h_levels[l].stride;
+        off += p.hw[l];
+        vec4 = vec4 && (p.hw[l] % 4 == 0) && (((uintptr_t)p.ptr[l]) % 16 == 0);
+    }
+    for (int l = n_levels; l <= KZD_MAX_LEVELS; ++l) p.off[l] = off;
+    for (int l = n_levels; l < KZD_MAX_LEVELS; ++l) p.ptr[l] = nullptr, p.hw[l] = 1, p.w[l] = 1, p.stride[l] = 0.f;
+    p.n_levels = n_levels, p.b = b, p.nc = nc, p.A = off;
+    vec4 = vec4 && (((uintptr_t)y) % 16 == 0);
+    if (b == 0) return 0;
+    KZD_CHECK_ARG(b <= 65535, "kzd_decode_infer: b=%d > 65535", b);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec4) {
+        dim3 grid((off / 4 + 127) / 128, b);
+        decode_infer_kernel<4><<<grid, 128, 0, st>>>(p, y);
+    } else {
+        dim3 grid((off + 127) / 128, b);
+        decode_infer_kernel<1><<<grid, 128, 0, st>>>(p, y);
+    }
+    KZD_LAUNCH_CHECK("decode_infer_kernel");
+    return 0;
+}
+
+static int train_grid(long long n_tiles, const void* fn) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TR_THREADS, TR_SMEM);
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)sm_count() * per_sm;
+    return (int)(n_tiles < g ? n_tiles : g);
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_decode_train(const float* pred_dist, const float* anchor_points, int b, int A, float* out_xyxy,
+                                void* stream) {
+    KZD_CHECK_ARG(pred_dist && anchor_points && out_xyxy, "kzd_decode_train: null pointer");
+    KZD_CHECK_ARG(b >= 0 && A >= 0, "kzd_decode_train: negative size");
+    KZD_CHECK_ARG(((uintptr_t)pred_dist) % 16 == 0, "kzd_decode_train: pred_dist must be 16-byte aligned");
+    const long long N = (long long)b * A;
+    if (N == 0) return 0;
+    KZD_CUDA(cudaFuncSetAttribute(decode_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+    const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
+    const int grid = train_grid(n_tiles, (const void*)decode_train_kernel);
+    decode_train_kernel<<<grid, TR_THREADS, TR_SMEM, (cudaStream_t)stream>>>(pred_dist, anchor_points, A, N, out_xyxy);
+    KZD_LAUNCH_CHECK("decode_train_kernel");
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_decode_train_bwd(const float* pred_dist, const float* grad_xyxy, int b, int A,
+                                    float* grad_pred_dist, void* stream) {
+    KZD_CHECK_ARG(pred_dist && grad_xyxy && grad_pred_dist, "kzd_decode_train_bwd: null pointer");
+    KZD_CHECK_ARG(b >= 0 && A >= 0, "kzd_decode_train_bwd: negative size");
+    KZD_CHECK_ARG(((uintptr_t)pred_dist) % 16 == 0 && ((uintptr_t)grad_pred_dist) % 16 == 0,
+                  "kzd_decode_train_bwd: tensors must be 16-byte aligned");
+    const long long N = (long long)b * A;
+    if (N == 0) return 0;
+    KZD_CUDA(cudaFuncSetAttribute(decode_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+    const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
+    const int grid = train_grid(n_tiles, (const void*)decode_train_bwd_kernel);
+    decode_train_bwd_kernel<<<grid, TR_THREADS, TR_SMEM, (cudaStream_t)stream>>>(pred_dist, grad_xyxy, N,
+                                                                                grad_pred_dist);
+    KZD_LAUNCH_CHECK("decode_train_bwd_kernel");
+    return 0;
+}

@@ -1,0 +1,101 @@
+"""Monkey-patch an importable ``ultralytics`` (the reference vendors 8.3.63 under ``yolov12/``) so that
+``v8DetectionLoss`` / the predictor / the validator use libkzd on CUDA tensors.
+
+The reference has no plugin registry for this path: the boundary is four module
+attributes, patched here and restored by ``uninstall()``:
+
+  ultralytics.utils.tal.TaskAlignedAssigner    <- tal.TaskAlignedAssigner      (utils/tal.py:14)
+  ultralytics.utils.loss.TaskAlignedAssigner   <- same (bound by ``from .tal import``, utils/loss.py:9)
+  ultralytics.utils.loss.v8DetectionLoss.bbox_decode <- head.loss_bbox_decode  (utils/loss.py:197)
+  ultralytics.nn.modules.head.Detect._inference      <- head.detect_inference  (nn/modules/head.py:100)
+  ultralytics.utils.ops.non_max_suppression    <- ops.non_max_suppression      (utils/ops.py:167)
+
+Calls that are outside this path's scope (CPU tensors, rotated boxes, masks, export formats) are
+handed to the reference's own, unpatched function - they never reach libkzd and libkzd never
+computes on the CPU.
+"""
+from __future__ import annotations
+
+import functools
+import importlib
+
+from . import head as _head
+from . import ops as _ops
+from . import tal as _tal
+
+_saved = {}
+
+
+def _is_cuda(x):
+    if isinstance(x, (list, tuple)):
+        x = x[0]
+    return bool(getattr(x, "is_cuda", False))
+
+
+def install(patch_decode_train=True):
+    """Patch the importable ``ultralytics``; returns the list of patched attribute names."""
+    if _saved:
+        return sorted(_saved)
+    u_tal = importlib.import_module("ultralytics.utils.tal")
+    u_loss = importlib.import_module("ultralytics.utils.loss")
+    u_ops = importlib.import_module("ultralytics.utils.ops")
+    u_head = importlib.import_module("ultralytics.nn.modules.head")
+
+    ref_assigner = u_tal.TaskAlignedAssigner
+    ref_nms = u_ops.non_max_suppression
+    ref_inference = u_head.Detect._inference
+    ref_bbox_decode = u_loss.v8DetectionLoss.bbox_decode
+
+    class TaskAlignedAssigner(_tal.TaskAlignedAssigner):
+        """libkzd on CUDA inputs; the reference's own module for anything else."""
+
+        def forward(self, pd_scores, *rest):
+            if not _is_cuda(pd_scores):
+                ref = ref_assigner(self.topk, self.num_classes, self.alpha, self.beta, self.eps)
+                return ref.forward(pd_scores, *rest)
+            return super().forward(pd_scores, *rest)
+
+    @functools.wraps(ref_nms)
+    def non_max_suppression(prediction, *args, **kwargs):
+        pred = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
+        if _is_cuda(pred):
+            try:
+                return _ops.non_max_suppression(prediction, *args, **kwargs)
+            except NotImplementedError:
+                pass  # rotated / masks / labels / end2end: not this path
+        return ref_nms(prediction, *args, **kwargs)
+
+    def _inference(self, x):
+        if self.export or not _is_cuda(x):
+            return ref_inference(self, x)
+        return _head.detect_inference(self, x)
+
+    def bbox_decode(self, anchor_points, pred_dist):
+        if not _is_cuda(pred_dist):
+            return ref_bbox_decode(self, anchor_points, pred_dist)
+        return _head.loss_bbox_decode(self, anchor_points, pred_dist)
+
+    _saved.update({
+        "tal.TaskAlignedAssigner": (u_tal, "TaskAlignedAssigner", ref_assigner),
+        "loss.TaskAlignedAssigner": (u_loss, "TaskAlignedAssigner", u_loss.TaskAlignedAssigner),
+        "ops.non_max_suppression": (u_ops, "non_max_suppression", ref_nms),
+        "head.Detect._inference": (u_head.Detect, "_inference", ref_inference),
+    })
+    u_tal.TaskAlignedAssigner = TaskAlignedAssigner
+    u_loss.TaskAlignedAssigner = TaskAlignedAssigner
+    u_ops.non_max_suppression = non_max_suppression
+    u_head.Detect._inference = _inference
+    if patch_decode_train:
+        _saved["loss.v8DetectionLoss.bbox_decode"] = (u_loss.v8DetectionLoss, "bbox_decode", ref_bbox_decode)
+        u_loss.v8DetectionLoss.bbox_decode = bbox_decode
+    return sorted(_saved)
+
+
+def uninstall():
+    for owner, name, orig in _saved.values():
+        setattr(owner, name, orig)
+    _saved.clear()
+
+
+def installed():
+    return bool(_saved)

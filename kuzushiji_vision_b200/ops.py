@@ -1,0 +1,119 @@
+"""Drop-in for ``ultralytics.utils.ops.non_max_suppression`` (detection task).
+
+Reference: ``yolov12/ultralytics/utils/ops.py:167-316`` (signature :167-182, checks :217-220, filter
+:234-286, class offset :289-295, ``torchvision.ops.nms`` :296, ``[:max_det]`` :297, gather :311) and
+``xywh2xyxy`` :416-433. All images of the batch run together in ``libkzd``; the host does one
+device->host read of ``2*b`` counters instead of the reference's per-image ``nonzero`` syncs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+DEFAULT_POOL = 32768   # first-try candidate pool per image
+DEFAULT_N_CAP = 4096   # first-try suppression capacity per image (mask = (n_cap/64)^2 * 512 B)
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def nms_batched(prediction, conf_thres, iou_thres, classes=None, agnostic=False, multi_label=False, max_det=300,
+                max_nms=30000, max_wh=7680.0, in_place=True, pool=None, n_cap=None):
+    """Batched NMS on a contiguous fp32 CUDA tensor ``prediction (b, 4+nc, A)``.
+
+    Returns ``(rows (b, max_det, 6), counts list[int])``; ``rows[i, :counts[i]]`` are image i's kept
+    detections ``[x1,y1,x2,y2,conf,cls]`` in descending score order. ``prediction[:, :4]`` is
+    overwritten with xyxy when ``in_place`` (the reference's side effect, utils/ops.py:243-244).
+    """
+    b, ch, A = prediction.shape
+    nc = ch - 4
+    dev = prediction.device
+    multi_label = bool(multi_label) and nc > 1
+    max_cand = A * nc if multi_label else A
+    pool = min(max_cand, pool or DEFAULT_POOL)
+    cls_t, n_cls = None, 0
+    if classes is not None:
+        cls_t = torch.as_tensor(list(classes), dtype=torch.int32, device=dev)
+        n_cls = cls_t.numel()
+        if n_cls == 0:  # nothing can pass the class filter
+            return torch.zeros((b, max_det, 6), device=dev), [0] * b
+    out_rows = torch.empty((b, max_det, 6), dtype=torch.float32, device=dev)
+    counts = torch.empty((2, b), dtype=torch.int32, device=dev)  # [0] candidates, [1] kept
+    lib = _lib.lib
+    mode = 1 if in_place else 0
+    with torch.cuda.device(dev):
+        while True:
+            keys = torch.empty((b, pool), dtype=torch.int64, device=dev)
+            rows = torch.empty((b, pool, 6), dtype=torch.float32, device=dev)
+            _lib.check(lib.kzd_nms_filter(prediction.data_ptr(), b, A, nc, float(conf_thres), int(multi_label),
+                                          cls_t.data_ptr() if n_cls else None, n_cls, mode, keys.data_ptr(),
+                                          rows.data_ptr(), counts[0].data_ptr(), pool, _stream(dev)),
+                       "kzd_nms_filter")
+            if mode == 1:
+                mode = 2  # boxes are xyxy from now on
+            cap = min(n_cap or DEFAULT_N_CAP, max_nms, pool)
+            cap = _round_up(max(cap, 64), 64)
+            while True:
+                ws_bytes = lib.kzd_nms_workspace_bytes(b, pool, cap)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                _lib.check(lib.kzd_nms_suppress(keys.data_ptr(), rows.data_ptr(), counts[0].data_ptr(), b, pool, cap,
+                                                float(iou_thres), int(bool(agnostic)), int(max_det), int(max_nms),
+                                                float(max_wh), out_rows.data_ptr(), counts[1].data_ptr(),
+                                                ws.data_ptr(), ws_bytes, _stream(dev)),
+                           "kzd_nms_suppress")
+                host = counts.cpu()  # the one synchronisation of the call
+                n_cand, n_keep = host[0].tolist(), host[1].tolist()
+                if min(n_keep) >= 0:
+                    return out_rows, n_keep
+                worst = max(n_cand)
+                if worst > pool:
+                    break  # pool overflow: redo the filter with room for everything
+                cap = _round_up(min(worst, max_nms), 64)
+            pool = max_cand
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
+                        multi_label=False, labels=(), max_det=300, nc=0, max_time_img=0.05, max_nms=30000,
+                        max_wh=7680, in_place=True, rotated=False):
+    """Same signature and return convention as the reference (utils/ops.py:167-182): a list of
+    ``(n_i, 6)`` tensors ``[x1,y1,x2,y2,conf,cls]`` per image, descending score, at most ``max_det``.
+
+    Out of scope (raise ``NotImplementedError``; ``install()`` routes those calls to the reference's
+    own function): rotated boxes, mask coefficients (``nm > 0``), apriori ``labels``, end-to-end
+    ``(b, n, 6)`` inputs. ``max_time_img`` is accepted and ignored: the batch takes well under the
+    reference's 2 s + 0.05 s/image budget.
+    """
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    if isinstance(prediction, (list, tuple)):
+        prediction = prediction[0]
+    if rotated or (labels is not None and len(labels)) or prediction.shape[-1] == 6:
+        raise NotImplementedError("kuzushiji_vision_b200.non_max_suppression: rotated / labels / end2end inputs")
+    _lib.require_cuda(prediction, "prediction")
+    bs = prediction.shape[0]
+    nc = nc or (prediction.shape[1] - 4)
+    if prediction.shape[1] - nc - 4 != 0:
+        raise NotImplementedError("kuzushiji_vision_b200.non_max_suppression: mask coefficients (nm > 0)")
+    direct = prediction.dtype == torch.float32 and prediction.is_contiguous()
+    work = prediction if direct else prediction.to(torch.float32).contiguous()
+    rows, n_keep = nms_batched(work, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms,
+                               float(max_wh), in_place)
+    if in_place and not direct:
+        prediction[:, :4] = work[:, :4].to(prediction.dtype)
+    empty = torch.zeros((0, 6), device=prediction.device)
+    return [rows[i, :n] if n else empty for i, n in zip(range(bs), n_keep)]
+
+
+def xywh2xyxy(x):
+    """utils/ops.py:416-433 (torch glue; the NMS kernel does this conversion itself)."""
+    assert x.shape[-1] == 4, f"input shape last dimension expected 4 but input shape is {x.shape}"
+    half = x[..., 2:] / 2
+    return torch.cat((x[..., :2] - half, x[..., :2] + half), -1)

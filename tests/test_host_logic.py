@@ -1,0 +1,116 @@
+"""CPU: host-side logic of the package - the C ABI loads and exports every symbol of include/kzd.h,
+argument validation, grid inference, synthetic pages, drop-in signatures, sharding."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import kuzushiji_vision_b200 as kzd
+from kuzushiji_vision_b200 import _lib, dist as kdist, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "kzd.h")).read()
+    declared = set(re.findall(r"\b(kzd_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(_lib.lib, name), f"libkzd.so does not export {name}"
+    assert declared == set(_lib.EXPORTS)
+    assert _lib.lib.kzd_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    # bad arguments are rejected before any CUDA call is made
+    rc = _lib.lib.kzd_decode_train(None, None, 1, 1, None, None)
+    assert rc == -1 and b"null" in _lib.lib.kzd_last_error()
+    lv, _ = _lib.levels_array([(4, 4, 8.0)])
+    rc = _lib.lib.kzd_tal_assign(1, 1, 1, 1, 1, 1, 1, 16, 1, 1, 99, 0.5, 6.0, 1e-9, lv, 1, 0, 1, 1, 1, 1, 1, None,
+                                 1, 0, None)
+    assert rc == -1 and b"topk" in _lib.lib.kzd_last_error()
+    assert _lib.lib.kzd_assign_workspace_bytes(16, 136000, 600) > 16 * 136000 * 16
+    assert _lib.lib.kzd_nms_workspace_bytes(2, 1000, 256) > 0
+
+
+def test_cpu_tensors_are_refused():
+    d = synth.assigner_inputs(1, 10, 128, 1, synth.P3_P5)
+    with pytest.raises(kzd.KzdError):
+        kzd.TaskAlignedAssigner(10, 1, 0.5, 6.0)(d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"],
+                                                  d["gt_bboxes"], d["mask_gt"])
+    with pytest.raises(kzd.KzdError):
+        kzd.non_max_suppression(torch.zeros(1, 5, 10))
+    with pytest.raises(kzd.KzdError):
+        kzd.bbox_decode(d["anchor_points"], d["pred_distri"])
+    with pytest.raises(kzd.KzdError):
+        kzd.decode_inference(d["levels"], synth.P3_P5, 1)
+
+
+def test_g0_branch_is_host_logic():
+    out = kzd.TaskAlignedAssigner(10, 3)(torch.rand(2, 50, 3), torch.rand(2, 50, 4), torch.rand(50, 2),
+                                         torch.zeros(2, 0, 1), torch.zeros(2, 0, 4), torch.zeros(2, 0, 1))
+    assert all(o.dtype == torch.float32 for o in out) and (out[0] == 3).all()
+
+
+def test_nms_asserts_like_reference():
+    with pytest.raises(AssertionError):
+        kzd.non_max_suppression(torch.zeros(1, 5, 10), conf_thres=1.5)
+    with pytest.raises(AssertionError):
+        kzd.non_max_suppression(torch.zeros(1, 5, 10), iou_thres=-0.1)
+
+
+def test_infer_levels():
+    d = synth.assigner_inputs(1, 5, 256, 1, synth.P2_P5)
+    assert kzd.infer_levels(d["anc_points"]) == [(64, 64, 4.0), (32, 32, 8.0), (16, 16, 16.0), (8, 8, 32.0)]
+    pts = d["anc_points"].clone()
+    pts[100, 0] += 0.25
+    assert kzd.infer_levels(pts) is None
+    assert kzd.infer_levels(torch.rand(50, 2)) is None
+    # non-square level
+    xs = (torch.arange(7.0) + 0.5) * 8
+    ys = (torch.arange(3.0) + 0.5) * 8
+    pts = torch.stack((xs.repeat(3), ys.repeat_interleave(7)), 1)
+    assert kzd.infer_levels(pts) == [(3, 7, 8.0)]
+
+
+def test_signatures_match_reference_interface():
+    sig = inspect.signature(kzd.non_max_suppression)
+    assert list(sig.parameters) == ["prediction", "conf_thres", "iou_thres", "classes", "agnostic", "multi_label",
+                                    "labels", "max_det", "nc", "max_time_img", "max_nms", "max_wh", "in_place",
+                                    "rotated"]
+    assert sig.parameters["iou_thres"].default == 0.45 and sig.parameters["max_det"].default == 300
+    sig = inspect.signature(kzd.TaskAlignedAssigner.__init__)
+    assert [p for p in sig.parameters][1:] == ["topk", "num_classes", "alpha", "beta", "eps"]
+    assert sig.parameters["topk"].default == 13 and sig.parameters["eps"].default == 1e-9
+    sig = inspect.signature(kzd.TaskAlignedAssigner.forward)
+    assert [p for p in sig.parameters][1:] == ["pd_scores", "pd_bboxes", "anc_points", "gt_labels", "gt_bboxes",
+                                               "mask_gt"]
+    a = kzd.TaskAlignedAssigner(topk=10, num_classes=4, alpha=0.5, beta=6.0)
+    assert (a.topk, a.num_classes, a.bg_idx, a.alpha, a.beta, a.eps) == (10, 4, 4, 0.5, 6.0, 1e-9)
+
+
+def test_synth_pages_are_seeded_and_well_formed():
+    l1, b1, m1 = synth.gt_pages(2, 100, 1280, nc=4, seed=3)
+    l2, b2, m2 = synth.gt_pages(2, 100, 1280, nc=4, seed=3)
+    assert torch.equal(b1, b2) and torch.equal(l1, l2)
+    n = m1.sum(1).flatten()
+    assert ((n >= 70) & (n <= 100)).all()
+    valid = m1.squeeze(-1).bool()
+    wh = (b1[..., 2:] - b1[..., :2])[valid]
+    assert (wh > 15.9).all() and (wh < 56.1).all()
+    assert (b1[valid][:, :2] > 20).all() and (b1[valid][:, 2:] < 1260).all()
+    assert (b1[~valid] == 0).all()
+    assert synth.num_anchors(1280, synth.P2_P5) == 136000 and synth.num_anchors(1536, synth.P2_P5) == 195840
+    lv = synth.head_outputs(1, 2, 128, synth.P2_P5, seed=1, sparse_cls=50)
+    assert [tuple(x.shape) for x in lv] == [(1, 66, 32, 32), (1, 66, 16, 16), (1, 66, 8, 8), (1, 66, 4, 4)]
+
+
+def test_shard_range_partitions_exactly():
+    for n, w in [(128, 8), (16, 3), (5, 8), (0, 2)]:
+        spans = [kdist.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1

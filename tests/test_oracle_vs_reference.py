@@ -1,0 +1,68 @@
+"""CPU, build container only: live comparison of the oracle with the unmodified reference imported
+from /root/reference (skipped where that tree does not exist, e.g. on the GPU box)."""
+import pytest
+import torch
+
+from oracle import ref_loader
+from oracle import torch_oracle as O
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def R():
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize("cfg", [
+    (2, 60, 320, 1, (8, 16, 32), "columns", 10, 0.5),
+    (1, 50, 256, 4, (4, 8, 16, 32), "uniform", 10, 0.5),
+    (1, 40, 256, 2, (4, 8, 16, 32), "columns", 13, 1.0),
+])
+def test_assign_live(R, cfg):
+    from kuzushiji_vision_b200 import synth
+
+    b, G, imgsz, nc, strides, layout, topk, alpha = cfg
+    d = synth.assigner_inputs(b, G, imgsz, nc, strides, seed=21, layout=layout)
+    args = (d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+    ref = R.TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=alpha, beta=6.0)(*args)
+    mine = O.tal_assign(*args, topk, nc, alpha, 6.0)
+    for r, m in zip(ref, mine):
+        assert r.dtype == m.dtype
+        if r.dtype == torch.float32:
+            torch.testing.assert_close(m, r, rtol=1e-5, atol=1e-8)
+        else:
+            assert torch.equal(r, m)
+
+
+def test_ciou_live(R):
+    g = torch.Generator().manual_seed(5)
+    a = torch.rand(2000, 2, generator=g) * 100
+    gt = torch.cat((a, a + torch.rand(2000, 2, generator=g) * 50 + 1), 1)
+    c = torch.rand(2000, 2, generator=g) * 100
+    pd = torch.cat((c, c + torch.rand(2000, 2, generator=g) * 50 + 1), 1)
+    ref = R.bbox_iou(gt, pd, xywh=False, CIoU=True).squeeze(-1)
+    torch.testing.assert_close(O.ciou_gt_pd(gt, pd), ref, rtol=0, atol=0)
+
+
+def test_anchors_live(R):
+    feats = [torch.zeros(1, 1, 5, 7), torch.zeros(1, 1, 3, 4)]
+    ra, rs = R.make_anchors(feats, [8, 16], 0.5)
+    oa, os_ = O.make_anchors([(5, 7), (3, 4)], [8, 16])
+    assert torch.equal(ra, oa) and torch.equal(rs, os_)
+    from kuzushiji_vision_b200 import make_anchors
+
+    ka, ks = make_anchors(feats, [8, 16], 0.5)
+    assert torch.equal(ra, ka) and torch.equal(rs, ks)
+
+
+def test_nms_live(R):
+    from kuzushiji_vision_b200 import synth
+
+    lv = synth.head_outputs(2, 3, 256, synth.P2_P5, seed=4, sparse_cls=300)
+    y = O.decode_infer(lv, synth.P2_P5, 3)
+    for kw in (dict(conf_thres=0.25, iou_thres=0.7, max_det=300), dict(conf_thres=0.25, iou_thres=0.5, agnostic=True),
+               dict(conf_thres=0.3, iou_thres=0.6, multi_label=True, max_det=50)):
+        a = R.non_max_suppression(y.clone(), **kw)
+        b_ = O.non_max_suppression(y.clone(), **kw)
+        assert all(torch.equal(x, z) for x, z in zip(a, b_))
