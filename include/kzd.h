@@ -89,14 +89,18 @@ size_t kzd_assign_workspace_bytes(int b, int A, int G);
  * Outputs (all written for every anchor):
  *   target_labels int64 (b,A), target_bboxes (b,A,4), target_scores (b,A,nc), fg_mask uint8 (b,A),
  *   target_gt_idx int64 (b,A); counters double[2] = { sum(target_scores), count(fg_mask) }
- *   (may be NULL). G must be >= 1 (the G == 0 early-out of tal.py:64-71 is host logic). */
+ *   (may be NULL). G must be >= 1 (the G == 0 early-out of tal.py:64-71 is host logic).
+ *   epoch: 0 = stateless: the call zeroes the per-anchor state in `workspace` itself (one extra
+ *     12 B/anchor memset). 1..255 = the caller keeps ONE workspace for this (b, A, G), zeroed it once
+ *     after allocation, and passes epochs 1, 2, ..., 255 on consecutive calls (re-zero before wrapping
+ *     to 1): stale state then loses every atomic and no memset is needed. */
 int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
                    const float* gt_labels, const float* gt_bboxes, const float* mask_gt,
                    int b, int A, int G, int nc, int topk, float alpha, float beta, float eps,
                    const kzd_level* h_levels, int n_levels, int zero_fill,
                    int64_t* target_labels, float* target_bboxes, float* target_scores,
                    uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
-                   void* workspace, size_t workspace_bytes, void* stream);
+                   void* workspace, size_t workspace_bytes, int epoch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * NMS

@@ -23,14 +23,22 @@ namespace kzd {
 
 typedef unsigned long long u64;
 
+// Per-anchor state words carry an 8-bit epoch in their top bits, so a persistent workspace never has
+// to be re-zeroed between calls: entries written under an older epoch lose every atomicMax / CAS.
+//   key  = epoch:8 | overlap_bits:30 | (KEY_GMASK - g):26     (overlap <= 1.0f  =>  bits < 2^30)
+//   sel  = epoch:8 | state:24   state = g+1 (exactly one selecting GT) or SEL_MULTI (several)
+constexpr int KEY_GBITS = 26;
+constexpr u64 KEY_GMASK = (1ull << KEY_GBITS) - 1ull;
+constexpr uint32_t SEL_MULTI = 0xffffffu;
+
 struct AssignWs {
-    u64* key;            // (b*A)  max over in-GT pairs of  overlap_bits<<32 | ~g
-    uint32_t* sel_cnt;   // (b*A)  number of GTs whose top-k selected the anchor
-    uint32_t* sel_g;     // (b*A)  max of ~g over selecting GTs (= smallest g)
+    u64* key;            // (b*A)  max over in-GT pairs of the packed (overlap, ~g) key
+    uint32_t* sel;       // (b*A)  which GT's top-k selected the anchor
     uint32_t* pos_align; // (b*G)  per-GT max alignment metric (float bits)
     uint32_t* pos_ov;    // (b*G)  per-GT max overlap (float bits)
-    int32_t* flags;      // [0] != 0: anc_points does not match the level table
-    size_t zero_bytes;   // prefix of the workspace that must be zero before the candidates kernel
+    uint32_t* fg_list;   // (b*A)  compact list of foreground anchors (flat index)
+    int32_t* flags;      // [0] != 0: anc_points does not match the level table; [1] = fg count
+    size_t state_bytes;  // key + sel: the part that must have been zeroed once
 };
 
 struct AssignParams {
@@ -39,6 +47,7 @@ struct AssignParams {
     float alpha, beta, eps;
     kzd_level lv[KZD_MAX_LEVELS];
     int n_levels, zero_fill;
+    uint32_t epoch;  // 1..255
     long long* target_labels;
     float* target_bboxes;
     float* target_scores;
@@ -137,14 +146,69 @@ __global__ void assign_verify_kernel(const float* __restrict__ anc, int A, Assig
 // ---- candidates + top-k ----------------------------------------------------------------------
 
 constexpr int CAND_THREADS = 256;
+constexpr int CAND_WARPS = CAND_THREADS / 32;
+
+struct TopK {
+    u64 tk;   // lane i holds the i-th best  metric_bits<<32 | ~anchor  (0 = empty)
+    u64 kth;  // entry topk-1: the bar a new candidate has to clear
+};
+
+// One in-GT pair per lane (a < 0: idle lane): overlap, metric, argmax key, streaming top-k insert.
+__device__ __forceinline__ void eval_pairs(const AssignParams& p, const GtBox& gt, int a, size_t img,
+                                           const float4* __restrict__ pdb, const float* __restrict__ pds, int g,
+                                           int topk, int lane, TopK& st) {
+    u64 key = 0ull;
+    if (a >= 0) {
+        const float4 pb = __ldg(pdb + a);
+        const float sc = __ldg(pds + (size_t)a * p.nc);
+        const float o = overlap_ciou(gt, pb);
+        if (o > 0.f)
+            atomicMax(p.ws.key + img + a, ((u64)p.epoch << 56) | ((u64)min(__float_as_uint(o), 0x3fffffffu) << KEY_GBITS) |
+                                              (KEY_GMASK - (u64)g));
+        const float al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
+        if (al > 0.f) key = ((u64)__float_as_uint(al) << 32) | (0xffffffffu - (uint32_t)a);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, key > st.kth);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const u64 ck = shfl64(key, src);
+        if (ck > st.kth) {  // kth may have risen since the ballot
+            const int pos = __popc(__ballot_sync(0xffffffffu, st.tk > ck));
+            const u64 up = shfl_up64(st.tk, 1);
+            if (lane == pos) st.tk = ck;
+            else if (lane > pos) st.tk = up;
+            st.kth = shfl64(st.tk, topk - 1);
+        }
+    }
+}
+
+// GT `g` selected anchor idx: first selector stores g+1, any later different selector stores MULTI.
+__device__ __forceinline__ void mark_selected(uint32_t* __restrict__ sel, uint32_t epoch, int g) {
+    const uint32_t mine = (epoch << 24) | (uint32_t)(g + 1);
+    uint32_t cur = *sel;
+    while (true) {
+        uint32_t want;
+        if ((cur >> 24) != epoch) want = mine;                       // stale or never written
+        else if (cur == mine || (cur & 0xffffffu) == SEL_MULTI) return;
+        else want = (epoch << 24) | SEL_MULTI;
+        const uint32_t old = atomicCAS(sel, cur, want);
+        if (old == cur) return;
+        cur = old;
+    }
+}
 
 __global__ void __launch_bounds__(CAND_THREADS) assign_candidates_kernel(const AssignParams p) {
-    const int lane = threadIdx.x & 31;
+    __shared__ int queue[CAND_WARPS][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= (long long)p.b * p.G) return;
     const int bi = (int)(wid / p.G), g = (int)(wid % p.G);
     if (lane == 0) p.ws.pos_align[wid] = 0u, p.ws.pos_ov[wid] = 0u;
-    if (wid == 0 && lane == 0 && p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
+    if (wid == 0 && lane == 0) {
+        p.ws.flags[1] = 0;
+        if (p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
+    }
     if (p.mask_gt[wid] == 0.f) return;  // padded GT: claims nothing, contributes zero overlap
 
     const GtBox gt = make_gt(*reinterpret_cast<const float4*>(p.gt_bboxes + wid * 4));
@@ -155,19 +219,19 @@ __global__ void __launch_bounds__(CAND_THREADS) assign_candidates_kernel(const A
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
     const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
     const float* __restrict__ pds = p.pd_scores + img * p.nc + label;
-    const uint32_t inv_g = 0xffffffffu - (uint32_t)g;
     const int topk = p.topk;
-
-    u64 tk = 0ull;   // lane i holds the i-th best  metric_bits<<32 | ~anchor  (0 = empty)
-    u64 kth = 0ull;  // entry topk-1: the bar a new candidate has to clear
+    int* q = queue[wib];
+    int qn = 0;  // queued in-GT anchors (warp-uniform)
+    TopK st{0ull, 0ull};
 
     const int n_pseudo = grid_ok ? p.n_levels : 1;
     for (int l = 0; l < n_pseudo; ++l) {
         int i0 = 0, j0 = 0, nx = p.A, ny = 1, W = 0, off = 0;
+        float s = 0.f;
         if (grid_ok) {
             // superset of the cells whose centre can be inside the GT (one spare cell each side);
             // the exact fp32 predicate below decides
-            const float s = p.lv[l].stride;
+            s = p.lv[l].stride;
             W = p.lv[l].w, off = p.lv[l].offset;
             const int H = p.lv[l].h;
             int ia = (int)floorf(gt.x1 / s - 0.5f) - 1, ib = (int)ceilf(gt.x2 / s - 0.5f) + 1;
@@ -179,54 +243,50 @@ __global__ void __launch_bounds__(CAND_THREADS) assign_candidates_kernel(const A
         const int total = nx * ny;
         for (int t0 = 0; t0 < total; t0 += 32) {
             const int t = t0 + lane;
-            u64 key = 0ull;
+            bool inside = false;
+            int a = 0;
             if (t < total) {
-                const int jj = t / nx;
-                const int a = off + (j0 + jj) * W + i0 + (t - jj * nx);
-                const float2 ap = __ldg(anc + a);
-                if (anchor_in_gt(ap.x, ap.y, gt)) {
-                    const float4 pb = __ldg(pdb + a);
-                    const float sc = __ldg(pds + (size_t)a * p.nc);
-                    const float o = overlap_ciou(gt, pb);
-                    if (o > 0.f) atomicMax(p.ws.key + img + a, ((u64)__float_as_uint(o) << 32) | inv_g);
-                    const float al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
-                    if (al > 0.f) key = ((u64)__float_as_uint(al) << 32) | (0xffffffffu - (uint32_t)a);
+                const int jj = t / nx, ii = t - jj * nx;
+                a = off + (j0 + jj) * W + i0 + ii;
+                float ax, ay;
+                if (grid_ok) {  // verified bit-identical to anc_points[a] by assign_verify_kernel
+                    ax = __fmul_rn((float)(i0 + ii) + 0.5f, s), ay = __fmul_rn((float)(j0 + jj) + 0.5f, s);
+                } else {
+                    const float2 ap = __ldg(anc + a);
+                    ax = ap.x, ay = ap.y;
                 }
+                inside = anchor_in_gt(ax, ay, gt);
             }
-            unsigned m = __ballot_sync(0xffffffffu, key > kth);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const u64 ck = shfl64(key, src);
-                if (ck > kth) {  // kth may have risen since the ballot
-                    const int pos = __popc(__ballot_sync(0xffffffffu, tk > ck));
-                    const u64 up = shfl_up64(tk, 1);
-                    if (lane == pos) tk = ck;
-                    else if (lane > pos) tk = up;
-                    kth = shfl64(tk, topk - 1);
-                }
+            // compact the in-GT anchors into the warp's queue; evaluate 32 at a time with all lanes busy
+            const unsigned m = __ballot_sync(0xffffffffu, inside);
+            if (inside) q[qn + __popc(m & ((1u << lane) - 1u))] = a;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                const int a32 = q[lane];
+                const int tail = q[32 + lane];
+                __syncwarp();
+                q[lane] = tail;
+                qn -= 32;
+                __syncwarp();
+                eval_pairs(p, gt, a32, img, pdb, pds, g, topk, lane, st);
             }
         }
     }
-    const bool has = lane < topk && tk != 0ull;
-    if (has) {
-        const uint32_t a = 0xffffffffu - (uint32_t)tk;
-        atomicAdd(p.ws.sel_cnt + img + a, 1u);
-        atomicMax(p.ws.sel_g + img + a, inv_g);
-    }
+    if (qn > 0) eval_pairs(p, gt, lane < qn ? q[lane] : -1, img, pdb, pds, g, topk, lane, st);
+
+    const bool has = lane < topk && st.tk != 0ull;
+    if (has) mark_selected(p.ws.sel + img + (0xffffffffu - (uint32_t)st.tk), p.epoch, g);
     if (p.zero_fill) {
         // torch.topk pads a short list with zero-metric entries, lowest anchor index first; a padded
         // pick only matters when that anchor lies inside this GT (utils/tal.py:128).
         int need = topk - __popc(__ballot_sync(0xffffffffu, has));
         for (int a = 0; need > 0 && a < p.A; ++a) {
-            const bool mine = has && (0xffffffffu - (uint32_t)tk) == (uint32_t)a;
+            const bool mine = has && (0xffffffffu - (uint32_t)st.tk) == (uint32_t)a;
             if (__any_sync(0xffffffffu, mine)) continue;  // positive pick, already counted
             --need;
             const float2 ap = __ldg(anc + a);
-            if (lane == 0 && anchor_in_gt(ap.x, ap.y, gt)) {
-                atomicAdd(p.ws.sel_cnt + img + a, 1u);
-                atomicMax(p.ws.sel_g + img + a, inv_g);
-            }
+            if (lane == 0 && anchor_in_gt(ap.x, ap.y, gt)) mark_selected(p.ws.sel + img + a, p.epoch, g);
         }
     }
 }
@@ -237,18 +297,17 @@ constexpr int RES_THREADS = 256;
 constexpr int RES_ITERS = 8;  // anchors per CTA = RES_THREADS * RES_ITERS
 
 // The image's GT table is staged in shared memory: boxes by one TMA bulk copy (always 16 B aligned),
-// labels and mask by plain loads. Each thread then owns RES_ITERS anchors.
+// labels and mask by plain loads. Each thread then owns RES_ITERS anchors (state words loaded up
+// front so RES_ITERS independent loads are in flight).
 __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const AssignParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    __shared__ int fg_block;
     float4* s_box = reinterpret_cast<float4*>(smem_raw);
     float* s_lab = reinterpret_cast<float*>(smem_raw + (size_t)p.G * 16);
     float* s_msk = s_lab + p.G;
     const int bi = blockIdx.y;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
-        fg_block = 0;
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
@@ -262,71 +321,85 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
         s_lab[g] = p.gt_labels[(size_t)bi * p.G + g];
         s_msk[g] = p.mask_gt[(size_t)bi * p.G + g];
     }
+    const size_t img = (size_t)bi * p.A;
+    const int a_base = blockIdx.x * RES_ITERS * RES_THREADS + tid;
+    uint32_t sel[RES_ITERS];
+#pragma unroll
+    for (int it = 0; it < RES_ITERS; ++it) {
+        const int a = a_base + it * RES_THREADS;
+        sel[it] = a < p.A ? p.ws.sel[img + a] : 0u;
+    }
     __syncthreads();
     mbar_wait(&bar, 0);
 
-    const size_t img = (size_t)bi * p.A;
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
-    int n_fg = 0;
-#pragma unroll 2
+#pragma unroll
     for (int it = 0; it < RES_ITERS; ++it) {
-        const int a = (blockIdx.x * RES_ITERS + it) * RES_THREADS + tid;
-        if (a >= p.A) break;
-        const size_t idx = img + a;
-        const uint32_t cnt = p.ws.sel_cnt[idx];
+        const int a = a_base + it * RES_THREADS;
+        const bool live = a < p.A;
+        const size_t idx = img + (live ? a : 0);
+        const bool fg = live && (sel[it] >> 24) == p.epoch;
         uint32_t g = 0;
-        if (cnt == 1u) {
-            g = 0xffffffffu - p.ws.sel_g[idx];
-        } else if (cnt > 1u) {  // contested: first-max argmax of overlaps over ALL GTs (utils/tal.py:286)
-            const u64 k = p.ws.key[idx];
-            g = (k >> 32) ? 0xffffffffu - (uint32_t)k : 0u;
-        }
-        const bool fg = cnt > 0u;
-        const float4 gb = s_box[g];
-        long long lab = (long long)s_lab[g];
-        lab = lab < 0 ? 0 : lab;
-        p.target_gt_idx[idx] = (long long)g;
-        p.target_labels[idx] = lab;
-        p.fg_mask[idx] = fg ? 1 : 0;
-        reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
-        float al = 0.f;
         if (fg) {
-            ++n_fg;
-            const GtBox gt = make_gt(gb);
-            const float2 ap = __ldg(anc + a);
-            if (s_msk[g] != 0.f && anchor_in_gt(ap.x, ap.y, gt)) {
-                const int li = lab >= p.nc ? p.nc - 1 : (int)lab;
-                const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
-                const float sc = __ldg(p.pd_scores + idx * p.nc + li);
-                const float o = overlap_ciou(gt, pb);
-                al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
-                atomicMax(p.ws.pos_ov + (size_t)bi * p.G + g, __float_as_uint(o));
-                atomicMax(p.ws.pos_align + (size_t)bi * p.G + g, __float_as_uint(al));
+            const uint32_t state = sel[it] & 0xffffffu;
+            if (state != SEL_MULTI) {
+                g = state - 1u;
+            } else {  // contested: first-max argmax of overlaps over ALL GTs (utils/tal.py:286)
+                const u64 k = p.ws.key[idx];
+                const bool any = (k >> 56) == p.epoch && ((k >> KEY_GBITS) & 0x3fffffffull) != 0ull;
+                g = any ? (uint32_t)(KEY_GMASK - (k & KEY_GMASK)) : 0u;
             }
         }
-        if (p.nc == 1) p.target_scores[idx] = al;
-        else if (fg) p.target_scores[idx * p.nc + (lab >= p.nc ? p.nc - 1 : lab)] = al;  // row pre-zeroed
-    }
-    if (p.counters) {
-        n_fg = __reduce_add_sync(0xffffffffu, n_fg);
-        if ((tid & 31) == 0 && n_fg) atomicAdd(&fg_block, n_fg);
-        __syncthreads();
-        if (tid == 0 && fg_block) atomicAdd(p.counters + 1, (double)fg_block);
+        float al = 0.f;
+        long long lab = 0;
+        if (live) {
+            const float4 gb = s_box[g];
+            lab = (long long)s_lab[g];
+            lab = lab < 0 ? 0 : lab;
+            p.target_gt_idx[idx] = (long long)g;
+            p.target_labels[idx] = lab;
+            p.fg_mask[idx] = fg ? 1 : 0;
+            reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
+            if (fg) {
+                const GtBox gt = make_gt(gb);
+                const float2 ap = __ldg(anc + a);
+                if (s_msk[g] != 0.f && anchor_in_gt(ap.x, ap.y, gt)) {
+                    const int li = lab >= p.nc ? p.nc - 1 : (int)lab;
+                    const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
+                    const float sc = __ldg(p.pd_scores + idx * p.nc + li);
+                    const float o = overlap_ciou(gt, pb);
+                    al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
+                    atomicMax(p.ws.pos_ov + (size_t)bi * p.G + g, __float_as_uint(o));
+                    atomicMax(p.ws.pos_align + (size_t)bi * p.G + g, __float_as_uint(al));
+                }
+            }
+            if (p.nc == 1) p.target_scores[idx] = al;
+            else if (fg) p.target_scores[idx * p.nc + (lab >= p.nc ? p.nc - 1 : lab)] = al;  // row pre-zeroed
+        }
+        // compact list of foreground anchors for the normalise pass (one atomic per warp)
+        const unsigned m = __ballot_sync(0xffffffffu, fg);
+        if (m) {
+            int base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(p.ws.flags + 1, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (fg) p.ws.fg_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)idx;
+        }
     }
 }
 
 // ---- normalise ---------------------------------------------------------------------------------
 
+// Foreground anchors only (compact list): target_scores = align * pos_ov / (pos_align + eps).
 __global__ void __launch_bounds__(256) assign_normalize_kernel(const AssignParams p) {
     __shared__ double s_sum;
     if (threadIdx.x == 0) s_sum = 0.0;
     __syncthreads();
-    const long long n = (long long)p.b * p.A;
+    const int n = p.ws.flags[1];
     float local = 0.f;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        if (!p.fg_mask[idx]) continue;
-        const int bi = (int)(idx / p.A);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t idx = p.ws.fg_list[i];
+        const int bi = (int)(idx / (size_t)p.A);
         const long long g = p.target_gt_idx[idx];
         long long lab = p.target_labels[idx];
         lab = lab >= p.nc ? p.nc - 1 : lab;
@@ -341,7 +414,10 @@ __global__ void __launch_bounds__(256) assign_normalize_kernel(const AssignParam
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
         if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(&s_sum, (double)local);
         __syncthreads();
-        if (threadIdx.x == 0 && s_sum != 0.0) atomicAdd(p.counters, s_sum);
+        if (threadIdx.x == 0) {
+            if (s_sum != 0.0) atomicAdd(p.counters, s_sum);
+            if (blockIdx.x == 0) p.counters[1] = (double)n;
+        }
     }
 }
 
@@ -363,12 +439,12 @@ static void split_ws(void* workspace, int b, int A, int G, AssignWs& ws, size_t&
     };
     const size_t n = (size_t)b * A;
     ws.key = (u64*)take(n * 8);
-    ws.sel_cnt = (uint32_t*)take(n * 4);
-    ws.sel_g = (uint32_t*)take(n * 4);
+    ws.sel = (uint32_t*)take(n * 4);
+    ws.state_bytes = o;
     ws.flags = (int32_t*)take(256);
-    ws.zero_bytes = o;
     ws.pos_align = (uint32_t*)take((size_t)b * G * 4);
     ws.pos_ov = (uint32_t*)take((size_t)b * G * 4);
+    ws.fg_list = (uint32_t*)take(n * 4);
     total = o;
 }
 
@@ -389,7 +465,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
                               int G, int nc, int topk, float alpha, float beta, float eps, const kzd_level* h_levels,
                               int n_levels, int zero_fill, int64_t* target_labels, float* target_bboxes,
                               float* target_scores, uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+                              void* workspace, size_t workspace_bytes, int epoch, void* stream) {
     KZD_CHECK_ARG(pd_scores && pd_bboxes && anc_points && gt_labels && gt_bboxes && mask_gt,
                   "kzd_tal_assign: null input");
     KZD_CHECK_ARG(target_labels && target_bboxes && target_scores && fg_mask && target_gt_idx && workspace,
@@ -399,6 +475,8 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     KZD_CHECK_ARG(n_levels >= 0 && n_levels <= KZD_MAX_LEVELS && (n_levels == 0 || h_levels),
                   "kzd_tal_assign: bad level table");
     KZD_CHECK_ARG(b <= 65535, "kzd_tal_assign: b=%d > 65535", b);
+    KZD_CHECK_ARG(epoch >= 0 && epoch <= 255, "kzd_tal_assign: epoch=%d not in [0,255]", epoch);
+    KZD_CHECK_ARG((double)b * A < 4294967295.0 && G < (1 << 24) - 2, "kzd_tal_assign: b*A or G too large");
     KZD_CHECK_ARG((size_t)G * 24 <= 200 * 1024, "kzd_tal_assign: G=%d exceeds the shared-memory GT table (8533)", G);
     KZD_CHECK_ARG(((uintptr_t)gt_bboxes) % 16 == 0 && ((uintptr_t)pd_bboxes) % 16 == 0 &&
                       ((uintptr_t)target_bboxes) % 16 == 0 && ((uintptr_t)anc_points) % 8 == 0 &&
@@ -429,7 +507,13 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     p.fg_mask = fg_mask, p.target_gt_idx = (long long*)target_gt_idx, p.counters = counters;
 
     cudaStream_t st = (cudaStream_t)stream;
-    KZD_CUDA(cudaMemsetAsync(workspace, 0, p.ws.zero_bytes, st));
+    if (epoch == 0) {  // stateless mode: zero the per-anchor state here and run as epoch 1
+        KZD_CUDA(cudaMemsetAsync(workspace, 0, p.ws.state_bytes, st));
+        p.epoch = 1u;
+    } else {
+        p.epoch = (uint32_t)epoch;
+    }
+    KZD_CUDA(cudaMemsetAsync(p.ws.flags, 0, 8, st));
     if (n_levels > 0) {
         assign_verify_kernel<<<(A + 255) / 256, 256, 0, st>>>(anc_points, A, p);
         KZD_LAUNCH_CHECK("assign_verify_kernel");
@@ -464,11 +548,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
         KZD_LAUNCH_CHECK("assign_resolve_kernel");
     }
     {
-        const long long n = (long long)b * A;
-        long long blocks = (n + 255) / 256;
-        const long long cap = (long long)sm_count() * 8;
-        if (blocks > cap) blocks = cap;
-        assign_normalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+        assign_normalize_kernel<<<(unsigned)sm_count() * 2, 256, 0, st>>>(p);
         KZD_LAUNCH_CHECK("assign_normalize_kernel");
     }
     return 0;

@@ -7,7 +7,7 @@
 // Pipeline (no host synchronisation inside; candidate counts live on the device):
 //   nms_filter_kernel  conf filter + best class / multi-label + xywh->xyxy, candidates appended to
 //                      a per-image pool with a 64-bit key  score_bits<<32 | ~order
-//   nms_sort_kernel    per image: bitonic sort of the keys (descending) = torchvision's stable
+//   nms_chunk_sort / nms_rank   512-key chunk sorts + rank by binary search = torchvision's stable
 //                      descending score sort; writes score-ordered, class-offset boxes
 //   nms_mask_kernel    persistent CTAs over 64x64 tiles of the upper triangle: bit (i,j) = IoU > thr
 //   nms_scan_kernel    per image: greedy scan in 64-row chunks; the diagonal chunk is resolved by
@@ -30,174 +30,264 @@ __device__ __forceinline__ bool class_allowed(int c, const int32_t* __restrict__
     return false;
 }
 
-// Append one candidate per set lane; slots are handed out with one atomic per warp.
-__device__ __forceinline__ void append_candidate(bool is_cand, float x1, float y1, float x2, float y2, float conf,
-                                                 int cls, uint32_t order, u64* __restrict__ keys,
-                                                 float* __restrict__ rows, int32_t* __restrict__ count, int cap) {
-    const unsigned m = __ballot_sync(0xffffffffu, is_cand);
-    if (m == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(count, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (is_cand) {
-        const int slot = base + __popc(m & ((1u << lane) - 1u));
-        if (slot < cap) {
-            keys[slot] = ((u64)__float_as_uint(conf) << 32) | (u64)(0xffffffffu - order);
-            float* r = rows + (size_t)slot * 6;
-            r[0] = x1, r[1] = y1, r[2] = x2, r[3] = y2, r[4] = conf, r[5] = (float)cls;
-        }
+__device__ __forceinline__ void write_candidate(int slot, int cap, float x1, float y1, float x2, float y2, float conf,
+                                                int cls, uint32_t order, u64* __restrict__ keys,
+                                                float* __restrict__ rows) {
+    if (slot < cap) {
+        keys[slot] = ((u64)__float_as_uint(conf) << 32) | (u64)(0xffffffffu - order);
+        float2* r = reinterpret_cast<float2*>(rows + (size_t)slot * 6);  // 24-byte rows are 8-byte aligned
+        r[0] = make_float2(x1, y1), r[1] = make_float2(x2, y2), r[2] = make_float2(conf, (float)cls);
     }
 }
 
+// Warp-aggregated slot allocation: every lane asks for `want` (0..VEC) consecutive slots.
+__device__ __forceinline__ int warp_alloc(int want, int32_t* __restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    int incl = want;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return 0;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(count, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - want;
+}
+
+// Best-class path, VEC consecutive anchors per thread (128-bit loads/stores when VEC == 4).
+template <int VEC>
 __global__ void __launch_bounds__(256) nms_filter_kernel(float* pred, int A, int nc, float conf_thres,
-                                                         int multi_label, const int32_t* __restrict__ classes,
-                                                         int n_classes, int in_place, u64* __restrict__ keys,
+                                                         const int32_t* __restrict__ classes, int n_classes,
+                                                         int in_place, u64* __restrict__ keys,
                                                          float* __restrict__ rows, int32_t* __restrict__ counts,
                                                          int cap) {
     const int bi = blockIdx.y;
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive for the ballots
+    const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;  // whole warps stay alive for the shuffles
+    const bool live = a0 < A;
+    float* base = pred + (size_t)bi * (4 + nc) * A;
+    float x1[VEC], y1[VEC], x2[VEC], y2[VEC], best[VEC];
+    int cls[VEC];
+    int want = 0;
+    bool is_cand[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) is_cand[i] = false;
+    if (live) {
+        float cx[VEC], cy[VEC], bw[VEC], bh[VEC];
+        if (VEC == 4) {
+            const float4 t0 = *reinterpret_cast<const float4*>(base + a0);
+            const float4 t1 = *reinterpret_cast<const float4*>(base + (size_t)A + a0);
+            const float4 t2 = *reinterpret_cast<const float4*>(base + 2 * (size_t)A + a0);
+            const float4 t3 = *reinterpret_cast<const float4*>(base + 3 * (size_t)A + a0);
+            cx[0] = t0.x, cx[1 % VEC] = t0.y, cx[2 % VEC] = t0.z, cx[3 % VEC] = t0.w;
+            cy[0] = t1.x, cy[1 % VEC] = t1.y, cy[2 % VEC] = t1.z, cy[3 % VEC] = t1.w;
+            bw[0] = t2.x, bw[1 % VEC] = t2.y, bw[2 % VEC] = t2.z, bw[3 % VEC] = t2.w;
+            bh[0] = t3.x, bh[1 % VEC] = t3.y, bh[2 % VEC] = t3.z, bh[3 % VEC] = t3.w;
+        } else {
+            cx[0] = base[a0], cy[0] = base[(size_t)A + a0], bw[0] = base[2 * (size_t)A + a0],
+            bh[0] = base[3 * (size_t)A + a0];
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            if (in_place == 2) {  // rows already hold xyxy (second pass after a pool overflow)
+                x1[i] = cx[i], y1[i] = cy[i], x2[i] = bw[i], y2[i] = bh[i];
+            } else {              // utils/ops.py:429-432
+                const float hw = bw[i] * 0.5f, hh = bh[i] * 0.5f;
+                x1[i] = cx[i] - hw, y1[i] = cy[i] - hh, x2[i] = cx[i] + hw, y2[i] = cy[i] + hh;
+            }
+        }
+        if (in_place == 1) {
+            if (VEC == 4) {
+                *reinterpret_cast<float4*>(base + a0) = make_float4(x1[0], x1[1 % VEC], x1[2 % VEC], x1[3 % VEC]);
+                *reinterpret_cast<float4*>(base + (size_t)A + a0) =
+                    make_float4(y1[0], y1[1 % VEC], y1[2 % VEC], y1[3 % VEC]);
+                *reinterpret_cast<float4*>(base + 2 * (size_t)A + a0) =
+                    make_float4(x2[0], x2[1 % VEC], x2[2 % VEC], x2[3 % VEC]);
+                *reinterpret_cast<float4*>(base + 3 * (size_t)A + a0) =
+                    make_float4(y2[0], y2[1 % VEC], y2[2 % VEC], y2[3 % VEC]);
+            } else {
+                base[a0] = x1[0], base[(size_t)A + a0] = y1[0], base[2 * (size_t)A + a0] = x2[0],
+                base[3 * (size_t)A + a0] = y2[0];
+            }
+        }
+        const float* csrc = base + 4 * (size_t)A + a0;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) best[i] = -INFINITY, cls[i] = 0;
+        for (int c = 0; c < nc; ++c) {
+            float s[VEC];
+            if (VEC == 4) {
+                const float4 t = *reinterpret_cast<const float4*>(csrc + (size_t)c * A);
+                s[0] = t.x, s[1 % VEC] = t.y, s[2 % VEC] = t.z, s[3 % VEC] = t.w;
+            } else {
+                s[0] = csrc[(size_t)c * A];
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+                if (c == 0 || s[i] > best[i]) best[i] = s[i], cls[i] = c;  // first maximum wins (utils/ops.py:274)
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            is_cand[i] = best[i] > conf_thres && class_allowed(cls[i], classes, n_classes);
+            want += is_cand[i] ? 1 : 0;
+        }
+    }
+    int slot = warp_alloc(want, counts + bi);
+    if (want) {
+        u64* k_img = keys + (size_t)bi * cap;
+        float* r_img = rows + (size_t)bi * cap * 6;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+            if (is_cand[i]) {
+                write_candidate(slot, cap, x1[i], y1[i], x2[i], y2[i], best[i], cls[i], (uint32_t)(a0 + i), k_img,
+                                r_img);
+                ++slot;
+            }
+    }
+}
+
+// Multi-label path (utils/ops.py:271-272): one row per (anchor, class) above conf; order = anchor*nc+class.
+__global__ void __launch_bounds__(256) nms_filter_multilabel_kernel(float* pred, int A, int nc, float conf_thres,
+                                                                    const int32_t* __restrict__ classes,
+                                                                    int n_classes, int in_place,
+                                                                    u64* __restrict__ keys, float* __restrict__ rows,
+                                                                    int32_t* __restrict__ counts, int cap) {
+    const int bi = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = a < A;
     float* base = pred + (size_t)bi * (4 + nc) * A;
-    u64* k_img = keys + (size_t)bi * cap;
-    float* r_img = rows + (size_t)bi * cap * 6;
-    int32_t* cnt = counts + bi;
-
     float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
     if (live) {
         const float cx = base[a], cy = base[(size_t)A + a];
         const float bw = base[2 * (size_t)A + a], bh = base[3 * (size_t)A + a];
-        if (in_place == 2) {  // rows already hold xyxy (second pass after a pool overflow)
+        if (in_place == 2) {
             x1 = cx, y1 = cy, x2 = bw, y2 = bh;
         } else {
             const float hw = bw * 0.5f, hh = bh * 0.5f;
-            x1 = cx - hw, y1 = cy - hh, x2 = cx + hw, y2 = cy + hh;  // utils/ops.py:429-432
-            if (in_place == 1) {
+            x1 = cx - hw, y1 = cy - hh, x2 = cx + hw, y2 = cy + hh;
+            if (in_place == 1)
                 base[a] = x1, base[(size_t)A + a] = y1, base[2 * (size_t)A + a] = x2, base[3 * (size_t)A + a] = y2;
-            }
         }
     }
     const float* cls = base + 4 * (size_t)A;
-    if (!multi_label) {
-        float best = 0.f;
-        int j = 0;
-        if (live) {
-            best = cls[a];
-            for (int c = 1; c < nc; ++c) {
-                const float s = cls[(size_t)c * A + a];
-                if (s > best) best = s, j = c;  // first maximum wins (utils/ops.py:274)
-            }
-        }
-        const bool is_cand = live && best > conf_thres && class_allowed(j, classes, n_classes);
-        append_candidate(is_cand, x1, y1, x2, y2, best, j, (uint32_t)a, k_img, r_img, cnt, cap);
-    } else {
-        for (int c = 0; c < nc; ++c) {  // utils/ops.py:271-272: one row per (anchor, class) above conf
-            const float s = live ? cls[(size_t)c * A + a] : 0.f;
-            const bool is_cand = live && s > conf_thres && class_allowed(c, classes, n_classes);
-            append_candidate(is_cand, x1, y1, x2, y2, s, c, (uint32_t)a * (uint32_t)nc + (uint32_t)c, k_img, r_img,
-                             cnt, cap);
-        }
+    u64* k_img = keys + (size_t)bi * cap;
+    float* r_img = rows + (size_t)bi * cap * 6;
+    for (int c = 0; c < nc; ++c) {
+        const float s = live ? cls[(size_t)c * A + a] : 0.f;
+        const bool is_cand = live && s > conf_thres && class_allowed(c, classes, n_classes);
+        const int slot = warp_alloc(is_cand ? 1 : 0, counts + bi);
+        if (is_cand)
+            write_candidate(slot, cap, x1, y1, x2, y2, s, c, (uint32_t)a * (uint32_t)nc + (uint32_t)c, k_img, r_img);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 2a: per-image sort
+// stage 2a: ordering.  chunk sort (512 keys per CTA, all SMs busy) + rank by binary search
 // ------------------------------------------------------------------------------------------
 
-constexpr int SORT_THREADS = 1024;
-constexpr int SORT_SMEM_ELEMS = 8192;  // 8192 * (8 + 4) B = 96 KB
+constexpr int CHUNK = 512;
+constexpr int CHUNK_THREADS = 256;
 
-__device__ __forceinline__ int next_pow2(int v) {
-    int p = 1;
-    while (p < v) p <<= 1;
-    return p;
-}
+struct SuppressWs {
+    float4* sbox;       // (b, n_cap)   score-ordered boxes, class offset applied
+    uint32_t* sslot;    // (b, n_cap)   pool slot of each ordered box
+    int32_t* n_sorted;  // (b)          boxes entering suppression, or -1 on overflow
+    u64* mask;          // (b, T_cap*T_cap*64)
+    u64* ckeys;         // (b, C_cap*CHUNK)  keys, sorted descending inside each chunk (0 = padding)
+    uint32_t* cvals;    // (b, C_cap*CHUNK)  pool slot of each key
+    int T_cap, C_cap;
+};
 
-// descending bitonic network over P = 2^k elements; padding keys are 0 and sink to the tail
-template <typename KeyPtr, typename ValPtr>
-__device__ __forceinline__ void bitonic_desc(KeyPtr keys, ValPtr vals, int P) {
-    for (int k = 2; k <= P; k <<= 1) {
+// CTA (chunk, image): bitonic sort of 512 keys in shared memory, descending; padding keys are 0.
+__global__ void __launch_bounds__(CHUNK_THREADS) nms_chunk_sort_kernel(const u64* __restrict__ cand_keys,
+                                                                       const int32_t* __restrict__ cand_counts,
+                                                                       int cand_cap, int n_cap, int max_nms,
+                                                                       SuppressWs ws) {
+    __shared__ u64 keys[CHUNK];
+    __shared__ uint32_t vals[CHUNK];
+    const int bi = blockIdx.y, chunk = blockIdx.x;
+    const int count = cand_counts[bi];
+    const int n = count < max_nms ? count : max_nms;
+    const bool overflow = count > cand_cap || n > n_cap;  // pool or suppression stage too small
+    if (chunk == 0 && threadIdx.x == 0) ws.n_sorted[bi] = overflow ? -1 : n;
+    if (overflow || chunk * CHUNK >= count) return;
+    const u64* __restrict__ src = cand_keys + (size_t)bi * cand_cap;
+    for (int t = threadIdx.x; t < CHUNK; t += CHUNK_THREADS) {
+        const int i = chunk * CHUNK + t;
+        keys[t] = i < count ? src[i] : 0ull;
+        vals[t] = (uint32_t)i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= CHUNK; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = i | j;
-                const u64 ki = keys[i], kp = keys[p];
-                const bool desc = (i & k) == 0;
-                if ((ki < kp) == desc) {
-                    keys[i] = kp, keys[p] = ki;
-                    const uint32_t vi = vals[i];
-                    vals[i] = vals[p], vals[p] = vi;
-                }
+            const int t = threadIdx.x;  // CHUNK/2 compare-exchanges, one per thread
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            const int p = i | j;
+            const u64 ki = keys[i], kp = keys[p];
+            if ((ki < kp) == ((i & k) == 0)) {
+                keys[i] = kp, keys[p] = ki;
+                const uint32_t vi = vals[i];
+                vals[i] = vals[p], vals[p] = vi;
             }
             __syncthreads();
         }
     }
+    u64* __restrict__ dk = ws.ckeys + ((size_t)bi * ws.C_cap + chunk) * CHUNK;
+    uint32_t* __restrict__ dv = ws.cvals + ((size_t)bi * ws.C_cap + chunk) * CHUNK;
+    for (int t = threadIdx.x; t < CHUNK; t += CHUNK_THREADS) dk[t] = keys[t], dv[t] = vals[t];
 }
 
-struct SuppressWs {
-    float4* sbox;     // (b, n_cap)   score-ordered boxes, class offset applied
-    uint32_t* sslot;  // (b, n_cap)   pool slot of each ordered box
-    int32_t* n_sorted;  // (b)        boxes entering suppression, or -1 on overflow
-    u64* mask;        // (b, T_cap*T_cap*64)
-    u64* gkeys;       // (b, P_cap)   global-memory sort buffers (only used above SORT_SMEM_ELEMS)
-    uint32_t* gvals;  // (b, P_cap)
-    int T_cap, P_cap;
-};
-
-__global__ void __launch_bounds__(SORT_THREADS) nms_sort_kernel(const u64* __restrict__ cand_keys,
-                                                                const float* __restrict__ cand_rows,
-                                                                const int32_t* __restrict__ cand_counts, int cand_cap,
-                                                                int n_cap, int max_nms, int agnostic, float max_wh,
-                                                                SuppressWs ws) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int bi = blockIdx.x;
+// CTA (chunk, image): global rank of each of the chunk's keys = position inside its own chunk + number of
+// larger keys in every other chunk (binary search; keys are unique). The rank is the box's position in
+// torchvision's stable descending score order; the first n boxes are emitted with their class offset.
+__global__ void __launch_bounds__(CHUNK_THREADS) nms_rank_kernel(const float* __restrict__ cand_rows,
+                                                                 const int32_t* __restrict__ cand_counts,
+                                                                 int cand_cap, int n_cap, int agnostic, float max_wh,
+                                                                 SuppressWs ws) {
+    __shared__ u64 other[CHUNK];
+    const int bi = blockIdx.y, chunk = blockIdx.x;
+    const int n = ws.n_sorted[bi];
+    if (n <= 0) return;
     const int count = cand_counts[bi];
-    int n_all = count;
-    int n = n_all < max_nms ? n_all : max_nms;
-    if (count > cand_cap || n > n_cap) {  // pool or suppression stage too small: report, caller retries
-        if (threadIdx.x == 0) ws.n_sorted[bi] = -1;
-        return;
+    if (chunk * CHUNK >= count) return;
+    const int n_chunks = (count + CHUNK - 1) / CHUNK;
+    const u64* __restrict__ ck = ws.ckeys + (size_t)bi * ws.C_cap * CHUNK;
+    const int t0 = threadIdx.x, t1 = threadIdx.x + CHUNK_THREADS;
+    const u64 k0 = ck[(size_t)chunk * CHUNK + t0], k1 = ck[(size_t)chunk * CHUNK + t1];
+    int r0 = t0, r1 = t1;
+    for (int c = 0; c < n_chunks; ++c) {
+        if (c == chunk) continue;  // uniform
+        __syncthreads();
+        other[t0] = ck[(size_t)c * CHUNK + t0];
+        other[t1] = ck[(size_t)c * CHUNK + t1];
+        __syncthreads();
+        int lo0 = 0, hi0 = CHUNK, lo1 = 0, hi1 = CHUNK;
+#pragma unroll
+        for (int s = 0; s < 10; ++s) {  // 2^9 = 512: 10 halvings always converge
+            const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+            const bool g0 = lo0 < hi0 && other[m0 < CHUNK ? m0 : CHUNK - 1] > k0;
+            const bool g1 = lo1 < hi1 && other[m1 < CHUNK ? m1 : CHUNK - 1] > k1;
+            if (lo0 < hi0) { if (g0) lo0 = m0 + 1; else hi0 = m0; }
+            if (lo1 < hi1) { if (g1) lo1 = m1 + 1; else hi1 = m1; }
+        }
+        r0 += lo0, r1 += lo1;
     }
-    if (threadIdx.x == 0) ws.n_sorted[bi] = n;
-    if (n == 0) return;
-    const u64* __restrict__ src = cand_keys + (size_t)bi * cand_cap;
-    const int P = next_pow2(n_all);
+    const uint32_t* __restrict__ cv = ws.cvals + ((size_t)bi * ws.C_cap + chunk) * CHUNK;
+    const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
     float4* __restrict__ sbox = ws.sbox + (size_t)bi * n_cap;
     uint32_t* __restrict__ sslot = ws.sslot + (size_t)bi * n_cap;
-    const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
-
-    auto emit = [&](auto keys, auto vals) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t slot = vals[i];
-            const float* r = rows + (size_t)slot * 6;
-            const float off = agnostic ? 0.f : __fmul_rn(r[5], max_wh);  // utils/ops.py:289
-            sbox[i] = make_float4(__fadd_rn(r[0], off), __fadd_rn(r[1], off), __fadd_rn(r[2], off),
-                                  __fadd_rn(r[3], off));                 // utils/ops.py:295
-            sslot[i] = slot;
-        }
+    auto emit = [&](u64 key, int rank, uint32_t slot) {
+        if (key == 0ull || rank >= n) return;
+        const float2* r = reinterpret_cast<const float2*>(rows + (size_t)slot * 6);
+        const float2 p0 = r[0], p1 = r[1], p2 = r[2];
+        const float off = agnostic ? 0.f : __fmul_rn(p2.y, max_wh);                      // utils/ops.py:289
+        sbox[rank] = make_float4(__fadd_rn(p0.x, off), __fadd_rn(p0.y, off), __fadd_rn(p1.x, off),
+                                 __fadd_rn(p1.y, off));                                   // utils/ops.py:295
+        sslot[rank] = slot;
     };
-    if (P <= SORT_SMEM_ELEMS) {
-        u64* keys = reinterpret_cast<u64*>(smem_raw);
-        uint32_t* vals = reinterpret_cast<uint32_t*>(smem_raw + (size_t)SORT_SMEM_ELEMS * 8);
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            keys[i] = i < n_all ? src[i] : 0ull;
-            vals[i] = (uint32_t)i;
-        }
-        __syncthreads();
-        bitonic_desc(keys, vals, P);
-        emit(keys, vals);
-    } else {
-        u64* keys = ws.gkeys + (size_t)bi * ws.P_cap;
-        uint32_t* vals = ws.gvals + (size_t)bi * ws.P_cap;
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            keys[i] = i < n_all ? src[i] : 0ull;
-            vals[i] = (uint32_t)i;
-        }
-        __syncthreads();
-        bitonic_desc(keys, vals, P);
-        emit(keys, vals);
-    }
+    emit(k0, r0, cv[t0]);
+    emit(k1, r1, cv[t1]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -211,7 +301,6 @@ constexpr int MASK_THREADS = 64;
 __device__ __forceinline__ bool iou_gt(const float4 a, const float sa, const float4 b, const float thr) {
     const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
     const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
-    if (!(w > 0.f && h > 0.f)) return false;  // inter == 0  =>  0/u (or NaN) is never > thr >= 0
     const float inter = __fmul_rn(w, h);
     const float u = __fsub_rn(__fmaf_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y), sa), inter);
     return __fdiv_rn(inter, u) > thr;
@@ -219,6 +308,8 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float sa, const flo
 
 // Work item = (image, row tile r, column tile c >= r) over all images; items are striped over a
 // persistent grid. Thread i of the CTA owns row r*64+i and writes one 64-bit word of the mask.
+// Pass 1 (branch-free, fully unrolled): which of the 64 column boxes intersect the row box at all.
+// Pass 2 (rare): exact IoU > thr only for those.
 // Mask layout: [image][r*T_cap + c][i]  (64 consecutive words per tile => coalesced 512 B stores,
 // and the scan reads whole tiles).
 __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap, float iou_thres, SuppressWs ws) {
@@ -244,25 +335,44 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
         const int T = (n + 63) >> 6;
         const int q = w - pre[bi];
         // invert q = r*T - r(r-1)/2 + (c - r)
-        int r = (int)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)q)) * 0.5);
-        if (r < 0) r = 0;
-        if (r > T - 1) r = T - 1;
+        const float tt = 2.f * T + 1.f;
+        int r = (int)((tt - sqrtf(fmaxf(tt * tt - 8.f * (float)q, 0.f))) * 0.5f);
+        r = max(0, min(r, T - 1));
         while (r > 0 && r * T - r * (r - 1) / 2 > q) --r;
         while (r + 1 < T && (r + 1) * T - (r + 1) * r / 2 <= q) ++r;
         const int c = r + (q - (r * T - r * (r - 1) / 2));
         const float4* __restrict__ sbox = ws.sbox + (size_t)bi * n_cap;
         const int row = r * 64 + i, col0 = c * 64;
+        const float4 a = (row < n) ? sbox[row] : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();  // previous item's colbox readers are done
         colbox[i] = (col0 + i < n) ? sbox[col0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        u64 word = 0;
-        if (row < n) {
-            const float4 a = sbox[row];
+        uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float4 cb = colbox[j];
+            const bool ov = (fminf(a.z, cb.z) > fmaxf(a.x, cb.x)) && (fminf(a.w, cb.w) > fmaxf(a.y, cb.y));
+            lo |= ov ? (1u << j) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float4 cb = colbox[32 + j];
+            const bool ov = (fminf(a.z, cb.z) > fmaxf(a.x, cb.x)) && (fminf(a.w, cb.w) > fmaxf(a.y, cb.y));
+            hi |= ov ? (1u << j) : 0u;
+        }
+        u64 cand = ((u64)hi << 32) | lo;
+        const int jn = n - col0;  // valid columns of this tile
+        if (jn < 64) cand &= (1ull << jn) - 1ull;
+        if (r == c) cand &= (i < 63) ? (~0ull << (i + 1)) : 0ull;  // only later boxes can be suppressed
+        if (row >= n) cand = 0ull;
+        u64 word = 0ull;
+        if (cand) {
             const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-            const int jn = min(64, n - col0);
-            const int j0 = (r == c) ? i + 1 : 0;
-            for (int j = j0; j < jn; ++j)
+            while (cand) {
+                const int j = __ffsll((long long)cand) - 1;
+                cand &= cand - 1ull;
                 if (iou_gt(a, sa, colbox[j], iou_thres)) word |= 1ull << j;
+            }
         }
         ws.mask[((size_t)bi * ws.T_cap * ws.T_cap + (size_t)r * ws.T_cap + c) * 64 + i] = word;
     }
@@ -350,8 +460,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
 
 static int split_ws(void* workspace, int b, int cand_cap, int n_cap, SuppressWs& ws, size_t& total) {
     const int T_cap = (n_cap + 63) / 64;
-    int P_cap = 1;
-    while (P_cap < cand_cap) P_cap <<= 1;
+    const int C_cap = (cand_cap + CHUNK - 1) / CHUNK;
     unsigned char* p = (unsigned char*)workspace;
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -363,11 +472,10 @@ static int split_ws(void* workspace, int b, int cand_cap, int n_cap, SuppressWs&
     ws.sslot = (uint32_t*)take((size_t)b * n_cap * sizeof(uint32_t));
     ws.n_sorted = (int32_t*)take((size_t)b * sizeof(int32_t));
     ws.mask = (u64*)take((size_t)b * T_cap * T_cap * 64 * sizeof(u64));
-    const bool need_global_sort = P_cap > SORT_SMEM_ELEMS;
-    ws.gkeys = (u64*)take(need_global_sort ? (size_t)b * P_cap * sizeof(u64) : 0);
-    ws.gvals = (uint32_t*)take(need_global_sort ? (size_t)b * P_cap * sizeof(uint32_t) : 0);
+    ws.ckeys = (u64*)take((size_t)b * C_cap * CHUNK * sizeof(u64));
+    ws.cvals = (uint32_t*)take((size_t)b * C_cap * CHUNK * sizeof(uint32_t));
     ws.T_cap = T_cap;
-    ws.P_cap = P_cap;
+    ws.C_cap = C_cap;
     total = o;
     return 0;
 }
@@ -383,16 +491,27 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_filter(float* pred
     KZD_CHECK_ARG(b >= 0 && A >= 0 && nc >= 1 && cand_cap >= 1, "kzd_nms_filter: bad sizes b=%d A=%d nc=%d cap=%d", b,
                   A, nc, cand_cap);
     KZD_CHECK_ARG(b <= 65535, "kzd_nms_filter: b=%d > 65535", b);
+    KZD_CHECK_ARG(in_place >= 0 && in_place <= 2, "kzd_nms_filter: in_place=%d not in {0,1,2}", in_place);
     KZD_CHECK_ARG(!multi_label || (double)A * nc < 4294967295.0, "kzd_nms_filter: A*nc overflows the order field");
     KZD_CHECK_ARG(n_classes == 0 || classes, "kzd_nms_filter: n_classes > 0 with null classes");
     cudaStream_t st = (cudaStream_t)stream;
     if (b == 0) return 0;
     KZD_CUDA(cudaMemsetAsync(cand_counts, 0, (size_t)b * sizeof(int32_t), st));
     if (A == 0) return 0;
-    dim3 grid((A + 255) / 256, b);
-    nms_filter_kernel<<<grid, 256, 0, st>>>(prediction, A, nc, conf_thres, multi_label && nc > 1,
-                                            n_classes ? classes : nullptr, n_classes, in_place,
-                                            (u64*)cand_keys, cand_rows, cand_counts, cand_cap);
+    const int32_t* cls = n_classes ? classes : nullptr;
+    if (multi_label && nc > 1) {
+        dim3 grid((A + 255) / 256, b);
+        nms_filter_multilabel_kernel<<<grid, 256, 0, st>>>(prediction, A, nc, conf_thres, cls, n_classes, in_place,
+                                                           (u64*)cand_keys, cand_rows, cand_counts, cand_cap);
+    } else if (A % 4 == 0 && ((uintptr_t)prediction) % 16 == 0) {
+        dim3 grid((A / 4 + 255) / 256, b);
+        nms_filter_kernel<4><<<grid, 256, 0, st>>>(prediction, A, nc, conf_thres, cls, n_classes, in_place,
+                                                   (u64*)cand_keys, cand_rows, cand_counts, cand_cap);
+    } else {
+        dim3 grid((A + 255) / 256, b);
+        nms_filter_kernel<1><<<grid, 256, 0, st>>>(prediction, A, nc, conf_thres, cls, n_classes, in_place,
+                                                   (u64*)cand_keys, cand_rows, cand_counts, cand_cap);
+    }
     KZD_LAUNCH_CHECK("nms_filter_kernel");
     return 0;
 }
@@ -413,6 +532,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
                   "kzd_nms_suppress: null pointer");
     KZD_CHECK_ARG(b >= 0 && cand_cap >= 1 && n_cap >= 1 && max_det >= 1 && max_nms >= 1,
                   "kzd_nms_suppress: bad sizes");
+    KZD_CHECK_ARG(b <= 65535, "kzd_nms_suppress: b=%d > 65535", b);
     KZD_CHECK_ARG(((uintptr_t)workspace) % 256 == 0, "kzd_nms_suppress: workspace must be 256-byte aligned");
     if (b == 0) return 0;
     SuppressWs ws;
@@ -423,11 +543,12 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
         return KZD_ENOSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t sort_smem = (size_t)SORT_SMEM_ELEMS * 12;
-    KZD_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    nms_sort_kernel<<<b, SORT_THREADS, sort_smem, st>>>((const u64*)cand_keys, cand_rows, cand_counts, cand_cap, n_cap,
-                                                        max_nms, agnostic, max_wh, ws);
-    KZD_LAUNCH_CHECK("nms_sort_kernel");
+    dim3 cgrid(ws.C_cap, b);
+    nms_chunk_sort_kernel<<<cgrid, CHUNK_THREADS, 0, st>>>((const u64*)cand_keys, cand_counts, cand_cap, n_cap, max_nms,
+                                                           ws);
+    KZD_LAUNCH_CHECK("nms_chunk_sort_kernel");
+    nms_rank_kernel<<<cgrid, CHUNK_THREADS, 0, st>>>(cand_rows, cand_counts, cand_cap, n_cap, agnostic, max_wh, ws);
+    KZD_LAUNCH_CHECK("nms_rank_kernel");
     const int grid = sm_count() * 16;
     nms_mask_kernel<<<grid, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(b, n_cap, iou_thres, ws);
     KZD_LAUNCH_CHECK("nms_mask_kernel");

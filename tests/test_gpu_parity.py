@@ -135,6 +135,27 @@ def test_assign_edge_cases():
     assert all(t.dtype == torch.float32 for t in z) and (z[0] == 2).all()
 
 
+def test_assign_epoch_wrap_and_stateless_mode():
+    """The persistent workspace is re-used with an 8-bit epoch (include/kzd.h): run past the wrap with
+    alternating inputs, then the stateless (epoch 0) mode; every result must still match the oracle."""
+    d1 = synth.assigner_inputs(1, 40, 256, 2, synth.P2_P5, seed=31, device=DEV, layout="uniform")
+    d2 = synth.assigner_inputs(1, 40, 256, 2, synth.P2_P5, seed=32, device=DEV, layout="columns")
+    asg = kzd.TaskAlignedAssigner(10, 2, 0.5, 6.0)
+    refs = []
+    for d in (d1, d2):
+        args = (d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+        refs.append((args, O.tal_assign(*args, 10, 2, 0.5, 6.0)))
+    for i in range(520):
+        args, ref = refs[i % 2]
+        out = asg(*args)
+        if i % 37 == 0 or i in (253, 254, 255, 256, 257, 509, 510, 511):
+            _check_assign(out, ref)
+    asg.stateless = True
+    for i in range(3):
+        args, ref = refs[i % 2]
+        _check_assign(asg(*args), ref)
+
+
 def test_assign_tie_heavy_micro_case():
     """SURVEY.md Appendix E micro-case: uniform predictions and scores give many bit-identical metrics,
     so the picks depend on torch.topk's tie order (CPU and CUDA differ). Checked against the oracle on
