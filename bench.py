@@ -21,7 +21,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -46,53 +45,59 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every ~5 ms while the timed region runs
+    (nvidia-smi -lms 200 is too coarse for a region of a few tens of milliseconds)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.reasons, self.max_mhz, self._stop, self.t = index, [], set(), None, False, None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.t = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.25)
-            self.proc.terminate()
+    def _run(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop:
             try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-
-    def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for n, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(n)
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            time.sleep(0.005)
+
+    def __exit__(self, *a):
+        self._stop = True
+        if self.t:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def algorithmic_bytes(b, A, G, nc, n_cand, n_keep):
@@ -109,24 +114,40 @@ def algorithmic_bytes(b, A, G, nc, n_cand, n_keep):
 # reference arm / CPU baseline: the oracle's torch port of the reference on the host cores
 # ------------------------------------------------------------------------------------------------
 
-def cpu_page_inputs(seed):
+def page_inputs(n_pages, seed, device="cpu"):
+    """Synthetic head outputs + GT for `n_pages` pages of the workload. ONE set of per-level head maps
+    feeds both halves of the step (as a model forward would): DFL logits ~ N(0,1); class logits like a
+    freshly initialised Detect head (bias_init drives them strongly negative: background -6) with
+    ~3000 object-like anchors per page at N(1,1). The training-side layout (pred_distri, pd_scores) is
+    derived from the maps with the reference's own glue ops (utils/loss.py:210-215,235)."""
     from kuzushiji_vision_b200 import synth
 
     w = WORKLOAD
-    d = synth.assigner_inputs(1, w["G"], w["imgsz"], w["nc"], w["strides"], seed=seed, device="cpu")
-    lv = synth.head_outputs(1, w["nc"], w["imgsz"], w["strides"], seed=seed + 100, device="cpu",
+    lv = synth.head_outputs(n_pages, w["nc"], w["imgsz"], w["strides"], seed=seed, device=device,
                             sparse_cls=w["nms_candidates"])
-    return d, lv
+    gl, gb, mg = synth.gt_pages(n_pages, w["G"], w["imgsz"], w["nc"], seed=seed, device=device)
+    return lv, gl, gb, mg
 
 
-def cpu_step(d, lv):
+def train_layout(lv, nc):
+    """utils/loss.py:210-215 + :235: cat levels, split, permute, contiguous, sigmoid (caller glue)."""
+    b = lv[0].shape[0]
+    cat = torch.cat([x.view(b, 64 + nc, -1) for x in lv], 2)
+    pred_distri = cat[:, :64].permute(0, 2, 1).contiguous()
+    pd_scores = cat[:, 64:].permute(0, 2, 1).contiguous().sigmoid()
+    return pred_distri, pd_scores
+
+
+def cpu_step(lv, gl, gb, mg):
     """One page through the CPU port: same four stages, same order, as the CUDA step."""
     from oracle import torch_oracle as O
 
     w = WORKLOAD
-    boxes = O.decode_train(d["pred_distri"], d["anchor_points"])
-    out = O.tal_assign(d["pd_scores"], boxes * d["stride_tensor"], d["anc_points"], d["gt_labels"], d["gt_bboxes"],
-                       d["mask_gt"], w["topk"], w["nc"], w["alpha"], w["beta"])
+    pred_distri, pd_scores = train_layout(lv, w["nc"])
+    anchor_points, stride_tensor = O.make_anchors([x.shape[2:] for x in lv], w["strides"])
+    boxes = O.decode_train(pred_distri, anchor_points)
+    out = O.tal_assign(pd_scores, boxes * stride_tensor, anchor_points * stride_tensor, gl, gb, mg, w["topk"],
+                       w["nc"], w["alpha"], w["beta"])
     y = O.decode_infer(lv, w["strides"], w["nc"])
     det = O.non_max_suppression(y, w["conf"], w["iou"], max_det=w["max_det"])
     return out, det
@@ -142,27 +163,44 @@ def cpu_threads():
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path (oracle torch port - the Python
+    reference cannot travel to the GPU box) on all host cores; one page of the workload per step. If K
+    full pages would not fit in ~4 minutes the page is cropped to a quarter (640x640, G/4) and each step
+    counts as 0.25 page - the reference's cost grows faster than linearly with page size, so the crop
+    only flatters the CPU arm."""
     if rank != 0:
         return
     threads = cpu_threads()
     torch.set_num_threads(threads)
-    d, lv = cpu_page_inputs(0)
-    for _ in range(args.warmup):
-        cpu_step(d, lv)
+    w = WORKLOAD
+    page = page_inputs(1, 0)
+    t0 = time.perf_counter()
+    cpu_step(*page)
+    t_page = time.perf_counter() - t0
+    frac, note = 1.0, "1 full page per step"
+    if t_page * (args.steps + args.warmup) > 240.0:
+        keep = dict(w)
+        w.update(imgsz=w["imgsz"] // 2, G=w["G"] // 4, nms_candidates=w["nms_candidates"] // 4)
+        page = page_inputs(1, 0)
+        frac, note = 0.25, "a quarter-page crop (640x640, G/4) per step, counted as 0.25 page"
+        cpu_step(*page)
+        w.update(keep)
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_step(*page)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(d, lv)
+        cpu_step(*page)
     dt = time.perf_counter() - t0
-    val = args.steps / dt
-    w = WORKLOAD
+    val = frac * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: 1280x1280 P2-P5 (A=136000), ~600 GT/page, nc=1; "
-                               "one page per step on the host CPU", **{k: w[k] for k in ("imgsz", "G", "nc")}},
+                               "NMS conf .25 iou .7 max_det 300 on ~3000 candidates/page; host CPU, " + note,
+                   **{k: w[k] for k in ("imgsz", "G", "nc")}},
         "cpu_baseline": {"value": val, "unit": "pages/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps x 1 page of the workload (oracle torch port of the reference, "
+                         "sample": f"{args.steps} steps x {note} (oracle torch port of the reference, "
                                    f"{threads} threads)"},
         "e2e": {"value": val, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -186,79 +224,79 @@ def run_kzd(args, rank, local_rank, world):
     w = WORKLOAD
     b, nc, G = w["batch"], w["nc"], w["G"]
     glo, ghi = kdist.shard_range(b * world, rank, world)  # this rank's pages of the global batch
+    warmup = max(args.warmup, 3)
 
-    # synthetic inputs: training-side head outputs (N(0,1)) and inference-side ones (sparse objects)
-    d = synth.assigner_inputs(b, G, w["imgsz"], nc, w["strides"], seed=glo, device="cpu")
-    lv_cpu = synth.head_outputs(b, nc, w["imgsz"], w["strides"], seed=glo + 100, device="cpu",
-                                sparse_cls=w["nms_candidates"])
-    A = d["anc_points"].shape[0]
-    host = {k: d[k].pin_memory() for k in ("pred_distri", "pd_scores", "gt_labels", "gt_bboxes", "mask_gt")}
+    lv_cpu, gl, gb, mg = page_inputs(b, seed=glo)
     host_lv = [l.pin_memory() for l in lv_cpu]
-    dv = {k: v.to(dev) for k, v in host.items()}
+    host_gt = [t.pin_memory() for t in (gl, gb, mg)]
+    A = synth.num_anchors(w["imgsz"], w["strides"])
+    pipe = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G, device=dev,
+                            topk=w["topk"], alpha=w["alpha"], beta=w["beta"], conf_thres=w["conf"],
+                            iou_thres=w["iou"], max_det=w["max_det"])
     dv_lv = [l.to(dev) for l in host_lv]
-    anchor_points, stride_tensor = d["anchor_points"].to(dev), d["stride_tensor"].to(dev)
-    anc_points = d["anc_points"].to(dev)
-    assigner = kzd.TaskAlignedAssigner(w["topk"], nc, w["alpha"], w["beta"])
+    pred_distri, pd_scores = train_layout(dv_lv, nc)
+    pipe.load(levels=dv_lv, pred_distri=pred_distri, pd_scores=pd_scores, gt_labels=host_gt[0], gt_bboxes=host_gt[1],
+              mask_gt=host_gt[2])
+    del pred_distri, pd_scores
     counters = torch.zeros(4, dtype=torch.float64, device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def step(t, lv, marks=None):
-        def mark():
-            if marks is not None:
-                e = ev()
-                e.record()
-                marks.append(e)
-        mark()
-        boxes = kzd.bbox_decode(anchor_points, t["pred_distri"])
-        mark()
-        pd_bboxes = boxes * stride_tensor  # caller glue (utils/loss.py:236), plain torch
-        mark()
-        tgt = assigner(t["pd_scores"], pd_bboxes, anc_points, t["gt_labels"], t["gt_bboxes"], t["mask_gt"])
-        mark()
-        y = kzd.decode_inference(lv, w["strides"], nc)
-        mark()
-        rows, n_keep = kzd.nms_batched(y, w["conf"], w["iou"], max_det=w["max_det"])
-        mark()
-        return tgt, rows, n_keep
-
-    # ---- device-resident timing ----
-    for _ in range(max(args.warmup, 3)):
-        tgt, rows, n_keep = step(dv, dv_lv)
+    # ---- device-resident timing: inputs already in HBM, the step is one CUDA-graph replay ----
+    for _ in range(warmup):
+        pipe.step()
+    out, n_keep = pipe.results()
     torch.cuda.synchronize()
     kdist.barrier()
-    marks = []
     with ClockSampler(local_rank) as clk:
         torch.cuda.synchronize()
         t_start, t_end = ev(), ev()
         t_start.record()
         for _ in range(args.steps):
-            tgt, rows, n_keep = step(dv, dv_lv, marks)
-        counters[0:2] = assigner.counters
+            pipe.step()
+        counters[0:2] = out["counters"]
         counters[2] = float(b)
-        counters[3] = float(sum(n_keep))
+        counters[3] = out["counts"][1].sum()
         kdist.all_reduce_counters(counters)  # the path's only collective: 32 bytes
         t_end.record()
         torch.cuda.synchronize()
     kdist.barrier()
+    out, n_keep = pipe.results()
     ms_total = kdist.max_over_ranks(t_start.elapsed_time(t_end), dev)
     pages = float(counters[2].item())
     value = pages * args.steps / (ms_total * 1e-3)
 
-    stage_names = ["decode_train", "glue_mul_stride", "assign", "decode_infer", "nms"]
-    stage_ms = {n: 0.0 for n in stage_names}
-    for s in range(args.steps):
-        m = marks[s * 6:(s + 1) * 6]
-        for i, n in enumerate(stage_names):
-            stage_ms[n] += m[i].elapsed_time(m[i + 1])
-    stage_ms = {n: v / args.steps for n, v in stage_ms.items()}
+    # ---- per-stage device times (separate pass, eager calls, CUDA events between the stages) ----
+    asg = pipe.assigner
+    st_names = ["decode_train", "assign", "decode_infer", "nms"]
+    st_ms = {n: 0.0 for n in st_names}
+    n_prof = 10
+    for i in range(n_prof + 2):
+        m = [ev() for _ in range(5)]
+        m[0].record()
+        boxes, px = kzd.bbox_decode(pipe.anchor_points, pipe.pred_distri, pipe.stride_tensor)
+        m[1].record()
+        asg(pipe.pd_scores, px, pipe.anc_points, pipe.gt_labels, pipe.gt_bboxes, pipe.mask_gt)
+        m[2].record()
+        y = kzd.decode_inference(pipe.levels, w["strides"], nc)
+        m[3].record()
+        kzd.nms_batched(y, w["conf"], w["iou"], max_det=w["max_det"])
+        m[4].record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            for k, n in enumerate(st_names):
+                st_ms[n] += m[k].elapsed_time(m[k + 1]) / n_prof
 
-    # ---- end to end from pinned host buffers ----
+    # ---- end to end: head maps + GT in pinned HOST memory, through the drop-in calls ----
     def e2e_step():
-        t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         lv = [l.to(dev, non_blocking=True) for l in host_lv]
-        tgt, rows, n_keep = step(t, lv)  # nms_batched reads its counters back (D2H + sync)
-        res = rows.cpu()
-        cnt = assigner.counters.cpu()
+        g_l, g_b, m_g = (t.to(dev, non_blocking=True) for t in host_gt)
+        p_d, p_s = train_layout(lv, nc)                       # reference caller glue, torch
+        boxes, px = kzd.bbox_decode(pipe.anchor_points, p_d, pipe.stride_tensor)
+        tgt = asg(p_s, px, pipe.anc_points, g_l, g_b, m_g)
+        y = kzd.decode_inference(lv, w["strides"], nc)
+        det = kzd.non_max_suppression(y, w["conf"], w["iou"], max_det=w["max_det"])
+        res = torch.cat([d_ for d_ in det]).cpu()            # detections back to the host
+        cnt = asg.counters.cpu()                              # target_scores_sum, n_fg
         return res, cnt
 
     for _ in range(2):
@@ -274,33 +312,38 @@ def run_kzd(args, rank, local_rank, world):
     torch.cuda.synchronize()
     e2e_ms = kdist.max_over_ranks(t0.elapsed_time(t1), dev)
     e2e_value = pages * e2e_steps / (e2e_ms * 1e-3)
-    h2d = sum(v.numel() * v.element_size() for v in host.values()) + sum(l.numel() * 4 for l in host_lv)
-    d2h = rows.numel() * 4 + 2 * 8 + 2 * b * 4
+    h2d = sum(l.numel() * 4 for l in host_lv) + sum(t.numel() * 4 for t in host_gt)
+    d2h = res.numel() * 4 + 2 * 8 + 2 * b * 4
 
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
-    n_cand = int(w["nms_candidates"] * b * 0.98)
+    n_cand = int(sum(pipe.counts_host[0].tolist()))
     ab = algorithmic_bytes(b, A, G, nc, n_cand, int(sum(n_keep)))
     single_kernel = {"decode_train": "decode_train_kernel", "decode_infer": "decode_infer_kernel<4>"}
-    dom = max(single_kernel, key=lambda n: stage_ms[n])
+    dom = max(single_kernel, key=lambda n: st_ms[n])
     peak, peak_src = hbm_peak()
-    achieved = ab[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    achieved = ab[dom] / (st_ms[dom] * 1e-3) / 1e9
+    total_ab = sum(v for v in ab.values() if v)
     roofline = {"bound": "hbm", "kernel": single_kernel[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom],
-                "stages": {n: {"ms": stage_ms[n], "algorithmic_bytes": ab.get(n),
-                               "gbs": (ab[n] / (stage_ms[n] * 1e-3) / 1e9) if ab.get(n) else None}
-                           for n in stage_names}}
+                "step": {"algorithmic_bytes": total_ab, "gbs": total_ab / (ms_total / args.steps * 1e-3) / 1e9,
+                         "frac": total_ab / (ms_total / args.steps * 1e-3) / 1e9 / peak},
+                "stages": {n: {"ms": st_ms[n], "algorithmic_bytes": ab.get(n),
+                               "gbs": (ab[n] / (st_ms[n] * 1e-3) / 1e9) if ab.get(n) else None}
+                           for n in st_names},
+                "stage_note": "stage ms are eager per-call times incl. launch latency (and, for nms, its host "
+                              "read-back); the timed region replays the same kernels as one CUDA graph"}
 
     # ---- CPU baseline on a bounded sample (one page, repeated) ----
     threads = cpu_threads()
     torch.set_num_threads(threads)
-    cd, clv = cpu_page_inputs(0)
+    page = page_inputs(1, 0)
     t0c = time.perf_counter()
     n_cpu = 0
     while n_cpu < 2 or (time.perf_counter() - t0c < 12.0 and n_cpu < 8):
-        cpu_step(cd, clv)
+        cpu_step(*page)
         n_cpu += 1
     cpu_dt = time.perf_counter() - t0c
     cpu_baseline = {"value": n_cpu / cpu_dt, "unit": "pages/s", "cores": threads, "kind": "port",
@@ -309,21 +352,22 @@ def run_kzd(args, rank, local_rank, world):
 
     line = {
         "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: YOLOv12x P2-P5 head outputs, 1280x1280 pages, batch 16 per GPU, "
                                "~600 GT/page, nc=1; NMS conf .25 iou .7 max_det 300 on ~3000 candidates/page",
                    "pages_per_gpu": b, "anchors_per_page": A, "gt_slots": G, "nc": nc,
                    "l2_policy": "inputs larger than L2 (1.16 GB read per step vs 126 MB L2)",
+                   "step": "PagePipeline: one CUDA-graph replay of decode_train+assign+decode_infer+NMS",
                    "parallelism": f"image-sharded x{world}"},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps},
-        "gpu_launches": 10 * args.steps,
+                "steps": e2e_steps, "path": "pinned host head maps + GT -> H2D -> drop-in calls -> detections + counters D2H"},
+        "gpu_launches": pipe.kernels_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "counters": {"target_scores_sum": float(counters[0]), "n_fg": float(counters[1]),
-                     "kept_boxes": float(counters[3])},
+                     "kept_boxes": float(counters[3]), "nms_candidates": n_cand},
     }
     print(json.dumps(line), flush=True)
 
@@ -331,7 +375,7 @@ def run_kzd(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kzd", choices=["kzd", "reference"])
     args = ap.parse_args()

@@ -62,9 +62,12 @@ int kzd_decode_infer(const float* const* h_level_ptrs, const kzd_level* h_levels
 /* v8DetectionLoss.bbox_decode (utils/loss.py:197-204) + dist2bbox(xywh=False).
  *   pred_dist     : (b, A, 64)  side-major, 16 bins per side
  *   anchor_points : (A, 2)      grid units
- *   out_xyxy      : (b, A, 4)   grid units */
-int kzd_decode_train(const float* pred_dist, const float* anchor_points, int b, int A,
-                     float* out_xyxy, void* stream);
+ *   out_xyxy      : (b, A, 4)   grid units
+ * Optional fused caller glue (utils/loss.py:236, `pred_bboxes * stride_tensor`, the assigner's
+ * pd_bboxes): when out_xyxy_px != NULL, stride_tensor (A) must be given and out_xyxy_px (b,A,4)
+ * receives out_xyxy * stride (one fp32 multiply, as the reference rounds it). */
+int kzd_decode_train(const float* pred_dist, const float* anchor_points, const float* stride_tensor,
+                     int b, int A, float* out_xyxy, float* out_xyxy_px, void* stream);
 
 /* Backward of kzd_decode_train wrt pred_dist (the CIoU/DFL losses back-propagate through the
  * decoded boxes, utils/loss.py:252-254): grad_pred_dist (b,A,64) from grad_xyxy (b,A,4). */
@@ -90,17 +93,18 @@ size_t kzd_assign_workspace_bytes(int b, int A, int G);
  *   target_labels int64 (b,A), target_bboxes (b,A,4), target_scores (b,A,nc), fg_mask uint8 (b,A),
  *   target_gt_idx int64 (b,A); counters double[2] = { sum(target_scores), count(fg_mask) }
  *   (may be NULL). G must be >= 1 (the G == 0 early-out of tal.py:64-71 is host logic).
- *   epoch: 0 = stateless: the call zeroes the per-anchor state in `workspace` itself (one extra
- *     12 B/anchor memset). 1..255 = the caller keeps ONE workspace for this (b, A, G), zeroed it once
- *     after allocation, and passes epochs 1, 2, ..., 255 on consecutive calls (re-zero before wrapping
- *     to 1): stale state then loses every atomic and no memset is needed. */
+ *   persistent: 0 = stateless: the call zeroes the per-anchor state in `workspace` itself (one extra
+ *     12 B/anchor memset). 1 = the caller keeps ONE workspace per (b, A, G), zeroed ONCE after
+ *     allocation, and passes it unchanged on every call: the state words carry an 8-bit epoch that the
+ *     library advances on the device (CUDA-graph friendly), stale entries lose every atomic, and the
+ *     state is wiped by the kernels themselves once per 255 calls. */
 int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
                    const float* gt_labels, const float* gt_bboxes, const float* mask_gt,
                    int b, int A, int G, int nc, int topk, float alpha, float beta, float eps,
                    const kzd_level* h_levels, int n_levels, int zero_fill,
                    int64_t* target_labels, float* target_bboxes, float* target_scores,
                    uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
-                   void* workspace, size_t workspace_bytes, int epoch, void* stream);
+                   void* workspace, size_t workspace_bytes, int persistent, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * NMS

@@ -6,6 +6,7 @@ Ultralytics YOLOv12) as hand-written sm_100a CUDA behind the reference's own Pyt
     v8DetectionLoss.bbox_decode             utils/loss.py:197    -> head.bbox_decode
     ops.non_max_suppression                 utils/ops.py:167     -> ops.non_max_suppression
     install()                               patches an importable ``ultralytics`` in place
+    PagePipeline                            the four stages of one page batch captured as one CUDA graph
 
 The compute lives in ``libkzd.so`` (C ABI: ``include/kzd.h``); importing this package loads it and
 raises if it is missing - there is no CPU or torch fallback.
@@ -15,6 +16,7 @@ from ._lib import KzdError
 from .head import bbox_decode, decode_inference, detect_inference
 from .install import install, installed, uninstall
 from .ops import nms_batched, non_max_suppression, xywh2xyxy
+from .pipeline import PagePipeline
 from .tal import TaskAlignedAssigner, dist2bbox, infer_levels, make_anchors
 
 __version__ = "0.1.0"
@@ -22,5 +24,5 @@ __all__ = [
     "TaskAlignedAssigner", "make_anchors", "dist2bbox", "infer_levels",
     "detect_inference", "decode_inference", "bbox_decode",
     "non_max_suppression", "nms_batched", "xywh2xyxy",
-    "install", "uninstall", "installed", "KzdError",
+    "PagePipeline", "install", "uninstall", "installed", "KzdError",
 ]

@@ -11,8 +11,9 @@
 //                             alignment metric, per-anchor argmax-overlap via 64-bit atomicMax,
 //                             warp-shuffle streaming top-k, selection counts
 //   assign_resolve_kernel     one thread per anchor: resolve the owner GT, write labels / boxes /
-//                             fg / gt_idx, recompute the owner pair's metric, per-GT maxima
-//   assign_normalize_kernel   foreground anchors: target_scores = align * pos_ov / (pos_align+eps)
+//                             fg / gt_idx for every anchor, append foreground anchors to a compact list
+//   assign_fg_metric_kernel   foreground list: recompute the owner pair's metric, per-GT maxima
+//   assign_normalize_kernel   foreground list: target_scores = align * pos_ov / (pos_align+eps)
 //
 // Bit-exactness: every fp32 operation of the eager reference rounds separately, so the pair
 // arithmetic below uses __fadd_rn/__fmul_rn/__fdiv_rn (never contracted into FMAs) and the same
@@ -37,8 +38,9 @@ struct AssignWs {
     uint32_t* pos_align; // (b*G)  per-GT max alignment metric (float bits)
     uint32_t* pos_ov;    // (b*G)  per-GT max overlap (float bits)
     uint32_t* fg_list;   // (b*A)  compact list of foreground anchors (flat index)
-    int32_t* flags;      // [0] != 0: anc_points does not match the level table; [1] = fg count
-    size_t state_bytes;  // key + sel: the part that must have been zeroed once
+    int32_t* flags;      // [0] != 0: anc_points does not match the level table; [1] = fg count;
+                         // [2] = current epoch (1..255), advanced on the device by assign_begin_kernel
+    size_t state_bytes;  // key + sel + flags: the part that must have been zeroed once
 };
 
 struct AssignParams {
@@ -47,7 +49,6 @@ struct AssignParams {
     float alpha, beta, eps;
     kzd_level lv[KZD_MAX_LEVELS];
     int n_levels, zero_fill;
-    uint32_t epoch;  // 1..255
     long long* target_labels;
     float* target_bboxes;
     float* target_scores;
@@ -128,6 +129,15 @@ __device__ __forceinline__ u64 shfl_up64(u64 v, int d) {
     return ((u64)hi << 32) | lo;
 }
 
+// ---- begin: per-call flags and the device-side epoch -----------------------------------------
+
+__global__ void assign_begin_kernel(AssignWs ws, int reset_epoch) {
+    ws.flags[0] = 0;
+    ws.flags[1] = 0;
+    const int e = reset_epoch ? 0 : ws.flags[2];
+    ws.flags[2] = (e % 255) + 1;  // 1..255; at 255 the resolve kernel wipes the state for the wrap to 1
+}
+
 // ---- verify ----------------------------------------------------------------------------------
 
 __global__ void assign_verify_kernel(const float* __restrict__ anc, int A, AssignParams p) {
@@ -156,14 +166,14 @@ struct TopK {
 // One in-GT pair per lane (a < 0: idle lane): overlap, metric, argmax key, streaming top-k insert.
 __device__ __forceinline__ void eval_pairs(const AssignParams& p, const GtBox& gt, int a, size_t img,
                                            const float4* __restrict__ pdb, const float* __restrict__ pds, int g,
-                                           int topk, int lane, TopK& st) {
+                                           int topk, int lane, uint32_t epoch, TopK& st) {
     u64 key = 0ull;
     if (a >= 0) {
         const float4 pb = __ldg(pdb + a);
         const float sc = __ldg(pds + (size_t)a * p.nc);
         const float o = overlap_ciou(gt, pb);
         if (o > 0.f)
-            atomicMax(p.ws.key + img + a, ((u64)p.epoch << 56) | ((u64)min(__float_as_uint(o), 0x3fffffffu) << KEY_GBITS) |
+            atomicMax(p.ws.key + img + a, ((u64)epoch << 56) | ((u64)min(__float_as_uint(o), 0x3fffffffu) << KEY_GBITS) |
                                               (KEY_GMASK - (u64)g));
         const float al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
         if (al > 0.f) key = ((u64)__float_as_uint(al) << 32) | (0xffffffffu - (uint32_t)a);
@@ -205,16 +215,14 @@ __global__ void __launch_bounds__(CAND_THREADS) assign_candidates_kernel(const A
     if (wid >= (long long)p.b * p.G) return;
     const int bi = (int)(wid / p.G), g = (int)(wid % p.G);
     if (lane == 0) p.ws.pos_align[wid] = 0u, p.ws.pos_ov[wid] = 0u;
-    if (wid == 0 && lane == 0) {
-        p.ws.flags[1] = 0;
-        if (p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
-    }
+    if (wid == 0 && lane == 0 && p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
     if (p.mask_gt[wid] == 0.f) return;  // padded GT: claims nothing, contributes zero overlap
 
     const GtBox gt = make_gt(*reinterpret_cast<const float4*>(p.gt_bboxes + wid * 4));
     int label = (int)p.gt_labels[wid];
     label = label < 0 ? 0 : (label >= p.nc ? p.nc - 1 : label);
     const bool grid_ok = p.n_levels > 0 && p.ws.flags[0] == 0;
+    const uint32_t epoch = (uint32_t)p.ws.flags[2];
     const size_t img = (size_t)bi * p.A;
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
     const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
@@ -269,14 +277,14 @@ __global__ void __launch_bounds__(CAND_THREADS) assign_candidates_kernel(const A
                 q[lane] = tail;
                 qn -= 32;
                 __syncwarp();
-                eval_pairs(p, gt, a32, img, pdb, pds, g, topk, lane, st);
+                eval_pairs(p, gt, a32, img, pdb, pds, g, topk, lane, epoch, st);
             }
         }
     }
-    if (qn > 0) eval_pairs(p, gt, lane < qn ? q[lane] : -1, img, pdb, pds, g, topk, lane, st);
+    if (qn > 0) eval_pairs(p, gt, lane < qn ? q[lane] : -1, img, pdb, pds, g, topk, lane, epoch, st);
 
     const bool has = lane < topk && st.tk != 0ull;
-    if (has) mark_selected(p.ws.sel + img + (0xffffffffu - (uint32_t)st.tk), p.epoch, g);
+    if (has) mark_selected(p.ws.sel + img + (0xffffffffu - (uint32_t)st.tk), epoch, g);
     if (p.zero_fill) {
         // torch.topk pads a short list with zero-metric entries, lowest anchor index first; a padded
         // pick only matters when that anchor lies inside this GT (utils/tal.py:128).
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(CAND_THREADS) assign_candidates_kernel(const A
             if (__any_sync(0xffffffffu, mine)) continue;  // positive pick, already counted
             --need;
             const float2 ap = __ldg(anc + a);
-            if (lane == 0 && anchor_in_gt(ap.x, ap.y, gt)) mark_selected(p.ws.sel + img + a, p.epoch, g);
+            if (lane == 0 && anchor_in_gt(ap.x, ap.y, gt)) mark_selected(p.ws.sel + img + a, epoch, g);
         }
     }
 }
@@ -302,11 +310,13 @@ constexpr int RES_ITERS = 8;  // anchors per CTA = RES_THREADS * RES_ITERS
 __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const AssignParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
+    __shared__ int warp_tot[RES_THREADS / 32];
+    __shared__ int block_base;
     float4* s_box = reinterpret_cast<float4*>(smem_raw);
     float* s_lab = reinterpret_cast<float*>(smem_raw + (size_t)p.G * 16);
     float* s_msk = s_lab + p.G;
     const int bi = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
@@ -321,6 +331,7 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
         s_lab[g] = p.gt_labels[(size_t)bi * p.G + g];
         s_msk[g] = p.mask_gt[(size_t)bi * p.G + g];
     }
+    const uint32_t epoch = (uint32_t)p.ws.flags[2];
     const size_t img = (size_t)bi * p.A;
     const int a_base = blockIdx.x * RES_ITERS * RES_THREADS + tid;
     uint32_t sel[RES_ITERS];
@@ -332,59 +343,94 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
     __syncthreads();
     mbar_wait(&bar, 0);
 
-    const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
+    unsigned fg_bits = 0u;
 #pragma unroll
     for (int it = 0; it < RES_ITERS; ++it) {
         const int a = a_base + it * RES_THREADS;
-        const bool live = a < p.A;
-        const size_t idx = img + (live ? a : 0);
-        const bool fg = live && (sel[it] >> 24) == p.epoch;
+        if (a >= p.A) break;
+        const size_t idx = img + a;
+        const bool fg = (sel[it] >> 24) == epoch;
         uint32_t g = 0;
         if (fg) {
+            fg_bits |= 1u << it;
             const uint32_t state = sel[it] & 0xffffffu;
             if (state != SEL_MULTI) {
                 g = state - 1u;
             } else {  // contested: first-max argmax of overlaps over ALL GTs (utils/tal.py:286)
                 const u64 k = p.ws.key[idx];
-                const bool any = (k >> 56) == p.epoch && ((k >> KEY_GBITS) & 0x3fffffffull) != 0ull;
+                const bool any = (k >> 56) == epoch && ((k >> KEY_GBITS) & 0x3fffffffull) != 0ull;
                 g = any ? (uint32_t)(KEY_GMASK - (k & KEY_GMASK)) : 0u;
             }
         }
+        const float4 gb = s_box[g];
+        long long lab = (long long)s_lab[g];
+        lab = lab < 0 ? 0 : lab;
+        p.target_gt_idx[idx] = (long long)g;
+        p.target_labels[idx] = lab;
+        p.fg_mask[idx] = fg ? 1 : 0;
+        reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
+        // foreground entries get their alignment metric from assign_fg_metric_kernel (compact list)
+        if (p.nc == 1) p.target_scores[idx] = 0.f;
+        if (epoch == 255u) {  // last epoch before the wrap: leave the state clean for epoch 1
+            p.ws.sel[idx] = 0u;
+            p.ws.key[idx] = 0ull;
+        }
+    }
+    // compact list of foreground anchors for the normalise pass: one global atomic per CTA
+    const int mine = __popc(fg_bits);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[wib] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < RES_THREADS / 32; ++w) {
+            const int t = warp_tot[w];
+            warp_tot[w] = tot;
+            tot += t;
+        }
+        block_base = tot ? atomicAdd(p.ws.flags + 1, tot) : 0;
+    }
+    __syncthreads();
+    int slot = block_base + warp_tot[wib] + incl - mine;
+#pragma unroll
+    for (int it = 0; it < RES_ITERS; ++it)
+        if (fg_bits & (1u << it)) p.ws.fg_list[slot++] = (uint32_t)(img + a_base + it * RES_THREADS);
+}
+
+// ---- foreground metric -------------------------------------------------------------------------
+
+// Compact foreground list, all lanes busy: alignment metric of each (anchor, owner GT) pair, recomputed
+// with the same instruction sequence as in assign_candidates_kernel (=> identical bits; also covers
+// anchors owned by a GT that did not top-k them), stored in the owner's target_scores slot, and the
+// per-GT maxima of utils/tal.py:112-114.
+__global__ void __launch_bounds__(256) assign_fg_metric_kernel(const AssignParams p) {
+    const int n = p.ws.flags[1];
+    const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t idx = p.ws.fg_list[i];
+        const int bi = (int)(idx / (size_t)p.A);
+        const int a = (int)(idx - (size_t)bi * p.A);
+        const long long g = p.target_gt_idx[idx];
+        long long lab = p.target_labels[idx];
+        lab = lab >= p.nc ? p.nc - 1 : lab;
+        const size_t gslot = (size_t)bi * p.G + g;
+        const GtBox gt = make_gt(*reinterpret_cast<const float4*>(p.gt_bboxes + gslot * 4));
+        const float2 ap = __ldg(anc + a);
         float al = 0.f;
-        long long lab = 0;
-        if (live) {
-            const float4 gb = s_box[g];
-            lab = (long long)s_lab[g];
-            lab = lab < 0 ? 0 : lab;
-            p.target_gt_idx[idx] = (long long)g;
-            p.target_labels[idx] = lab;
-            p.fg_mask[idx] = fg ? 1 : 0;
-            reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
-            if (fg) {
-                const GtBox gt = make_gt(gb);
-                const float2 ap = __ldg(anc + a);
-                if (s_msk[g] != 0.f && anchor_in_gt(ap.x, ap.y, gt)) {
-                    const int li = lab >= p.nc ? p.nc - 1 : (int)lab;
-                    const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
-                    const float sc = __ldg(p.pd_scores + idx * p.nc + li);
-                    const float o = overlap_ciou(gt, pb);
-                    al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
-                    atomicMax(p.ws.pos_ov + (size_t)bi * p.G + g, __float_as_uint(o));
-                    atomicMax(p.ws.pos_align + (size_t)bi * p.G + g, __float_as_uint(al));
-                }
-            }
-            if (p.nc == 1) p.target_scores[idx] = al;
-            else if (fg) p.target_scores[idx * p.nc + (lab >= p.nc ? p.nc - 1 : lab)] = al;  // row pre-zeroed
+        if (p.mask_gt[gslot] != 0.f && anchor_in_gt(ap.x, ap.y, gt)) {
+            const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
+            const float sc = __ldg(p.pd_scores + idx * p.nc + lab);
+            const float o = overlap_ciou(gt, pb);
+            al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
+            atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
+            atomicMax(p.ws.pos_align + gslot, __float_as_uint(al));
         }
-        // compact list of foreground anchors for the normalise pass (one atomic per warp)
-        const unsigned m = __ballot_sync(0xffffffffu, fg);
-        if (m) {
-            int base = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) base = atomicAdd(p.ws.flags + 1, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (fg) p.ws.fg_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)idx;
-        }
+        p.target_scores[idx * p.nc + lab] = al;
     }
 }
 
@@ -440,8 +486,8 @@ static void split_ws(void* workspace, int b, int A, int G, AssignWs& ws, size_t&
     const size_t n = (size_t)b * A;
     ws.key = (u64*)take(n * 8);
     ws.sel = (uint32_t*)take(n * 4);
-    ws.state_bytes = o;
     ws.flags = (int32_t*)take(256);
+    ws.state_bytes = o;
     ws.pos_align = (uint32_t*)take((size_t)b * G * 4);
     ws.pos_ov = (uint32_t*)take((size_t)b * G * 4);
     ws.fg_list = (uint32_t*)take(n * 4);
@@ -465,7 +511,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
                               int G, int nc, int topk, float alpha, float beta, float eps, const kzd_level* h_levels,
                               int n_levels, int zero_fill, int64_t* target_labels, float* target_bboxes,
                               float* target_scores, uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
-                              void* workspace, size_t workspace_bytes, int epoch, void* stream) {
+                              void* workspace, size_t workspace_bytes, int persistent, void* stream) {
     KZD_CHECK_ARG(pd_scores && pd_bboxes && anc_points && gt_labels && gt_bboxes && mask_gt,
                   "kzd_tal_assign: null input");
     KZD_CHECK_ARG(target_labels && target_bboxes && target_scores && fg_mask && target_gt_idx && workspace,
@@ -475,7 +521,6 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     KZD_CHECK_ARG(n_levels >= 0 && n_levels <= KZD_MAX_LEVELS && (n_levels == 0 || h_levels),
                   "kzd_tal_assign: bad level table");
     KZD_CHECK_ARG(b <= 65535, "kzd_tal_assign: b=%d > 65535", b);
-    KZD_CHECK_ARG(epoch >= 0 && epoch <= 255, "kzd_tal_assign: epoch=%d not in [0,255]", epoch);
     KZD_CHECK_ARG((double)b * A < 4294967295.0 && G < (1 << 24) - 2, "kzd_tal_assign: b*A or G too large");
     KZD_CHECK_ARG((size_t)G * 24 <= 200 * 1024, "kzd_tal_assign: G=%d exceeds the shared-memory GT table (8533)", G);
     KZD_CHECK_ARG(((uintptr_t)gt_bboxes) % 16 == 0 && ((uintptr_t)pd_bboxes) % 16 == 0 &&
@@ -507,13 +552,9 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     p.fg_mask = fg_mask, p.target_gt_idx = (long long*)target_gt_idx, p.counters = counters;
 
     cudaStream_t st = (cudaStream_t)stream;
-    if (epoch == 0) {  // stateless mode: zero the per-anchor state here and run as epoch 1
-        KZD_CUDA(cudaMemsetAsync(workspace, 0, p.ws.state_bytes, st));
-        p.epoch = 1u;
-    } else {
-        p.epoch = (uint32_t)epoch;
-    }
-    KZD_CUDA(cudaMemsetAsync(p.ws.flags, 0, 8, st));
+    if (!persistent) KZD_CUDA(cudaMemsetAsync(workspace, 0, p.ws.state_bytes, st));  // stateless mode
+    assign_begin_kernel<<<1, 1, 0, st>>>(p.ws, persistent ? 0 : 1);
+    KZD_LAUNCH_CHECK("assign_begin_kernel");
     if (n_levels > 0) {
         assign_verify_kernel<<<(A + 255) / 256, 256, 0, st>>>(anc_points, A, p);
         KZD_LAUNCH_CHECK("assign_verify_kernel");
@@ -548,6 +589,8 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
         KZD_LAUNCH_CHECK("assign_resolve_kernel");
     }
     {
+        assign_fg_metric_kernel<<<(unsigned)sm_count() * 2, 256, 0, st>>>(p);
+        KZD_LAUNCH_CHECK("assign_fg_metric_kernel");
         assign_normalize_kernel<<<(unsigned)sm_count() * 2, 256, 0, st>>>(p);
         KZD_LAUNCH_CHECK("assign_normalize_kernel");
     }

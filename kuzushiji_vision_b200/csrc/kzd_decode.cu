@@ -142,7 +142,7 @@ __device__ __forceinline__ void side_stats(const float* row, int tid, float& d, 
     float sum = 0.f, wsum = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float base = (float)(q[j] * 4);
+        const float base = __uint_as_float(0x4b000000u | (uint32_t)(q[j] * 4)) - 8388608.f;  // exact int->float
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float e = __expf(v[j][k] - m);
@@ -159,8 +159,10 @@ __device__ __forceinline__ void side_stats(const float* row, int tid, float& d, 
 // on an mbarrier), all 256 threads consume: thread t owns (anchor t/4, side t%4) of the tile and
 // writes output element t of the tile's 256 contiguous floats.
 __global__ void __launch_bounds__(TR_THREADS) decode_train_kernel(const float* __restrict__ pred,
-                                                                  const float* __restrict__ anc, int A,
-                                                                  long long N, float* __restrict__ out) {
+                                                                  const float* __restrict__ anc,
+                                                                  const float* __restrict__ stride, int A,
+                                                                  long long N, float* __restrict__ out,
+                                                                  float* __restrict__ out_px) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* buf = reinterpret_cast<float*>(smem_raw);
     __shared__ uint64_t full[TR_STAGES];
@@ -191,14 +193,21 @@ __global__ void __launch_bounds__(TR_THREADS) decode_train_kernel(const float* _
         const long long tile = blockIdx.x + it * gridDim.x;
         if (tile >= n_tiles) break;
         const int stage = (int)(it % TR_STAGES);
-        mbar_wait(&full[stage], (uint32_t)((it / TR_STAGES) & 1));
         const long long n = tile * TR_ANCH + a_local;
+        // anchor (and stride) fetched before waiting on the tile so their latency hides behind the TMA
+        const int a_img = (N <= 0x7fffffffLL) ? (int)((uint32_t)n % (uint32_t)A) : (int)(n % A);
+        float ap = 0.f, st = 0.f;
+        if (n < N) {
+            ap = __ldg(anc + a_img * 2 + (side & 1));
+            if (out_px) st = __ldg(stride + a_img);
+        }
+        mbar_wait(&full[stage], (uint32_t)((it / TR_STAGES) & 1));
         if (n < N) {
             float d, m, s;
             side_stats(buf + stage * TR_FLOATS + tid * 16, tid, d, m, s);
-            const int a_img = (int)(n % A);
-            const float ap = __ldg(anc + a_img * 2 + (side & 1));
-            out[n * 4 + side] = (side < 2) ? (ap - d) : (ap + d);
+            const float v = (side < 2) ? (ap - d) : (ap + d);
+            out[n * 4 + side] = v;
+            if (out_px) out_px[n * 4 + side] = __fmul_rn(v, st);  // utils/loss.py:236
         }
         __syncthreads();  // every thread is done with this stage before it is refilled
         if (tid == 0) {
@@ -321,17 +330,19 @@ static int train_grid(long long n_tiles, const void* fn) {
     return (int)(n_tiles < g ? n_tiles : g);
 }
 
-extern "C" __attribute__((visibility("default"))) int kzd_decode_train(const float* pred_dist, const float* anchor_points, int b, int A, float* out_xyxy,
-                                void* stream) {
+extern "C" __attribute__((visibility("default"))) int kzd_decode_train(const float* pred_dist, const float* anchor_points, const float* stride_tensor,
+                                int b, int A, float* out_xyxy, float* out_xyxy_px, void* stream) {
     KZD_CHECK_ARG(pred_dist && anchor_points && out_xyxy, "kzd_decode_train: null pointer");
     KZD_CHECK_ARG(b >= 0 && A >= 0, "kzd_decode_train: negative size");
     KZD_CHECK_ARG(((uintptr_t)pred_dist) % 16 == 0, "kzd_decode_train: pred_dist must be 16-byte aligned");
+    KZD_CHECK_ARG(!out_xyxy_px || stride_tensor, "kzd_decode_train: out_xyxy_px needs stride_tensor");
     const long long N = (long long)b * A;
     if (N == 0) return 0;
     KZD_CUDA(cudaFuncSetAttribute(decode_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
     const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
     const int grid = train_grid(n_tiles, (const void*)decode_train_kernel);
-    decode_train_kernel<<<grid, TR_THREADS, TR_SMEM, (cudaStream_t)stream>>>(pred_dist, anchor_points, A, N, out_xyxy);
+    decode_train_kernel<<<grid, TR_THREADS, TR_SMEM, (cudaStream_t)stream>>>(pred_dist, anchor_points, stride_tensor, A, N,
+                                                                            out_xyxy, out_xyxy_px);
     KZD_LAUNCH_CHECK("decode_train_kernel");
     return 0;
 }

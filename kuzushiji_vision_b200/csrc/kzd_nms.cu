@@ -347,18 +347,17 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
         __syncthreads();  // previous item's colbox readers are done
         colbox[i] = (col0 + i < n) ? sbox[col0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
+        // superset test (4 compares, no min/max): a true intersection implies all four
         uint32_t lo = 0u, hi = 0u;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const float4 cb = colbox[j];
-            const bool ov = (fminf(a.z, cb.z) > fmaxf(a.x, cb.x)) && (fminf(a.w, cb.w) > fmaxf(a.y, cb.y));
-            lo |= ov ? (1u << j) : 0u;
+            if (a.z > cb.x && cb.z > a.x && a.w > cb.y && cb.w > a.y) lo |= (1u << j);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const float4 cb = colbox[32 + j];
-            const bool ov = (fminf(a.z, cb.z) > fmaxf(a.x, cb.x)) && (fminf(a.w, cb.w) > fmaxf(a.y, cb.y));
-            hi |= ov ? (1u << j) : 0u;
+            if (a.z > cb.x && cb.z > a.x && a.w > cb.y && cb.w > a.y) hi |= (1u << j);
         }
         u64 cand = ((u64)hi << 32) | lo;
         const int jn = n - col0;  // valid columns of this tile

@@ -62,23 +62,34 @@ def detect_inference(self, x):
 
 
 class _BboxDecodeFn(torch.autograd.Function):
-    """``softmax(16 bins) . arange(16)`` per side, then ``anchor -/+ distance`` (xyxy, grid units)."""
+    """``softmax(16 bins) . arange(16)`` per side, then ``anchor -/+ distance`` (xyxy, grid units).
+    With ``stride_tensor`` the kernel also emits the pixel-space copy ``xyxy * stride`` (non-differentiable,
+    the assigner's ``pd_bboxes``, utils/loss.py:236)."""
 
     @staticmethod
-    def forward(ctx, pred_dist, anchor_points):
+    def forward(ctx, pred_dist, anchor_points, stride_tensor):
         b, A, c = pred_dist.shape
         pd = pred_dist.to(torch.float32).contiguous()
         anc = anchor_points.to(torch.float32).contiguous()
         out = torch.empty((b, A, 4), dtype=torch.float32, device=pd.device)
+        st = px = None
+        if stride_tensor is not None:
+            st = stride_tensor.to(torch.float32).contiguous()
+            px = torch.empty_like(out)
         with torch.cuda.device(pd.device):
-            rc = _lib.lib.kzd_decode_train(pd.data_ptr(), anc.data_ptr(), b, A, out.data_ptr(), _stream(pd.device))
+            rc = _lib.lib.kzd_decode_train(pd.data_ptr(), anc.data_ptr(), st.data_ptr() if st is not None else None,
+                                           b, A, out.data_ptr(), px.data_ptr() if px is not None else None,
+                                           _stream(pd.device))
         _lib.check(rc, "kzd_decode_train")
         ctx.save_for_backward(pd)
         ctx.in_dtype = pred_dist.dtype
-        return out
+        if px is None:
+            return out
+        ctx.mark_non_differentiable(px)
+        return out, px
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, *unused):
         (pd,) = ctx.saved_tensors
         b, A, _ = pd.shape
         g = grad_out.to(torch.float32).contiguous()
@@ -86,17 +97,20 @@ class _BboxDecodeFn(torch.autograd.Function):
         with torch.cuda.device(pd.device):
             rc = _lib.lib.kzd_decode_train_bwd(pd.data_ptr(), g.data_ptr(), b, A, gin.data_ptr(), _stream(pd.device))
         _lib.check(rc, "kzd_decode_train_bwd")
-        return gin.to(ctx.in_dtype), None
+        return gin.to(ctx.in_dtype), None, None
 
 
-def bbox_decode(anchor_points, pred_dist):
+def bbox_decode(anchor_points, pred_dist, stride_tensor=None):
     """Training-side decode: ``pred_dist (b,A,64)``, ``anchor_points (A,2)`` grid units -> xyxy
     ``(b,A,4)``. Same argument order as ``v8DetectionLoss.bbox_decode`` (utils/loss.py:197);
-    differentiable wrt ``pred_dist`` (the box / DFL losses back-propagate through it, loss.py:252)."""
+    differentiable wrt ``pred_dist`` (the box / DFL losses back-propagate through it, loss.py:252).
+
+    Extension: with ``stride_tensor (A,1)`` it returns ``(xyxy, xyxy_px)`` where ``xyxy_px = xyxy *
+    stride_tensor`` is produced by the same kernel (the caller glue of utils/loss.py:236)."""
     _lib.require_cuda(pred_dist, "pred_dist")
     if pred_dist.shape[-1] != 4 * REG_MAX:
         raise _lib.KzdError(f"pred_dist has {pred_dist.shape[-1]} channels, expected {4 * REG_MAX}")
-    return _BboxDecodeFn.apply(pred_dist, anchor_points)
+    return _BboxDecodeFn.apply(pred_dist, anchor_points, stride_tensor)
 
 
 def loss_bbox_decode(self, anchor_points, pred_dist):

