@@ -7,7 +7,8 @@ One "step" = one pass of the hot path over one batch of synthetic kuzushiji page
     bbox_decode (utils/loss.py:197)  ->  x stride (caller glue, torch)  ->  TaskAlignedAssigner.forward
     Detect._inference decode (nn/modules/head.py:100)  ->  ops.non_max_suppression
 Workload (BASELINE.json configs[1]): YOLOv12x P2-P5 head, 1280x1280 pages, batch 16 per GPU,
-~600 GT boxes/page, single class; NMS at the predictor defaults conf 0.25 / iou 0.7 / max_det 300 on
+~600 GT boxes/page, single class; NMS at the reference's kuzushiji test-script settings (conf 0.25, iou 0.7,
+max_det 1000: scripts/test_character_detection.py:237-243) on
 inference-like class logits (~3000 candidates/page). Images are sharded over ranks
 (weak scaling: 16 pages per GPU); the only collective is an all-reduce of 4 counters.
 
@@ -31,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(imgsz=1280, batch=16, G=600, nc=1, strides=(4, 8, 16, 32), topk=10, alpha=0.5, beta=6.0,
-                conf=0.25, iou=0.7, max_det=300, nms_candidates=3000)
+                conf=0.25, iou=0.7, max_det=1000, nms_candidates=3000)
 METRIC = "pages/sec assign+decode+NMS @1280^2 P2-P5"
 FALLBACK_HBM_GBS = 6650.0
 
@@ -197,7 +198,7 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: 1280x1280 P2-P5 (A=136000), ~600 GT/page, nc=1; "
-                               "NMS conf .25 iou .7 max_det 300 on ~3000 candidates/page; host CPU, " + note,
+                               "NMS conf .25 iou .7 max_det 1000 on ~3000 candidates/page; host CPU, " + note,
                    **{k: w[k] for k in ("imgsz", "G", "nc")}},
         "cpu_baseline": {"value": val, "unit": "pages/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {note} (oracle torch port of the reference, "
@@ -355,7 +356,7 @@ def run_kzd(args, rank, local_rank, world):
         "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: YOLOv12x P2-P5 head outputs, 1280x1280 pages, batch 16 per GPU, "
-                               "~600 GT/page, nc=1; NMS conf .25 iou .7 max_det 300 on ~3000 candidates/page",
+                               "~600 GT/page, nc=1; NMS conf .25 iou .7 max_det 1000 on ~3000 candidates/page",
                    "pages_per_gpu": b, "anchors_per_page": A, "gt_slots": G, "nc": nc,
                    "l2_policy": "inputs larger than L2 (1.16 GB read per step vs 126 MB L2)",
                    "step": "PagePipeline: one CUDA-graph replay of decode_train+assign+decode_infer+NMS",

@@ -161,7 +161,24 @@ constexpr int CAND_WARPS = CAND_THREADS / 32;
 struct TopK {
     u64 tk;   // lane i holds the i-th best  metric_bits<<32 | ~anchor  (0 = empty)
     u64 kth;  // entry topk-1: the bar a new candidate has to clear
+    bool empty;
 };
+
+// 32 keys, one per lane -> descending order across the lanes (bitonic network on shuffles)
+__device__ __forceinline__ u64 warp_sort_desc(u64 v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, j);
+            const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), j);
+            const u64 o = ((u64)hi << 32) | lo;
+            const bool want_max = (((lane & k) == 0) == ((lane & j) == 0));  // descending overall
+            v = (want_max == (o > v)) ? o : v;
+        }
+    }
+    return v;
+}
 
 // One in-GT pair per lane (a < 0: idle lane): overlap, metric, argmax key, streaming top-k insert.
 __device__ __forceinline__ void eval_pairs(const AssignParams& p, const GtBox& gt, int a, size_t img,
@@ -177,6 +194,12 @@ __device__ __forceinline__ void eval_pairs(const AssignParams& p, const GtBox& g
                                               (KEY_GMASK - (u64)g));
         const float al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
         if (al > 0.f) key = ((u64)__float_as_uint(al) << 32) | (0xffffffffu - (uint32_t)a);
+    }
+    if (st.empty) {  // first batch: one warp sort instead of up to 32 serial insertions
+        st.tk = warp_sort_desc(key, lane);
+        st.kth = shfl64(st.tk, topk - 1);
+        st.empty = false;
+        return;
     }
     unsigned m = __ballot_sync(0xffffffffu, key > st.kth);
     while (m) {
@@ -230,31 +253,34 @@ __global__ void __launch_bounds__(CAND_THREADS) assign_candidates_kernel(const A
     const int topk = p.topk;
     int* q = queue[wib];
     int qn = 0;  // queued in-GT anchors (warp-uniform)
-    TopK st{0ull, 0ull};
+    TopK st{0ull, 0ull, true};
 
     const int n_pseudo = grid_ok ? p.n_levels : 1;
     for (int l = 0; l < n_pseudo; ++l) {
         int i0 = 0, j0 = 0, nx = p.A, ny = 1, W = 0, off = 0;
         float s = 0.f;
         if (grid_ok) {
-            // superset of the cells whose centre can be inside the GT (one spare cell each side);
-            // the exact fp32 predicate below decides
+            // superset of the cells whose centre can be inside the GT; the exact fp32 predicate decides
             s = p.lv[l].stride;
             W = p.lv[l].w, off = p.lv[l].offset;
             const int H = p.lv[l].h;
-            int ia = (int)floorf(gt.x1 / s - 0.5f) - 1, ib = (int)ceilf(gt.x2 / s - 0.5f) + 1;
-            int ja = (int)floorf(gt.y1 / s - 0.5f) - 1, jb = (int)ceilf(gt.y2 / s - 0.5f) + 1;
+            // centres inside need index in (x1/s-0.5, x2/s-0.5); [floor, ceil] of the computed bounds
+            // contains it even when the fp32 quotient is off by an ulp
+            int ia = (int)floorf(gt.x1 / s - 0.5f), ib = (int)ceilf(gt.x2 / s - 0.5f);
+            int ja = (int)floorf(gt.y1 / s - 0.5f), jb = (int)ceilf(gt.y2 / s - 0.5f);
             ia = max(ia, 0), ja = max(ja, 0), ib = min(ib, W - 1), jb = min(jb, H - 1);
             if (ia > ib || ja > jb) continue;
             i0 = ia, j0 = ja, nx = ib - ia + 1, ny = jb - ja + 1;
         }
         const int total = nx * ny;
+        const float inv_nx = 1.f / (float)nx;
+        const bool small = total < (1 << 21);  // (t+0.5)/nx is then exact enough to floor
         for (int t0 = 0; t0 < total; t0 += 32) {
             const int t = t0 + lane;
             bool inside = false;
             int a = 0;
             if (t < total) {
-                const int jj = t / nx, ii = t - jj * nx;
+                const int jj = small ? (int)(((float)t + 0.5f) * inv_nx) : t / nx, ii = t - jj * nx;
                 a = off + (j0 + jj) * W + i0 + ii;
                 float ax, ay;
                 if (grid_ok) {  // verified bit-identical to anc_points[a] by assign_verify_kernel

@@ -306,22 +306,32 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float sa, const flo
     return __fdiv_rn(inter, u) > thr;
 }
 
-// Work item = (image, row tile r, column tile c >= r) over all images; items are striped over a
-// persistent grid. Thread i of the CTA owns row r*64+i and writes one 64-bit word of the mask.
-// Pass 1 (branch-free, fully unrolled): which of the 64 column boxes intersect the row box at all.
-// Pass 2 (rare): exact IoU > thr only for those.
+// Work item = (image, row tile r, group of MASK_CG consecutive column tiles) restricted to the upper
+// triangle; items of all images are striped over a persistent grid. Thread i of the CTA owns row
+// r*64+i and writes one 64-bit word of the mask per column tile.
+// Pass 1 (branch-free, fully unrolled): which of the 64 column boxes can intersect the row box at all
+// (4 compares; a superset of the true intersections). Pass 2 (rare): exact IoU > thr only for those.
 // Mask layout: [image][r*T_cap + c][i]  (64 consecutive words per tile => coalesced 512 B stores,
 // and the scan reads whole tiles).
+constexpr int MASK_CG = 4;
+
+__device__ __forceinline__ int mask_items(int n) {  // column group g holds rows 0..min(T, 4g+4)-1
+    if (n <= 0) return 0;
+    const int T = (n + 63) >> 6, Gc = (T + MASK_CG - 1) / MASK_CG;
+    // sum_{g<Gc} min(T, MASK_CG*(g+1))
+    const int full = 2 * (Gc - 1) * Gc;  // MASK_CG * (1 + ... + (Gc-1)) with MASK_CG == 4
+    return full + T;
+}
+
 __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap, float iou_thres, SuppressWs ws) {
-    extern __shared__ int pre[];  // (b+1) prefix of tile-pair counts
-    __shared__ float4 colbox[64];
+    extern __shared__ int pre[];  // (b+1) prefix of item counts
+    __shared__ float4 colbox[MASK_CG * 64];
+    static_assert(MASK_CG == 4, "mask_items() assumes groups of 4 column tiles");
     if (threadIdx.x == 0) {
         int acc = 0;
         for (int i = 0; i < b; ++i) {
             pre[i] = acc;
-            const int n = ws.n_sorted[i];
-            const int T = n > 0 ? (n + 63) >> 6 : 0;
-            acc += T * (T + 1) / 2;
+            acc += mask_items(ws.n_sorted[i]);
         }
         pre[b] = acc;
     }
@@ -334,46 +344,53 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
         const int n = ws.n_sorted[bi];
         const int T = (n + 63) >> 6;
         const int q = w - pre[bi];
-        // invert q = r*T - r(r-1)/2 + (c - r)
-        const float tt = 2.f * T + 1.f;
-        int r = (int)((tt - sqrtf(fmaxf(tt * tt - 8.f * (float)q, 0.f))) * 0.5f);
-        r = max(0, min(r, T - 1));
-        while (r > 0 && r * T - r * (r - 1) / 2 > q) --r;
-        while (r + 1 < T && (r + 1) * T - (r + 1) * r / 2 <= q) ++r;
-        const int c = r + (q - (r * T - r * (r - 1) / 2));
+        // items are ordered by column group g, then row r:  offset(g) = 2 g (g+1)
+        int g = (int)((sqrtf(1.f + 2.f * (float)q) - 1.f) * 0.5f);
+        g = max(g, 0);
+        while (2 * g * (g + 1) > q) --g;
+        while (2 * (g + 1) * (g + 2) <= q) ++g;
+        const int r = q - 2 * g * (g + 1);
+        const int c_first = g * MASK_CG;
         const float4* __restrict__ sbox = ws.sbox + (size_t)bi * n_cap;
-        const int row = r * 64 + i, col0 = c * 64;
+        const int row = r * 64 + i;
         const float4 a = (row < n) ? sbox[row] : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();  // previous item's colbox readers are done
-        colbox[i] = (col0 + i < n) ? sbox[col0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < MASK_CG; ++k) {
+            const int col = (c_first + k) * 64 + i;
+            colbox[k * 64 + i] = (col < n) ? sbox[col] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         __syncthreads();
-        // superset test (4 compares, no min/max): a true intersection implies all four
-        uint32_t lo = 0u, hi = 0u;
+        const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+#pragma unroll 1
+        for (int k = 0; k < MASK_CG; ++k) {
+            const int c = c_first + k;
+            if (c < r || c >= T) continue;  // below the diagonal / beyond the last tile (uniform)
+            const float4* cb_tile = colbox + k * 64;
+            uint32_t lo = 0u, hi = 0u;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float4 cb = colbox[j];
-            if (a.z > cb.x && cb.z > a.x && a.w > cb.y && cb.w > a.y) lo |= (1u << j);
-        }
+            for (int j = 0; j < 32; ++j) {
+                const float4 cb = cb_tile[j];
+                if (a.z > cb.x && cb.z > a.x && a.w > cb.y && cb.w > a.y) lo |= (1u << j);
+            }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float4 cb = colbox[32 + j];
-            if (a.z > cb.x && cb.z > a.x && a.w > cb.y && cb.w > a.y) hi |= (1u << j);
-        }
-        u64 cand = ((u64)hi << 32) | lo;
-        const int jn = n - col0;  // valid columns of this tile
-        if (jn < 64) cand &= (1ull << jn) - 1ull;
-        if (r == c) cand &= (i < 63) ? (~0ull << (i + 1)) : 0ull;  // only later boxes can be suppressed
-        if (row >= n) cand = 0ull;
-        u64 word = 0ull;
-        if (cand) {
-            const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+            for (int j = 0; j < 32; ++j) {
+                const float4 cb = cb_tile[32 + j];
+                if (a.z > cb.x && cb.z > a.x && a.w > cb.y && cb.w > a.y) hi |= (1u << j);
+            }
+            u64 cand = ((u64)hi << 32) | lo;
+            const int jn = n - c * 64;  // valid columns of this tile
+            if (jn < 64) cand &= (1ull << jn) - 1ull;
+            if (r == c) cand &= (i < 63) ? (~0ull << (i + 1)) : 0ull;  // only later boxes can be suppressed
+            if (row >= n) cand = 0ull;
+            u64 word = 0ull;
             while (cand) {
                 const int j = __ffsll((long long)cand) - 1;
                 cand &= cand - 1ull;
-                if (iou_gt(a, sa, colbox[j], iou_thres)) word |= 1ull << j;
+                if (iou_gt(a, sa, cb_tile[j], iou_thres)) word |= 1ull << j;
             }
+            ws.mask[((size_t)bi * ws.T_cap * ws.T_cap + (size_t)r * ws.T_cap + c) * 64 + i] = word;
         }
-        ws.mask[((size_t)bi * ws.T_cap * ws.T_cap + (size_t)r * ws.T_cap + c) * 64 + i] = word;
     }
 }
 
@@ -381,7 +398,9 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
 // stage 2c: greedy scan + row gather
 // ------------------------------------------------------------------------------------------
 
-constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_BATCH = 4;  // column tiles per warp whose loads are in flight together
 
 __device__ __forceinline__ u64 shfl64(u64 v, int src) {
     const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
@@ -389,6 +408,11 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src) {
     return ((u64)hi << 32) | lo;
 }
 
+// One CTA per image walks the 64-row chunks in score order. Per chunk the only serial work is the
+// diagonal tile (warp 0: ballot of the rows that suppress anything inside the chunk, shuffle their
+// words, test/OR); its loads are issued one chunk ahead. The other tiles of the row (c > r) are
+// loaded by all warps BEFORE the keep mask is known - SCAN_BATCH tiles per warp in flight - and masked
+// afterwards, so one L2 round trip per chunk is on the critical path instead of one per tile.
 __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __restrict__ cand_rows, int cand_cap,
                                                                 int n_cap, int max_det, SuppressWs ws,
                                                                 float* __restrict__ out_rows,
@@ -402,20 +426,28 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
         return;
     }
     const int T = (n + 63) >> 6;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = SCAN_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = threadIdx.x; c < T; c += SCAN_THREADS) removed[c] = 0ull;
-    __syncthreads();
     const u64* __restrict__ mask = ws.mask + (size_t)bi * ws.T_cap * ws.T_cap * 64;
     const uint32_t* __restrict__ sslot = ws.sslot + (size_t)bi * n_cap;
     const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
     float* __restrict__ out = out_rows + (size_t)bi * max_det * 6;
+    u64 d_lo = 0ull, d_hi = 0ull;  // warp 0: diagonal tile of the current chunk
+    if (warp == 0 && T > 0) d_lo = mask[lane], d_hi = mask[lane + 32];
+    __syncthreads();
     int kept = 0;
     for (int r = 0; r < T; ++r) {
         const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
+        // (a) every warp: loads of its first batch of later tiles, independent of the keep mask
+        u64 v_lo[SCAN_BATCH], v_hi[SCAN_BATCH];
+#pragma unroll
+        for (int k = 0; k < SCAN_BATCH; ++k) {
+            const int c = r + 1 + warp + k * SCAN_WARPS;
+            v_lo[k] = v_hi[k] = 0ull;
+            if (c < T) v_lo[k] = tile_row[(size_t)c * 64 + lane], v_hi[k] = tile_row[(size_t)c * 64 + lane + 32];
+        }
+        // (b) warp 0: resolve the diagonal tile, then prefetch the next one
         if (warp == 0) {
-            // diagonal tile: rows r*64..r*64+63 against themselves (bits j > i only)
-            const u64* d = tile_row + (size_t)r * 64;
-            const u64 d_lo = d[lane], d_hi = d[lane + 32];
             u64 rem = removed[r];
             const int valid = n - r * 64;  // rows of this chunk that exist
             if (valid < 64) rem |= ~0ull << valid;
@@ -428,30 +460,50 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
                 if (!((rem >> i) & 1ull)) rem |= di;
             }
             if (lane == 0) keep_sh = ~rem;
+            if (r + 1 < T) {
+                const u64* nd = mask + ((size_t)(r + 1) * ws.T_cap + (r + 1)) * 64;
+                d_lo = nd[lane], d_hi = nd[lane + 32];
+            }
         }
         __syncthreads();
         const u64 keep = keep_sh;
-        // gather kept rows of this chunk, in order
-        if (threadIdx.x < 64 && ((keep >> threadIdx.x) & 1ull)) {
-            const int pos = kept + __popcll(keep & ((1ull << threadIdx.x) - 1ull));
-            if (pos < max_det) {
-                const float* src = rows + (size_t)sslot[r * 64 + threadIdx.x] * 6;
-                float* dst = out + (size_t)pos * 6;
+        const int kept_before = kept;
+        kept += __popcll(keep);
+        const bool last = kept >= max_det || r + 1 == T;  // uniform
+        // (c) OR the kept rows into the removed words of the later chunks
+        if (!last) {
+            const bool k_lo = (keep >> lane) & 1ull, k_hi = (keep >> (lane + 32)) & 1ull;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) dst[k] = src[k];
+            for (int k = 0; k < SCAN_BATCH; ++k) {
+                const int c = r + 1 + warp + k * SCAN_WARPS;
+                if (c < T) {
+                    const u64 v = (k_lo ? v_lo[k] : 0ull) | (k_hi ? v_hi[k] : 0ull);
+                    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
+                    const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+                    if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
+                }
+            }
+            for (int c = r + 1 + warp + SCAN_BATCH * SCAN_WARPS; c < T; c += SCAN_WARPS) {  // long rows
+                const u64* t = tile_row + (size_t)c * 64;
+                const u64 v = (k_lo ? t[lane] : 0ull) | (k_hi ? t[lane + 32] : 0ull);
+                const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
+                const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+                if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
             }
         }
-        kept += __popcll(keep);
-        if (kept >= max_det) break;  // uniform: later boxes cannot enter the first max_det
-        // OR the kept rows into the removed words of the later chunks
-        const bool k_lo = (keep >> lane) & 1ull, k_hi = (keep >> (lane + 32)) & 1ull;
-        for (int c = r + 1 + warp; c < T; c += n_warps) {
-            const u64* t = tile_row + (size_t)c * 64;
-            u64 v = (k_lo ? t[lane] : 0ull) | (k_hi ? t[lane + 32] : 0ull);
-            const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
-            const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
-            if (lane == 0) removed[c] |= ((u64)hi << 32) | lo;
+        // (d) gather the kept rows of this chunk, in order (off the critical path: stores only)
+        if (threadIdx.x >= SCAN_THREADS - 64) {
+            const int i = threadIdx.x - (SCAN_THREADS - 64);
+            if ((keep >> i) & 1ull) {
+                const int pos = kept_before + __popcll(keep & ((1ull << i) - 1ull));
+                if (pos < max_det) {
+                    const float2* src = reinterpret_cast<const float2*>(rows + (size_t)sslot[r * 64 + i] * 6);
+                    float2* dst = reinterpret_cast<float2*>(out + (size_t)pos * 6);
+                    dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
+                }
+            }
         }
+        if (last) break;  // later boxes cannot enter the first max_det
         __syncthreads();
     }
     if (threadIdx.x == 0) out_counts[bi] = kept < max_det ? kept : max_det;

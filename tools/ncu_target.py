@@ -14,9 +14,9 @@ d = synth.assigner_inputs(b, G, imgsz, nc, synth.P2_P5, seed=0, device=dev)
 lv = synth.head_outputs(b, nc, imgsz, synth.P2_P5, seed=100, device=dev, sparse_cls=3000)
 asg = kzd.TaskAlignedAssigner(10, nc, 0.5, 6.0)
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
-    boxes = kzd.bbox_decode(d["anchor_points"], d["pred_distri"])
-    out = asg(d["pd_scores"], boxes * d["stride_tensor"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+    boxes, px = kzd.bbox_decode(d["anchor_points"], d["pred_distri"], d["stride_tensor"])
+    out = asg(d["pd_scores"], px, d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
     y = kzd.decode_inference(lv, synth.P2_P5, nc)
-    det = kzd.nms_batched(y, 0.25, 0.7, max_det=300)
+    det = kzd.nms_batched(y, 0.25, 0.7, max_det=1000)
 torch.cuda.synchronize()
 print("ok", int(out[3].sum()), sum(det[1]))

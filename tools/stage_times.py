@@ -21,7 +21,7 @@ ap.add_argument("--config", type=int, default=2)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 if args.config == 2:
-    b, G, imgsz, nc, cands, max_det = 16, 600, 1280, 1, 3000, 300
+    b, G, imgsz, nc, cands, max_det = 16, 600, 1280, 1, 3000, 1000
 else:
     b, G, imgsz, nc, cands, max_det = 32, 600, 1536, 1, 3000, 2000
 strides = synth.P2_P5
