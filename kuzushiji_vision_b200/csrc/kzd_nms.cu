@@ -410,14 +410,14 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src) {
 
 // One CTA per image walks the 64-row chunks in score order. Per chunk the only serial work is the
 // diagonal tile (warp 0: ballot of the rows that suppress anything inside the chunk, shuffle their
-// words, test/OR); its loads are issued one chunk ahead. The other tiles of the row (c > r) are
-// loaded by all warps BEFORE the keep mask is known - SCAN_BATCH tiles per warp in flight - and masked
-// afterwards, so one L2 round trip per chunk is on the critical path instead of one per tile.
+// words, test/OR). All global loads are issued one chunk ahead and independent of the keep mask (it is
+// applied afterwards), so no memory round trip sits on the chunk-to-chunk critical path. The keep
+// masks are parked in shared memory and the kept rows are gathered by all threads after the walk.
 __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __restrict__ cand_rows, int cand_cap,
                                                                 int n_cap, int max_det, SuppressWs ws,
                                                                 float* __restrict__ out_rows,
                                                                 int32_t* __restrict__ out_counts) {
-    extern __shared__ u64 removed[];  // T_cap words
+    extern __shared__ u64 sm64[];  // removed[T_cap], keepmask[T_cap], then int kept_before[T_cap]
     __shared__ u64 keep_sh;
     const int bi = blockIdx.x;
     const int n = ws.n_sorted[bi];
@@ -425,28 +425,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
         if (threadIdx.x == 0) out_counts[bi] = -1;
         return;
     }
+    u64* removed = sm64;
+    u64* keepmask = sm64 + ws.T_cap;
+    int* kept_before = reinterpret_cast<int*>(sm64 + 2 * ws.T_cap);
     const int T = (n + 63) >> 6;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = threadIdx.x; c < T; c += SCAN_THREADS) removed[c] = 0ull;
     const u64* __restrict__ mask = ws.mask + (size_t)bi * ws.T_cap * ws.T_cap * 64;
-    const uint32_t* __restrict__ sslot = ws.sslot + (size_t)bi * n_cap;
-    const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
-    float* __restrict__ out = out_rows + (size_t)bi * max_det * 6;
-    u64 d_lo = 0ull, d_hi = 0ull;  // warp 0: diagonal tile of the current chunk
-    if (warp == 0 && T > 0) d_lo = mask[lane], d_hi = mask[lane + 32];
-    __syncthreads();
-    int kept = 0;
-    for (int r = 0; r < T; ++r) {
+    u64 d_lo = 0ull, d_hi = 0ull;          // warp 0: diagonal tile of the current chunk
+    u64 v_lo[SCAN_BATCH], v_hi[SCAN_BATCH];  // every warp: its later tiles of the current chunk's row
+    auto load_row = [&](int r) {
         const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
-        // (a) every warp: loads of its first batch of later tiles, independent of the keep mask
-        u64 v_lo[SCAN_BATCH], v_hi[SCAN_BATCH];
 #pragma unroll
         for (int k = 0; k < SCAN_BATCH; ++k) {
             const int c = r + 1 + warp + k * SCAN_WARPS;
             v_lo[k] = v_hi[k] = 0ull;
             if (c < T) v_lo[k] = tile_row[(size_t)c * 64 + lane], v_hi[k] = tile_row[(size_t)c * 64 + lane + 32];
         }
-        // (b) warp 0: resolve the diagonal tile, then prefetch the next one
+        if (warp == 0) d_lo = tile_row[(size_t)r * 64 + lane], d_hi = tile_row[(size_t)r * 64 + lane + 32];
+    };
+    if (T > 0) load_row(0);
+    __syncthreads();
+    int kept = 0, chunks = 0;
+    for (int r = 0; r < T; ++r) {
+        // (a) warp 0: resolve the diagonal tile
         if (warp == 0) {
             u64 rem = removed[r];
             const int valid = n - r * 64;  // rows of this chunk that exist
@@ -459,52 +461,52 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
                 const u64 di = (i < 32) ? shfl64(d_lo, i) : shfl64(d_hi, i - 32);
                 if (!((rem >> i) & 1ull)) rem |= di;
             }
-            if (lane == 0) keep_sh = ~rem;
-            if (r + 1 < T) {
-                const u64* nd = mask + ((size_t)(r + 1) * ws.T_cap + (r + 1)) * 64;
-                d_lo = nd[lane], d_hi = nd[lane + 32];
-            }
+            if (lane == 0) keep_sh = ~rem, keepmask[r] = ~rem, kept_before[r] = kept;
         }
         __syncthreads();
         const u64 keep = keep_sh;
-        const int kept_before = kept;
         kept += __popcll(keep);
-        const bool last = kept >= max_det || r + 1 == T;  // uniform
-        // (c) OR the kept rows into the removed words of the later chunks
-        if (!last) {
-            const bool k_lo = (keep >> lane) & 1ull, k_hi = (keep >> (lane + 32)) & 1ull;
+        chunks = r + 1;
+        if (kept >= max_det || r + 1 == T) break;  // uniform: later boxes cannot enter the first max_det
+        // (b) OR the kept rows into the removed words of the later chunks (data loaded a chunk ago)
+        const bool k_lo = (keep >> lane) & 1ull, k_hi = (keep >> (lane + 32)) & 1ull;
+        const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
 #pragma unroll
-            for (int k = 0; k < SCAN_BATCH; ++k) {
-                const int c = r + 1 + warp + k * SCAN_WARPS;
-                if (c < T) {
-                    const u64 v = (k_lo ? v_lo[k] : 0ull) | (k_hi ? v_hi[k] : 0ull);
-                    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
-                    const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
-                    if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
-                }
-            }
-            for (int c = r + 1 + warp + SCAN_BATCH * SCAN_WARPS; c < T; c += SCAN_WARPS) {  // long rows
-                const u64* t = tile_row + (size_t)c * 64;
-                const u64 v = (k_lo ? t[lane] : 0ull) | (k_hi ? t[lane + 32] : 0ull);
+        for (int k = 0; k < SCAN_BATCH; ++k) {
+            const int c = r + 1 + warp + k * SCAN_WARPS;
+            if (c < T) {
+                const u64 v = (k_lo ? v_lo[k] : 0ull) | (k_hi ? v_hi[k] : 0ull);
                 const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
                 const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
                 if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
             }
         }
-        // (d) gather the kept rows of this chunk, in order (off the critical path: stores only)
-        if (threadIdx.x >= SCAN_THREADS - 64) {
-            const int i = threadIdx.x - (SCAN_THREADS - 64);
-            if ((keep >> i) & 1ull) {
-                const int pos = kept_before + __popcll(keep & ((1ull << i) - 1ull));
-                if (pos < max_det) {
-                    const float2* src = reinterpret_cast<const float2*>(rows + (size_t)sslot[r * 64 + i] * 6);
-                    float2* dst = reinterpret_cast<float2*>(out + (size_t)pos * 6);
-                    dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
-                }
+        for (int c = r + 1 + warp + SCAN_BATCH * SCAN_WARPS; c < T; c += SCAN_WARPS) {  // very long rows
+            const u64* t = tile_row + (size_t)c * 64;
+            const u64 v = (k_lo ? t[lane] : 0ull) | (k_hi ? t[lane + 32] : 0ull);
+            const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
+            const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+            if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
+        }
+        load_row(r + 1);  // in flight while the barrier and the next diagonal resolve run
+        __syncthreads();
+    }
+    __syncthreads();
+    // (c) gather the kept rows in score order, all threads
+    const uint32_t* __restrict__ sslot = ws.sslot + (size_t)bi * n_cap;
+    const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
+    float* __restrict__ out = out_rows + (size_t)bi * max_det * 6;
+    for (int t = threadIdx.x; t < chunks * 64; t += SCAN_THREADS) {
+        const int r = t >> 6, i = t & 63;
+        const u64 keep = keepmask[r];
+        if ((keep >> i) & 1ull) {
+            const int pos = kept_before[r] + __popcll(keep & ((1ull << i) - 1ull));
+            if (pos < max_det) {
+                const float2* src = reinterpret_cast<const float2*>(rows + (size_t)sslot[t] * 6);
+                float2* dst = reinterpret_cast<float2*>(out + (size_t)pos * 6);
+                dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
             }
         }
-        if (last) break;  // later boxes cannot enter the first max_det
-        __syncthreads();
     }
     if (threadIdx.x == 0) out_counts[bi] = kept < max_det ? kept : max_det;
 }
@@ -603,7 +605,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
     const int grid = sm_count() * 16;
     nms_mask_kernel<<<grid, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(b, n_cap, iou_thres, ws);
     KZD_LAUNCH_CHECK("nms_mask_kernel");
-    nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * sizeof(u64), st>>>(cand_rows, cand_cap, n_cap, max_det, ws,
+    nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * (2 * sizeof(u64) + sizeof(int)), st>>>(cand_rows, cand_cap, n_cap, max_det, ws,
                                                                             out_rows, out_counts);
     KZD_LAUNCH_CHECK("nms_scan_kernel");
     return 0;

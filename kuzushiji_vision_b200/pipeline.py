@@ -63,7 +63,7 @@ class PagePipeline:
         self.done = torch.cuda.Event()
         self.out = None
         self.graph = None
-        self.kernels_per_step = 14  # decode_train, assign x7, decode_infer, nms x5 (memsets not counted)
+        self.kernels_per_step = 13  # decode_train, assign x6, decode_infer, nms x5 (memset nodes not counted)
         if use_graph:
             self._capture()
 
