@@ -246,6 +246,7 @@ def run_kzd(args, rank, local_rank, world):
     for _ in range(warmup):
         pipe.step()
     out, n_keep = pipe.results()
+    kdist.all_reduce_counters(counters)  # warm the collective (communicator setup) outside the timed region
     torch.cuda.synchronize()
     kdist.barrier()
     with ClockSampler(local_rank) as clk:
@@ -256,36 +257,73 @@ def run_kzd(args, rank, local_rank, world):
             pipe.step()
         counters[0:2] = out["counters"]
         counters[2] = float(b)
-        counters[3] = out["counts"][1].sum()
+        counters[3] = float(sum(n_keep))
         kdist.all_reduce_counters(counters)  # the path's only collective: 32 bytes
         t_end.record()
         torch.cuda.synchronize()
     kdist.barrier()
     out, n_keep = pipe.results()
-    ms_total = kdist.max_over_ranks(t_start.elapsed_time(t_end), dev)
+    ms_local = t_start.elapsed_time(t_end)
+    ms_total = kdist.max_over_ranks(ms_local, dev)
+    per_rank_ms = kdist.all_gather_summaries(torch.tensor([ms_local / args.steps], dtype=torch.float64, device=dev))
+    per_rank_ms = [round(float(v), 4) for v in per_rank_ms.flatten().tolist()]
     pages = float(counters[2].item())
     value = pages * args.steps / (ms_total * 1e-3)
 
-    # ---- per-stage device times (separate pass, eager calls, CUDA events between the stages) ----
+    # ---- per-stage device times: each stage captured as its own CUDA graph and replayed back to back
+    # (pure device time of that stage's kernels; decode stages are a single kernel launch each) ----
+    import ctypes as C
+
+    from kuzushiji_vision_b200 import _lib
+
     asg = pipe.assigner
     st_names = ["decode_train", "assign", "decode_infer", "nms"]
-    st_ms = {n: 0.0 for n in st_names}
-    n_prof = 10
-    for i in range(n_prof + 2):
-        m = [ev() for _ in range(5)]
-        m[0].record()
-        boxes, px = kzd.bbox_decode(pipe.anchor_points, pipe.pred_distri, pipe.stride_tensor)
-        m[1].record()
-        asg(pipe.pd_scores, px, pipe.anc_points, pipe.gt_labels, pipe.gt_bboxes, pipe.mask_gt)
-        m[2].record()
-        y = kzd.decode_inference(pipe.levels, w["strides"], nc)
-        m[3].record()
-        kzd.nms_batched(y, w["conf"], w["iou"], max_det=w["max_det"])
-        m[4].record()
+    y_static = kzd.decode_inference(pipe.levels, w["strides"], nc)
+    px_static = pipe.out["pd_bboxes"]
+
+    def nms_calls():
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.lib.kzd_nms_filter(y_static.data_ptr(), b, A, nc, w["conf"], 0, None, 0, 0,
+                                           pipe.keys.data_ptr(), pipe.rows.data_ptr(), pipe.counts[0].data_ptr(),
+                                           pipe.pool, st), "kzd_nms_filter")
+        _lib.check(_lib.lib.kzd_nms_suppress(pipe.keys.data_ptr(), pipe.rows.data_ptr(), pipe.counts[0].data_ptr(), b,
+                                             pipe.pool, pipe.n_cap, w["iou"], 0, w["max_det"], 30000, 7680.0,
+                                             pipe.det_rows.data_ptr(), pipe.counts[1].data_ptr(),
+                                             pipe.nms_ws.data_ptr(), pipe.ws_bytes, st), "kzd_nms_suppress")
+
+    stage_fns = {
+        "decode_train": lambda: kzd.bbox_decode(pipe.anchor_points, pipe.pred_distri, pipe.stride_tensor),
+        "assign": lambda: asg(pipe.pd_scores, px_static, pipe.anc_points, pipe.gt_labels, pipe.gt_bboxes,
+                              pipe.mask_gt),
+        "decode_infer": lambda: kzd.decode_inference(pipe.levels, w["strides"], nc),
+        "nms": nms_calls,
+    }
+    st_ms = {}
+    n_prof = 20
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2: evict between stage replays
+    for n in st_names:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            stage_fns[n]()
+        torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        if i >= 2:
-            for k, n in enumerate(st_names):
-                st_ms[n] += m[k].elapsed_time(m[k + 1]) / n_prof
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g), torch.no_grad():
+            keep_alive = stage_fns[n]()
+        tot = 0.0
+        for i in range(n_prof + 2):
+            flush.zero_()
+            e0, e1 = ev(), ev()
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                tot += e0.elapsed_time(e1)
+        st_ms[n] = tot / n_prof
+        del g, keep_alive
+    del flush
 
     # ---- end to end: head maps + GT in pinned HOST memory, through the drop-in calls ----
     def e2e_step():
@@ -319,7 +357,7 @@ def run_kzd(args, rank, local_rank, world):
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
-    n_cand = int(sum(pipe.counts_host[0].tolist()))
+    n_cand = int(sum(pipe.candidate_counts()))
     ab = algorithmic_bytes(b, A, G, nc, n_cand, int(sum(n_keep)))
     single_kernel = {"decode_train": "decode_train_kernel", "decode_infer": "decode_infer_kernel<4>"}
     dom = max(single_kernel, key=lambda n: st_ms[n])
@@ -334,8 +372,8 @@ def run_kzd(args, rank, local_rank, world):
                 "stages": {n: {"ms": st_ms[n], "algorithmic_bytes": ab.get(n),
                                "gbs": (ab[n] / (st_ms[n] * 1e-3) / 1e9) if ab.get(n) else None}
                            for n in st_names},
-                "stage_note": "stage ms are eager per-call times incl. launch latency (and, for nms, its host "
-                              "read-back); the timed region replays the same kernels as one CUDA graph"}
+                "stage_note": "stage ms = device time of that stage's kernels (own CUDA graph, L2 flushed before each "
+                              "replay, CUDA events); the timed region replays all four stages as one graph"}
 
     # ---- CPU baseline on a bounded sample (one page, repeated) ----
     threads = cpu_threads()
@@ -365,6 +403,7 @@ def run_kzd(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "path": "pinned host head maps + GT -> H2D -> drop-in calls -> detections + counters D2H"},
         "gpu_launches": pipe.kernels_per_step * args.steps,
+        "per_rank_ms_per_step": per_rank_ms,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "counters": {"target_scores_sum": float(counters[0]), "n_fg": float(counters[1]),

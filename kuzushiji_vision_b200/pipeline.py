@@ -58,6 +58,9 @@ class PagePipeline:
         self.det_rows = torch.zeros((b, self.max_det, 6), dtype=f32, device=dev)
         self.ws_bytes = _lib.lib.kzd_nms_workspace_bytes(b, self.pool, self.n_cap)
         self.nms_ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        # kept-per-image counts are written by the scan kernel straight into pinned host memory (UVA:
+        # the pinned pointer is valid on the device), so a step needs no D2H copy node at all
+        self.keep_host = torch.full((b,), 0, dtype=torch.int32).pin_memory()
         self.counts_host = torch.zeros((2, b), dtype=torch.int32).pin_memory()
         self.counters_host = torch.zeros(2, dtype=torch.float64).pin_memory()
         self.done = torch.cuda.Event()
@@ -83,7 +86,7 @@ class PagePipeline:
         _lib.check(lib.kzd_nms_suppress(self.keys.data_ptr(), self.rows.data_ptr(), self.counts[0].data_ptr(), self.b,
                                         self.pool, self.n_cap, self.iou, int(self.agnostic), self.max_det,
                                         self.max_nms, self.max_wh, self.det_rows.data_ptr(),
-                                        self.counts[1].data_ptr(), self.nms_ws.data_ptr(), self.ws_bytes, st),
+                                        self.keep_host.data_ptr(), self.nms_ws.data_ptr(), self.ws_bytes, st),
                    "kzd_nms_suppress")
         return dict(pred_bboxes=boxes, pd_bboxes=boxes_px, target_labels=tgt[0], target_bboxes=tgt[1],
                     target_scores=tgt[2], fg_mask=tgt[3], target_gt_idx=tgt[4], counters=self.assigner.counters, y=y,
@@ -119,8 +122,6 @@ class PagePipeline:
             self.graph.replay()
         else:
             self.out = self._body()
-        self.counts_host.copy_(self.counts, non_blocking=True)
-        self.counters_host.copy_(self.out["counters"], non_blocking=True)
         self.done.record()
         return self.out
 
@@ -128,11 +129,21 @@ class PagePipeline:
         """Wait for the last step; returns (outputs dict, kept-per-image list). Raises if the fixed NMS
         capacities overflowed (re-create the pipeline with a larger ``pool`` / ``n_cap``)."""
         self.done.synchronize()
-        n_cand, n_keep = self.counts_host[0].tolist(), self.counts_host[1].tolist()
+        n_keep = self.keep_host.tolist()
         if min(n_keep) < 0:
+            n_cand = self.counts[0].tolist()
             raise _lib.KzdError(f"PagePipeline: NMS capacity exceeded (candidates/page up to {max(n_cand)}, "
                                 f"pool={self.pool}, n_cap={self.n_cap})")
         return self.out, n_keep
+
+    def counters(self):
+        """[sum(target_scores), count(fg_mask)] of the last step as Python floats (one small D2H)."""
+        self.done.synchronize()
+        return self.out["counters"].tolist()
+
+    def candidate_counts(self):
+        self.done.synchronize()
+        return self.counts[0].tolist()
 
     def detections(self):
         out, n_keep = self.results()

@@ -423,4 +423,4 @@ def test_pipeline_graph_matches_eager():
         y = kzd.decode_inference(lv, synth.P2_P5, nc)
         assert torch.equal(out["y"][:, 4:], y[:, 4:])
         _check_nms(pipe.detections(), O.non_max_suppression(y.clone(), 0.25, 0.7, max_det=300))
-        assert float(pipe.counters_host[1]) == float(ref[3].sum())
+        assert pipe.counters()[1] == float(ref[3].sum())
