@@ -143,6 +143,40 @@ int kzd_nms_suppress(const uint64_t* cand_keys, const float* cand_rows, const in
                      int max_nms, float max_wh, float* out_rows, int32_t* out_counts,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * next rows of the path
+ * ------------------------------------------------------------------------------------------ */
+
+/* v8DetectionLoss.preprocess (utils/loss.py:180-195), step 1: per-image target counts.
+ *   targets (n, 6) = [image index, class, cx, cy, w, h]; counts (b) int32; first (b) int32 = first row
+ *   of each image; flags[0] bit 0: image indices not non-decreasing (caller must group them with a
+ *   stable sort and call again), bit 1: an index outside [0, b). */
+int kzd_gt_count(const float* targets, int n, int b, int32_t* counts, int32_t* first, int32_t* flags,
+                 void* stream);
+
+/* Step 2: out (b, G, 5) = [class, x1, y1, x2, y2] px, zero padded; scale4 = device float[4]
+ * (w, h, w, h in pixels: utils/loss.py:224). Rows keep their order of appearance. */
+int kzd_gt_pack(const float* targets, int n, int b, int G, const float* scale4, const int32_t* counts,
+                const int32_t* first, float* out, void* stream);
+
+/* Loss tail on the assigned targets (utils/loss.py:243-258; BboxLoss :91-113, DFLoss :65-88):
+ *   loss3[0] = sum_fg (1 - CIoU(pred_box, target_box/stride)) * w / tss   (box, before hyp.box)
+ *   loss3[1] = sum BCEWithLogits(pred_scores, target_scores) / tss         (cls)
+ *   loss3[2] = sum_fg DFL(pred_dist, target ltrb) * w / tss                (dfl)
+ * with w = target_scores.sum(-1), tss = max(*target_scores_sum, 1). The predicted box is re-decoded
+ * from pred_dist (b,A,64) in the kernel. pred_scores are logits (b,A,nc); target_bboxes are in pixels
+ * (the assigner's output, divided by stride_tensor (A) here); fg_mask uint8 (b,A).
+ * sums_ws: double[3] scratch. The backward writes dense grad_pred_scores (b,A,nc) and grad_pred_dist
+ * (b,A,64) for grad_loss3 = d(final)/d(loss3) (device float[3]). */
+int kzd_loss_tail_fwd(const float* pred_scores, const float* pred_dist, const float* anchor_points,
+                      const float* stride_tensor, const float* target_bboxes, const float* target_scores,
+                      const uint8_t* fg_mask, const float* target_scores_sum, int b, int A, int nc,
+                      double* sums_ws, float* loss3, void* stream);
+int kzd_loss_tail_bwd(const float* pred_scores, const float* pred_dist, const float* anchor_points,
+                      const float* stride_tensor, const float* target_bboxes, const float* target_scores,
+                      const uint8_t* fg_mask, const float* target_scores_sum, int b, int A, int nc,
+                      const float* grad_loss3, float* grad_pred_scores, float* grad_pred_dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

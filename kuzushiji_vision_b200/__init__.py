@@ -5,6 +5,8 @@ Ultralytics YOLOv12) as hand-written sm_100a CUDA behind the reference's own Pyt
     Detect._inference / DFL decode          nn/modules/head.py:100 -> head.detect_inference, head.decode_inference
     v8DetectionLoss.bbox_decode             utils/loss.py:197    -> head.bbox_decode
     ops.non_max_suppression                 utils/ops.py:167     -> ops.non_max_suppression
+    v8DetectionLoss.preprocess              utils/loss.py:180    -> loss.preprocess
+    v8DetectionLoss.__call__ (loss tail)    utils/loss.py:206    -> loss.DetectionLoss, loss.loss_tail
     install()                               patches an importable ``ultralytics`` in place
     PagePipeline                            the four stages of one page batch captured as one CUDA graph
 
@@ -15,6 +17,7 @@ from . import _lib  # noqa: F401  (loads libkzd.so or raises)
 from ._lib import KzdError
 from .head import bbox_decode, decode_inference, detect_inference
 from .install import install, installed, uninstall
+from .loss import DetectionLoss, loss_tail, preprocess
 from .ops import nms_batched, non_max_suppression, xywh2xyxy
 from .pipeline import PagePipeline
 from .tal import TaskAlignedAssigner, dist2bbox, infer_levels, make_anchors
@@ -24,5 +27,5 @@ __all__ = [
     "TaskAlignedAssigner", "make_anchors", "dist2bbox", "infer_levels",
     "detect_inference", "decode_inference", "bbox_decode",
     "non_max_suppression", "nms_batched", "xywh2xyxy",
-    "PagePipeline", "install", "uninstall", "installed", "KzdError",
+    "DetectionLoss", "loss_tail", "preprocess", "PagePipeline", "install", "uninstall", "installed", "KzdError",
 ]

@@ -44,6 +44,10 @@ def _load():
         "kzd_tal_assign": (C.c_int, [vp] * 6 + [i32] * 5 + [f32] * 3 + [C.POINTER(Level), i32, i32] + [vp] * 6 + [vp, sz, i32, vp]),
         "kzd_nms_filter": (C.c_int, [vp, i32, i32, i32, f32, i32, vp, i32, i32, vp, vp, vp, i32, vp]),
         "kzd_nms_workspace_bytes": (sz, [i32, i32, i32]),
+        "kzd_gt_count": (C.c_int, [vp, i32, i32, vp, vp, vp, vp]),
+        "kzd_gt_pack": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
+        "kzd_loss_tail_fwd": (C.c_int, [vp] * 8 + [i32] * 3 + [vp, vp, vp]),
+        "kzd_loss_tail_bwd": (C.c_int, [vp] * 8 + [i32] * 3 + [vp, vp, vp, vp]),
         "kzd_nms_suppress": (C.c_int, [vp, vp, vp, i32, i32, i32, f32, i32, i32, i32, f32, vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sigs.items():

@@ -156,6 +156,9 @@ __global__ void assign_verify_kernel(const float* __restrict__ anc, int A, Assig
 // ---- candidates + top-k ----------------------------------------------------------------------
 
 constexpr int CAND_THREADS = 256;
+#ifndef KZD_CAND_MINB
+#define KZD_CAND_MINB 5
+#endif
 constexpr int CAND_WARPS = CAND_THREADS / 32;
 
 struct TopK {
@@ -231,7 +234,7 @@ __device__ __forceinline__ void mark_selected(uint32_t* __restrict__ sel, uint32
     }
 }
 
-__global__ void __launch_bounds__(CAND_THREADS) assign_candidates_kernel(const AssignParams p) {
+__global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates_kernel(const AssignParams p) {
     __shared__ int queue[CAND_WARPS][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -7,6 +7,10 @@
 //                   layout (reference: utils/loss.py:197-204), and its backward.
 //
 // Both are pure streaming kernels bound by HBM bandwidth (272 B per anchor).
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "kzd_common.cuh"
 
 namespace kzd {
@@ -117,14 +121,22 @@ __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, 
 // training decode: TMA bulk-copy pipeline
 // ------------------------------------------------------------------------------------------
 
-constexpr int TR_ANCH = 64;                     // anchors per tile
+constexpr int TR_ANCH = 64;                     // anchors per tile (backward kernel)
 constexpr int TR_FLOATS = TR_ANCH * 64;         // 4096 floats = 16 KB
 constexpr int TR_STAGES = 4;                    // 64 KB of loads in flight per CTA
 constexpr int TR_THREADS = TR_ANCH * 4;         // one thread per (anchor, side)
 constexpr int TR_SMEM = TR_STAGES * TR_FLOATS * 4;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Softmax expectation of the 16 bins at smem row `row` (16 floats, 64 B). The four 16-byte chunks
 // are visited in a per-thread rotated order so that every quarter-warp hits 8 distinct bank groups.
+// exp(v - m) = ex2(v*log2e - m*log2e): one FFMA + one MUFU per bin; the bin weights are applied per
+// 4-bin chunk (sum_k (4q+k) e_k = 4q * sum_k e_k + (e_1 + 2 e_2 + 3 e_3)).
 __device__ __forceinline__ void side_stats(const float* row, int tid, float& d, float& m_out, float& sum_out) {
     float v[4][4];
     int q[4];
@@ -139,81 +151,85 @@ __device__ __forceinline__ void side_stats(const float* row, int tid, float& d, 
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int k = 0; k < 4; ++k) m = fmaxf(m, v[j][k]);
+    const float L2E = 1.4426950408889634f;
+    const float ml = -m * L2E;
     float sum = 0.f, wsum = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float base = __uint_as_float(0x4b000000u | (uint32_t)(q[j] * 4)) - 8388608.f;  // exact int->float
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float e = __expf(v[j][k] - m);
-            sum += e;
-            wsum = fmaf(base + (float)k, e, wsum);
-        }
+        const float e0 = ex2_approx(fmaf(v[j][0], L2E, ml)), e1 = ex2_approx(fmaf(v[j][1], L2E, ml));
+        const float e2 = ex2_approx(fmaf(v[j][2], L2E, ml)), e3 = ex2_approx(fmaf(v[j][3], L2E, ml));
+        const float sc = (e0 + e1) + (e2 + e3);
+        const float tc = fmaf(3.f, e3, fmaf(2.f, e2, e1));
+        sum += sc;
+        wsum += fmaf(base, sc, tc);
     }
     d = wsum / sum;
     m_out = m;
     sum_out = sum;
 }
 
-// Persistent CTAs; thread 0 is the TMA producer (cp.async.bulk of one 16 KB tile per stage, signalled
-// on an mbarrier), all 256 threads consume: thread t owns (anchor t/4, side t%4) of the tile and
-// writes output element t of the tile's 256 contiguous floats.
-__global__ void __launch_bounds__(TR_THREADS) decode_train_kernel(const float* __restrict__ pred,
-                                                                  const float* __restrict__ anc,
-                                                                  const float* __restrict__ stride, int A,
-                                                                  long long N, float* __restrict__ out,
-                                                                  float* __restrict__ out_px) {
+// Persistent CTAs; thread 0 is the TMA producer (cp.async.bulk of one ANCH*256 B tile per stage, signalled
+// on an mbarrier), all ANCH*4 threads consume: thread t owns (anchor t/4, side t%4) of the tile and
+// writes output element t of the tile's ANCH*4 contiguous floats. IDX = int when b*A < 2^31.
+template <int ANCH, int STAGES, typename IDX>
+__global__ void __launch_bounds__(ANCH * 4) decode_train_kernel(const float* __restrict__ pred,
+                                                                const float* __restrict__ anc,
+                                                                const float* __restrict__ stride, int A, IDX N,
+                                                                float* __restrict__ out,
+                                                                float* __restrict__ out_px) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* buf = reinterpret_cast<float*>(smem_raw);
-    __shared__ uint64_t full[TR_STAGES];
+    __shared__ uint64_t full[STAGES];
+    constexpr int FLOATS = ANCH * 64;
     const int tid = threadIdx.x;
-    const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
+    const IDX n_tiles = (N + ANCH - 1) / ANCH;
 
     if (tid == 0) {
-        for (int s = 0; s < TR_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
     }
     __syncthreads();
 
-    auto issue = [&](long long tile, int stage) {
-        const long long first = tile * TR_ANCH;
-        const long long cnt = (N - first < TR_ANCH) ? (N - first) : TR_ANCH;
+    auto issue = [&](IDX tile, int stage) {
+        const IDX first = tile * ANCH;
+        const IDX cnt = (N - first < ANCH) ? (N - first) : (IDX)ANCH;
         const uint32_t bytes = (uint32_t)cnt * 256u;
         mbar_expect_tx(&full[stage], bytes);
-        tma_load_1d(buf + stage * TR_FLOATS, pred + first * 64, bytes, &full[stage]);
+        tma_load_1d(buf + stage * FLOATS, pred + (size_t)first * 64, bytes, &full[stage]);
     };
     if (tid == 0) {
-        for (int s = 0; s < TR_STAGES; ++s) {
-            const long long tile = blockIdx.x + (long long)s * gridDim.x;
+        for (int s = 0; s < STAGES; ++s) {
+            const IDX tile = blockIdx.x + (IDX)s * gridDim.x;
             if (tile < n_tiles) issue(tile, s);
         }
     }
     const int a_local = tid >> 2, side = tid & 3;
-    for (long long it = 0;; ++it) {
-        const long long tile = blockIdx.x + it * gridDim.x;
-        if (tile >= n_tiles) break;
-        const int stage = (int)(it % TR_STAGES);
-        const long long n = tile * TR_ANCH + a_local;
+    int stage = 0;
+    uint32_t parity = 0;
+    for (IDX tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const IDX n = tile * ANCH + a_local;
         // anchor (and stride) fetched before waiting on the tile so their latency hides behind the TMA
-        const int a_img = (N <= 0x7fffffffLL) ? (int)((uint32_t)n % (uint32_t)A) : (int)(n % A);
+        const int a_img = (int)((typename std::make_unsigned<IDX>::type)n % (typename std::make_unsigned<IDX>::type)A);
         float ap = 0.f, st = 0.f;
         if (n < N) {
             ap = __ldg(anc + a_img * 2 + (side & 1));
             if (out_px) st = __ldg(stride + a_img);
         }
-        mbar_wait(&full[stage], (uint32_t)((it / TR_STAGES) & 1));
+        mbar_wait(&full[stage], parity);
         if (n < N) {
             float d, m, s;
-            side_stats(buf + stage * TR_FLOATS + tid * 16, tid, d, m, s);
+            side_stats(buf + stage * FLOATS + tid * 16, tid, d, m, s);
             const float v = (side < 2) ? (ap - d) : (ap + d);
-            out[n * 4 + side] = v;
-            if (out_px) out_px[n * 4 + side] = __fmul_rn(v, st);  // utils/loss.py:236
+            out[(size_t)n * 4 + side] = v;
+            if (out_px) out_px[(size_t)n * 4 + side] = __fmul_rn(v, st);  // utils/loss.py:236
         }
         __syncthreads();  // every thread is done with this stage before it is refilled
         if (tid == 0) {
-            const long long next = tile + (long long)TR_STAGES * gridDim.x;
+            const IDX next = tile + (IDX)STAGES * gridDim.x;
             if (next < n_tiles) issue(next, stage);
         }
+        if (++stage == STAGES) stage = 0, parity ^= 1u;
     }
 }
 
@@ -322,12 +338,25 @@ extern "C" __attribute__((visibility("default"))) int kzd_decode_infer(const flo
     return 0;
 }
 
-static int train_grid(long long n_tiles, const void* fn) {
+static int train_grid(long long n_tiles, const void* fn, int threads, int smem) {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TR_THREADS, TR_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
     if (per_sm < 1) per_sm = 1;
     long long g = (long long)sm_count() * per_sm;
     return (int)(n_tiles < g ? n_tiles : g);
+}
+
+template <int ANCH, int STAGES, typename IDX>
+static int launch_train(const float* pred_dist, const float* anchor_points, const float* stride_tensor, int A,
+                        long long N, float* out_xyxy, float* out_xyxy_px, cudaStream_t st) {
+    constexpr int SMEM = STAGES * ANCH * 256;
+    auto fn = decode_train_kernel<ANCH, STAGES, IDX>;
+    KZD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const long long n_tiles = (N + ANCH - 1) / ANCH;
+    const int grid = train_grid(n_tiles, (const void*)fn, ANCH * 4, SMEM);
+    fn<<<grid, ANCH * 4, SMEM, st>>>(pred_dist, anchor_points, stride_tensor, A, (IDX)N, out_xyxy, out_xyxy_px);
+    KZD_LAUNCH_CHECK("decode_train_kernel");
+    return 0;
 }
 
 extern "C" __attribute__((visibility("default"))) int kzd_decode_train(const float* pred_dist, const float* anchor_points, const float* stride_tensor,
@@ -338,13 +367,21 @@ extern "C" __attribute__((visibility("default"))) int kzd_decode_train(const flo
     KZD_CHECK_ARG(!out_xyxy_px || stride_tensor, "kzd_decode_train: out_xyxy_px needs stride_tensor");
     const long long N = (long long)b * A;
     if (N == 0) return 0;
-    KZD_CUDA(cudaFuncSetAttribute(decode_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
-    const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
-    const int grid = train_grid(n_tiles, (const void*)decode_train_kernel);
-    decode_train_kernel<<<grid, TR_THREADS, TR_SMEM, (cudaStream_t)stream>>>(pred_dist, anchor_points, stride_tensor, A, N,
-                                                                            out_xyxy, out_xyxy_px);
-    KZD_LAUNCH_CHECK("decode_train_kernel");
-    return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N + 4096 >= 0x7fffffffLL)
+        return launch_train<64, 3, long long>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+    static int variant = -1;  // tuning knob: KZD_TRAIN_VARIANT=0..3 (default 1)
+    if (variant < 0) {
+        const char* e = getenv("KZD_TRAIN_VARIANT");
+        variant = e ? atoi(e) : 1;
+    }
+    switch (variant) {
+        case 0: return launch_train<64, 4, int>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+        case 2: return launch_train<32, 4, int>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+        case 3: return launch_train<32, 6, int>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+        case 4: return launch_train<128, 2, int>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+        default: return launch_train<64, 3, int>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+    }
 }
 
 extern "C" __attribute__((visibility("default"))) int kzd_decode_train_bwd(const float* pred_dist, const float* grad_xyxy, int b, int A,
@@ -357,7 +394,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_decode_train_bwd(const
     if (N == 0) return 0;
     KZD_CUDA(cudaFuncSetAttribute(decode_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
     const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
-    const int grid = train_grid(n_tiles, (const void*)decode_train_bwd_kernel);
+    const int grid = train_grid(n_tiles, (const void*)decode_train_bwd_kernel, TR_THREADS, TR_SMEM);
     decode_train_bwd_kernel<<<grid, TR_THREADS, TR_SMEM, (cudaStream_t)stream>>>(pred_dist, grad_xyxy, N,
                                                                                 grad_pred_dist);
     KZD_LAUNCH_CHECK("decode_train_bwd_kernel");

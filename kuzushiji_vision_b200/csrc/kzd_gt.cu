@@ -1,0 +1,80 @@
+// Ground-truth packing (sm_100a): v8DetectionLoss.preprocess without the per-image Python loop.
+//
+// reference: utils/loss.py:180-195 - targets (n, 6) = [image index, class, cx, cy, w, h] (normalised)
+// -> out (b, G, 5) = [class, x1, y1, x2, y2] in pixels, G = the largest per-image count, zero rows as
+// padding; rows keep their order of appearance inside an image (out[j, :n] = targets[i == j, 1:]).
+// The reference syncs the host once per image (matches.sum()); here: one count kernel, one read-back of
+// (counts, first, sortedness) to size the output, one pack kernel.
+#include "kzd_common.cuh"
+
+namespace kzd {
+
+// counts[j] = number of targets of image j; first[j] = smallest row index of image j;
+// flags[0] != 0 when the image indices are not non-decreasing (the pack kernel needs them grouped).
+__global__ void gt_count_kernel(const float* __restrict__ targets, int n, int b, int32_t* __restrict__ counts,
+                                int32_t* __restrict__ first, int32_t* __restrict__ flags) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int j = (int)targets[(size_t)t * 6];
+    if (j < 0 || j >= b) {
+        atomicOr(flags, 2);
+        return;
+    }
+    atomicAdd(counts + j, 1);
+    atomicMin(first + j, t);
+    if (t > 0 && targets[(size_t)(t - 1) * 6] > targets[(size_t)t * 6]) atomicOr(flags, 1);
+}
+
+// One thread per output row (image j, slot s): row first[j]+s of the (grouped) targets, or zeros.
+__global__ void gt_pack_kernel(const float* __restrict__ targets, int b, int G, const float* __restrict__ scale,
+                               const int32_t* __restrict__ counts, const int32_t* __restrict__ first,
+                               float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b * G) return;
+    const int j = idx / G, s = idx - j * G;
+    float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (s < counts[j]) {
+        const float* r = targets + (size_t)(first[j] + s) * 6;
+        // out[..., 1:5].mul_(scale_tensor) then xywh2xyxy (utils/loss.py:194, utils/ops.py:429-432)
+        const float cx = __fmul_rn(r[2], scale[0]), cy = __fmul_rn(r[3], scale[1]);
+        const float hw = __fmul_rn(__fmul_rn(r[4], scale[2]), 0.5f), hh = __fmul_rn(__fmul_rn(r[5], scale[3]), 0.5f);
+        o[0] = r[1];
+        o[1] = __fsub_rn(cx, hw), o[2] = __fsub_rn(cy, hh), o[3] = __fadd_rn(cx, hw), o[4] = __fadd_rn(cy, hh);
+    }
+    float* d = out + (size_t)idx * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) d[k] = o[k];
+}
+
+}  // namespace kzd
+
+using namespace kzd;
+
+extern "C" __attribute__((visibility("default"))) int kzd_gt_count(const float* targets, int n, int b,
+                                                                     int32_t* counts, int32_t* first,
+                                                                     int32_t* flags, void* stream) {
+    KZD_CHECK_ARG(targets && counts && first && flags, "kzd_gt_count: null pointer");
+    KZD_CHECK_ARG(n >= 0 && b >= 1, "kzd_gt_count: bad sizes n=%d b=%d", n, b);
+    cudaStream_t st = (cudaStream_t)stream;
+    KZD_CUDA(cudaMemsetAsync(counts, 0, (size_t)b * 4, st));
+    KZD_CUDA(cudaMemsetAsync(first, 0x7f, (size_t)b * 4, st));
+    KZD_CUDA(cudaMemsetAsync(flags, 0, 4, st));
+    if (n == 0) return 0;
+    gt_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(targets, n, b, counts, first, flags);
+    KZD_LAUNCH_CHECK("gt_count_kernel");
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_gt_pack(const float* targets, int n, int b, int G,
+                                                                    const float* scale4, const int32_t* counts,
+                                                                    const int32_t* first, float* out, void* stream) {
+    KZD_CHECK_ARG(targets && scale4 && counts && first && out, "kzd_gt_pack: null pointer");
+    KZD_CHECK_ARG(n >= 0 && b >= 1 && G >= 0, "kzd_gt_pack: bad sizes");
+    if (G == 0) return 0;
+    const long long rows = (long long)b * G;
+    KZD_CHECK_ARG(rows < 0x7fffffffLL, "kzd_gt_pack: b*G too large");
+    gt_pack_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(targets, b, G, scale4, counts,
+                                                                                   first, out);
+    KZD_LAUNCH_CHECK("gt_pack_kernel");
+    return 0;
+}

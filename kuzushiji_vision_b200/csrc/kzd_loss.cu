@@ -1,0 +1,293 @@
+// Loss tail on the assigned targets (sm_100a): BCE over (b,A,nc) + CIoU / DFL losses on the
+// foreground anchors, forward and backward, without materialising any per-foreground gather.
+//
+// reference: utils/loss.py:243-258 (v8DetectionLoss.__call__ after the assigner), BboxLoss.forward
+// :91-113, DFLoss :65-88, bbox2dist utils/tal.py:360-363, bbox_iou(CIoU) utils/metrics.py:96-130
+// (called as bbox_iou(pred, target): box1 = prediction, box2 = target; alpha is a no_grad constant),
+// nn.BCEWithLogitsLoss(reduction="none").
+//
+//   loss[0] = sum_fg (1 - CIoU(pred_box, target_box/stride)) * w / tss          (box, before hyp.box)
+//   loss[1] = sum_{b,a,c} BCEWithLogits(pred_scores, target_scores) / tss        (cls)
+//   loss[2] = sum_fg mean_side(CE(dist, tl) wl + CE(dist, tr) wr) * w / tss      (dfl)
+//   w = target_scores.sum(-1) of the anchor, tss = max(target_scores.sum(), 1)
+// The predicted box is re-decoded from pred_dist inside the kernel (softmax expectation), so the
+// backward chains through the decode directly into grad_pred_dist.
+#include "kzd_common.cuh"
+
+namespace kzd {
+
+struct LossParams {
+    const float *pred_scores, *pred_dist, *anchor_points, *stride, *target_bboxes, *target_scores;
+    const uint8_t* fg_mask;
+    const float* tss;  // device scalar: target_scores.sum() (max(., 1) is applied here)
+    int b, A, nc;
+};
+
+// ---- BCE ----------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float bce_logits(float x, float t) {
+    // (1 - t) x + max(-x, 0) + log(exp(-max(-x,0)) + exp(-x - max(-x,0)))   (aten binary_cross_entropy_with_logits)
+    const float mv = fmaxf(-x, 0.f);
+    return (1.f - t) * x + mv + logf(expf(-mv) + expf(-x - mv));
+}
+
+__device__ __forceinline__ void block_add(double v, double* dst, double* s_red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_red[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+        if (t != 0.0) atomicAdd(dst, t);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                      size_t n, double* __restrict__ sums) {
+    __shared__ double s_red[8];
+    float acc = 0.f;
+    double total = 0.0;
+    int k = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        acc += bce_logits(__ldcs(x + i), __ldcs(t + i));
+        if (++k == 64) total += (double)acc, acc = 0.f, k = 0;  // bound the fp32 partial
+    }
+    total += (double)acc;
+    block_add(total, sums + 1, s_red);
+}
+
+__global__ void __launch_bounds__(256) bce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                      size_t n, const float* __restrict__ tss,
+                                                      const float* __restrict__ gout, float* __restrict__ gx) {
+    const float scale = gout[1] / fmaxf(*tss, 1.f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float xv = __ldcs(x + i);
+        const float sg = 1.f / (1.f + expf(-xv));
+        __stcs(gx + i, (sg - __ldcs(t + i)) * scale);
+    }
+}
+
+// ---- foreground anchors: one warp per anchor, lane l owns bins 2(l%8), 2(l%8)+1 of side l/8 ------
+
+struct FgTerms {
+    float box;      // (1 - ciou) * w
+    float dfl;      // mean over sides of the DFL cross entropies * w
+    float gd;       // this lane's side: d(box term)/d(distance of the side)
+    float p0, p1;   // softmax of this lane's two bins
+    float d;        // expectation of this lane's side
+    float wl, wr;   // DFL weights of this lane's side
+    int tl;         // left DFL bin of this lane's side
+    float w;        // anchor weight
+};
+
+__device__ __forceinline__ float group8_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+}
+__device__ __forceinline__ float group8_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v + __shfl_xor_sync(0xffffffffu, v, 4);
+}
+
+template <bool GRAD>
+__device__ __forceinline__ FgTerms fg_anchor(const LossParams& p, size_t idx, int a, int lane) {
+    FgTerms r;
+    const int side = lane >> 3, j0 = (lane & 7) * 2;
+    const float2 x = *reinterpret_cast<const float2*>(p.pred_dist + idx * 64 + lane * 2);
+    const float m = group8_max(fmaxf(x.x, x.y));
+    const float e0 = expf(x.x - m), e1 = expf(x.y - m);
+    const float sum = group8_sum(e0 + e1);
+    const float wsum = group8_sum((float)j0 * e0 + (float)(j0 + 1) * e1);
+    const float d = wsum / sum;
+    const float lse = m + logf(sum);
+    r.p0 = e0 / sum, r.p1 = e1 / sum, r.d = d;
+    // anchor weight
+    float w = 0.f;
+    for (int c = lane; c < p.nc; c += 32) w += p.target_scores[idx * p.nc + c];
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    r.w = w;
+    // boxes in grid units
+    const float ax = p.anchor_points[2 * a], ay = p.anchor_points[2 * a + 1], st = p.stride[a];
+    const float4 tbp = *reinterpret_cast<const float4*>(p.target_bboxes + idx * 4);
+    const float tx1 = tbp.x / st, ty1 = tbp.y / st, tx2 = tbp.z / st, ty2 = tbp.w / st;  // utils/loss.py:251
+    const float dl = __shfl_sync(0xffffffffu, d, 0), dt = __shfl_sync(0xffffffffu, d, 8);
+    const float dr = __shfl_sync(0xffffffffu, d, 16), db = __shfl_sync(0xffffffffu, d, 24);
+    const float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + db;
+    // CIoU(box1 = prediction, box2 = target)
+    const float eps = 1e-7f;
+    const float w1 = x2 - x1, h1 = y2 - y1 + eps, w2 = tx2 - tx1, h2 = ty2 - ty1 + eps;
+    const float iw_raw = fminf(x2, tx2) - fmaxf(x1, tx1), ih_raw = fminf(y2, ty2) - fmaxf(y1, ty1);
+    const float iw = fmaxf(iw_raw, 0.f), ih = fmaxf(ih_raw, 0.f);
+    const float inter = iw * ih;
+    const float uni = w1 * h1 + w2 * h2 - inter + eps;
+    const float iou = inter / uni;
+    const float cw = fmaxf(x2, tx2) - fminf(x1, tx1), ch = fmaxf(y2, ty2) - fminf(y1, ty1);
+    const float c2 = cw * cw + ch * ch + eps;
+    const float dx = tx1 + tx2 - x1 - x2, dy = ty1 + ty2 - y1 - y2;
+    const float rho2 = (dx * dx + dy * dy) * 0.25f;
+    const float at = atanf(w2 / h2) - atanf(w1 / h1);
+    const float kv = 0.40528473456935109f;
+    const float v = kv * at * at;
+    const float alpha = v / (v - iou + (1.f + eps));
+    const float ciou = iou - (rho2 / c2 + v * alpha);
+    r.box = (1.f - ciou) * w;
+    // DFL targets of this lane's side (bbox2dist, utils/tal.py:360-363; DFLoss utils/loss.py:80-88)
+    const float tcoord = side == 0 ? ax - tx1 : side == 1 ? ay - ty1 : side == 2 ? tx2 - ax : ty2 - ay;
+    const float tgt = fminf(fmaxf(tcoord, 0.f), 14.99f);
+    const int tl = (int)tgt;
+    const float wl = (float)(tl + 1) - tgt, wr = 1.f - wl;
+    r.tl = tl, r.wl = wl, r.wr = wr;
+    // logits of bins tl and tl+1 of this side live in lanes side*8 + tl/2 and side*8 + (tl+1)/2
+    const float xl_a = __shfl_sync(0xffffffffu, x.x, side * 8 + (tl >> 1));
+    const float xl_b = __shfl_sync(0xffffffffu, x.y, side * 8 + (tl >> 1));
+    const float xr_a = __shfl_sync(0xffffffffu, x.x, side * 8 + ((tl + 1) >> 1));
+    const float xr_b = __shfl_sync(0xffffffffu, x.y, side * 8 + ((tl + 1) >> 1));
+    const float x_tl = (tl & 1) ? xl_b : xl_a, x_tr = ((tl + 1) & 1) ? xr_b : xr_a;
+    const float ce = (lse - x_tl) * wl + (lse - x_tr) * wr;
+    float ce_sum = ce;  // one value per side group: add the four groups
+    ce_sum += __shfl_xor_sync(0xffffffffu, ce_sum, 8);
+    ce_sum += __shfl_xor_sync(0xffffffffu, ce_sum, 16);
+    r.dfl = ce_sum * 0.25f * w;
+    r.gd = 0.f;
+    if (GRAD) {
+        // d ciou / d (x1, y1, x2, y2), alpha held constant (utils/metrics.py:127-128)
+        const float ox = iw_raw > 0.f ? 1.f : 0.f, oy = ih_raw > 0.f ? 1.f : 0.f;
+        const float diw_x1 = (x1 > tx1) ? -ox : 0.f, diw_x2 = (x2 < tx2) ? ox : 0.f;
+        const float dih_y1 = (y1 > ty1) ? -oy : 0.f, dih_y2 = (y2 < ty2) ? oy : 0.f;
+        const float dcw_x1 = (x1 < tx1) ? -1.f : 0.f, dcw_x2 = (x2 > tx2) ? 1.f : 0.f;
+        const float dch_y1 = (y1 < ty1) ? -1.f : 0.f, dch_y2 = (y2 > ty2) ? 1.f : 0.f;
+        const float u = w1 / h1;
+        const float dv_du = -2.f * kv * at / (1.f + u * u);
+        // per coordinate: inter', (w1 h1)', c2', rho2', u'
+        float din, dwh, dc2, drho, du;
+        if (side == 0)      din = ih * diw_x1, dwh = -h1, dc2 = 2.f * cw * dcw_x1, drho = -0.5f * dx, du = -1.f / h1;
+        else if (side == 1) din = iw * dih_y1, dwh = -w1, dc2 = 2.f * ch * dch_y1, drho = -0.5f * dy, du = w1 / (h1 * h1);
+        else if (side == 2) din = ih * diw_x2, dwh = h1, dc2 = 2.f * cw * dcw_x2, drho = -0.5f * dx, du = 1.f / h1;
+        else                din = iw * dih_y2, dwh = w1, dc2 = 2.f * ch * dch_y2, drho = -0.5f * dy, du = -w1 / (h1 * h1);
+        const float duni = dwh - din;
+        const float diou = (din * uni - inter * duni) / (uni * uni);
+        const float dciou = diou - (drho * c2 - rho2 * dc2) / (c2 * c2) - alpha * dv_du * du;
+        // coordinate = anchor -/+ distance of the side
+        const float dcoord_dd = side < 2 ? -1.f : 1.f;
+        r.gd = -dciou * dcoord_dd * w;  // d[(1-ciou) w] / d(distance)
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) fg_fwd_kernel(const LossParams p, double* __restrict__ sums) {
+    __shared__ double s_red[8];
+    const int lane = threadIdx.x & 31;
+    const long long n = (long long)p.b * p.A;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    double box = 0.0, dfl = 0.0;
+    for (long long base = warp0 * 32; base < n; base += n_warps * 32) {
+        const long long mine = base + lane;
+        unsigned m = __ballot_sync(0xffffffffu, mine < n && p.fg_mask[mine]);
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const size_t idx = (size_t)(base + k);
+            const FgTerms t = fg_anchor<false>(p, idx, (int)(idx % (size_t)p.A), lane);
+            if (lane == 0) box += (double)t.box, dfl += (double)t.dfl;
+        }
+    }
+    block_add(box, sums + 0, s_red);
+    block_add(dfl, sums + 2, s_red);
+}
+
+// grad_pred_dist for every anchor: zeros for background rows, decode + CIoU + DFL chain for foreground.
+__global__ void __launch_bounds__(256) fg_bwd_kernel(const LossParams p, const float* __restrict__ gout,
+                                                     float* __restrict__ gdist) {
+    const int lane = threadIdx.x & 31;
+    const long long n = (long long)p.b * p.A;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float inv_tss = 1.f / fmaxf(*p.tss, 1.f);
+    const float g_box = gout[0] * inv_tss, g_dfl = gout[2] * inv_tss;
+    for (long long base = warp0 * 32; base < n; base += n_warps * 32) {
+        const long long mine = base + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, mine < n && p.fg_mask[mine]);
+        const int cnt = (int)min(32LL, n - base);
+        for (int k = 0; k < cnt; ++k) {
+            const size_t idx = (size_t)(base + k);
+            float2 g = make_float2(0.f, 0.f);
+            if ((m >> k) & 1u) {
+                const FgTerms t = fg_anchor<true>(p, idx, (int)(idx % (size_t)p.A), lane);
+                const int j0 = (lane & 7) * 2;
+                const float gd = g_box * t.gd;               // through the expectation d = sum_j j p_j
+                const float gc = g_dfl * 0.25f * t.w;        // through the two cross entropies
+                g.x = gd * t.p0 * ((float)j0 - t.d) + gc * (t.p0 - (j0 == t.tl ? t.wl : 0.f) - (j0 == t.tl + 1 ? t.wr : 0.f));
+                g.y = gd * t.p1 * ((float)(j0 + 1) - t.d) +
+                      gc * (t.p1 - (j0 + 1 == t.tl ? t.wl : 0.f) - (j0 + 1 == t.tl + 1 ? t.wr : 0.f));
+            }
+            __stcs(reinterpret_cast<float2*>(gdist + idx * 64) + lane, g);
+        }
+    }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ tss,
+                                     float* __restrict__ loss) {
+    const double d = fmax((double)*tss, 1.0);
+    if (threadIdx.x < 3) loss[threadIdx.x] = (float)(sums[threadIdx.x] / d);
+}
+
+}  // namespace kzd
+
+using namespace kzd;
+
+static int check_loss_args(const LossParams& p, const char* who) {
+    KZD_CHECK_ARG(p.pred_scores && p.pred_dist && p.anchor_points && p.stride && p.target_bboxes && p.target_scores &&
+                      p.fg_mask && p.tss,
+                  "%s: null pointer", who);
+    KZD_CHECK_ARG(p.b >= 1 && p.A >= 1 && p.nc >= 1, "%s: bad sizes", who);
+    KZD_CHECK_ARG(((uintptr_t)p.pred_dist) % 8 == 0 && ((uintptr_t)p.target_bboxes) % 16 == 0, "%s: misaligned tensor",
+                  who);
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_fwd(
+    const float* pred_scores, const float* pred_dist, const float* anchor_points, const float* stride_tensor,
+    const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* target_scores_sum,
+    int b, int A, int nc, double* sums_ws, float* loss3, void* stream) {
+    LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
+                 target_scores_sum, b, A, nc};
+    if (int rc = check_loss_args(p, "kzd_loss_tail_fwd")) return rc;
+    KZD_CHECK_ARG(sums_ws && loss3, "kzd_loss_tail_fwd: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    KZD_CUDA(cudaMemsetAsync(sums_ws, 0, 3 * sizeof(double), st));
+    const size_t n = (size_t)b * A * nc;
+    const int cap = sm_count() * 8;
+    bce_fwd_kernel<<<(unsigned)((n + 255) / 256 < (size_t)cap ? (n + 255) / 256 : cap), 256, 0, st>>>(
+        pred_scores, target_scores, n, sums_ws);
+    KZD_LAUNCH_CHECK("bce_fwd_kernel");
+    fg_fwd_kernel<<<cap, 256, 0, st>>>(p, sums_ws);
+    KZD_LAUNCH_CHECK("fg_fwd_kernel");
+    loss_finalize_kernel<<<1, 32, 0, st>>>(sums_ws, target_scores_sum, loss3);
+    KZD_LAUNCH_CHECK("loss_finalize_kernel");
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_bwd(
+    const float* pred_scores, const float* pred_dist, const float* anchor_points, const float* stride_tensor,
+    const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* target_scores_sum,
+    int b, int A, int nc, const float* grad_loss3, float* grad_pred_scores, float* grad_pred_dist, void* stream) {
+    LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
+                 target_scores_sum, b, A, nc};
+    if (int rc = check_loss_args(p, "kzd_loss_tail_bwd")) return rc;
+    KZD_CHECK_ARG(grad_loss3 && grad_pred_scores && grad_pred_dist, "kzd_loss_tail_bwd: null pointer");
+    KZD_CHECK_ARG(((uintptr_t)grad_pred_dist) % 8 == 0, "kzd_loss_tail_bwd: misaligned grad_pred_dist");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)b * A * nc;
+    const int cap = sm_count() * 8;
+    bce_bwd_kernel<<<(unsigned)((n + 255) / 256 < (size_t)cap ? (n + 255) / 256 : cap), 256, 0, st>>>(
+        pred_scores, target_scores, n, target_scores_sum, grad_loss3, grad_pred_scores);
+    KZD_LAUNCH_CHECK("bce_bwd_kernel");
+    fg_bwd_kernel<<<cap * 2, 256, 0, st>>>(p, grad_loss3, grad_pred_dist);
+    KZD_LAUNCH_CHECK("fg_bwd_kernel");
+    return 0;
+}

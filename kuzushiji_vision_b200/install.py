@@ -9,6 +9,7 @@ attributes, patched here and restored by ``uninstall()``:
   ultralytics.utils.loss.v8DetectionLoss.bbox_decode <- head.loss_bbox_decode  (utils/loss.py:197)
   ultralytics.nn.modules.head.Detect._inference      <- head.detect_inference  (nn/modules/head.py:100)
   ultralytics.utils.ops.non_max_suppression    <- ops.non_max_suppression      (utils/ops.py:167)
+  ultralytics.utils.loss.v8DetectionLoss.preprocess  <- loss.preprocess         (utils/loss.py:180)
 
 Calls that are outside this path's scope (CPU tensors, rotated boxes, masks, export formats) are
 handed to the reference's own, unpatched function - they never reach libkzd and libkzd never
@@ -20,6 +21,7 @@ import functools
 import importlib
 
 from . import head as _head
+from . import loss as _loss
 from . import ops as _ops
 from . import tal as _tal
 
@@ -32,7 +34,7 @@ def _is_cuda(x):
     return bool(getattr(x, "is_cuda", False))
 
 
-def install(patch_decode_train=True):
+def install(patch_decode_train=True, patch_preprocess=True):
     """Patch the importable ``ultralytics``; returns the list of patched attribute names."""
     if _saved:
         return sorted(_saved)
@@ -45,6 +47,7 @@ def install(patch_decode_train=True):
     ref_nms = u_ops.non_max_suppression
     ref_inference = u_head.Detect._inference
     ref_bbox_decode = u_loss.v8DetectionLoss.bbox_decode
+    ref_preprocess = u_loss.v8DetectionLoss.preprocess
 
     class TaskAlignedAssigner(_tal.TaskAlignedAssigner):
         """libkzd on CUDA inputs; the reference's own module for anything else."""
@@ -75,6 +78,11 @@ def install(patch_decode_train=True):
             return ref_bbox_decode(self, anchor_points, pred_dist)
         return _head.loss_bbox_decode(self, anchor_points, pred_dist)
 
+    def preprocess(self, targets, batch_size, scale_tensor):
+        if not _is_cuda(targets):
+            return ref_preprocess(self, targets, batch_size, scale_tensor)
+        return _loss.preprocess(targets, batch_size, scale_tensor)
+
     _saved.update({
         "tal.TaskAlignedAssigner": (u_tal, "TaskAlignedAssigner", ref_assigner),
         "loss.TaskAlignedAssigner": (u_loss, "TaskAlignedAssigner", u_loss.TaskAlignedAssigner),
@@ -88,6 +96,9 @@ def install(patch_decode_train=True):
     if patch_decode_train:
         _saved["loss.v8DetectionLoss.bbox_decode"] = (u_loss.v8DetectionLoss, "bbox_decode", ref_bbox_decode)
         u_loss.v8DetectionLoss.bbox_decode = bbox_decode
+    if patch_preprocess:
+        _saved["loss.v8DetectionLoss.preprocess"] = (u_loss.v8DetectionLoss, "preprocess", ref_preprocess)
+        u_loss.v8DetectionLoss.preprocess = preprocess
     return sorted(_saved)
 
 

@@ -320,3 +320,82 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
         keep = nms_fn(x[:, :4] + off, x[:, 4], iou_thres)[:max_det]
         out[i] = x[keep]
     return out
+
+
+# --------------------------------------------------------------------------------------
+# GT packing  (utils/loss.py:180-195)
+# --------------------------------------------------------------------------------------
+
+
+def preprocess(targets, batch_size, scale_tensor):
+    """Restatement of ``v8DetectionLoss.preprocess`` (utils/loss.py:180-195): targets (n,6) =
+    [image, class, cx, cy, w, h] -> (batch_size, G, 5) = [class, x1, y1, x2, y2] px, zero padded."""
+    n, ne = targets.shape
+    if n == 0:
+        return torch.zeros(batch_size, 0, ne - 1, device=targets.device)
+    img = targets[:, 0]
+    counts = torch.stack([(img == j).sum() for j in range(batch_size)])
+    G = int(img.unique(return_counts=True)[1].max())
+    out = torch.zeros(batch_size, G, ne - 1, device=targets.device)
+    for j in range(batch_size):
+        c = int(counts[j])
+        if c:
+            out[j, :c] = targets[img == j, 1:]
+    out[..., 1:5] = xywh2xyxy(out[..., 1:5].mul_(scale_tensor))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# loss tail  (utils/loss.py:65-113, 243-258)
+# --------------------------------------------------------------------------------------
+
+
+def ciou_generic(box1, box2):
+    """bbox_iou(box1, box2, xywh=False, CIoU=True) for autograd use (utils/metrics.py:96-130); the
+    weighting factor alpha is computed under no_grad as in the reference."""
+    e = _CIOU_EPS
+    b1x1, b1y1, b1x2, b1y2 = box1.chunk(4, -1)
+    b2x1, b2y1, b2x2, b2y2 = box2.chunk(4, -1)
+    w1, h1 = b1x2 - b1x1, b1y2 - b1y1 + e
+    w2, h2 = b2x2 - b2x1, b2y2 - b2y1 + e
+    inter = (torch.minimum(b1x2, b2x2) - torch.maximum(b1x1, b2x1)).clamp(min=0) * (
+        torch.minimum(b1y2, b2y2) - torch.maximum(b1y1, b2y1)).clamp(min=0)
+    union = w1 * h1 + w2 * h2 - inter + e
+    iou = inter / union
+    cw = torch.maximum(b1x2, b2x2) - torch.minimum(b1x1, b2x1)
+    ch = torch.maximum(b1y2, b2y2) - torch.minimum(b1y1, b2y1)
+    c2 = cw.pow(2) + ch.pow(2) + e
+    rho2 = ((b2x1 + b2x2 - b1x1 - b1x2).pow(2) + (b2y1 + b2y2 - b1y1 - b1y2).pow(2)) / 4
+    v = (4 / math.pi**2) * ((w2 / h2).atan() - (w1 / h1).atan()).pow(2)
+    with torch.no_grad():
+        alpha = v / (v - iou + (1 + e))
+    return iou - (rho2 / c2 + v * alpha)
+
+
+def loss_tail(pred_scores, pred_distri, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask):
+    """[box, cls, dfl] before the hyp gains, restating utils/loss.py:243-254 with BboxLoss.forward
+    (:99-113), DFLoss (:72-88) and bbox2dist (utils/tal.py:360-363). ``target_bboxes`` in pixels."""
+    import torch.nn.functional as F
+
+    reg_max = REG_MAX
+    pred_bboxes = decode_train(pred_distri, anchor_points)
+    tss = target_scores.sum().clamp(min=1)
+    cls = F.binary_cross_entropy_with_logits(pred_scores, target_scores, reduction="none").sum() / tss
+    box = pred_scores.new_zeros(())
+    dfl = pred_scores.new_zeros(())
+    if fg_mask.sum():
+        tb = target_bboxes / stride_tensor
+        weight = target_scores.sum(-1)[fg_mask].unsqueeze(-1)
+        iou = ciou_generic(pred_bboxes[fg_mask], tb[fg_mask])
+        box = ((1.0 - iou) * weight).sum() / tss
+        x1y1, x2y2 = tb.chunk(2, -1)
+        ltrb = torch.cat((anchor_points - x1y1, x2y2 - anchor_points), -1).clamp(0, reg_max - 1 - 0.01)
+        t = ltrb[fg_mask]
+        tl = t.long()
+        wl = (tl + 1) - t
+        wr = 1 - wl
+        logits = pred_distri[fg_mask].view(-1, reg_max)
+        ce = (F.cross_entropy(logits, tl.view(-1), reduction="none").view(tl.shape) * wl
+              + F.cross_entropy(logits, (tl + 1).view(-1), reduction="none").view(tl.shape) * wr).mean(-1, keepdim=True)
+        dfl = (ce * weight).sum() / tss
+    return torch.stack((box, cls, dfl))

@@ -424,3 +424,93 @@ def test_pipeline_graph_matches_eager():
         assert torch.equal(out["y"][:, 4:], y[:, 4:])
         _check_nms(pipe.detections(), O.non_max_suppression(y.clone(), 0.25, 0.7, max_det=300))
         assert pipe.counters()[1] == float(ref[3].sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# next rows
+# ---------------------------------------------------------------------------------------------
+
+def _collated_targets(b, per_image, seed, shuffle=False):
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for j, n in enumerate(per_image):
+        cxcy = torch.rand(n, 2, generator=g) * 0.8 + 0.1
+        wh = torch.rand(n, 2, generator=g) * 0.05 + 0.01
+        cls = torch.randint(0, 5, (n, 1), generator=g).float()
+        rows.append(torch.cat((torch.full((n, 1), float(j)), cls, cxcy, wh), 1))
+    t = torch.cat(rows)
+    if shuffle:
+        t = t[torch.randperm(t.shape[0], generator=g)]
+    return t
+
+
+@pytest.mark.parametrize("per_image,shuffle", [([5, 0, 17, 3], False), ([600] * 16, False), ([4, 9, 0, 0, 2], True),
+                                               ([0, 0, 1], False)])
+def test_preprocess_matches_oracle(per_image, shuffle):
+    from kuzushiji_vision_b200 import loss as kloss
+
+    b = len(per_image)
+    t = _collated_targets(b, per_image, seed=3, shuffle=shuffle).to(DEV)
+    scale = torch.tensor([1280.0, 960.0, 1280.0, 960.0], device=DEV)
+    out = kloss.preprocess(t, b, scale)
+    ref = O.preprocess(t, b, scale)
+    assert out.shape == ref.shape and torch.equal(out, ref)
+    empty = kloss.preprocess(t[:0], b, scale)
+    assert empty.shape == (b, 0, 5)
+
+
+@pytest.mark.parametrize("cfg", [(2, 60, 320, 1, "columns"), (2, 80, 320, 5, "uniform"), (4, 300, 1280, 1, "columns")])
+def test_loss_tail_forward_backward_matches_oracle(cfg):
+    from kuzushiji_vision_b200 import loss as kloss
+
+    b, G, imgsz, nc, layout = cfg
+    d = synth.assigner_inputs(b, G, imgsz, nc, synth.P2_P5, seed=14, device=DEV, layout=layout)
+    logits = torch.cat([l.view(b, 64 + nc, -1) for l in d["levels"]], 2)[:, 64:].permute(0, 2, 1).contiguous()
+    tl, tb, ts, fg, gi = kzd.TaskAlignedAssigner(10, nc, 0.5, 6.0)(d["pd_scores"], d["pd_bboxes"], d["anc_points"],
+                                                                    d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+    x1, p1 = logits.clone().requires_grad_(True), d["pred_distri"].clone().requires_grad_(True)
+    x2, p2 = logits.clone().requires_grad_(True), d["pred_distri"].clone().requires_grad_(True)
+    gains = torch.tensor([7.5, 0.5, 1.5], device=DEV)
+    mine = kloss.loss_tail(x1, p1, d["anchor_points"], d["stride_tensor"], tb, ts, fg)
+    ref = O.loss_tail(x2, p2, d["anchor_points"], d["stride_tensor"], tb, ts, fg)
+    torch.testing.assert_close(mine, ref, rtol=1e-5, atol=1e-6)
+    ((mine * gains).sum() * b).backward()
+    ((ref * gains).sum() * b).backward()
+    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-4, atol=1e-7)
+    scale = p2.grad.abs().max().item()
+    assert (p1.grad - p2.grad).abs().max().item() <= 2e-5 * scale, ((p1.grad - p2.grad).abs().max().item(), scale)
+    assert (p1.grad[~fg] == 0).all()
+
+
+def test_detection_loss_criterion_matches_oracle_composition():
+    """DetectionLoss.__call__(preds, batch): GT packing -> decode -> assign -> loss tail, all on libkzd,
+    against the same composition of oracle stages (utils/loss.py:206-260)."""
+    from kuzushiji_vision_b200 import loss as kloss
+
+    b, nc, imgsz, strides = 3, 2, 320, synth.P2_P5
+    feats = [f.requires_grad_(True) for f in synth.head_outputs(b, nc, imgsz, strides, seed=21, device=DEV)]
+    t = _collated_targets(b, [25, 0, 40], seed=5)
+    t[:, 4:] = t[:, 4:] * 2 + 0.05
+    batch = {"batch_idx": t[:, 0].to(DEV), "cls": (t[:, 1:2] % nc).to(DEV), "bboxes": t[:, 2:].to(DEV)}
+    crit = kloss.DetectionLoss(strides, nc)
+    total, items = crit(feats, batch)
+    total.backward()
+    g_mine = [f.grad.clone() for f in feats]
+    # oracle composition
+    feats2 = [f.detach().clone().requires_grad_(True) for f in feats]
+    cat = torch.cat([x.view(b, 64 + nc, -1) for x in feats2], 2)
+    pd, ps = cat[:, :64].permute(0, 2, 1).contiguous(), cat[:, 64:].permute(0, 2, 1).contiguous()
+    anc, st = O.make_anchors([x.shape[2:] for x in feats2], strides, device=DEV)
+    imgsz_t = torch.tensor([imgsz, imgsz, imgsz, imgsz], device=DEV, dtype=torch.float32)
+    tg = O.preprocess(torch.cat((batch["batch_idx"].view(-1, 1), batch["cls"].view(-1, 1), batch["bboxes"]), 1), b,
+                      imgsz_t)
+    gl, gb = tg.split((1, 4), 2)
+    mg = gb.sum(2, keepdim=True).gt_(0.0)
+    boxes = O.decode_train(pd, anc)
+    _, tb, ts, fg, _ = O.tal_assign(ps.detach().sigmoid(), boxes.detach() * st, anc * st, gl, gb, mg, 10, nc, 0.5, 6.0)
+    l3 = O.loss_tail(ps, pd, anc, st, tb, ts, fg) * torch.tensor([7.5, 0.5, 1.5], device=DEV)
+    (l3.sum() * b).backward()
+    torch.testing.assert_close(items, l3.detach(), rtol=2e-5, atol=1e-6)
+    for a_, r_ in zip(g_mine, feats2):
+        scale = r_.grad.abs().max().item()
+        assert (a_ - r_.grad).abs().max().item() <= 5e-5 * scale

@@ -114,3 +114,35 @@ def test_shard_range_partitions_exactly():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_install_patches_and_restores_reference_attributes():
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present")
+    ref_loader.load()
+    import ultralytics.nn.modules.head as u_head
+    import ultralytics.utils.loss as u_loss
+    import ultralytics.utils.ops as u_ops
+    import ultralytics.utils.tal as u_tal
+
+    orig = (u_tal.TaskAlignedAssigner, u_loss.TaskAlignedAssigner, u_ops.non_max_suppression,
+            u_head.Detect._inference, u_loss.v8DetectionLoss.bbox_decode, u_loss.v8DetectionLoss.preprocess)
+    names = kzd.install()
+    try:
+        assert len(names) == 6 and kzd.installed()
+        assert issubclass(u_loss.TaskAlignedAssigner, kzd.TaskAlignedAssigner)
+        assert u_tal.TaskAlignedAssigner is u_loss.TaskAlignedAssigner
+        # CPU tensors go to the reference's own code, never to libkzd
+        d = synth.assigner_inputs(1, 10, 128, 1, synth.P3_P5)
+        asg = u_loss.TaskAlignedAssigner(topk=10, num_classes=1, alpha=0.5, beta=6.0)
+        out = asg(d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+        ref = orig[0](topk=10, num_classes=1, alpha=0.5, beta=6.0)(d["pd_scores"], d["pd_bboxes"], d["anc_points"],
+                                                                   d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+        assert all(torch.equal(a, b) for a, b in zip(out, ref))
+        assert len(u_ops.non_max_suppression(torch.zeros(1, 5, 10))) == 1
+    finally:
+        kzd.uninstall()
+    assert (u_tal.TaskAlignedAssigner, u_loss.TaskAlignedAssigner, u_ops.non_max_suppression, u_head.Detect._inference,
+            u_loss.v8DetectionLoss.bbox_decode, u_loss.v8DetectionLoss.preprocess) == orig

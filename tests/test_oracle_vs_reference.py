@@ -66,3 +66,31 @@ def test_nms_live(R):
         a = R.non_max_suppression(y.clone(), **kw)
         b_ = O.non_max_suppression(y.clone(), **kw)
         assert all(torch.equal(x, z) for x, z in zip(a, b_))
+
+
+def test_loss_tail_and_preprocess_live(R):
+    import types
+
+    from kuzushiji_vision_b200 import synth
+
+    b, G, imgsz, nc = 2, 40, 320, 3
+    d = synth.assigner_inputs(b, G, imgsz, nc, synth.P2_P5, seed=4)
+    logits = torch.cat([l.view(b, 64 + nc, -1) for l in d["levels"]], 2)[:, 64:].permute(0, 2, 1).contiguous()
+    tl, tb, ts, fg, gi = O.tal_assign(d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"],
+                                      d["mask_gt"], 10, nc, 0.5, 6.0)
+    tss = max(ts.sum(), 1)
+    ref_cls = torch.nn.BCEWithLogitsLoss(reduction="none")(logits, ts).sum() / tss
+    pred_bboxes = R.dist2bbox(d["pred_distri"].view(b, -1, 4, 16).softmax(3).matmul(torch.arange(16.0)),
+                              d["anchor_points"], xywh=False)
+    ref_box, ref_dfl = R.loss.BboxLoss(16)(d["pred_distri"], pred_bboxes, d["anchor_points"], tb / d["stride_tensor"],
+                                           ts, tss, fg)
+    mine = O.loss_tail(logits, d["pred_distri"], d["anchor_points"], d["stride_tensor"], tb, ts, fg)
+    torch.testing.assert_close(mine, torch.stack((ref_box, ref_cls, ref_dfl)), rtol=1e-6, atol=0)
+    # preprocess
+    g = torch.Generator().manual_seed(0)
+    rows = [torch.cat((torch.full((n, 1), float(j)), torch.randint(0, 5, (n, 1), generator=g).float(),
+                       torch.rand(n, 4, generator=g)), 1) for j, n in enumerate([5, 0, 17, 3])]
+    t = torch.cat(rows)
+    sc = torch.tensor([1280.0, 960.0, 1280.0, 960.0])
+    ref = R.v8DetectionLoss.preprocess(types.SimpleNamespace(device="cpu"), t.clone(), 4, sc)
+    assert torch.equal(ref, O.preprocess(t.clone(), 4, sc))

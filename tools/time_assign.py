@@ -1,0 +1,22 @@
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import kuzushiji_vision_b200 as kzd
+from kuzushiji_vision_b200 import synth
+dev="cuda:0"
+d = synth.assigner_inputs(16, 600, 1280, 1, synth.P2_P5, seed=0, device=dev)
+asg = kzd.TaskAlignedAssigner(10, 1, 0.5, 6.0)
+args = (d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for _ in range(3): asg(*args)
+torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(s): asg(*args)
+torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+with torch.cuda.graph(g): out = asg(*args)
+tot=0
+for i in range(22):
+    flush.zero_(); e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    if i>=2: tot+=e0.elapsed_time(e1)
+print(sys.argv[1] if len(sys.argv)>1 else "", "assign graph us:", round(tot/20*1e3,1), "fg", int(out[3].sum()))
