@@ -157,7 +157,7 @@ __global__ void assign_verify_kernel(const float* __restrict__ anc, int A, Assig
 
 constexpr int CAND_THREADS = 256;
 #ifndef KZD_CAND_MINB
-#define KZD_CAND_MINB 5
+#define KZD_CAND_MINB 4
 #endif
 constexpr int CAND_WARPS = CAND_THREADS / 32;
 
