@@ -27,14 +27,15 @@ typedef unsigned long long u64;
 // Per-anchor state words carry an 8-bit epoch in their top bits, so a persistent workspace never has
 // to be re-zeroed between calls: entries written under an older epoch lose every atomicMax / CAS.
 //   key  = epoch:8 | overlap_bits:30 | (KEY_GMASK - g):26     (overlap <= 1.0f  =>  bits < 2^30)
-//   sel  = epoch:8 | state:24   state = g+1 (exactly one selecting GT) or SEL_MULTI (several)
+//   sel  = { epoch:8 | (SEL_GMASK - g):24 ,  epoch:8 | g:24 }  both updated with atomicMax (no return
+//          value needed): smallest and largest selecting GT; equal => exactly one selector
 constexpr int KEY_GBITS = 26;
 constexpr u64 KEY_GMASK = (1ull << KEY_GBITS) - 1ull;
-constexpr uint32_t SEL_MULTI = 0xffffffu;
+constexpr uint32_t SEL_GMASK = 0xffffffu;
 
 struct AssignWs {
     u64* key;            // (b*A)  max over in-GT pairs of the packed (overlap, ~g) key
-    uint32_t* sel;       // (b*A)  which GT's top-k selected the anchor
+    uint2* sel;          // (b*A)  smallest / largest GT whose top-k selected the anchor
     uint32_t* pos_align; // (b*G)  per-GT max alignment metric (float bits)
     uint32_t* pos_ov;    // (b*G)  per-GT max overlap (float bits)
     uint32_t* fg_list;   // (b*A)  compact list of foreground anchors (flat index)
@@ -219,19 +220,10 @@ __device__ __forceinline__ void eval_pairs(const AssignParams& p, const GtBox& g
     }
 }
 
-// GT `g` selected anchor idx: first selector stores g+1, any later different selector stores MULTI.
-__device__ __forceinline__ void mark_selected(uint32_t* __restrict__ sel, uint32_t epoch, int g) {
-    const uint32_t mine = (epoch << 24) | (uint32_t)(g + 1);
-    uint32_t cur = *sel;
-    while (true) {
-        uint32_t want;
-        if ((cur >> 24) != epoch) want = mine;                       // stale or never written
-        else if (cur == mine || (cur & 0xffffffu) == SEL_MULTI) return;
-        else want = (epoch << 24) | SEL_MULTI;
-        const uint32_t old = atomicCAS(sel, cur, want);
-        if (old == cur) return;
-        cur = old;
-    }
+// GT `g` selected the anchor: two fire-and-forget atomicMax (smallest and largest selecting GT).
+__device__ __forceinline__ void mark_selected(uint2* __restrict__ sel, uint32_t epoch, int g) {
+    atomicMax(&sel->x, (epoch << 24) | (SEL_GMASK - (uint32_t)g));
+    atomicMax(&sel->y, (epoch << 24) | (uint32_t)g);
 }
 
 __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates_kernel(const AssignParams p) {
@@ -258,56 +250,59 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     int qn = 0;  // queued in-GT anchors (warp-uniform)
     TopK st{0ull, 0ull, true};
 
-    const int n_pseudo = grid_ok ? p.n_levels : 1;
-    for (int l = 0; l < n_pseudo; ++l) {
-        int i0 = 0, j0 = 0, nx = p.A, ny = 1, W = 0, off = 0;
-        float s = 0.f;
-        if (grid_ok) {
-            // superset of the cells whose centre can be inside the GT; the exact fp32 predicate decides
-            s = p.lv[l].stride;
-            W = p.lv[l].w, off = p.lv[l].offset;
-            const int H = p.lv[l].h;
+    // In-GT test (utils/tal.py:259-262): min of the four fp32 differences > 1e-9  <=>  each one is,
+    // so it separates into an x test per column and a y test per row of the level's grid.
+    auto flush32 = [&]() {
+        const int a32 = q[lane];
+        const int tail = q[32 + lane];
+        __syncwarp();
+        q[lane] = tail;
+        qn -= 32;
+        __syncwarp();
+        eval_pairs(p, gt, a32, img, pdb, pds, g, topk, lane, epoch, st);
+    };
+    if (grid_ok) {
+        for (int l = 0; l < p.n_levels; ++l) {
+            // superset of the cells whose centre can be inside the GT; the exact fp32 predicates decide.
             // centres inside need index in (x1/s-0.5, x2/s-0.5); [floor, ceil] of the computed bounds
-            // contains it even when the fp32 quotient is off by an ulp
-            int ia = (int)floorf(gt.x1 / s - 0.5f), ib = (int)ceilf(gt.x2 / s - 0.5f);
-            int ja = (int)floorf(gt.y1 / s - 0.5f), jb = (int)ceilf(gt.y2 / s - 0.5f);
+            // contains it even when the quotient is off by an ulp
+            const float s = p.lv[l].stride, inv_s = 1.f / s;
+            const int W = p.lv[l].w, H = p.lv[l].h, off = p.lv[l].offset;
+            int ia = (int)floorf(gt.x1 * inv_s - 0.5f) - 1, ib = (int)ceilf(gt.x2 * inv_s - 0.5f) + 1;
+            int ja = (int)floorf(gt.y1 * inv_s - 0.5f) - 1, jb = (int)ceilf(gt.y2 * inv_s - 0.5f) + 1;
             ia = max(ia, 0), ja = max(ja, 0), ib = min(ib, W - 1), jb = min(jb, H - 1);
             if (ia > ib || ja > jb) continue;
-            i0 = ia, j0 = ja, nx = ib - ia + 1, ny = jb - ja + 1;
-        }
-        const int total = nx * ny;
-        const float inv_nx = 1.f / (float)nx;
-        const bool small = total < (1 << 21);  // (t+0.5)/nx is then exact enough to floor
-        for (int t0 = 0; t0 < total; t0 += 32) {
-            const int t = t0 + lane;
-            bool inside = false;
-            int a = 0;
-            if (t < total) {
-                const int jj = small ? (int)(((float)t + 0.5f) * inv_nx) : t / nx, ii = t - jj * nx;
-                a = off + (j0 + jj) * W + i0 + ii;
-                float ax, ay;
-                if (grid_ok) {  // verified bit-identical to anc_points[a] by assign_verify_kernel
-                    ax = __fmul_rn((float)(i0 + ii) + 0.5f, s), ay = __fmul_rn((float)(j0 + jj) + 0.5f, s);
-                } else {
-                    const float2 ap = __ldg(anc + a);
-                    ax = ap.x, ay = ap.y;
+            for (int i0 = ia; i0 <= ib; i0 += 32) {  // 32 columns at a time (one pass unless the GT is huge)
+                const int ii = i0 + lane;
+                // anchor x verified bit-identical to anc_points by assign_verify_kernel
+                const float ax = __fmul_rn((float)ii + 0.5f, s);
+                const bool x_in = ii <= ib && __fsub_rn(ax, gt.x1) > 1e-9f && __fsub_rn(gt.x2, ax) > 1e-9f;
+                const unsigned xm = __ballot_sync(0xffffffffu, x_in);
+                if (xm == 0u) continue;
+                const int nxm = __popc(xm), my_pos = __popc(xm & ((1u << lane) - 1u));
+                for (int jj = ja; jj <= jb; ++jj) {
+                    const float ay = __fmul_rn((float)jj + 0.5f, s);
+                    if (!(__fsub_rn(ay, gt.y1) > 1e-9f && __fsub_rn(gt.y2, ay) > 1e-9f)) continue;  // uniform
+                    if (x_in) q[qn + my_pos] = off + jj * W + ii;
+                    qn += nxm;
+                    __syncwarp();
+                    if (qn >= 32) flush32();
                 }
-                inside = anchor_in_gt(ax, ay, gt);
             }
-            // compact the in-GT anchors into the warp's queue; evaluate 32 at a time with all lanes busy
+        }
+    } else {
+        for (int t0 = 0; t0 < p.A; t0 += 32) {  // anchors are not a make_anchors grid: test them all
+            const int a = t0 + lane;
+            bool inside = false;
+            if (a < p.A) {
+                const float2 ap = __ldg(anc + a);
+                inside = anchor_in_gt(ap.x, ap.y, gt);
+            }
             const unsigned m = __ballot_sync(0xffffffffu, inside);
             if (inside) q[qn + __popc(m & ((1u << lane) - 1u))] = a;
             qn += __popc(m);
             __syncwarp();
-            if (qn >= 32) {
-                const int a32 = q[lane];
-                const int tail = q[32 + lane];
-                __syncwarp();
-                q[lane] = tail;
-                qn -= 32;
-                __syncwarp();
-                eval_pairs(p, gt, a32, img, pdb, pds, g, topk, lane, epoch, st);
-            }
+            if (qn >= 32) flush32();
         }
     }
     if (qn > 0) eval_pairs(p, gt, lane < qn ? q[lane] : -1, img, pdb, pds, g, topk, lane, epoch, st);
@@ -363,11 +358,11 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
     const uint32_t epoch = (uint32_t)p.ws.flags[2];
     const size_t img = (size_t)bi * p.A;
     const int a_base = blockIdx.x * RES_ITERS * RES_THREADS + tid;
-    uint32_t sel[RES_ITERS];
+    uint2 sel[RES_ITERS];
 #pragma unroll
     for (int it = 0; it < RES_ITERS; ++it) {
         const int a = a_base + it * RES_THREADS;
-        sel[it] = a < p.A ? p.ws.sel[img + a] : 0u;
+        sel[it] = a < p.A ? p.ws.sel[img + a] : make_uint2(0u, 0u);
     }
     __syncthreads();
     mbar_wait(&bar, 0);
@@ -378,13 +373,13 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
         const int a = a_base + it * RES_THREADS;
         if (a >= p.A) break;
         const size_t idx = img + a;
-        const bool fg = (sel[it] >> 24) == epoch;
+        const bool fg = (sel[it].y >> 24) == epoch;
         uint32_t g = 0;
         if (fg) {
             fg_bits |= 1u << it;
-            const uint32_t state = sel[it] & 0xffffffu;
-            if (state != SEL_MULTI) {
-                g = state - 1u;
+            const uint32_t g_min = SEL_GMASK - (sel[it].x & SEL_GMASK), g_max = sel[it].y & SEL_GMASK;
+            if (g_min == g_max) {
+                g = g_min;
             } else {  // contested: first-max argmax of overlaps over ALL GTs (utils/tal.py:286)
                 const u64 k = p.ws.key[idx];
                 const bool any = (k >> 56) == epoch && ((k >> KEY_GBITS) & 0x3fffffffull) != 0ull;
@@ -401,7 +396,7 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
         // foreground entries get their alignment metric from assign_fg_metric_kernel (compact list)
         if (p.nc == 1) p.target_scores[idx] = 0.f;
         if (epoch == 255u) {  // last epoch before the wrap: leave the state clean for epoch 1
-            p.ws.sel[idx] = 0u;
+            p.ws.sel[idx] = make_uint2(0u, 0u);
             p.ws.key[idx] = 0ull;
         }
     }
@@ -514,7 +509,7 @@ static void split_ws(void* workspace, int b, int A, int G, AssignWs& ws, size_t&
     };
     const size_t n = (size_t)b * A;
     ws.key = (u64*)take(n * 8);
-    ws.sel = (uint32_t*)take(n * 4);
+    ws.sel = (uint2*)take(n * 8);
     ws.flags = (int32_t*)take(256);
     ws.state_bytes = o;
     ws.pos_align = (uint32_t*)take((size_t)b * G * 4);

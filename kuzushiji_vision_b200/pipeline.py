@@ -144,13 +144,18 @@ class PagePipeline:
             if src is not None:
                 getattr(self, name).copy_(src.reshape(getattr(self, name).shape), non_blocking=True)
 
-    def step(self):
-        """Enqueue one pass over the current inputs (graph replay, or the eager body)."""
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self.out = self._body()
-        self.done.record()
+    def step(self, stream=None):
+        """Enqueue one pass over the current inputs (graph replay, or the eager body) on ``stream``
+        (default: the current stream). Two pipelines stepped alternately on two streams overlap one
+        batch's issue-bound kernels with the other batch's HBM-bound decodes."""
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(stream):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.out = self._body()
+            self.done.record(stream)
         return self.out
 
     def results(self):
