@@ -89,6 +89,9 @@ size_t kzd_assign_workspace_bytes(int b, int A, int G);
  *   zero_fill: how torch.topk's padding with zero-metric entries is reproduced when a GT has fewer
  *     than topk positive candidates: 0 = padding never lands inside the GT (true whenever anchors
  *     0..topk-1 are outside every GT); 1 = emulate "lowest anchor indices first".
+ *   score_dtype: dtype pd_scores had at the reference call site (0 fp32, 1 fp16, 2 bf16). The kernel
+ *     reads fp32 values; under AMP the reference rounds pd_scores.pow(alpha) to that dtype
+ *     (utils/tal.py:137,150) and the kernel reproduces that one rounding.
  * Outputs (all written for every anchor):
  *   target_labels int64 (b,A), target_bboxes (b,A,4), target_scores (b,A,nc), fg_mask uint8 (b,A),
  *   target_gt_idx int64 (b,A); counters double[2] = { sum(target_scores), count(fg_mask) }
@@ -101,7 +104,7 @@ size_t kzd_assign_workspace_bytes(int b, int A, int G);
 int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
                    const float* gt_labels, const float* gt_bboxes, const float* mask_gt,
                    int b, int A, int G, int nc, int topk, float alpha, float beta, float eps,
-                   const kzd_level* h_levels, int n_levels, int zero_fill,
+                   const kzd_level* h_levels, int n_levels, int zero_fill, int score_dtype,
                    int64_t* target_labels, float* target_bboxes, float* target_scores,
                    uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
                    void* workspace, size_t workspace_bytes, int persistent, void* stream);

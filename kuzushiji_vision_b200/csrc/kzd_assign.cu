@@ -18,6 +18,9 @@
 // Bit-exactness: every fp32 operation of the eager reference rounds separately, so the pair
 // arithmetic below uses __fadd_rn/__fmul_rn/__fdiv_rn (never contracted into FMAs) and the same
 // libdevice atanf / powf / sqrtf that aten's CUDA kernels call.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "kzd_common.cuh"
 
 namespace kzd {
@@ -50,6 +53,7 @@ struct AssignParams {
     float alpha, beta, eps;
     kzd_level lv[KZD_MAX_LEVELS];
     int n_levels, zero_fill;
+    int score_dtype;  // dtype pd_scores had at the call site: 0 fp32, 1 fp16, 2 bf16 (AMP, utils/tal.py:137)
     long long* target_labels;
     float* target_bboxes;
     float* target_scores;
@@ -73,6 +77,15 @@ __device__ __forceinline__ float pow_scalar(float x, float p) {
     if (p == -1.f) return __fdiv_rn(1.f, x);
     if (p == -2.f) return __fdiv_rn(1.f, __fmul_rn(x, x));
     return powf(x, p);
+}
+
+// bbox_scores inherits pd_scores' dtype (utils/tal.py:137), so under AMP bbox_scores.pow(alpha) is rounded
+// to half precision before it meets the fp32 overlaps (utils/tal.py:150).
+__device__ __forceinline__ float score_pow(float s, float alpha, int score_dtype) {
+    const float v = pow_scalar(s, alpha);
+    if (score_dtype == 1) return __half2float(__float2half_rn(v));
+    if (score_dtype == 2) return __bfloat162float(__float2bfloat16_rn(v));
+    return v;
 }
 
 struct GtBox {
@@ -196,7 +209,7 @@ __device__ __forceinline__ void eval_pairs(const AssignParams& p, const GtBox& g
         if (o > 0.f)
             atomicMax(p.ws.key + img + a, ((u64)epoch << 56) | ((u64)min(__float_as_uint(o), 0x3fffffffu) << KEY_GBITS) |
                                               (KEY_GMASK - (u64)g));
-        const float al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
+        const float al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
         if (al > 0.f) key = ((u64)__float_as_uint(al) << 32) | (0xffffffffu - (uint32_t)a);
     }
     if (st.empty) {  // first batch: one warp sort instead of up to 32 serial insertions
@@ -450,7 +463,7 @@ __global__ void __launch_bounds__(256) assign_fg_metric_kernel(const AssignParam
             const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
             const float sc = __ldg(p.pd_scores + idx * p.nc + lab);
             const float o = overlap_ciou(gt, pb);
-            al = __fmul_rn(pow_scalar(sc, p.alpha), pow_scalar(o, p.beta));
+            al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
             atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
             atomicMax(p.ws.pos_align + gslot, __float_as_uint(al));
         }
@@ -533,7 +546,7 @@ extern "C" __attribute__((visibility("default"))) size_t kzd_assign_workspace_by
 extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
                               const float* gt_labels, const float* gt_bboxes, const float* mask_gt, int b, int A,
                               int G, int nc, int topk, float alpha, float beta, float eps, const kzd_level* h_levels,
-                              int n_levels, int zero_fill, int64_t* target_labels, float* target_bboxes,
+                              int n_levels, int zero_fill, int score_dtype, int64_t* target_labels, float* target_bboxes,
                               float* target_scores, uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
                               void* workspace, size_t workspace_bytes, int persistent, void* stream) {
     KZD_CHECK_ARG(pd_scores && pd_bboxes && anc_points && gt_labels && gt_bboxes && mask_gt,
@@ -545,6 +558,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     KZD_CHECK_ARG(n_levels >= 0 && n_levels <= KZD_MAX_LEVELS && (n_levels == 0 || h_levels),
                   "kzd_tal_assign: bad level table");
     KZD_CHECK_ARG(b <= 65535, "kzd_tal_assign: b=%d > 65535", b);
+    KZD_CHECK_ARG(score_dtype >= 0 && score_dtype <= 2, "kzd_tal_assign: score_dtype=%d not in {0,1,2}", score_dtype);
     KZD_CHECK_ARG((double)b * A < 4294967295.0 && G < (1 << 24) - 2, "kzd_tal_assign: b*A or G too large");
     KZD_CHECK_ARG((size_t)G * 24 <= 200 * 1024, "kzd_tal_assign: G=%d exceeds the shared-memory GT table (8533)", G);
     KZD_CHECK_ARG(((uintptr_t)gt_bboxes) % 16 == 0 && ((uintptr_t)pd_bboxes) % 16 == 0 &&
@@ -571,7 +585,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     p.gt_labels = gt_labels, p.gt_bboxes = gt_bboxes, p.mask_gt = mask_gt;
     p.b = b, p.A = A, p.G = G, p.nc = nc, p.topk = topk;
     p.alpha = alpha, p.beta = beta, p.eps = eps;
-    p.n_levels = n_levels, p.zero_fill = zero_fill;
+    p.n_levels = n_levels, p.zero_fill = zero_fill, p.score_dtype = score_dtype;
     p.target_labels = (long long*)target_labels, p.target_bboxes = target_bboxes, p.target_scores = target_scores;
     p.fg_mask = fg_mask, p.target_gt_idx = (long long*)target_gt_idx, p.counters = counters;
 

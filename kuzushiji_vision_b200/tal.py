@@ -107,6 +107,9 @@ class TaskAlignedAssigner(nn.Module):
         b, A, nc = pd_scores.shape
         G = self.n_max_boxes
         f32 = torch.float32
+        # AMP: the reference keeps bbox_scores in pd_scores' dtype (utils/tal.py:137); libkzd reads fp32
+        # values and reproduces that one rounding
+        score_dtype = {torch.float16: 1, torch.bfloat16: 2}.get(pd_scores.dtype, 0)
         pd_scores_c = pd_scores.to(f32).contiguous()
         pd_bboxes_c = pd_bboxes.to(f32).contiguous()
         anc_c = anc_points.to(f32).contiguous()
@@ -134,7 +137,7 @@ class TaskAlignedAssigner(nn.Module):
             rc = _lib.lib.kzd_tal_assign(
                 pd_scores_c.data_ptr(), pd_bboxes_c.data_ptr(), anc_c.data_ptr(), gl.data_ptr(), gb.data_ptr(),
                 mg.data_ptr(), b, A, G, nc, int(self.topk), float(self.alpha), float(self.beta), float(self.eps),
-                levels, n_levels, int(self.zero_fill),
+                levels, n_levels, int(self.zero_fill), score_dtype,
                 target_labels.data_ptr(), target_bboxes.data_ptr(), target_scores.data_ptr(), fg_u8.data_ptr(),
                 target_gt_idx.data_ptr(), counters.data_ptr(), ws.data_ptr(), ws.numel(), persistent,
                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream),

@@ -156,6 +156,19 @@ def test_assign_epoch_wrap_and_stateless_mode():
         _check_assign(asg(*args), ref)
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_assign_amp_score_dtype(dt):
+    """Under AMP the assigner gets half-precision pd_scores and fp32 boxes (utils/loss.py:233-236,
+    engine/trainer.py:379): the one half-precision rounding of pd_scores.pow(alpha) is reproduced."""
+    d = synth.assigner_inputs(2, 120, 640, 3, synth.P2_P5, seed=17, device=DEV)
+    args = (d["pd_scores"].to(dt), d["pd_bboxes"], d["anc_points"].to(dt), d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+    mine = kzd.TaskAlignedAssigner(10, 3, 0.5, 6.0)(*args)
+    ref = O.tal_assign(*args, 10, 3, 0.5, 6.0)
+    assert torch.equal(mine[3], ref[3]) and torch.equal(mine[4], ref[4]) and torch.equal(mine[0], ref[0])
+    assert torch.equal(mine[1], ref[1])
+    torch.testing.assert_close(mine[2], ref[2].float(), rtol=RTOL, atol=1e-9)
+
+
 def test_assign_tie_heavy_micro_case():
     """SURVEY.md Appendix E micro-case: uniform predictions and scores give many bit-identical metrics,
     so the picks depend on torch.topk's tie order (CPU and CUDA differ). Checked against the oracle on

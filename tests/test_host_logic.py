@@ -28,7 +28,7 @@ def test_argument_validation_without_gpu():
     rc = _lib.lib.kzd_decode_train(None, None, None, 1, 1, None, None, None)
     assert rc == -1 and b"null" in _lib.lib.kzd_last_error()
     lv, _ = _lib.levels_array([(4, 4, 8.0)])
-    rc = _lib.lib.kzd_tal_assign(1, 1, 1, 1, 1, 1, 1, 16, 1, 1, 99, 0.5, 6.0, 1e-9, lv, 1, 0, 1, 1, 1, 1, 1, None,
+    rc = _lib.lib.kzd_tal_assign(1, 1, 1, 1, 1, 1, 1, 16, 1, 1, 99, 0.5, 6.0, 1e-9, lv, 1, 0, 0, 1, 1, 1, 1, 1, None,
                                  1, 0, 0, None)
     assert rc == -1 and b"topk" in _lib.lib.kzd_last_error()
     assert _lib.lib.kzd_assign_workspace_bytes(16, 136000, 600) > 16 * 136000 * 16
