@@ -400,6 +400,7 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
 
 constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_HELPERS = SCAN_WARPS - 1;  // warp 0 only resolves diagonal tiles
 constexpr int SCAN_BATCH = 4;  // column tiles per warp whose loads are in flight together
 
 __device__ __forceinline__ u64 shfl64(u64 v, int src) {
@@ -410,9 +411,15 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src) {
 
 // One CTA per image walks the 64-row chunks in score order. Per chunk the only serial work is the
 // diagonal tile (warp 0: ballot of the rows that suppress anything inside the chunk, shuffle their
-// words, test/OR). All global loads are issued one chunk ahead and independent of the keep mask (it is
-// applied afterwards), so no memory round trip sits on the chunk-to-chunk critical path. The keep
-// masks are parked in shared memory and the kept rows are gathered by all threads after the walk.
+// words, test/OR). All global loads are issued TWO chunks ahead into a rotating set of three register
+// buffers and are independent of the keep mask (it is applied afterwards), so no memory round trip
+// sits on the chunk-to-chunk critical path. The keep masks are parked in shared memory and the kept
+// rows are gathered by all threads after the walk.
+struct ScanRow {
+    u64 v_lo[SCAN_BATCH], v_hi[SCAN_BATCH];  // every warp: its later tiles of the row
+    u64 d_lo, d_hi;                          // warp 0: the diagonal tile
+};
+
 __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __restrict__ cand_rows, int cand_cap,
                                                                 int n_cap, int max_det, SuppressWs ws,
                                                                 float* __restrict__ out_rows,
@@ -432,33 +439,39 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = threadIdx.x; c < T; c += SCAN_THREADS) removed[c] = 0ull;
     const u64* __restrict__ mask = ws.mask + (size_t)bi * ws.T_cap * ws.T_cap * 64;
-    u64 d_lo = 0ull, d_hi = 0ull;          // warp 0: diagonal tile of the current chunk
-    u64 v_lo[SCAN_BATCH], v_hi[SCAN_BATCH];  // every warp: its later tiles of the current chunk's row
-    auto load_row = [&](int r) {
-        const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
+    // warp 0 loads only diagonal tiles; warps 1.. load the later tiles of the row, helper w taking
+    // c = r + 1 + (w-1), + SCAN_HELPERS, ...   (pointers advance by a constant per chunk)
+    const int hw = warp - 1;
+    auto load_row = [&](int r, ScanRow& row) {
+        row.d_lo = row.d_hi = 0ull;
 #pragma unroll
-        for (int k = 0; k < SCAN_BATCH; ++k) {
-            const int c = r + 1 + warp + k * SCAN_WARPS;
-            v_lo[k] = v_hi[k] = 0ull;
-            if (c < T) v_lo[k] = tile_row[(size_t)c * 64 + lane], v_hi[k] = tile_row[(size_t)c * 64 + lane + 32];
-        }
-        if (warp == 0) d_lo = tile_row[(size_t)r * 64 + lane], d_hi = tile_row[(size_t)r * 64 + lane + 32];
-    };
-    if (T > 0) load_row(0);
-    __syncthreads();
-    int kept = 0, chunks = 0;
-    for (int r = 0; r < T; ++r) {
-        // (a) warp 0: resolve the diagonal tile
+        for (int k = 0; k < SCAN_BATCH; ++k) row.v_lo[k] = row.v_hi[k] = 0ull;
+        if (r >= T) return;
+        const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
         if (warp == 0) {
+            row.d_lo = tile_row[(size_t)r * 64 + lane], row.d_hi = tile_row[(size_t)r * 64 + lane + 32];
+        } else {
+            const u64* __restrict__ t = tile_row + (size_t)(r + 1 + hw) * 64 + lane;
+#pragma unroll
+            for (int k = 0; k < SCAN_BATCH; ++k)
+                if (r + 1 + hw + k * SCAN_HELPERS < T)
+                    row.v_lo[k] = t[(size_t)k * SCAN_HELPERS * 64], row.v_hi[k] = t[(size_t)k * SCAN_HELPERS * 64 + 32];
+        }
+    };
+    int kept = 0, chunks = 0;
+    // one chunk; returns true when the walk is over
+    auto step = [&](int r, ScanRow& cur, ScanRow& fut) -> bool {
+        load_row(r + 2, fut);  // in flight for two chunks
+        if (warp == 0) {       // (a) resolve the diagonal tile
             u64 rem = removed[r];
             const int valid = n - r * 64;  // rows of this chunk that exist
             if (valid < 64) rem |= ~0ull << valid;
-            u64 nz = (u64)__ballot_sync(0xffffffffu, d_lo != 0ull) |
-                     ((u64)__ballot_sync(0xffffffffu, d_hi != 0ull) << 32);
+            u64 nz = (u64)__ballot_sync(0xffffffffu, cur.d_lo != 0ull) |
+                     ((u64)__ballot_sync(0xffffffffu, cur.d_hi != 0ull) << 32);
             while (nz) {  // only rows that suppress something inside the chunk need the serial step
                 const int i = __ffsll((long long)nz) - 1;
                 nz &= nz - 1;
-                const u64 di = (i < 32) ? shfl64(d_lo, i) : shfl64(d_hi, i - 32);
+                const u64 di = (i < 32) ? shfl64(cur.d_lo, i) : shfl64(cur.d_hi, i - 32);
                 if (!((rem >> i) & 1ull)) rem |= di;
             }
             if (lane == 0) keep_sh = ~rem, keepmask[r] = ~rem, kept_before[r] = kept;
@@ -467,29 +480,40 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
         const u64 keep = keep_sh;
         kept += __popcll(keep);
         chunks = r + 1;
-        if (kept >= max_det || r + 1 == T) break;  // uniform: later boxes cannot enter the first max_det
-        // (b) OR the kept rows into the removed words of the later chunks (data loaded a chunk ago)
-        const bool k_lo = (keep >> lane) & 1ull, k_hi = (keep >> (lane + 32)) & 1ull;
-        const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
+        if (kept >= max_det || r + 1 == T) return true;  // uniform: later boxes cannot enter the first max_det
+        // (b) helpers OR the kept rows into the removed words of the later chunks (data loaded two chunks ago)
+        if (warp > 0) {
+            const bool k_lo = (keep >> lane) & 1ull, k_hi = (keep >> (lane + 32)) & 1ull;
 #pragma unroll
-        for (int k = 0; k < SCAN_BATCH; ++k) {
-            const int c = r + 1 + warp + k * SCAN_WARPS;
-            if (c < T) {
-                const u64 v = (k_lo ? v_lo[k] : 0ull) | (k_hi ? v_hi[k] : 0ull);
+            for (int k = 0; k < SCAN_BATCH; ++k) {
+                const int c = r + 1 + hw + k * SCAN_HELPERS;
+                if (c < T) {
+                    const u64 v = (k_lo ? cur.v_lo[k] : 0ull) | (k_hi ? cur.v_hi[k] : 0ull);
+                    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
+                    const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+                    if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
+                }
+            }
+            const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
+            for (int c = r + 1 + hw + SCAN_BATCH * SCAN_HELPERS; c < T; c += SCAN_HELPERS) {  // very long rows
+                const u64* t = tile_row + (size_t)c * 64;
+                const u64 v = (k_lo ? t[lane] : 0ull) | (k_hi ? t[lane + 32] : 0ull);
                 const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
                 const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
                 if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
             }
         }
-        for (int c = r + 1 + warp + SCAN_BATCH * SCAN_WARPS; c < T; c += SCAN_WARPS) {  // very long rows
-            const u64* t = tile_row + (size_t)c * 64;
-            const u64 v = (k_lo ? t[lane] : 0ull) | (k_hi ? t[lane + 32] : 0ull);
-            const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
-            const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
-            if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
-        }
-        load_row(r + 1);  // in flight while the barrier and the next diagonal resolve run
         __syncthreads();
+        return false;
+    };
+    ScanRow b0, b1, b2;
+    load_row(0, b0);
+    load_row(1, b1);
+    __syncthreads();
+    for (int r = 0; r < T; r += 3) {
+        if (step(r, b0, b2)) break;
+        if (step(r + 1, b1, b0)) break;
+        if (step(r + 2, b2, b1)) break;
     }
     __syncthreads();
     // (c) gather the kept rows in score order, all threads
