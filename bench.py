@@ -104,7 +104,9 @@ class ClockSampler:
 def algorithmic_bytes(b, A, G, nc, n_cand, n_keep):
     """SURVEY.md 8(d) per-page figures x pages per launch (all stated again in DESIGN.md)."""
     return {
-        "decode_train": 272 * A * b,
+        # 272*A for the decode + 16*A for the pixel-space copy (x stride, utils/loss.py:236) that the
+        # same kernel writes (the reference's separate elementwise pass would read 16*A more)
+        "decode_train": (272 + 16) * A * b,
         "assign": int((57 + 8 / b) * A + 24 * G) * b if nc == 1 else None,
         "decode_infer": (272 + 8 * nc) * A * b,
         "nms": int((32 + 4 * nc) * A * b + 24 * (n_cand + n_keep)),
@@ -424,8 +426,14 @@ def run_kzd(args, rank, local_rank, world):
     peak, peak_src = hbm_peak()
     achieved = ab[dom] / (st_ms[dom] * 1e-3) / 1e9
     total_ab = sum(v for v in ab.values() if v)
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = next(v["traffic_bytes"] for k, v in tj.items() if k.startswith(single_kernel[dom].split("<")[0]))
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": single_kernel[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom],
                 "step": {"algorithmic_bytes": total_ab, "gbs": total_ab / (ms_total / args.steps * 1e-3) / 1e9,
                          "frac": total_ab / (ms_total / args.steps * 1e-3) / 1e9 / peak},
