@@ -247,27 +247,30 @@ def run_kzd(args, rank, local_rank, world):
     # ---- device-resident timing: inputs already in HBM; a step is one CUDA-graph replay. Two pipelines
     # (two input/output buffer sets, same page batch) are stepped alternately on two streams, so batch
     # i+1's HBM-bound decodes overlap batch i's issue-bound assign / NMS kernels (double buffering). ----
-    pipe2 = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G, device=dev,
-                             topk=w["topk"], alpha=w["alpha"], beta=w["beta"], conf_thres=w["conf"],
-                             iou_thres=w["iou"], max_det=w["max_det"])
-    pipe2.load(levels=pipe.levels, pred_distri=pipe.pred_distri, pd_scores=pipe.pd_scores, gt_labels=pipe.gt_labels,
-               gt_bboxes=pipe.gt_bboxes, mask_gt=pipe.mask_gt)
-    pipes = [pipe, pipe2]
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    depth = max(1, int(os.environ.get("KZD_BENCH_DEPTH", "2")))
+    pipes = [pipe]
+    for _ in range(depth - 1):
+        pn = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G, device=dev,
+                              topk=w["topk"], alpha=w["alpha"], beta=w["beta"], conf_thres=w["conf"],
+                              iou_thres=w["iou"], max_det=w["max_det"])
+        pn.load(levels=pipe.levels, pred_distri=pipe.pred_distri, pd_scores=pipe.pd_scores, gt_labels=pipe.gt_labels,
+                gt_bboxes=pipe.gt_bboxes, mask_gt=pipe.mask_gt)
+        pipes.append(pn)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(depth, 2))]
     cur = torch.cuda.current_stream(dev)
 
     def run_steps(k):
         for s_ in streams:
             s_.wait_stream(cur)
         for i in range(k):
-            pipes[i % 2].step(streams[i % 2])
+            pipes[i % depth].step(streams[i % depth])
         for s_ in streams:
             cur.wait_stream(s_)
 
-    run_steps(warmup + (warmup % 2))
+    run_steps(warmup + (-warmup) % depth)
     out, n_keep = pipe.results()
-    _, n_keep2 = pipe2.results()
-    assert n_keep == n_keep2
+    for pn in pipes[1:]:
+        assert pn.results()[1] == n_keep
     kdist.all_reduce_counters(counters)  # warm the collective (communicator setup) outside the timed region
     torch.cuda.synchronize()
     kdist.barrier()
@@ -298,7 +301,7 @@ def run_kzd(args, rank, local_rank, world):
     t1s.record()
     torch.cuda.synchronize()
     ms_single = t0s.elapsed_time(t1s) / 50
-    del pipe2, pipes
+    del pipes[1:]
 
     # ---- per-stage device times: each stage captured as its own CUDA graph and replayed back to back
     # (pure device time of that stage's kernels; decode stages are a single kernel launch each) ----
@@ -466,7 +469,7 @@ def run_kzd(args, rank, local_rank, world):
                    "pages_per_gpu": b, "anchors_per_page": A, "gt_slots": G, "nc": nc,
                    "l2_policy": "inputs larger than L2 (1.16 GB read per step vs 126 MB L2)",
                    "step": "PagePipeline: one CUDA-graph replay of decode_train+assign+decode_infer+NMS per step; "
-                           "two pipelines alternate on two streams (double buffering)",
+                           f"{depth} pipelines alternate on {depth} streams (multi-buffering)",
                    "ms_per_step_single_stream": ms_single,
                    "parallelism": f"image-sharded x{world}"},
         "clocks": clk.summary(),

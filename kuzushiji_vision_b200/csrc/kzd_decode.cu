@@ -19,6 +19,12 @@ namespace kzd {
 // inference decode
 // ------------------------------------------------------------------------------------------
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct InferParams {
     const float* ptr[KZD_MAX_LEVELS];
     int hw[KZD_MAX_LEVELS];
@@ -75,12 +81,17 @@ __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, 
             float m = v[0][i];
 #pragma unroll
             for (int k = 1; k < KZD_REG_MAX; ++k) m = fmaxf(m, v[k][i]);
+            // exp(v - m) = ex2(v*log2e - m*log2e): one FFMA + one MUFU per bin; weights per 4-bin chunk
+            const float L2E = 1.4426950408889634f;
+            const float ml = -m * L2E;
             float sum = 0.f, wsum = 0.f;
 #pragma unroll
-            for (int k = 0; k < KZD_REG_MAX; ++k) {
-                const float e = __expf(v[k][i] - m);
-                sum += e;
-                wsum = fmaf((float)k, e, wsum);
+            for (int c = 0; c < KZD_REG_MAX; c += 4) {
+                const float e0 = ex2_approx(fmaf(v[c][i], L2E, ml)), e1 = ex2_approx(fmaf(v[c + 1][i], L2E, ml));
+                const float e2 = ex2_approx(fmaf(v[c + 2][i], L2E, ml)), e3 = ex2_approx(fmaf(v[c + 3][i], L2E, ml));
+                const float sc = (e0 + e1) + (e2 + e3);
+                sum += sc;
+                wsum += fmaf((float)c, sc, fmaf(3.f, e3, fmaf(2.f, e2, e1)));
             }
             d[s][i] = wsum / sum;
         }
@@ -126,12 +137,6 @@ constexpr int TR_FLOATS = TR_ANCH * 64;         // 4096 floats = 16 KB
 constexpr int TR_STAGES = 4;                    // 64 KB of loads in flight per CTA
 constexpr int TR_THREADS = TR_ANCH * 4;         // one thread per (anchor, side)
 constexpr int TR_SMEM = TR_STAGES * TR_FLOATS * 4;
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 // Softmax expectation of the 16 bins at smem row `row` (16 floats, 64 B). The four 16-byte chunks
 // are visited in a per-thread rotated order so that every quarter-warp hits 8 distinct bank groups.

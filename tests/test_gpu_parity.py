@@ -527,3 +527,47 @@ def test_detection_loss_criterion_matches_oracle_composition():
     for a_, r_ in zip(g_mine, feats2):
         scale = r_.grad.abs().max().item()
         assert (a_ - r_.grad).abs().max().item() <= 5e-5 * scale
+
+
+# ---------------------------------------------------------------------------------------------
+# randomized sweeps (many small seeded cases; indices must stay bit-exact in every one)
+# ---------------------------------------------------------------------------------------------
+
+def test_assign_randomized_sweep():
+    g = torch.Generator().manual_seed(1234)
+    n_cases = 0
+    for case in range(40):
+        b = int(torch.randint(1, 4, (1,), generator=g))
+        G = int(torch.randint(1, 90, (1,), generator=g))
+        nc = int(torch.randint(1, 7, (1,), generator=g))
+        imgsz = int(torch.randint(3, 12, (1,), generator=g)) * 32
+        strides = synth.P2_P5 if case % 2 else synth.P3_P5
+        topk = int(torch.randint(1, 16, (1,), generator=g))
+        alpha = [0.5, 1.0, 2.0][case % 3]
+        layout = "uniform" if case % 4 else "columns"
+        d = synth.assigner_inputs(b, G, imgsz, nc, strides, seed=1000 + case, device=DEV, layout=layout)
+        if case % 5 == 0:  # oversized GTs: many anchors per GT, borders included
+            d["gt_bboxes"][:, 0] = torch.tensor([0.0, 0.0, imgsz * 0.9, imgsz * 0.7], device=DEV)
+            d["mask_gt"][:, 0] = 1
+        mine, ref, _ = _assign_both(d, nc, topk, alpha)
+        _check_assign(mine, ref)
+        n_cases += 1
+    assert n_cases == 40
+
+
+def test_nms_randomized_sweep():
+    g = torch.Generator().manual_seed(4321)
+    for case in range(30):
+        b = int(torch.randint(1, 4, (1,), generator=g))
+        nc = int(torch.randint(1, 6, (1,), generator=g))
+        imgsz = int(torch.randint(3, 10, (1,), generator=g)) * 32
+        n_obj = int(torch.randint(0, 700, (1,), generator=g))
+        lv = synth.head_outputs(b, nc, imgsz, synth.P2_P5, seed=2000 + case, device=DEV, sparse_cls=n_obj)
+        y = O.decode_infer(lv, synth.P2_P5, nc)
+        if case % 3 == 0:  # clustered duplicates: long suppression chains
+            y[:, :2] = (y[:, :2] / 24).round() * 24
+        kw = dict(conf_thres=[0.25, 0.5, 0.05][case % 3], iou_thres=[0.7, 0.45, 0.2][case % 3],
+                  agnostic=bool(case % 2), multi_label=(case % 4 == 3), max_det=[300, 50, 1000][case % 3])
+        mine, ref, p1, p2 = _nms_both(y, **kw)
+        _check_nms(mine, ref)
+        assert torch.equal(p1, p2)
