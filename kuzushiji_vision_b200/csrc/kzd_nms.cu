@@ -196,6 +196,9 @@ struct SuppressWs {
     u64* mask;          // (b, T_cap*T_cap*64)
     u64* ckeys;         // (b, C_cap*CHUNK)  keys, sorted descending inside each chunk (0 = padding)
     uint32_t* cvals;    // (b, C_cap*CHUNK)  pool slot of each key
+    int32_t* state;     // (b, 4)       scan state carried between phases: done, kept, chunks walked
+    u64* keepmask;      // (b, T_cap)   keep mask of every walked chunk
+    int32_t* kept_before;  // (b, T_cap)
     int T_cap, C_cap;
 };
 
@@ -315,23 +318,30 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float sa, const flo
 // and the scan reads whole tiles).
 constexpr int MASK_CG = 4;
 
-__device__ __forceinline__ int mask_items(int n) {  // column group g holds rows 0..min(T, 4g+4)-1
-    if (n <= 0) return 0;
-    const int T = (n + 63) >> 6, Gc = (T + MASK_CG - 1) / MASK_CG;
-    // sum_{g<Gc} min(T, MASK_CG*(g+1))
-    const int full = 2 * (Gc - 1) * Gc;  // MASK_CG * (1 + ... + (Gc-1)) with MASK_CG == 4
-    return full + T;
+// items of column groups [0, g) for an image of T tiles: group k holds rows 0..min(T, 4k+4)-1
+__device__ __forceinline__ int items_before(int T, int g) {
+    const int Gc = (T + MASK_CG - 1) / MASK_CG;
+    if (g <= 0 || T <= 0) return 0;
+    if (g >= Gc) return 2 * (Gc - 1) * Gc + T;  // MASK_CG * (1 + ... + (Gc-1)) + T, MASK_CG == 4
+    return 2 * g * (g + 1);
 }
 
-__global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap, float iou_thres, SuppressWs ws) {
+// Phase = column groups [g_lo, g_hi) of every image that is not finished yet (the greedy walk stops as
+// soon as max_det boxes are kept, so later columns are often never needed: see kzd_nms_suppress).
+__global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap, float iou_thres, int phase,
+                                                                int g_lo, int g_hi, SuppressWs ws) {
     extern __shared__ int pre[];  // (b+1) prefix of item counts
     __shared__ float4 colbox[MASK_CG * 64];
-    static_assert(MASK_CG == 4, "mask_items() assumes groups of 4 column tiles");
+    static_assert(MASK_CG == 4, "items_before() assumes groups of 4 column tiles");
     if (threadIdx.x == 0) {
         int acc = 0;
         for (int i = 0; i < b; ++i) {
             pre[i] = acc;
-            acc += mask_items(ws.n_sorted[i]);
+            const int n = ws.n_sorted[i];
+            if (n > 0 && !(phase > 0 && ws.state[i * 4])) {
+                const int T = (n + 63) >> 6;
+                acc += items_before(T, g_hi) - items_before(T, g_lo);
+            }
         }
         pre[b] = acc;
     }
@@ -343,7 +353,7 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
         while (pre[bi + 1] <= w) ++bi;  // w only grows
         const int n = ws.n_sorted[bi];
         const int T = (n + 63) >> 6;
-        const int q = w - pre[bi];
+        const int q = w - pre[bi] + items_before(T, g_lo);
         // items are ordered by column group g, then row r:  offset(g) = 2 g (g+1)
         int g = (int)((sqrtf(1.f + 2.f * (float)q) - 1.f) * 0.5f);
         g = max(g, 0);
@@ -421,32 +431,52 @@ struct ScanRow {
 };
 
 __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __restrict__ cand_rows, int cand_cap,
-                                                                int n_cap, int max_det, SuppressWs ws,
+                                                                int n_cap, int max_det, int phase, int t_lo,
+                                                                int t_hi, SuppressWs ws,
                                                                 float* __restrict__ out_rows,
                                                                 int32_t* __restrict__ out_counts) {
-    extern __shared__ u64 sm64[];  // removed[T_cap], keepmask[T_cap], then int kept_before[T_cap]
+    extern __shared__ u64 removed[];  // T_cap words
     __shared__ u64 keep_sh;
     const int bi = blockIdx.x;
     const int n = ws.n_sorted[bi];
+    int32_t* state = ws.state + bi * 4;  // [0] done, [1] kept, [2] chunks walked
     if (n < 0) {
-        if (threadIdx.x == 0) out_counts[bi] = -1;
+        if (threadIdx.x == 0 && phase == 0) out_counts[bi] = -1, state[0] = 1;
         return;
     }
-    u64* removed = sm64;
-    u64* keepmask = sm64 + ws.T_cap;
-    int* kept_before = reinterpret_cast<int*>(sm64 + 2 * ws.T_cap);
+    if (phase > 0 && state[0]) return;
     const int T = (n + 63) >> 6;
+    const int hi = t_hi < T ? t_hi : T;  // this phase walks chunks [t_lo, hi); mask columns < hi exist
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = threadIdx.x; c < T; c += SCAN_THREADS) removed[c] = 0ull;
+    u64* __restrict__ keepmask = ws.keepmask + (size_t)bi * ws.T_cap;
+    int32_t* __restrict__ kept_before = ws.kept_before + (size_t)bi * ws.T_cap;
     const u64* __restrict__ mask = ws.mask + (size_t)bi * ws.T_cap * ws.T_cap * 64;
+    for (int c = threadIdx.x; c < hi; c += SCAN_THREADS) removed[c] = 0ull;
+    __syncthreads();
+    int kept = 0, chunks = 0;
+    if (phase > 0) {
+        kept = state[1], chunks = state[2];
+        // columns [t_lo, hi) are new: apply the kept rows of every chunk walked so far to them
+        const int width = hi - t_lo;
+        for (int item = warp; item < t_lo * width; item += SCAN_WARPS) {
+            const int r = item / width, c = t_lo + item % width;
+            const u64 keep = keepmask[r];
+            const u64* t = mask + ((size_t)r * ws.T_cap + c) * 64;
+            const u64 v = (((keep >> lane) & 1ull) ? t[lane] : 0ull) | (((keep >> (lane + 32)) & 1ull) ? t[lane + 32] : 0ull);
+            const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
+            const uint32_t hi32 = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+            if (lane == 0 && (lo | hi32)) atomicOr(reinterpret_cast<unsigned long long*>(removed + c), ((u64)hi32 << 32) | lo);
+        }
+        __syncthreads();
+    }
     // warp 0 loads only diagonal tiles; warps 1.. load the later tiles of the row, helper w taking
-    // c = r + 1 + (w-1), + SCAN_HELPERS, ...   (pointers advance by a constant per chunk)
+    // c = r + 1 + (w-1), + SCAN_HELPERS, ...
     const int hw = warp - 1;
     auto load_row = [&](int r, ScanRow& row) {
         row.d_lo = row.d_hi = 0ull;
 #pragma unroll
         for (int k = 0; k < SCAN_BATCH; ++k) row.v_lo[k] = row.v_hi[k] = 0ull;
-        if (r >= T) return;
+        if (r >= hi) return;
         const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
         if (warp == 0) {
             row.d_lo = tile_row[(size_t)r * 64 + lane], row.d_hi = tile_row[(size_t)r * 64 + lane + 32];
@@ -454,12 +484,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
             const u64* __restrict__ t = tile_row + (size_t)(r + 1 + hw) * 64 + lane;
 #pragma unroll
             for (int k = 0; k < SCAN_BATCH; ++k)
-                if (r + 1 + hw + k * SCAN_HELPERS < T)
+                if (r + 1 + hw + k * SCAN_HELPERS < hi)
                     row.v_lo[k] = t[(size_t)k * SCAN_HELPERS * 64], row.v_hi[k] = t[(size_t)k * SCAN_HELPERS * 64 + 32];
         }
     };
-    int kept = 0, chunks = 0;
-    // one chunk; returns true when the walk is over
+    bool finished = (hi <= t_lo);  // nothing new to walk: the image ended in an earlier phase's range
+    // one chunk; returns true when this phase's walk is over
     auto step = [&](int r, ScanRow& cur, ScanRow& fut) -> bool {
         load_row(r + 2, fut);  // in flight for two chunks
         if (warp == 0) {       // (a) resolve the diagonal tile
@@ -480,43 +510,53 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
         const u64 keep = keep_sh;
         kept += __popcll(keep);
         chunks = r + 1;
-        if (kept >= max_det || r + 1 == T) return true;  // uniform: later boxes cannot enter the first max_det
+        if (kept >= max_det || r + 1 == T) {  // uniform: later boxes cannot enter the first max_det
+            finished = true;
+            return true;
+        }
+        if (r + 1 == hi) return true;  // end of this phase's columns
         // (b) helpers OR the kept rows into the removed words of the later chunks (data loaded two chunks ago)
         if (warp > 0) {
             const bool k_lo = (keep >> lane) & 1ull, k_hi = (keep >> (lane + 32)) & 1ull;
 #pragma unroll
             for (int k = 0; k < SCAN_BATCH; ++k) {
                 const int c = r + 1 + hw + k * SCAN_HELPERS;
-                if (c < T) {
+                if (c < hi) {
                     const u64 v = (k_lo ? cur.v_lo[k] : 0ull) | (k_hi ? cur.v_hi[k] : 0ull);
                     const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
-                    const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
-                    if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
+                    const uint32_t hi32 = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+                    if (lane == 0 && (lo | hi32)) removed[c] |= ((u64)hi32 << 32) | lo;
                 }
             }
             const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
-            for (int c = r + 1 + hw + SCAN_BATCH * SCAN_HELPERS; c < T; c += SCAN_HELPERS) {  // very long rows
+            for (int c = r + 1 + hw + SCAN_BATCH * SCAN_HELPERS; c < hi; c += SCAN_HELPERS) {  // very long rows
                 const u64* t = tile_row + (size_t)c * 64;
                 const u64 v = (k_lo ? t[lane] : 0ull) | (k_hi ? t[lane + 32] : 0ull);
                 const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
-                const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
-                if (lane == 0 && (lo | hi)) removed[c] |= ((u64)hi << 32) | lo;
+                const uint32_t hi32 = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+                if (lane == 0 && (lo | hi32)) removed[c] |= ((u64)hi32 << 32) | lo;
             }
         }
         __syncthreads();
         return false;
     };
-    ScanRow b0, b1, b2;
-    load_row(0, b0);
-    load_row(1, b1);
-    __syncthreads();
-    for (int r = 0; r < T; r += 3) {
-        if (step(r, b0, b2)) break;
-        if (step(r + 1, b1, b0)) break;
-        if (step(r + 2, b2, b1)) break;
+    if (!finished) {
+        ScanRow b0, b1, b2;
+        load_row(t_lo, b0);
+        load_row(t_lo + 1, b1);
+        for (int r = t_lo; r < hi; r += 3) {
+            if (step(r, b0, b2)) break;
+            if (step(r + 1, b1, b0)) break;
+            if (step(r + 2, b2, b1)) break;
+        }
     }
     __syncthreads();
-    // (c) gather the kept rows in score order, all threads
+    if (n == 0) finished = true;
+    if (!finished) {  // more columns are needed: the next phase continues from here
+        if (threadIdx.x == 0) state[0] = 0, state[1] = kept, state[2] = chunks;
+        return;
+    }
+    // gather the kept rows in score order, all threads
     const uint32_t* __restrict__ sslot = ws.sslot + (size_t)bi * n_cap;
     const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
     float* __restrict__ out = out_rows + (size_t)bi * max_det * 6;
@@ -532,7 +572,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
             }
         }
     }
-    if (threadIdx.x == 0) out_counts[bi] = kept < max_det ? kept : max_det;
+    if (threadIdx.x == 0) out_counts[bi] = kept < max_det ? kept : max_det, state[0] = 1;
 }
 
 static int split_ws(void* workspace, int b, int cand_cap, int n_cap, SuppressWs& ws, size_t& total) {
@@ -551,6 +591,9 @@ static int split_ws(void* workspace, int b, int cand_cap, int n_cap, SuppressWs&
     ws.mask = (u64*)take((size_t)b * T_cap * T_cap * 64 * sizeof(u64));
     ws.ckeys = (u64*)take((size_t)b * C_cap * CHUNK * sizeof(u64));
     ws.cvals = (uint32_t*)take((size_t)b * C_cap * CHUNK * sizeof(uint32_t));
+    ws.state = (int32_t*)take((size_t)b * 4 * sizeof(int32_t));
+    ws.keepmask = (u64*)take((size_t)b * T_cap * sizeof(u64));
+    ws.kept_before = (int32_t*)take((size_t)b * T_cap * sizeof(int32_t));
     ws.T_cap = T_cap;
     ws.C_cap = C_cap;
     total = o;
@@ -626,11 +669,24 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
     KZD_LAUNCH_CHECK("nms_chunk_sort_kernel");
     nms_rank_kernel<<<cgrid, CHUNK_THREADS, 0, st>>>(cand_rows, cand_counts, cand_cap, n_cap, agnostic, max_wh, ws);
     KZD_LAUNCH_CHECK("nms_rank_kernel");
+    // The greedy walk stops as soon as max_det boxes are kept, so the mask is built and walked in phases
+    // of growing column ranges: first enough tiles for max_det kept boxes plus 25 %, then 4x more per
+    // phase. Finished images skip the later phases on the device (no host round trip).
     const int grid = sm_count() * 16;
-    nms_mask_kernel<<<grid, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(b, n_cap, iou_thres, ws);
-    KZD_LAUNCH_CHECK("nms_mask_kernel");
-    nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * (2 * sizeof(u64) + sizeof(int)), st>>>(cand_rows, cand_cap, n_cap, max_det, ws,
-                                                                            out_rows, out_counts);
-    KZD_LAUNCH_CHECK("nms_scan_kernel");
+    int t_prev = 0;
+    int t_next = ((max_det + max_det / 4 + 64 + 63) / 64 + MASK_CG - 1) / MASK_CG * MASK_CG;
+    for (int phase = 0; t_prev < ws.T_cap; ++phase) {
+        if (t_next > ws.T_cap) t_next = ws.T_cap;
+        const int g_lo = t_prev / MASK_CG, g_hi = (t_next + MASK_CG - 1) / MASK_CG;
+        nms_mask_kernel<<<grid, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(b, n_cap, iou_thres, phase, g_lo,
+                                                                                 g_hi, ws);
+        KZD_LAUNCH_CHECK("nms_mask_kernel");
+        nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * sizeof(u64), st>>>(cand_rows, cand_cap, n_cap, max_det,
+                                                                                phase, t_prev, t_next, ws, out_rows,
+                                                                                out_counts);
+        KZD_LAUNCH_CHECK("nms_scan_kernel");
+        t_prev = t_next;
+        t_next = (t_next * 4 + MASK_CG - 1) / MASK_CG * MASK_CG;
+    }
     return 0;
 }
