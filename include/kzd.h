@@ -162,6 +162,13 @@ int kzd_gt_count(const float* targets, int n, int b, int32_t* counts, int32_t* f
 int kzd_gt_pack(const float* targets, int n, int b, int G, const float* scale4, const int32_t* counts,
                 const int32_t* first, float* out, void* stream);
 
+/* Post-NMS tail: ops.scale_boxes (utils/ops.py:92-127, padding=True, xywh=False) + clip_boxes
+ * (:319-338) for all detections of a batch, in place (models/yolo/detect/predict.py:37-41 does it per
+ * image). rows (b, max_det, row_stride) with the xyxy box in columns 0..3; counts (b) int32 or NULL (all
+ * rows); params (b,5) device floats = [pad_x, pad_y, gain, w0, h0] of each image. */
+int kzd_scale_boxes(float* rows, const int32_t* counts, int b, int max_det, int row_stride,
+                    const float* params, void* stream);
+
 /* Loss tail on the assigned targets (utils/loss.py:243-258; BboxLoss :91-113, DFLoss :65-88):
  *   loss3[0] = sum_fg (1 - CIoU(pred_box, target_box/stride)) * w / tss   (box, before hyp.box)
  *   loss3[1] = sum BCEWithLogits(pred_scores, target_scores) / tss         (cls)

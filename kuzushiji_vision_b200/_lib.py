@@ -48,6 +48,7 @@ def _load():
         "kzd_gt_pack": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
         "kzd_loss_tail_fwd": (C.c_int, [vp] * 8 + [i32] * 3 + [vp, vp, vp]),
         "kzd_loss_tail_bwd": (C.c_int, [vp] * 8 + [i32] * 3 + [vp, vp, vp, vp]),
+        "kzd_scale_boxes": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
         "kzd_nms_suppress": (C.c_int, [vp, vp, vp, i32, i32, i32, f32, i32, i32, i32, f32, vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sigs.items():

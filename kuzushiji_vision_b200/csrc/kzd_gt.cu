@@ -78,3 +78,45 @@ extern "C" __attribute__((visibility("default"))) int kzd_gt_pack(const float* t
     KZD_LAUNCH_CHECK("gt_pack_kernel");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// post-NMS tail: scale_boxes + clip_boxes for a whole batch of detections
+// reference: utils/ops.py:92-127 (scale_boxes, padding=True, xywh=False) and :319-338 (clip_boxes),
+// called per image from models/yolo/detect/predict.py:37-41.
+//   x -= pad_x; y -= pad_y;  then  *= 1/gain  (aten divides by a Python scalar as a * (1.0f/b));
+//   then clamp x to [0, w0], y to [0, h0].
+// params (b, 5) = [pad_x, pad_y, gain, w0, h0]; rows (b, max_det, stride) with the box in columns 0..3.
+// ------------------------------------------------------------------------------------------------
+
+namespace kzd {
+
+__global__ void scale_boxes_kernel(float* __restrict__ rows, const int32_t* __restrict__ counts, int b, int max_det,
+                                   int stride, const float* __restrict__ params) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b * max_det) return;
+    const int bi = idx / max_det, k = idx - bi * max_det;
+    if (counts && k >= counts[bi]) return;
+    const float* p = params + bi * 5;
+    const float inv = __fdiv_rn(1.f, p[2]);
+    float* r = rows + (size_t)idx * stride;
+    const float x1 = __fmul_rn(__fsub_rn(r[0], p[0]), inv), y1 = __fmul_rn(__fsub_rn(r[1], p[1]), inv);
+    const float x2 = __fmul_rn(__fsub_rn(r[2], p[0]), inv), y2 = __fmul_rn(__fsub_rn(r[3], p[1]), inv);
+    r[0] = fminf(fmaxf(x1, 0.f), p[3]), r[1] = fminf(fmaxf(y1, 0.f), p[4]);
+    r[2] = fminf(fmaxf(x2, 0.f), p[3]), r[3] = fminf(fmaxf(y2, 0.f), p[4]);
+}
+
+}  // namespace kzd
+
+extern "C" __attribute__((visibility("default"))) int kzd_scale_boxes(float* rows, const int32_t* counts, int b,
+                                                                        int max_det, int row_stride,
+                                                                        const float* params, void* stream) {
+    KZD_CHECK_ARG(rows && params, "kzd_scale_boxes: null pointer");
+    KZD_CHECK_ARG(b >= 0 && max_det >= 0 && row_stride >= 4, "kzd_scale_boxes: bad sizes");
+    const long long n = (long long)b * max_det;
+    if (n == 0) return 0;
+    KZD_CHECK_ARG(n < 0x7fffffffLL, "kzd_scale_boxes: b*max_det too large");
+    kzd::scale_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, counts, b, max_det,
+                                                                                          row_stride, params);
+    KZD_LAUNCH_CHECK("scale_boxes_kernel");
+    return 0;
+}

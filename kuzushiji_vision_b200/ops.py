@@ -117,3 +117,49 @@ def xywh2xyxy(x):
     assert x.shape[-1] == 4, f"input shape last dimension expected 4 but input shape is {x.shape}"
     half = x[..., 2:] / 2
     return torch.cat((x[..., :2] - half, x[..., :2] + half), -1)
+
+
+def _scale_params(img1_shape, img0_shape, ratio_pad=None):
+    """gain and (pad_x, pad_y) exactly as utils/ops.py:110-119 computes them (Python floats)."""
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1),
+               round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
+    else:
+        gain, pad = ratio_pad[0][0], ratio_pad[1]
+    return [float(pad[0]), float(pad[1]), float(gain), float(img0_shape[1]), float(img0_shape[0])]
+
+
+def scale_boxes_batched(rows, n_keep, img1_shape, orig_shapes):
+    """``ops.scale_boxes`` + ``clip_boxes`` (utils/ops.py:92-127, 319-338) for the whole NMS output of a
+    batch at once, in place: ``rows (b, max_det, 6)`` as returned by ``nms_batched``, ``n_keep`` the kept
+    counts (list or None), ``img1_shape`` the network input (h, w), ``orig_shapes`` one (h0, w0[, c]) per
+    image - what ``DetectionPredictor.postprocess`` does image by image (detect/predict.py:37-41)."""
+    _lib.require_cuda(rows, "rows")
+    b, max_det, stride = rows.shape
+    dev = rows.device
+    params = torch.tensor([_scale_params(img1_shape, s) for s in orig_shapes], dtype=torch.float32).to(dev)
+    counts = None if n_keep is None else torch.as_tensor(n_keep, dtype=torch.int32).to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.kzd_scale_boxes(rows.data_ptr(), counts.data_ptr() if counts is not None else None, b,
+                                            max_det, stride, params.data_ptr(), _stream(dev)), "kzd_scale_boxes")
+    return rows
+
+
+def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None, padding=True, xywh=False):
+    """Drop-in for ``ops.scale_boxes`` on one image's ``(n, >=4)`` CUDA boxes (same signature,
+    utils/ops.py:92); rescales in place and returns ``boxes``. ``padding=False`` / ``xywh=True`` are not
+    on this path."""
+    if not padding or xywh:
+        raise NotImplementedError("kuzushiji_vision_b200.scale_boxes: padding=False / xywh=True")
+    _lib.require_cuda(boxes, "boxes")
+    if boxes.numel() == 0:
+        return boxes
+    if boxes.dtype != torch.float32 or boxes.stride(-1) != 1 or boxes.dim() != 2:
+        raise _lib.KzdError("scale_boxes expects a 2-D fp32 tensor with unit stride in the last dimension")
+    dev = boxes.device
+    params = torch.tensor([_scale_params(img1_shape, img0_shape, ratio_pad)], dtype=torch.float32).to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.kzd_scale_boxes(boxes.data_ptr(), None, 1, boxes.shape[0], boxes.stride(0),
+                                            params.data_ptr(), _stream(dev)), "kzd_scale_boxes")
+    return boxes

@@ -68,7 +68,12 @@ class PagePipeline:
         self._side = torch.cuda.Stream(device=dev, priority=-1)  # the small NMS kernels go first
         self.out = None
         self.graph = None
-        self.kernels_per_step = 13  # decode_train, assign x6, decode_infer, nms x5 (memset nodes not counted)
+        # decode_train, assign x6, decode_infer, nms filter + chunk sort + rank + (mask, scan) per phase
+        t0 = ((self.max_det + self.max_det // 4 + 127) // 64 + 3) // 4 * 4
+        t_cap, phases = (self.n_cap + 63) // 64, 1
+        while t0 < t_cap:
+            t0, phases = t0 * 4, phases + 1
+        self.kernels_per_step = 1 + 6 + 1 + 3 + 2 * phases
         if use_graph:
             self._capture()
 

@@ -399,3 +399,26 @@ def loss_tail(pred_scores, pred_distri, anchor_points, stride_tensor, target_bbo
               + F.cross_entropy(logits, (tl + 1).view(-1), reduction="none").view(tl.shape) * wr).mean(-1, keepdim=True)
         dfl = (ce * weight).sum() / tss
     return torch.stack((box, cls, dfl))
+
+
+# --------------------------------------------------------------------------------------
+# post-NMS tail  (utils/ops.py:92-127, 319-338)
+# --------------------------------------------------------------------------------------
+
+
+def scale_boxes(img1_shape, boxes, img0_shape):
+    """Restatement of ``ops.scale_boxes(img1_shape, boxes, img0_shape)`` with the default
+    ``ratio_pad=None, padding=True, xywh=False`` followed by ``clip_boxes`` (in place, returns boxes)."""
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad_x = round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1)
+    pad_y = round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1)
+    boxes[..., 0] -= pad_x
+    boxes[..., 1] -= pad_y
+    boxes[..., 2] -= pad_x
+    boxes[..., 3] -= pad_y
+    boxes[..., :4] /= gain
+    boxes[..., 0] = boxes[..., 0].clamp(0, img0_shape[1])
+    boxes[..., 1] = boxes[..., 1].clamp(0, img0_shape[0])
+    boxes[..., 2] = boxes[..., 2].clamp(0, img0_shape[1])
+    boxes[..., 3] = boxes[..., 3].clamp(0, img0_shape[0])
+    return boxes

@@ -571,3 +571,19 @@ def test_nms_randomized_sweep():
         mine, ref, p1, p2 = _nms_both(y, **kw)
         _check_nms(mine, ref)
         assert torch.equal(p1, p2)
+
+
+def test_scale_boxes_matches_oracle():
+    """Post-NMS tail (utils/ops.py:92-127, 319-338): batched over the NMS output and as the single-image
+    drop-in, bit-exact against the oracle."""
+    lv = synth.head_outputs(3, 2, 320, synth.P2_P5, seed=33, device=DEV, sparse_cls=400)
+    y = O.decode_infer(lv, synth.P2_P5, 2)
+    rows, n_keep = kzd.nms_batched(y, 0.25, 0.6, max_det=300)
+    img1, origs = (320, 320), [(1080, 1920, 3), (700, 500, 3), (333, 333, 3)]
+    ref = [O.scale_boxes(img1, rows[i, :n_keep[i], :4].clone(), origs[i]) for i in range(3)]
+    single = [kzd.scale_boxes(img1, rows[i, :n_keep[i]].clone(), origs[i]) for i in range(3)]
+    out = kzd.scale_boxes_batched(rows.clone(), n_keep, img1, origs)
+    for i in range(3):
+        assert torch.equal(out[i, :n_keep[i], :4], ref[i])
+        assert torch.equal(single[i][:, :4], ref[i])
+        assert torch.equal(out[i, :n_keep[i], 4:], rows[i, :n_keep[i], 4:])

@@ -94,3 +94,11 @@ def test_loss_tail_and_preprocess_live(R):
     sc = torch.tensor([1280.0, 960.0, 1280.0, 960.0])
     ref = R.v8DetectionLoss.preprocess(types.SimpleNamespace(device="cpu"), t.clone(), 4, sc)
     assert torch.equal(ref, O.preprocess(t.clone(), 4, sc))
+
+
+def test_scale_boxes_live(R):
+    g = torch.Generator().manual_seed(2)
+    boxes = torch.rand(200, 4, generator=g) * 700 - 30
+    for img1, img0 in [((640, 640), (1080, 1920, 3)), ((320, 512), (700, 500)), ((1280, 1280), (333, 333))]:
+        ref = R.ops.scale_boxes(img1, boxes.clone(), img0)
+        assert torch.equal(ref, O.scale_boxes(img1, boxes.clone(), img0))
