@@ -54,20 +54,24 @@ int kzd_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Detect._inference (nn/modules/head.py:100-131) + DFL.forward (nn/modules/block.py:71-74) +
  * dist2bbox(xywh=True, dim=1) (utils/tal.py:348-357) + cls.sigmoid(), fused.
  *   h_level_ptrs[l] : device pointer to level l's map (b, 64+nc, h_l, w_l), contiguous NCHW
+ *   in_dtype        : element type of the maps: 0 fp32, 1 fp16, 2 bf16 (AMP / half inference,
+ *                     engine/validator.py:115-117); the arithmetic and y are always fp32
  *   y               : (b, 4+nc, A)  [cx, cy, w, h] in pixels, then sigmoid(class logits)
  * The per-level `cat` copy (head.py:104) is skipped; anchors and strides come from `levels`. */
-int kzd_decode_infer(const float* const* h_level_ptrs, const kzd_level* h_levels, int n_levels,
-                     int b, int nc, float* y, void* stream);
+int kzd_decode_infer(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels,
+                     int n_levels, int b, int nc, float* y, void* stream);
 
 /* v8DetectionLoss.bbox_decode (utils/loss.py:197-204) + dist2bbox(xywh=False).
- *   pred_dist     : (b, A, 64)  side-major, 16 bins per side
+ *   pred_dist     : (b, A, 64)  side-major, 16 bins per side; in_dtype 0 fp32, 1 fp16, 2 bf16
+ *                   (under AMP the head emits fp16, engine/trainer.py:379); outputs are fp32
  *   anchor_points : (A, 2)      grid units
  *   out_xyxy      : (b, A, 4)   grid units
  * Optional fused caller glue (utils/loss.py:236, `pred_bboxes * stride_tensor`, the assigner's
  * pd_bboxes): when out_xyxy_px != NULL, stride_tensor (A) must be given and out_xyxy_px (b,A,4)
  * receives out_xyxy * stride (one fp32 multiply, as the reference rounds it). */
-int kzd_decode_train(const float* pred_dist, const float* anchor_points, const float* stride_tensor,
-                     int b, int A, float* out_xyxy, float* out_xyxy_px, void* stream);
+int kzd_decode_train(const void* pred_dist, int in_dtype, const float* anchor_points,
+                     const float* stride_tensor, int b, int A, float* out_xyxy, float* out_xyxy_px,
+                     void* stream);
 
 /* Backward of kzd_decode_train wrt pred_dist (the CIoU/DFL losses back-propagate through the
  * decoded boxes, utils/loss.py:252-254): grad_pred_dist (b,A,64) from grad_xyxy (b,A,4). */

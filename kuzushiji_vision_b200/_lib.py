@@ -37,8 +37,8 @@ def _load():
         "kzd_version": (C.c_int, []),
         "kzd_last_error": (C.c_char_p, []),
         "kzd_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
-        "kzd_decode_infer": (C.c_int, [C.POINTER(vp), C.POINTER(Level), i32, i32, i32, vp, vp]),
-        "kzd_decode_train": (C.c_int, [vp, vp, vp, i32, i32, vp, vp, vp]),
+        "kzd_decode_infer": (C.c_int, [C.POINTER(vp), i32, C.POINTER(Level), i32, i32, i32, vp, vp]),
+        "kzd_decode_train": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp, vp]),
         "kzd_decode_train_bwd": (C.c_int, [vp, vp, i32, i32, vp, vp]),
         "kzd_assign_workspace_bytes": (sz, [i32, i32, i32]),
         "kzd_tal_assign": (C.c_int, [vp] * 6 + [i32] * 5 + [f32] * 3 + [C.POINTER(Level), i32, i32, i32] + [vp] * 6 + [vp, sz, i32, vp]),
@@ -76,6 +76,13 @@ def levels_array(levels):
         arr[i] = Level(int(h), int(w), off, float(s))
         off += int(h) * int(w)
     return arr, off
+
+
+def dtype_code(dtype):
+    """0 fp32, 1 fp16, 2 bf16 (the `in_dtype` / `score_dtype` arguments of include/kzd.h)."""
+    import torch
+
+    return {torch.float16: 1, torch.bfloat16: 2}.get(dtype, 0)
 
 
 def require_cuda(t, name):

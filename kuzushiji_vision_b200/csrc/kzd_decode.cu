@@ -7,6 +7,9 @@
 //                   layout (reference: utils/loss.py:197-204), and its backward.
 //
 // Both are pure streaming kernels bound by HBM bandwidth (272 B per anchor).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include <type_traits>
 
 #include "kzd_common.cuh"
@@ -24,7 +27,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 struct InferParams {
-    const float* ptr[KZD_MAX_LEVELS];
+    const void* ptr[KZD_MAX_LEVELS];
     int hw[KZD_MAX_LEVELS];
     int w[KZD_MAX_LEVELS];
     int off[KZD_MAX_LEVELS + 1];
@@ -32,29 +35,55 @@ struct InferParams {
     int n_levels, b, nc, A;
 };
 
-template <int VEC>
-struct Vec;
+// VEC consecutive elements of a head map -> fp32 registers (128-bit loads for fp32 x4, 64-bit for half x4)
+template <int VEC, typename T>
+struct In;
 template <>
-struct Vec<4> {
-    using T = float4;
+struct In<4, float> {
     static __device__ __forceinline__ void load(float (&v)[4], const float* p) {
-        float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
         v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
     }
+};
+template <>
+struct In<4, __half> {
+    static __device__ __forceinline__ void load(float (&v)[4], const __half* p) {
+        const uint2 t = __ldcs(reinterpret_cast<const uint2*>(p));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+        v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+    }
+};
+template <>
+struct In<4, __nv_bfloat16> {
+    static __device__ __forceinline__ void load(float (&v)[4], const __nv_bfloat16* p) {
+        const uint2 t = __ldcs(reinterpret_cast<const uint2*>(p));
+        v[0] = __uint_as_float(t.x << 16), v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16), v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+};
+template <typename T>
+struct In<1, T> {
+    static __device__ __forceinline__ void load(float (&v)[1], const T* p) { v[0] = (float)*p; }
+};
+
+template <int VEC>
+struct Out;
+template <>
+struct Out<4> {
     static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
         __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
     }
 };
 template <>
-struct Vec<1> {
-    static __device__ __forceinline__ void load(float (&v)[1], const float* p) { v[0] = __ldcs(p); }
+struct Out<1> {
     static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { __stcs(p, v[0]); }
 };
 
 // One thread decodes VEC consecutive anchors of one image: 4 sides x 16 bins are read as 64
 // coalesced VEC-wide loads (anchors are the fastest dimension of the NCHW maps), the softmax
 // expectation is evaluated in registers, and the 4+nc output rows are written VEC-wide.
-template <int VEC>
+template <int VEC, typename T>
 __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, float* __restrict__ y) {
     const int bi = blockIdx.y;
     const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
@@ -66,14 +95,14 @@ __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, 
     const int hw = p.hw[l];
     const int pos = a0 - p.off[l];
     const int no = 4 * KZD_REG_MAX + p.nc;
-    const float* __restrict__ src = p.ptr[l] + (size_t)bi * no * hw + pos;
+    const T* __restrict__ src = reinterpret_cast<const T*>(p.ptr[l]) + (size_t)bi * no * hw + pos;
 
     float d[4][VEC];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         float v[KZD_REG_MAX][VEC];
 #pragma unroll
-        for (int k = 0; k < KZD_REG_MAX; ++k) Vec<VEC>::load(v[k], src + (size_t)(s * KZD_REG_MAX + k) * hw);
+        for (int k = 0; k < KZD_REG_MAX; ++k) In<VEC, T>::load(v[k], src + (size_t)(s * KZD_REG_MAX + k) * hw);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             float m = v[0][i];
@@ -110,19 +139,19 @@ __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, 
         oh[i] = (y2 - y1) * st;
     }
     float* __restrict__ dst = y + (size_t)bi * (4 + p.nc) * p.A + a0;
-    Vec<VEC>::store(dst, ox);
-    Vec<VEC>::store(dst + (size_t)p.A, oy);
-    Vec<VEC>::store(dst + 2 * (size_t)p.A, ow);
-    Vec<VEC>::store(dst + 3 * (size_t)p.A, oh);
-    const float* __restrict__ csrc = src + (size_t)(4 * KZD_REG_MAX) * hw;
+    Out<VEC>::store(dst, ox);
+    Out<VEC>::store(dst + (size_t)p.A, oy);
+    Out<VEC>::store(dst + 2 * (size_t)p.A, ow);
+    Out<VEC>::store(dst + 3 * (size_t)p.A, oh);
+    const T* __restrict__ csrc = src + (size_t)(4 * KZD_REG_MAX) * hw;
     float* __restrict__ cdst = dst + 4 * (size_t)p.A;
 #pragma unroll 4
     for (int c = 0; c < p.nc; ++c) {
         float v[VEC], o[VEC];
-        Vec<VEC>::load(v, csrc + (size_t)c * hw);
+        In<VEC, T>::load(v, csrc + (size_t)c * hw);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o[i] = 1.f / (1.f + __expf(-v[i]));  // |err| < 2e-7: ex2.approx + IEEE div
-        Vec<VEC>::store(cdst + (size_t)c * p.A, o);
+        Out<VEC>::store(cdst + (size_t)c * p.A, o);
     }
 }
 
@@ -136,32 +165,70 @@ constexpr int TR_STAGES = 4;                    // 64 KB of loads in flight per 
 constexpr int TR_THREADS = TR_ANCH * 4;         // one thread per (anchor, side)
 constexpr int TR_SMEM = TR_STAGES * TR_FLOATS * 4;
 
-// Softmax expectation of the 16 bins at smem row `row` (16 floats, 64 B). The four 16-byte chunks
-// are visited in a per-thread rotated order so that every quarter-warp hits 8 distinct bank groups.
-// exp(v - m) = ex2(v*log2e - m*log2e): one FFMA + one MUFU per bin; the bin weights are applied per
-// 4-bin chunk (sum_k (4q+k) e_k = 4q * sum_k e_k + (e_1 + 2 e_2 + 3 e_3)).
-__device__ __forceinline__ void side_stats(const float* row, int tid, float& d, float& m_out, float& sum_out) {
-    float v[4][4];
-    int q[4];
+// The 16 bins of one (anchor, side) from the shared-memory tile, as fp32, plus the bin index of each
+// register. fp32 rows are 64 B (four 16-byte chunks), half rows 32 B (two chunks); the chunks are visited
+// in a per-thread rotated order so that every quarter-warp hits 8 distinct bank groups.
+template <typename T>
+struct Bins;
+template <>
+struct Bins<float> {
+    static __device__ __forceinline__ void load(const void* tile, int tid, float (&v)[16], int (&first)[4]) {
+        const float* row = reinterpret_cast<const float*>(tile) + tid * 16;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        q[j] = (j + (tid >> 1)) & 3;
-        const float4 t = *reinterpret_cast<const float4*>(row + q[j] * 4);
-        v[j][0] = t.x, v[j][1] = t.y, v[j][2] = t.z, v[j][3] = t.w;
+        for (int j = 0; j < 4; ++j) {
+            const int q = (j + (tid >> 1)) & 3;
+            const float4 t = *reinterpret_cast<const float4*>(row + q * 4);
+            v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+            first[j] = q * 4;
+        }
     }
-    float m = v[0][0];
+};
+template <typename H>
+struct BinsHalf {
+    static __device__ __forceinline__ void load(const void* tile, int tid, float (&v)[16], int (&first)[4]) {
+        const uint4* row = reinterpret_cast<const uint4*>(tile) + tid * 2;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 2; ++j) {
+            const int q = (j + (tid >> 2)) & 1;
+            const uint4 t = row[q];
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) m = fmaxf(m, v[j][k]);
+            for (int k = 0; k < 4; ++k) {
+                if (std::is_same<H, __half>::value) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+                    v[8 * j + 2 * k] = f.x, v[8 * j + 2 * k + 1] = f.y;
+                } else {
+                    v[8 * j + 2 * k] = __uint_as_float(w[k] << 16), v[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+                }
+            }
+            first[2 * j] = q * 8, first[2 * j + 1] = q * 8 + 4;
+        }
+    }
+};
+template <>
+struct Bins<__half> : BinsHalf<__half> {};
+template <>
+struct Bins<__nv_bfloat16> : BinsHalf<__nv_bfloat16> {};
+
+// Softmax expectation of the 16 bins of one (anchor, side).
+// exp(v - m) = ex2(v*log2e - m*log2e): one FFMA + one MUFU per bin; the bin weights are applied per
+// 4-bin group (sum_k (f+k) e_k = f * sum_k e_k + (e_1 + 2 e_2 + 3 e_3)).
+template <typename T>
+__device__ __forceinline__ void side_stats(const void* tile, int tid, float& d, float& m_out, float& sum_out) {
+    float v[16];
+    int first[4];
+    Bins<T>::load(tile, tid, v, first);
+    float m = v[0];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) m = fmaxf(m, v[k]);
     const float L2E = 1.4426950408889634f;
     const float ml = -m * L2E;
     float sum = 0.f, wsum = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float base = __uint_as_float(0x4b000000u | (uint32_t)(q[j] * 4)) - 8388608.f;  // exact int->float
-        const float e0 = ex2_approx(fmaf(v[j][0], L2E, ml)), e1 = ex2_approx(fmaf(v[j][1], L2E, ml));
-        const float e2 = ex2_approx(fmaf(v[j][2], L2E, ml)), e3 = ex2_approx(fmaf(v[j][3], L2E, ml));
+        const float base = __uint_as_float(0x4b000000u | (uint32_t)first[j]) - 8388608.f;  // exact int->float
+        const float e0 = ex2_approx(fmaf(v[4 * j], L2E, ml)), e1 = ex2_approx(fmaf(v[4 * j + 1], L2E, ml));
+        const float e2 = ex2_approx(fmaf(v[4 * j + 2], L2E, ml)), e3 = ex2_approx(fmaf(v[4 * j + 3], L2E, ml));
         const float sc = (e0 + e1) + (e2 + e3);
         const float tc = fmaf(3.f, e3, fmaf(2.f, e2, e1));
         sum += sc;
@@ -175,16 +242,16 @@ __device__ __forceinline__ void side_stats(const float* row, int tid, float& d, 
 // Persistent CTAs; thread 0 is the TMA producer (cp.async.bulk of one ANCH*256 B tile per stage, signalled
 // on an mbarrier), all ANCH*4 threads consume: thread t owns (anchor t/4, side t%4) of the tile and
 // writes output element t of the tile's ANCH*4 contiguous floats. IDX = int when b*A < 2^31.
-template <int ANCH, int STAGES, typename IDX>
-__global__ void __launch_bounds__(ANCH * 4) decode_train_kernel(const float* __restrict__ pred,
+template <int ANCH, int STAGES, typename IDX, typename T>
+__global__ void __launch_bounds__(ANCH * 4) decode_train_kernel(const T* __restrict__ pred,
                                                                 const float* __restrict__ anc,
                                                                 const float* __restrict__ stride, int A, IDX N,
                                                                 float* __restrict__ out,
                                                                 float* __restrict__ out_px) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* buf = reinterpret_cast<float*>(smem_raw);
+    T* buf = reinterpret_cast<T*>(smem_raw);
     __shared__ uint64_t full[STAGES];
-    constexpr int FLOATS = ANCH * 64;
+    constexpr int FLOATS = ANCH * 64;  // elements per tile
     const int tid = threadIdx.x;
     const IDX n_tiles = (N + ANCH - 1) / ANCH;
 
@@ -197,7 +264,7 @@ __global__ void __launch_bounds__(ANCH * 4) decode_train_kernel(const float* __r
     auto issue = [&](IDX tile, int stage) {
         const IDX first = tile * ANCH;
         const IDX cnt = (N - first < ANCH) ? (N - first) : (IDX)ANCH;
-        const uint32_t bytes = (uint32_t)cnt * 256u;
+        const uint32_t bytes = (uint32_t)cnt * (uint32_t)(64 * sizeof(T));
         mbar_expect_tx(&full[stage], bytes);
         tma_load_1d(buf + stage * FLOATS, pred + (size_t)first * 64, bytes, &full[stage]);
     };
@@ -222,7 +289,7 @@ __global__ void __launch_bounds__(ANCH * 4) decode_train_kernel(const float* __r
         mbar_wait(&full[stage], parity);
         if (n < N) {
             float d, m, s;
-            side_stats(buf + stage * FLOATS + tid * 16, tid, d, m, s);
+            side_stats<T>(buf + stage * FLOATS, tid, d, m, s);
             const float v = (side < 2) ? (ap - d) : (ap + d);
             out[(size_t)n * 4 + side] = v;
             if (out_px) out_px[(size_t)n * 4 + side] = __fmul_rn(v, st);  // utils/loss.py:236
@@ -273,7 +340,7 @@ __global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const floa
         if (n < N) {
             const float* row = buf + stage * TR_FLOATS + tid * 16;
             float d, m, s;
-            side_stats(row, tid, d, m, s);
+            side_stats<float>(buf + stage * TR_FLOATS, tid, d, m, s);
             float g = gout[n * 4 + side];
             g = (side < 2) ? -g : g;
             const float inv = g / s;
@@ -302,15 +369,28 @@ __global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const floa
 
 using namespace kzd;
 
-extern "C" __attribute__((visibility("default"))) int kzd_decode_infer(const float* const* h_level_ptrs, const kzd_level* h_levels, int n_levels, int b,
-                                int nc, float* y, void* stream) {
+template <typename T>
+static void launch_infer(const InferParams& p, int total, int b, bool vec4, float* y, cudaStream_t st) {
+    if (vec4) {
+        dim3 grid((total / 4 + 127) / 128, b);
+        decode_infer_kernel<4, T><<<grid, 128, 0, st>>>(p, y);
+    } else {
+        dim3 grid((total + 127) / 128, b);
+        decode_infer_kernel<1, T><<<grid, 128, 0, st>>>(p, y);
+    }
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_decode_infer(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels,
+                                int n_levels, int b, int nc, float* y, void* stream) {
     KZD_CHECK_ARG(h_level_ptrs && h_levels && y, "kzd_decode_infer: null pointer");
     KZD_CHECK_ARG(n_levels >= 1 && n_levels <= KZD_MAX_LEVELS, "kzd_decode_infer: n_levels=%d not in [1,%d]", n_levels,
                   KZD_MAX_LEVELS);
     KZD_CHECK_ARG(b >= 0 && nc >= 0, "kzd_decode_infer: negative size");
+    KZD_CHECK_ARG(in_dtype >= 0 && in_dtype <= 2, "kzd_decode_infer: in_dtype=%d not in {0 fp32, 1 fp16, 2 bf16}", in_dtype);
     InferParams p;
     int off = 0;
     bool vec4 = true;
+    const uintptr_t in_align = in_dtype == 0 ? 16 : 8;  // 4 elements per load
     for (int l = 0; l < n_levels; ++l) {
         KZD_CHECK_ARG(h_levels[l].h > 0 && h_levels[l].w > 0, "kzd_decode_infer: empty level %d", l);
         KZD_CHECK_ARG(h_levels[l].offset == off, "kzd_decode_infer: level %d offset %d, expected %d", l,
@@ -321,7 +401,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_decode_infer(const flo
         p.off[l] = off;
         p.stride[l] = h_levels[l].stride;
         off += p.hw[l];
-        vec4 = vec4 && (p.hw[l] % 4 == 0) && (((uintptr_t)p.ptr[l]) % 16 == 0);
+        vec4 = vec4 && (p.hw[l] % 4 == 0) && (((uintptr_t)p.ptr[l]) % in_align == 0);
     }
     for (int l = n_levels; l <= KZD_MAX_LEVELS; ++l) p.off[l] = off;
     for (int l = n_levels; l < KZD_MAX_LEVELS; ++l) p.ptr[l] = nullptr, p.hw[l] = 1, p.w[l] = 1, p.stride[l] = 0.f;
@@ -330,13 +410,9 @@ extern "C" __attribute__((visibility("default"))) int kzd_decode_infer(const flo
     if (b == 0) return 0;
     KZD_CHECK_ARG(b <= 65535, "kzd_decode_infer: b=%d > 65535", b);
     cudaStream_t st = (cudaStream_t)stream;
-    if (vec4) {
-        dim3 grid((off / 4 + 127) / 128, b);
-        decode_infer_kernel<4><<<grid, 128, 0, st>>>(p, y);
-    } else {
-        dim3 grid((off + 127) / 128, b);
-        decode_infer_kernel<1><<<grid, 128, 0, st>>>(p, y);
-    }
+    if (in_dtype == 1) launch_infer<__half>(p, off, b, vec4, y, st);
+    else if (in_dtype == 2) launch_infer<__nv_bfloat16>(p, off, b, vec4, y, st);
+    else launch_infer<float>(p, off, b, vec4, y, st);
     KZD_LAUNCH_CHECK("decode_infer_kernel");
     return 0;
 }
@@ -349,33 +425,46 @@ static int train_grid(long long n_tiles, const void* fn, int threads, int smem) 
     return (int)(n_tiles < g ? n_tiles : g);
 }
 
-template <int ANCH, int STAGES, typename IDX>
-static int launch_train(const float* pred_dist, const float* anchor_points, const float* stride_tensor, int A,
+template <int ANCH, int STAGES, typename IDX, typename T>
+static int launch_train(const void* pred_dist, const float* anchor_points, const float* stride_tensor, int A,
                         long long N, float* out_xyxy, float* out_xyxy_px, cudaStream_t st) {
-    constexpr int SMEM = STAGES * ANCH * 256;
-    auto fn = decode_train_kernel<ANCH, STAGES, IDX>;
+    constexpr int SMEM = STAGES * ANCH * 64 * (int)sizeof(T);
+    auto fn = decode_train_kernel<ANCH, STAGES, IDX, T>;
     KZD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const long long n_tiles = (N + ANCH - 1) / ANCH;
     const int grid = train_grid(n_tiles, (const void*)fn, ANCH * 4, SMEM);
-    fn<<<grid, ANCH * 4, SMEM, st>>>(pred_dist, anchor_points, stride_tensor, A, (IDX)N, out_xyxy, out_xyxy_px);
+    fn<<<grid, ANCH * 4, SMEM, st>>>(reinterpret_cast<const T*>(pred_dist), anchor_points, stride_tensor, A, (IDX)N,
+                                     out_xyxy, out_xyxy_px);
     KZD_LAUNCH_CHECK("decode_train_kernel");
     return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int kzd_decode_train(const float* pred_dist, const float* anchor_points, const float* stride_tensor,
-                                int b, int A, float* out_xyxy, float* out_xyxy_px, void* stream) {
+template <typename T>
+static int launch_train_idx(const void* pred_dist, const float* anchor_points, const float* stride_tensor, int A,
+                            long long N, float* out_xyxy, float* out_xyxy_px, cudaStream_t st) {
+    // 64-anchor tiles, 3 stages (4 CTAs/SM for fp32): tile/stage variants (32..128 anchors, 2..6 stages) were
+    // swept on B200 and are all within 1 % of each other - the kernel is HBM-bound.
+    if (N + 4096 >= 0x7fffffffLL)
+        return launch_train<64, 3, long long, T>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+    return launch_train<64, 3, int, T>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_decode_train(const void* pred_dist, int in_dtype, const float* anchor_points,
+                                const float* stride_tensor, int b, int A, float* out_xyxy, float* out_xyxy_px,
+                                void* stream) {
     KZD_CHECK_ARG(pred_dist && anchor_points && out_xyxy, "kzd_decode_train: null pointer");
     KZD_CHECK_ARG(b >= 0 && A >= 0, "kzd_decode_train: negative size");
+    KZD_CHECK_ARG(in_dtype >= 0 && in_dtype <= 2, "kzd_decode_train: in_dtype=%d not in {0 fp32, 1 fp16, 2 bf16}", in_dtype);
     KZD_CHECK_ARG(((uintptr_t)pred_dist) % 16 == 0, "kzd_decode_train: pred_dist must be 16-byte aligned");
     KZD_CHECK_ARG(!out_xyxy_px || stride_tensor, "kzd_decode_train: out_xyxy_px needs stride_tensor");
     const long long N = (long long)b * A;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (N + 4096 >= 0x7fffffffLL)
-        return launch_train<64, 3, long long>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
-    // 64-anchor tiles, 3 stages (48 KB, 4 CTAs/SM): tile/stage variants (32..128 anchors, 2..6 stages)
-    // were swept on B200 and are all within 1 % of each other - the kernel is HBM-bound.
-    return launch_train<64, 3, int>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+    if (in_dtype == 1)
+        return launch_train_idx<__half>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+    if (in_dtype == 2)
+        return launch_train_idx<__nv_bfloat16>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
+    return launch_train_idx<float>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
 }
 
 extern "C" __attribute__((visibility("default"))) int kzd_decode_train_bwd(const float* pred_dist, const float* grad_xyxy, int b, int A,

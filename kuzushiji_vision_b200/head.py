@@ -30,16 +30,19 @@ def decode_inference(levels_x, strides, nc):
     _lib.require_cuda(x0, "Detect input")
     b = x0.shape[0]
     no = 4 * REG_MAX + nc
+    # fp16 / bf16 maps (half inference, AMP) are read natively; anything else is taken as fp32
+    code = _lib.dtype_code(x0.dtype)
+    in_dtype = x0.dtype if code else torch.float32
     xs = []
     for xi in levels_x:
         if xi.shape[1] != no:
             raise _lib.KzdError(f"level has {xi.shape[1]} channels, expected 64+nc={no}")
-        xs.append(xi.to(torch.float32).contiguous())
+        xs.append(xi.to(in_dtype).contiguous())
     lv, A = _lib.levels_array([(xi.shape[2], xi.shape[3], float(s)) for xi, s in zip(xs, strides)])
     ptrs = (C.c_void_p * len(xs))(*[xi.data_ptr() for xi in xs])
     y = torch.empty((b, 4 + nc, A), dtype=torch.float32, device=x0.device)
     with torch.cuda.device(x0.device):
-        rc = _lib.lib.kzd_decode_infer(ptrs, lv, len(xs), b, nc, y.data_ptr(), _stream(x0.device))
+        rc = _lib.lib.kzd_decode_infer(ptrs, code, lv, len(xs), b, nc, y.data_ptr(), _stream(x0.device))
     _lib.check(rc, "kzd_decode_infer")
     return y
 
@@ -69,7 +72,8 @@ class _BboxDecodeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred_dist, anchor_points, stride_tensor):
         b, A, c = pred_dist.shape
-        pd = pred_dist.to(torch.float32).contiguous()
+        code = _lib.dtype_code(pred_dist.dtype)  # fp16 / bf16 (AMP) are read natively
+        pd = pred_dist.contiguous() if code else pred_dist.to(torch.float32).contiguous()
         anc = anchor_points.to(torch.float32).contiguous()
         out = torch.empty((b, A, 4), dtype=torch.float32, device=pd.device)
         st = px = None
@@ -77,7 +81,7 @@ class _BboxDecodeFn(torch.autograd.Function):
             st = stride_tensor.to(torch.float32).contiguous()
             px = torch.empty_like(out)
         with torch.cuda.device(pd.device):
-            rc = _lib.lib.kzd_decode_train(pd.data_ptr(), anc.data_ptr(), st.data_ptr() if st is not None else None,
+            rc = _lib.lib.kzd_decode_train(pd.data_ptr(), code, anc.data_ptr(), st.data_ptr() if st is not None else None,
                                            b, A, out.data_ptr(), px.data_ptr() if px is not None else None,
                                            _stream(pd.device))
         _lib.check(rc, "kzd_decode_train")
@@ -91,6 +95,7 @@ class _BboxDecodeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, *unused):
         (pd,) = ctx.saved_tensors
+        pd = pd.to(torch.float32)
         b, A, _ = pd.shape
         g = grad_out.to(torch.float32).contiguous()
         gin = torch.empty_like(pd)

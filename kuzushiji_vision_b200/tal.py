@@ -109,7 +109,7 @@ class TaskAlignedAssigner(nn.Module):
         f32 = torch.float32
         # AMP: the reference keeps bbox_scores in pd_scores' dtype (utils/tal.py:137); libkzd reads fp32
         # values and reproduces that one rounding
-        score_dtype = {torch.float16: 1, torch.bfloat16: 2}.get(pd_scores.dtype, 0)
+        score_dtype = _lib.dtype_code(pd_scores.dtype)
         pd_scores_c = pd_scores.to(f32).contiguous()
         pd_bboxes_c = pd_bboxes.to(f32).contiguous()
         anc_c = anc_points.to(f32).contiguous()

@@ -587,3 +587,33 @@ def test_scale_boxes_matches_oracle():
         assert torch.equal(out[i, :n_keep[i], :4], ref[i])
         assert torch.equal(single[i][:, :4], ref[i])
         assert torch.equal(out[i, :n_keep[i], 4:], rows[i, :n_keep[i], 4:])
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_decodes_read_half_precision_inputs_natively(dt):
+    """fp16 / bf16 head outputs (AMP training, half inference): the kernels read them directly and compute in
+    fp32 - identical to decoding the same values up-cast to fp32 (and therefore closer to exact than the
+    reference's half-precision softmax / matmul, which rounds to ~1e-3)."""
+    b, nc, imgsz = 2, 3, 320
+    lv = [l.to(dt) for l in synth.head_outputs(b, nc, imgsz, synth.P2_P5, seed=41, device=DEV)]
+    y = kzd.decode_inference(lv, synth.P2_P5, nc)
+    y32 = kzd.decode_inference([l.float() for l in lv], synth.P2_P5, nc)
+    assert y.dtype == torch.float32 and torch.equal(y, y32)
+    ref = O.decode_infer([l.float() for l in lv], synth.P2_P5, nc)
+    _, st = O.make_anchors([l.shape[2:] for l in lv], synth.P2_P5, device=DEV)
+    assert _box_rel_err(y, ref, st) < RTOL
+    d = synth.assigner_inputs(b, 4, imgsz, nc, synth.P2_P5, seed=42, device=DEV)
+    pdh = d["pred_distri"].to(dt)
+    out, px = kzd.bbox_decode(d["anchor_points"], pdh, d["stride_tensor"])
+    out32 = kzd.bbox_decode(d["anchor_points"], pdh.float())  # same values, bins summed in another order
+    assert ((out - out32).abs() / out32.abs().clamp(min=1.0)).max() < 1e-6
+    assert torch.equal(px, out * d["stride_tensor"])
+    ref_t = O.decode_train(pdh.float(), d["anchor_points"])
+    assert ((out - ref_t).abs() / ref_t.abs().clamp(min=1.0)).max() < RTOL
+    # odd level sizes -> scalar path
+    lv2 = [l.to(dt) for l in synth.head_outputs(1, 1, 200, synth.P3_P5, seed=43, device=DEV)]
+    assert torch.equal(kzd.decode_inference(lv2, synth.P3_P5, 1), kzd.decode_inference([l.float() for l in lv2], synth.P3_P5, 1))
+    # gradients flow back in the input dtype
+    x = pdh.clone().requires_grad_(True)
+    kzd.bbox_decode(d["anchor_points"], x).sum().backward()
+    assert x.grad.dtype == dt and torch.isfinite(x.grad.float()).all()

@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol():
 
 def test_argument_validation_without_gpu():
     # bad arguments are rejected before any CUDA call is made
-    rc = _lib.lib.kzd_decode_train(None, None, None, 1, 1, None, None, None)
+    rc = _lib.lib.kzd_decode_train(None, 0, None, None, 1, 1, None, None, None)
     assert rc == -1 and b"null" in _lib.lib.kzd_last_error()
     lv, _ = _lib.levels_array([(4, 4, 8.0)])
     rc = _lib.lib.kzd_tal_assign(1, 1, 1, 1, 1, 1, 1, 16, 1, 1, 99, 0.5, 6.0, 1e-9, lv, 1, 0, 0, 1, 1, 1, 1, 1, None,
