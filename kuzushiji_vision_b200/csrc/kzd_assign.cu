@@ -5,11 +5,13 @@
 // select_highest_overlaps :264-295) and CIoU utils/metrics.py:96-130.
 //
 // Kernels (one stream, no host sync):
+//   assign_begin_kernel       per-call flags and the device-side epoch of the persistent state
 //   assign_verify_kernel      checks anc_points against the level table (grid accelerator is only
 //                             used when every anchor matches bit-for-bit)
-//   assign_candidates_kernel  one warp per (image, GT): enumerate the anchors inside the GT, CIoU +
-//                             alignment metric, per-anchor argmax-overlap via 64-bit atomicMax,
-//                             warp-shuffle streaming top-k, selection counts
+//   assign_candidates_kernel  one warp per (image, GT): enumerate the anchors inside the GT (separable
+//                             x / y tests), queue them, CIoU + alignment metric 32 pairs at a time,
+//                             per-anchor argmax-overlap via 64-bit atomicMax, warp-shuffle top-k,
+//                             selecting GTs recorded with two atomicMax words
 //   assign_resolve_kernel     one thread per anchor: resolve the owner GT, write labels / boxes /
 //                             fg / gt_idx for every anchor, append foreground anchors to a compact list
 //   assign_fg_metric_kernel   foreground list: recompute the owner pair's metric, per-GT maxima

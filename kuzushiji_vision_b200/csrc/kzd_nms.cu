@@ -10,9 +10,12 @@
 //   nms_chunk_sort / nms_rank   512-key chunk sorts + rank by binary search = torchvision's stable
 //                      descending score sort; writes score-ordered, class-offset boxes
 //   nms_mask_kernel    persistent CTAs over 64x64 tiles of the upper triangle: bit (i,j) = IoU > thr
-//   nms_scan_kernel    per image: greedy scan in 64-row chunks; the diagonal chunk is resolved by
-//                      one warp with ballot/shuffle, the rest of the row OR-reduced by all warps;
-//                      the first max_det kept rows are gathered in score order
+//                      (4-compare superset test for all pairs, exact IoU only for intersecting ones)
+//   nms_scan_kernel    per image: greedy walk in 64-row chunks; the diagonal chunk is resolved by
+//                      one warp with ballot/shuffle, the rest of the row OR-reduced by helper warps,
+//                      loads two chunks ahead; the first max_det kept rows are gathered in score order
+//   mask + scan run in phases of growing column ranges: the walk stops once max_det boxes are kept,
+//   so finished images skip the later phases on the device (kzd_nms_suppress)
 #include "kzd_common.cuh"
 
 namespace kzd {
