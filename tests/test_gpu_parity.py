@@ -617,3 +617,56 @@ def test_decodes_read_half_precision_inputs_natively(dt):
     x = pdh.clone().requires_grad_(True)
     kzd.bbox_decode(d["anchor_points"], x).sum().backward()
     assert x.grad.dtype == dt and torch.isfinite(x.grad.float()).all()
+
+
+def test_install_routes_reference_call_sites_to_libkzd():
+    """install() against a package with the reference's module layout and call flow (tests/fake_ref: the real
+    reference is absent on the GPU box): v8DetectionLoss.__call__ and Detect.forward -> NMS give the same
+    answers before and after patching, and after patching the calls really reach libkzd."""
+    import importlib
+    import os
+    import sys
+
+    fake = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fake_ref")
+    for m in [k for k in sys.modules if k == "ultralytics" or k.startswith("ultralytics.")]:
+        del sys.modules[m]
+    sys.path.insert(0, fake)
+    try:
+        u_loss = importlib.import_module("ultralytics.utils.loss")
+        u_ops = importlib.import_module("ultralytics.utils.ops")
+        u_head = importlib.import_module("ultralytics.nn.modules.head")
+        b, nc, imgsz, strides = 2, 2, 320, synth.P2_P5
+        feats = synth.head_outputs(b, nc, imgsz, strides, seed=51, device=DEV, sparse_cls=300)
+        t = _collated_targets(b, [30, 12], seed=6)
+        t[:, 4:] = t[:, 4:] * 2 + 0.05
+        batch = {"batch_idx": t[:, 0].to(DEV), "cls": (t[:, 1:2] % nc).to(DEV), "bboxes": t[:, 2:].to(DEV)}
+
+        def flow():
+            crit = u_loss.v8DetectionLoss(list(strides), nc, DEV)  # built after patching, like nn/tasks.py:288
+            total, items, (tb, ts, fg) = crit([f.clone() for f in feats], batch)
+            det = u_head.Detect(nc, strides).to(DEV).eval()
+            y, _ = det([f.clone() for f in feats])
+            y_pre = y.clone()  # NMS rewrites the box rows of its input in place (utils/ops.py:243-244)
+            out = u_ops.non_max_suppression(y, 0.25, 0.7, max_det=300)
+            return crit, total, items, tb, ts, fg, y_pre, out
+
+        ref = flow()
+        assert not isinstance(ref[0].assigner, kzd.TaskAlignedAssigner)
+        names = kzd.install()
+        try:
+            assert len(names) == 6
+            got = flow()
+            assert isinstance(got[0].assigner, kzd.TaskAlignedAssigner) and got[0].assigner.counters is not None
+        finally:
+            kzd.uninstall()
+        assert torch.equal(got[5], ref[5]) and torch.equal(got[3], ref[3])       # fg_mask, target_bboxes
+        torch.testing.assert_close(got[4], ref[4], rtol=RTOL, atol=1e-9)         # target_scores
+        torch.testing.assert_close(got[2], ref[2], rtol=2e-5, atol=1e-6)         # loss items
+        _, st = O.make_anchors([f.shape[2:] for f in feats], strides, device=DEV)
+        assert _box_rel_err(got[6], ref[6], st) < RTOL
+        # NMS rows: each path ran on its own decode output; compare like with like on the patched y
+        _check_nms(got[7], O.non_max_suppression(got[6].clone(), 0.25, 0.7, max_det=300))
+    finally:
+        sys.path.remove(fake)
+        for m in [k for k in sys.modules if k == "ultralytics" or k.startswith("ultralytics.")]:
+            del sys.modules[m]
