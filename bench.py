@@ -3,14 +3,18 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl kzd|reference]
 
-One "step" = one pass of the hot path over one batch of synthetic kuzushiji pages per GPU:
-    bbox_decode (utils/loss.py:197)  ->  x stride (caller glue, torch)  ->  TaskAlignedAssigner.forward
-    Detect._inference decode (nn/modules/head.py:100)  ->  ops.non_max_suppression
+One "step" = one pass of the hot path over one batch of synthetic kuzushiji pages per GPU, from the
+per-level head maps a model forward emits to assignment targets and final detections:
+    training-side decode  bbox_decode (utils/loss.py:197) x stride  ->  TaskAlignedAssigner.forward
+    inference decode      Detect._inference (nn/modules/head.py:100)  ->  ops.non_max_suppression
+Both decodes consume the same head outputs (the validation-during-training flow,
+engine/validator.py:180-185), so by default ONE kernel reads the maps once and emits both (PagePipeline
+fuse_decodes); KZD_BENCH_FUSE=0 times the two separate decode kernels of the drop-in signatures.
 Workload (BASELINE.json configs[1]): YOLOv12x P2-P5 head, 1280x1280 pages, batch 16 per GPU,
 ~600 GT boxes/page, single class; NMS at the reference's kuzushiji test-script settings (conf 0.25, iou 0.7,
-max_det 1000: scripts/test_character_detection.py:237-243) on
-inference-like class logits (~3000 candidates/page). Images are sharded over ranks
-(weak scaling: 16 pages per GPU); the only collective is an all-reduce of 4 counters.
+max_det 1000: scripts/test_character_detection.py:237-243) on inference-like class logits (~3000
+candidates/page). Images are sharded over ranks (weak scaling: 16 pages per GPU); the only
+collective is an all-reduce of 4 counters.
 
 Prints ONE JSON line (rank 0). `value` = pages/s with inputs resident in HBM (CUDA events, max over
 ranks); `e2e` = the same step fed from pinned HOST buffers with the H2D copy and the D2H of the results
@@ -109,6 +113,8 @@ def algorithmic_bytes(b, A, G, nc, n_cand, n_keep):
         "decode_train": (272 + 16) * A * b,
         "assign": int((57 + 8 / b) * A + 24 * G) * b if nc == 1 else None,
         "decode_infer": (272 + 8 * nc) * A * b,
+        # fused: one read of the maps 4(64+nc)A, writes y 4(4+nc)A + grid-unit boxes 16A + pixel boxes 16A
+        "decode_dual": (4 * (64 + nc) + 4 * (4 + nc) + 32) * A * b,
         "nms": int((32 + 4 * nc) * A * b + 24 * (n_cand + n_keep)),
     }
 
@@ -233,9 +239,13 @@ def run_kzd(args, rank, local_rank, world):
     host_lv = [l.pin_memory() for l in lv_cpu]
     host_gt = [t.pin_memory() for t in (gl, gb, mg)]
     A = synth.num_anchors(w["imgsz"], w["strides"])
-    pipe = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G, device=dev,
-                            topk=w["topk"], alpha=w["alpha"], beta=w["beta"], conf_thres=w["conf"],
-                            iou_thres=w["iou"], max_det=w["max_det"])
+    # one kernel decodes the head maps once for both halves (validation-during-training flow); set
+    # KZD_BENCH_FUSE=0 to time the two separate decode kernels of the drop-in signatures instead
+    fuse = os.environ.get("KZD_BENCH_FUSE", "1") != "0"
+    pipe_kw = dict(device=dev, topk=w["topk"], alpha=w["alpha"], beta=w["beta"], conf_thres=w["conf"],
+                   iou_thres=w["iou"], max_det=w["max_det"])
+    pipe = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G, fuse_decodes=fuse,
+                            **pipe_kw)
     dv_lv = [l.to(dev) for l in host_lv]
     pred_distri, pd_scores = train_layout(dv_lv, nc)
     pipe.load(levels=dv_lv, pred_distri=pred_distri, pd_scores=pd_scores, gt_labels=host_gt[0], gt_bboxes=host_gt[1],
@@ -250,9 +260,8 @@ def run_kzd(args, rank, local_rank, world):
     depth = max(1, int(os.environ.get("KZD_BENCH_DEPTH", "2")))
     pipes = [pipe]
     for _ in range(depth - 1):
-        pn = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G, device=dev,
-                              topk=w["topk"], alpha=w["alpha"], beta=w["beta"], conf_thres=w["conf"],
-                              iou_thres=w["iou"], max_det=w["max_det"])
+        pn = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G,
+                              fuse_decodes=fuse, **pipe_kw)
         pn.load(levels=pipe.levels, pred_distri=pipe.pred_distri, pd_scores=pipe.pd_scores, gt_labels=pipe.gt_labels,
                 gt_bboxes=pipe.gt_bboxes, mask_gt=pipe.mask_gt)
         pipes.append(pn)
@@ -310,7 +319,7 @@ def run_kzd(args, rank, local_rank, world):
     from kuzushiji_vision_b200 import _lib
 
     asg = pipe.assigner
-    st_names = ["decode_train", "assign", "decode_infer", "nms"]
+    st_names = ["decode_dual", "assign", "nms"] if fuse else ["decode_train", "assign", "decode_infer", "nms"]
     y_static = kzd.decode_inference(pipe.levels, w["strides"], nc)
     px_static = pipe.out["pd_bboxes"]
 
@@ -325,6 +334,7 @@ def run_kzd(args, rank, local_rank, world):
                                              pipe.nms_ws.data_ptr(), pipe.ws_bytes, st), "kzd_nms_suppress")
 
     stage_fns = {
+        "decode_dual": lambda: kzd.decode_inference(pipe.levels, w["strides"], nc, with_train_boxes=True),
         "decode_train": lambda: kzd.bbox_decode(pipe.anchor_points, pipe.pred_distri, pipe.stride_tensor),
         "assign": lambda: asg(pipe.pd_scores, px_static, pipe.anc_points, pipe.gt_labels, pipe.gt_bboxes,
                               pipe.mask_gt),
@@ -362,9 +372,8 @@ def run_kzd(args, rank, local_rank, world):
     # buffers, the reference's caller glue (train layout + sigmoid, torch), one graph replay, and the
     # detections + counters copied back to the host. Two pipelines / streams: batch i+1's H2D overlaps
     # batch i's kernels; every step's results are read on the host before its buffers are reused. ----
-    pipe_b = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G, device=dev,
-                              topk=w["topk"], alpha=w["alpha"], beta=w["beta"], conf_thres=w["conf"],
-                              iou_thres=w["iou"], max_det=w["max_det"])
+    pipe_b = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G,
+                              fuse_decodes=fuse, **pipe_kw)
     e_pipes = [pipe, pipe_b]
     det_host = [torch.empty((b, w["max_det"], 6)).pin_memory() for _ in range(2)]
     cnt_host = [torch.empty(2, dtype=torch.float64).pin_memory() for _ in range(2)]
@@ -377,7 +386,8 @@ def run_kzd(args, rank, local_rank, world):
             for lvl in pp.levels:  # utils/loss.py:210-215,235: split / permute / sigmoid (caller glue, torch)
                 hw = lvl.shape[2] * lvl.shape[3]
                 v = lvl.view(b, 64 + nc, hw)
-                pp.pred_distri[:, off:off + hw].copy_(v[:, :64].permute(0, 2, 1))
+                if not fuse:  # the fused decode reads the NCHW maps directly
+                    pp.pred_distri[:, off:off + hw].copy_(v[:, :64].permute(0, 2, 1))
                 pp.pd_scores[:, off:off + hw].copy_(v[:, 64:].permute(0, 2, 1).sigmoid())
                 off += hw
             out_ = pp.step(st_)
@@ -424,15 +434,16 @@ def run_kzd(args, rank, local_rank, world):
     # ---- roofline of the dominant kernel ----
     n_cand = int(sum(pipe.candidate_counts()))
     ab = algorithmic_bytes(b, A, G, nc, n_cand, int(sum(n_keep)))
-    single_kernel = {"decode_train": "decode_train_kernel", "decode_infer": "decode_infer_kernel<4>"}
+    single_kernel = ({"decode_dual": "decode_infer_kernel<4, float, true>"} if fuse else
+                     {"decode_train": "decode_train_kernel", "decode_infer": "decode_infer_kernel<4, float, false>"})
     dom = max(single_kernel, key=lambda n: st_ms[n])
     peak, peak_src = hbm_peak()
     achieved = ab[dom] / (st_ms[dom] * 1e-3) / 1e9
-    total_ab = sum(v for v in ab.values() if v)
+    total_ab = sum(ab[n] for n in st_names if ab.get(n))
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        traffic = next(v["traffic_bytes"] for k, v in tj.items() if k.startswith(single_kernel[dom].split("<")[0]))
+        traffic = next(v["traffic_bytes"] for k, v in tj.items() if k.replace(" ", "") == single_kernel[dom].replace(" ", ""))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": single_kernel[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -467,7 +478,9 @@ def run_kzd(args, rank, local_rank, world):
         "config": {"workload": "BASELINE configs[1]: YOLOv12x P2-P5 head outputs, 1280x1280 pages, batch 16 per GPU, "
                                "~600 GT/page, nc=1; NMS conf .25 iou .7 max_det 1000 on ~3000 candidates/page",
                    "pages_per_gpu": b, "anchors_per_page": A, "gt_slots": G, "nc": nc,
-                   "l2_policy": "inputs larger than L2 (1.16 GB read per step vs 126 MB L2)",
+                   "l2_policy": "inputs larger than L2 (0.6-1.2 GB read per step vs 126 MB L2)",
+                   "decodes": ("fused: one kernel reads the head maps once and emits y + the training-side boxes"
+                               if fuse else "separate decode_train (b,A,64) and decode_infer (NCHW maps) kernels"),
                    "step": "PagePipeline: one CUDA-graph replay of decode_train+assign+decode_infer+NMS per step; "
                            f"{depth} pipelines alternate on {depth} streams (multi-buffering)",
                    "ms_per_step_single_stream": ms_single,

@@ -61,6 +61,15 @@ int kzd_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int kzd_decode_infer(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels,
                      int n_levels, int b, int nc, float* y, void* stream);
 
+/* Both decodes of the same head maps in one pass: y as kzd_decode_infer, plus the training-side boxes
+ * out_xyxy (b,A,4) in grid units (v8DetectionLoss.bbox_decode, utils/loss.py:197-204) and, when
+ * out_xyxy_px != NULL, their pixel-space copy (utils/loss.py:236). For validation during training
+ * (engine/validator.py:180-185: eval-mode Detect, then model.loss on the same maps): the maps are read
+ * once instead of twice and the (b,A,64) transposed copy is not needed for the decode. */
+int kzd_decode_dual(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels,
+                    int n_levels, int b, int nc, float* y, float* out_xyxy, float* out_xyxy_px,
+                    void* stream);
+
 /* v8DetectionLoss.bbox_decode (utils/loss.py:197-204) + dist2bbox(xywh=False).
  *   pred_dist     : (b, A, 64)  side-major, 16 bins per side; in_dtype 0 fp32, 1 fp16, 2 bf16
  *                   (under AMP the head emits fp16, engine/trainer.py:379); outputs are fp32

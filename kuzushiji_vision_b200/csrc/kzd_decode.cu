@@ -83,8 +83,14 @@ struct Out<1> {
 // One thread decodes VEC consecutive anchors of one image: 4 sides x 16 bins are read as 64
 // coalesced VEC-wide loads (anchors are the fastest dimension of the NCHW maps), the softmax
 // expectation is evaluated in registers, and the 4+nc output rows are written VEC-wide.
-template <int VEC, typename T>
-__global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, float* __restrict__ y) {
+// DUAL: additionally emit the training-side decode of the same maps - xyxy in grid units (b,A,4) and
+// its pixel-space copy (utils/loss.py:197-204,236) - so that validation-during-training
+// (engine/validator.py:180-185: eval-mode Detect, then model.loss on the same maps) reads the head
+// outputs once instead of twice.
+template <int VEC, typename T, bool DUAL>
+__global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, float* __restrict__ y,
+                                                           float* __restrict__ out_xyxy,
+                                                           float* __restrict__ out_px) {
     const int bi = blockIdx.y;
     const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (a0 >= p.A) return;
@@ -137,6 +143,13 @@ __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, 
         oy[i] = ((y1 + y2) * 0.5f) * st;
         ow[i] = (x2 - x1) * st;
         oh[i] = (y2 - y1) * st;
+        if (DUAL) {
+            const size_t o = ((size_t)bi * p.A + a0 + i) * 4;
+            __stcs(reinterpret_cast<float4*>(out_xyxy + o), make_float4(x1, y1, x2, y2));
+            if (out_px)
+                __stcs(reinterpret_cast<float4*>(out_px + o),
+                       make_float4(__fmul_rn(x1, st), __fmul_rn(y1, st), __fmul_rn(x2, st), __fmul_rn(y2, st)));
+        }
     }
     float* __restrict__ dst = y + (size_t)bi * (4 + p.nc) * p.A + a0;
     Out<VEC>::store(dst, ox);
@@ -370,31 +383,55 @@ __global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const floa
 using namespace kzd;
 
 template <typename T>
-static void launch_infer(const InferParams& p, int total, int b, bool vec4, float* y, cudaStream_t st) {
+static void launch_infer(const InferParams& p, int total, int b, bool vec4, float* y, float* out_xyxy, float* out_px,
+                         cudaStream_t st) {
     if (vec4) {
         dim3 grid((total / 4 + 127) / 128, b);
-        decode_infer_kernel<4, T><<<grid, 128, 0, st>>>(p, y);
+        if (out_xyxy) decode_infer_kernel<4, T, true><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px);
+        else decode_infer_kernel<4, T, false><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr);
     } else {
         dim3 grid((total + 127) / 128, b);
-        decode_infer_kernel<1, T><<<grid, 128, 0, st>>>(p, y);
+        if (out_xyxy) decode_infer_kernel<1, T, true><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px);
+        else decode_infer_kernel<1, T, false><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr);
     }
 }
 
+static int decode_maps(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels, int n_levels, int b,
+                       int nc, float* y, float* out_xyxy, float* out_px, void* stream, const char* who);
+
 extern "C" __attribute__((visibility("default"))) int kzd_decode_infer(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels,
                                 int n_levels, int b, int nc, float* y, void* stream) {
-    KZD_CHECK_ARG(h_level_ptrs && h_levels && y, "kzd_decode_infer: null pointer");
-    KZD_CHECK_ARG(n_levels >= 1 && n_levels <= KZD_MAX_LEVELS, "kzd_decode_infer: n_levels=%d not in [1,%d]", n_levels,
+    return decode_maps(h_level_ptrs, in_dtype, h_levels, n_levels, b, nc, y, nullptr, nullptr, stream,
+                       "kzd_decode_infer");
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_decode_dual(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels,
+                               int n_levels, int b, int nc, float* y, float* out_xyxy, float* out_xyxy_px,
+                               void* stream) {
+    if (!out_xyxy) {
+        set_error("kzd_decode_dual: null out_xyxy");
+        return KZD_EINVAL;
+    }
+    return decode_maps(h_level_ptrs, in_dtype, h_levels, n_levels, b, nc, y, out_xyxy, out_xyxy_px, stream,
+                       "kzd_decode_dual");
+}
+
+static int decode_maps(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels, int n_levels, int b,
+                       int nc, float* y, float* out_xyxy, float* out_px, void* stream, const char* who) {
+    KZD_CHECK_ARG(h_level_ptrs && h_levels && y, "%s: null pointer", who);
+    KZD_CHECK_ARG(n_levels >= 1 && n_levels <= KZD_MAX_LEVELS, "%s: n_levels=%d not in [1,%d]", who, n_levels,
                   KZD_MAX_LEVELS);
-    KZD_CHECK_ARG(b >= 0 && nc >= 0, "kzd_decode_infer: negative size");
-    KZD_CHECK_ARG(in_dtype >= 0 && in_dtype <= 2, "kzd_decode_infer: in_dtype=%d not in {0 fp32, 1 fp16, 2 bf16}", in_dtype);
+    KZD_CHECK_ARG(b >= 0 && nc >= 0, "%s: negative size", who);
+    KZD_CHECK_ARG(in_dtype >= 0 && in_dtype <= 2, "%s: in_dtype=%d not in {0 fp32, 1 fp16, 2 bf16}", who, in_dtype);
+    KZD_CHECK_ARG((!out_xyxy || ((uintptr_t)out_xyxy) % 16 == 0) && (!out_px || ((uintptr_t)out_px) % 16 == 0),
+                  "%s: box outputs must be 16-byte aligned", who);
     InferParams p;
     int off = 0;
     bool vec4 = true;
     const uintptr_t in_align = in_dtype == 0 ? 16 : 8;  // 4 elements per load
     for (int l = 0; l < n_levels; ++l) {
-        KZD_CHECK_ARG(h_levels[l].h > 0 && h_levels[l].w > 0, "kzd_decode_infer: empty level %d", l);
-        KZD_CHECK_ARG(h_levels[l].offset == off, "kzd_decode_infer: level %d offset %d, expected %d", l,
-                      h_levels[l].offset, off);
+        KZD_CHECK_ARG(h_levels[l].h > 0 && h_levels[l].w > 0, "%s: empty level %d", who, l);
+        KZD_CHECK_ARG(h_levels[l].offset == off, "%s: level %d offset %d, expected %d", who, l, h_levels[l].offset, off);
         p.ptr[l] = h_level_ptrs[l];
         p.hw[l] = h_levels[l].h * h_levels[l].w;
         p.w[l] = h_levels[l].w;
@@ -408,11 +445,11 @@ extern "C" __attribute__((visibility("default"))) int kzd_decode_infer(const voi
     p.n_levels = n_levels, p.b = b, p.nc = nc, p.A = off;
     vec4 = vec4 && (((uintptr_t)y) % 16 == 0);
     if (b == 0) return 0;
-    KZD_CHECK_ARG(b <= 65535, "kzd_decode_infer: b=%d > 65535", b);
+    KZD_CHECK_ARG(b <= 65535, "%s: b=%d > 65535", who, b);
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_dtype == 1) launch_infer<__half>(p, off, b, vec4, y, st);
-    else if (in_dtype == 2) launch_infer<__nv_bfloat16>(p, off, b, vec4, y, st);
-    else launch_infer<float>(p, off, b, vec4, y, st);
+    if (in_dtype == 1) launch_infer<__half>(p, off, b, vec4, y, out_xyxy, out_px, st);
+    else if (in_dtype == 2) launch_infer<__nv_bfloat16>(p, off, b, vec4, y, out_xyxy, out_px, st);
+    else launch_infer<float>(p, off, b, vec4, y, out_xyxy, out_px, st);
     KZD_LAUNCH_CHECK("decode_infer_kernel");
     return 0;
 }

@@ -20,11 +20,16 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def decode_inference(levels_x, strides, nc):
+def decode_inference(levels_x, strides, nc, with_train_boxes=False):
     """Fused DFL softmax-expectation + dist2bbox(xywh) + x stride + class sigmoid.
 
     ``levels_x``: list of per-level maps ``(b, 64+nc, H_l, W_l)`` (CUDA), ``strides``: floats.
     Returns ``y (b, 4+nc, A)`` fp32 - exactly what ``Detect._inference`` returns (head.py:131).
+
+    ``with_train_boxes=True`` returns ``(y, xyxy, xyxy_px)``: the same kernel also emits the training-side
+    decode of these maps - ``v8DetectionLoss.bbox_decode`` (utils/loss.py:197-204) in grid units and its
+    ``* stride_tensor`` copy (loss.py:236) - so validation-during-training (engine/validator.py:180-185)
+    reads the head outputs once and needs no ``(b,A,64)`` transposed copy for the decode.
     """
     x0 = levels_x[0]
     _lib.require_cuda(x0, "Detect input")
@@ -41,6 +46,14 @@ def decode_inference(levels_x, strides, nc):
     lv, A = _lib.levels_array([(xi.shape[2], xi.shape[3], float(s)) for xi, s in zip(xs, strides)])
     ptrs = (C.c_void_p * len(xs))(*[xi.data_ptr() for xi in xs])
     y = torch.empty((b, 4 + nc, A), dtype=torch.float32, device=x0.device)
+    if with_train_boxes:
+        xyxy = torch.empty((b, A, 4), dtype=torch.float32, device=x0.device)
+        px = torch.empty_like(xyxy)
+        with torch.cuda.device(x0.device):
+            rc = _lib.lib.kzd_decode_dual(ptrs, code, lv, len(xs), b, nc, y.data_ptr(), xyxy.data_ptr(), px.data_ptr(),
+                                          _stream(x0.device))
+        _lib.check(rc, "kzd_decode_dual")
+        return y, xyxy, px
     with torch.cuda.device(x0.device):
         rc = _lib.lib.kzd_decode_infer(ptrs, code, lv, len(xs), b, nc, y.data_ptr(), _stream(x0.device))
     _lib.check(rc, "kzd_decode_infer")

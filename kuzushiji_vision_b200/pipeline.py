@@ -28,7 +28,7 @@ from .tal import TaskAlignedAssigner, make_anchors
 class PagePipeline:
     def __init__(self, batch, level_hw, strides, nc, n_max_boxes, device="cuda:0", topk=10, alpha=0.5, beta=6.0,
                  conf_thres=0.25, iou_thres=0.7, max_det=300, max_nms=30000, agnostic=False, max_wh=7680.0,
-                 pool=32768, n_cap=4096, use_graph=True, overlap=True):
+                 pool=32768, n_cap=4096, use_graph=True, overlap=True, fuse_decodes=False):
         dev = torch.device(device)
         self.device, self.b, self.nc, self.G = dev, int(batch), int(nc), int(n_max_boxes)
         self.level_hw = [(int(h), int(w)) for h, w in level_hw]
@@ -65,6 +65,9 @@ class PagePipeline:
         self.counters_host = torch.zeros(2, dtype=torch.float64).pin_memory()
         self.done = torch.cuda.Event()
         self.overlap = bool(overlap)
+        # one kernel reads the head maps once and emits both y and the training-side boxes (the
+        # validation-during-training flow, engine/validator.py:180-185); pred_distri is then not read
+        self.fuse_decodes = bool(fuse_decodes)
         self._side = torch.cuda.Stream(device=dev, priority=-1)  # the small NMS kernels go first
         self.out = None
         self.graph = None
@@ -73,24 +76,17 @@ class PagePipeline:
         t_cap, phases = (self.n_cap + 63) // 64, 1
         while t0 < t_cap:
             t0, phases = t0 * 4, phases + 1
-        self.kernels_per_step = 1 + 6 + 1 + 3 + 2 * phases
+        self.kernels_per_step = (1 if self.fuse_decodes else 2) + 6 + 3 + 2 * phases
         if use_graph:
             self._capture()
 
     # -- the step body: the same libkzd calls as the drop-ins ------------------------------------
-    def _train_half(self):
+    def _assign(self, boxes_px):
         with torch.no_grad():
-            boxes, boxes_px = bbox_decode(self.anchor_points, self.pred_distri, self.stride_tensor)
-            tgt = self.assigner(self.pd_scores, boxes_px, self.anc_points, self.gt_labels, self.gt_bboxes,
-                                self.mask_gt)
-        return boxes, boxes_px, tgt
+            return self.assigner(self.pd_scores, boxes_px, self.anc_points, self.gt_labels, self.gt_bboxes, self.mask_gt)
 
-    def _infer_half(self, decoded_event=None):
+    def _nms(self, y):
         dev = self.device
-        with torch.no_grad():
-            y = decode_inference(self.levels, self.strides, self.nc)
-        if decoded_event is not None:
-            decoded_event.record(torch.cuda.current_stream(dev))
         lib = _lib.lib
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(lib.kzd_nms_filter(y.data_ptr(), self.b, self.A, self.nc, self.conf, 0, None, 0, 1,
@@ -101,26 +97,37 @@ class PagePipeline:
                                         self.max_nms, self.max_wh, self.det_rows.data_ptr(),
                                         self.keep_host.data_ptr(), self.nms_ws.data_ptr(), self.ws_bytes, st),
                    "kzd_nms_suppress")
-        return y
 
     # -- the step body: the same libkzd calls as the drop-ins. The training half (decode -> assign) and
     # the inference half (decode -> NMS) do not depend on each other, so they are forked onto two
     # streams (two branches of the captured graph). The two HBM-bound decodes are kept back to back
     # (running them concurrently only splits the bandwidth); the issue/latency-bound NMS chain then
-    # overlaps the training decode, and the assigner runs last.
+    # overlaps the training decode, and the assigner runs last. With fuse_decodes one kernel produces
+    # both decodes from a single read of the maps, then NMS and assign run side by side.
     def _body(self):
         main = torch.cuda.current_stream(self.device)
-        if self.overlap:
-            self._side.wait_stream(main)
-            decoded = torch.cuda.Event()
-            with torch.cuda.stream(self._side):
-                y = self._infer_half(decoded)
-            main.wait_event(decoded)
-            boxes, boxes_px, tgt = self._train_half()
-            main.wait_stream(self._side)
+        side = self._side if self.overlap else main
+        if self.fuse_decodes:
+            with torch.no_grad():
+                y, boxes, boxes_px = decode_inference(self.levels, self.strides, self.nc, with_train_boxes=True)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._nms(y)
+            tgt = self._assign(boxes_px)
+            main.wait_stream(side)
         else:
-            boxes, boxes_px, tgt = self._train_half()
-            y = self._infer_half()
+            side.wait_stream(main)
+            decoded = torch.cuda.Event()
+            with torch.cuda.stream(side):
+                with torch.no_grad():
+                    y = decode_inference(self.levels, self.strides, self.nc)
+                decoded.record(side)
+                self._nms(y)
+            main.wait_event(decoded)
+            with torch.no_grad():
+                boxes, boxes_px = bbox_decode(self.anchor_points, self.pred_distri, self.stride_tensor)
+            tgt = self._assign(boxes_px)
+            main.wait_stream(side)
         return dict(pred_bboxes=boxes, pd_bboxes=boxes_px, target_labels=tgt[0], target_bboxes=tgt[1],
                     target_scores=tgt[2], fg_mask=tgt[3], target_gt_idx=tgt[4], counters=self.assigner.counters, y=y,
                     det_rows=self.det_rows, counts=self.counts)

@@ -414,26 +414,36 @@ def test_chained_path_page_batch():
     _check_nms(m, r)
 
 
-def test_pipeline_graph_matches_eager():
+@pytest.mark.parametrize("fuse", [False, True])
+def test_pipeline_graph_matches_eager(fuse):
     """PagePipeline (one CUDA graph for decode -> assign and decode -> NMS) returns the same bits as the
-    eager drop-in calls and the oracle, across several replays with different inputs."""
-    b, G, imgsz, nc = 4, 200, 640, 1
-    pipe = kzd.PagePipeline(b, synth.level_shapes(imgsz, synth.P2_P5), synth.P2_P5, nc, G, device=DEV,
-                            conf_thres=0.25, iou_thres=0.7, max_det=300)
+    eager drop-in calls and the oracle, across several replays with different inputs. With fuse_decodes
+    both decodes come from one read of the head maps."""
+    b, G, imgsz, nc, strides = 4, 200, 640, 1, synth.P2_P5
+    pipe = kzd.PagePipeline(b, synth.level_shapes(imgsz, strides), strides, nc, G, device=DEV,
+                            conf_thres=0.25, iou_thres=0.7, max_det=300, fuse_decodes=fuse)
+    anchor_points, stride_tensor = O.make_anchors(synth.level_shapes(imgsz, strides), strides, device=DEV)
     for seed in (1, 2, 3):
-        d = synth.assigner_inputs(b, G, imgsz, nc, synth.P2_P5, seed=seed, device=DEV)
-        lv = synth.head_outputs(b, nc, imgsz, synth.P2_P5, seed=seed + 50, device=DEV, sparse_cls=800)
-        pipe.load(levels=lv, pred_distri=d["pred_distri"], pd_scores=d["pd_scores"], gt_labels=d["gt_labels"],
-                  gt_bboxes=d["gt_bboxes"], mask_gt=d["mask_gt"])
+        lv = synth.head_outputs(b, nc, imgsz, strides, seed=seed + 50, device=DEV, sparse_cls=800)
+        cat = torch.cat([x.view(b, 64 + nc, -1) for x in lv], 2)  # the reference's glue (utils/loss.py:210-215)
+        pred_distri = cat[:, :64].permute(0, 2, 1).contiguous()
+        pd_scores = cat[:, 64:].permute(0, 2, 1).contiguous().sigmoid()
+        gl, gb, mg = synth.gt_pages(b, G, imgsz, nc, seed=seed, device=DEV)
+        pipe.load(levels=lv, pred_distri=pred_distri, pd_scores=pd_scores, gt_labels=gl, gt_bboxes=gb, mask_gt=mg)
         pipe.step()
         out, n_keep = pipe.results()
-        boxes, px = kzd.bbox_decode(d["anchor_points"], d["pred_distri"], d["stride_tensor"])
+        if fuse:
+            _, boxes, px = kzd.decode_inference(lv, strides, nc, with_train_boxes=True)
+        else:
+            boxes, px = kzd.bbox_decode(anchor_points, pred_distri, stride_tensor)
         assert torch.equal(out["pred_bboxes"], boxes) and torch.equal(out["pd_bboxes"], px)
-        args = (d["pd_scores"], px, d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+        ref_boxes = O.decode_train(pred_distri, anchor_points)
+        assert ((boxes - ref_boxes).abs() / ref_boxes.abs().clamp(min=1.0)).max() < RTOL
+        args = (pd_scores, px, anchor_points * stride_tensor, gl, gb, mg)
         ref = O.tal_assign(*args, 10, nc, 0.5, 6.0)
         _check_assign((out["target_labels"], out["target_bboxes"], out["target_scores"], out["fg_mask"],
                        out["target_gt_idx"]), ref)
-        y = kzd.decode_inference(lv, synth.P2_P5, nc)
+        y = kzd.decode_inference(lv, strides, nc)
         assert torch.equal(out["y"][:, 4:], y[:, 4:])
         _check_nms(pipe.detections(), O.non_max_suppression(y.clone(), 0.25, 0.7, max_det=300))
         assert pipe.counters()[1] == float(ref[3].sum())
@@ -670,3 +680,14 @@ def test_install_routes_reference_call_sites_to_libkzd():
         sys.path.remove(fake)
         for m in [k for k in sys.modules if k == "ultralytics" or k.startswith("ultralytics.")]:
             del sys.modules[m]
+
+
+def test_decode_dual_matches_both_single_decodes():
+    """One read of the head maps -> y and the training-side boxes: identical to the two single kernels."""
+    for b, nc, imgsz, strides in [(2, 1, 640, synth.P2_P5), (1, 3, 200, synth.P3_P5)]:
+        d = synth.assigner_inputs(b, 4, imgsz, nc, strides, seed=61, device=DEV)
+        y, xyxy, px = kzd.decode_inference(d["levels"], strides, nc, with_train_boxes=True)
+        assert torch.equal(y, kzd.decode_inference(d["levels"], strides, nc))
+        ref = O.decode_train(d["pred_distri"], d["anchor_points"])
+        assert ((xyxy - ref).abs() / ref.abs().clamp(min=1.0)).max() < RTOL
+        assert torch.equal(px, xyxy * d["stride_tensor"])
