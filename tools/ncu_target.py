@@ -17,6 +17,7 @@ for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     boxes, px = kzd.bbox_decode(d["anchor_points"], d["pred_distri"], d["stride_tensor"])
     out = asg(d["pd_scores"], px, d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
     y = kzd.decode_inference(lv, synth.P2_P5, nc)
+    y2, xyxy, px2 = kzd.decode_inference(lv, synth.P2_P5, nc, with_train_boxes=True)  # fused decode of the same maps
     det = kzd.nms_batched(y, 0.25, 0.7, max_det=1000)
 torch.cuda.synchronize()
 print("ok", int(out[3].sum()), sum(det[1]))
