@@ -691,3 +691,41 @@ def test_decode_dual_matches_both_single_decodes():
         ref = O.decode_train(d["pred_distri"], d["anchor_points"])
         assert ((xyxy - ref).abs() / ref.abs().clamp(min=1.0)).max() < RTOL
         assert torch.equal(px, xyxy * d["stride_tensor"])
+
+
+def test_extreme_shapes():
+    """Corners of the size envelope: thousands of GT slots (shared-memory GT table of 72 KB), 80 classes,
+    a single tiny level, and an NMS input where every candidate is the same box (one survivor, the longest
+    possible suppression chain) or where no box overlaps any other."""
+    # many GT slots
+    d = synth.assigner_inputs(1, 3000, 640, 2, synth.P2_P5, seed=71, device=DEV, layout="uniform")
+    mine, ref, _ = _assign_both(d, 2)
+    _check_assign(mine, ref)
+    # 80 classes, tiny grid (A = 16 + 4 + 1)
+    d = synth.assigner_inputs(2, 3, 32, 80, (8, 16, 32), seed=72, device=DEV, layout="uniform")
+    d["gt_bboxes"][:, 0] = torch.tensor([2.0, 2.0, 30.0, 30.0], device=DEV)
+    d["mask_gt"][:, 0] = 1
+    mine, ref, _ = _assign_both(d, 80)
+    _check_assign(mine, ref)
+    y = kzd.decode_inference(d["levels"], (8, 16, 32), 80)
+    m, r, _, _ = _nms_both(y, conf_thres=0.3, iou_thres=0.5, multi_label=True, max_det=50)
+    _check_nms(m, r)
+    # identical boxes
+    y = torch.zeros(2, 5, 3000, device=DEV)
+    y[:, 0:2] = 100.0
+    y[:, 2:4] = 40.0
+    y[:, 4] = torch.rand(2, 3000, device=DEV) * 0.5 + 0.4
+    m, r, _, _ = _nms_both(y, conf_thres=0.25, iou_thres=0.5, max_det=300)
+    _check_nms(m, r)
+    assert all(t.shape[0] == 1 for t in m)
+    # disjoint boxes: everything is kept, max_det truncates
+    y = torch.zeros(1, 5, 4096, device=DEV)
+    idx = torch.arange(4096, device=DEV)
+    y[0, 0] = (idx % 64) * 20.0 + 10
+    y[0, 1] = (idx // 64) * 20.0 + 10
+    y[0, 2:4] = 10.0
+    y[0, 4] = torch.rand(4096, device=DEV) * 0.5 + 0.4
+    for md in (100, 5000):
+        m, r, _, _ = _nms_both(y, conf_thres=0.25, iou_thres=0.5, max_det=md)
+        _check_nms(m, r)
+        assert m[0].shape[0] == min(md, 4096)
