@@ -220,19 +220,20 @@ __device__ __forceinline__ void eval_pairs(const AssignParams& p, const GtBox& g
         st.empty = false;
         return;
     }
+    // The list stays sorted over all 32 lanes, so inserting a key that the k-th entry has meanwhile
+    // overtaken is harmless (it lands at a lane >= topk): the bar is refreshed once per batch.
     unsigned m = __ballot_sync(0xffffffffu, key > st.kth);
+    if (m == 0u) return;
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const u64 ck = shfl64(key, src);
-        if (ck > st.kth) {  // kth may have risen since the ballot
-            const int pos = __popc(__ballot_sync(0xffffffffu, st.tk > ck));
-            const u64 up = shfl_up64(st.tk, 1);
-            if (lane == pos) st.tk = ck;
-            else if (lane > pos) st.tk = up;
-            st.kth = shfl64(st.tk, topk - 1);
-        }
+        const int pos = __popc(__ballot_sync(0xffffffffu, st.tk > ck));
+        const u64 up = shfl_up64(st.tk, 1);
+        if (lane == pos) st.tk = ck;
+        else if (lane > pos) st.tk = up;
     }
+    st.kth = shfl64(st.tk, topk - 1);
 }
 
 // GT `g` selected the anchor: two fire-and-forget atomicMax (smallest and largest selecting GT).

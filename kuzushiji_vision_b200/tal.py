@@ -129,7 +129,8 @@ class TaskAlignedAssigner(nn.Module):
         ws_key = (b, A, G, str(dev))
         ws = self._ws.get(ws_key)
         if ws is None:
-            self._ws.clear()
+            if len(self._ws) >= 4:  # train / val batch shapes alternate: keep a few, drop the oldest
+                self._ws.pop(next(iter(self._ws)))
             ws = torch.zeros(_lib.lib.kzd_assign_workspace_bytes(b, A, G), dtype=torch.uint8, device=dev)
             self._ws[ws_key] = ws
         persistent = 0 if self.stateless else 1
