@@ -26,12 +26,13 @@ def _round_up(v, m):
 
 
 def nms_batched(prediction, conf_thres, iou_thres, classes=None, agnostic=False, multi_label=False, max_det=300,
-                max_nms=30000, max_wh=7680.0, in_place=True, pool=None, n_cap=None):
+                max_nms=30000, max_wh=7680.0, in_place=True, pool=None, n_cap=None, xyxy_input=False):
     """Batched NMS on a contiguous fp32 CUDA tensor ``prediction (b, 4+nc, A)``.
 
     Returns ``(rows (b, max_det, 6), counts list[int])``; ``rows[i, :counts[i]]`` are image i's kept
     detections ``[x1,y1,x2,y2,conf,cls]`` in descending score order. ``prediction[:, :4]`` is
     overwritten with xyxy when ``in_place`` (the reference's side effect, utils/ops.py:243-244).
+    ``xyxy_input=True``: the box rows already hold xyxy (e.g. a tensor a previous call converted in place).
     """
     b, ch, A = prediction.shape
     nc = ch - 4
@@ -48,7 +49,7 @@ def nms_batched(prediction, conf_thres, iou_thres, classes=None, agnostic=False,
     out_rows = torch.empty((b, max_det, 6), dtype=torch.float32, device=dev)
     counts = torch.empty((2, b), dtype=torch.int32, device=dev)  # [0] candidates, [1] kept
     lib = _lib.lib
-    mode = 1 if in_place else 0
+    mode = 2 if xyxy_input else (1 if in_place else 0)
     with torch.cuda.device(dev):
         while True:
             keys = torch.empty((b, pool), dtype=torch.int64, device=dev)

@@ -171,14 +171,20 @@ class PagePipeline:
         return self.out
 
     def results(self):
-        """Wait for the last step; returns (outputs dict, kept-per-image list). Raises if the fixed NMS
-        capacities overflowed (re-create the pipeline with a larger ``pool`` / ``n_cap``)."""
+        """Wait for the last step; returns (outputs dict, kept-per-image list). If the fixed NMS capacities
+        of the graph overflowed (more candidates per page than ``pool`` / ``n_cap``), the NMS of this step is
+        redone eagerly with capacities sized from the actual counts (the graph itself is left as it is)."""
         self.done.synchronize()
         n_keep = self.keep_host.tolist()
         if min(n_keep) < 0:
-            n_cand = self.counts[0].tolist()
-            raise _lib.KzdError(f"PagePipeline: NMS capacity exceeded (candidates/page up to {max(n_cand)}, "
-                                f"pool={self.pool}, n_cap={self.n_cap})")
+            from .ops import nms_batched
+
+            # the graph's filter already rewrote y's box rows as xyxy
+            rows, n_keep = nms_batched(self.out["y"], self.conf, self.iou, agnostic=self.agnostic, max_det=self.max_det,
+                                       max_nms=self.max_nms, max_wh=self.max_wh, in_place=False, xyxy_input=True,
+                                       pool=self.A, n_cap=self.max_nms)
+            self.det_rows.copy_(rows)
+            self.keep_host.copy_(torch.as_tensor(n_keep, dtype=torch.int32))
         return self.out, n_keep
 
     def counters(self):

@@ -729,3 +729,18 @@ def test_extreme_shapes():
         m, r, _, _ = _nms_both(y, conf_thres=0.25, iou_thres=0.5, max_det=md)
         _check_nms(m, r)
         assert m[0].shape[0] == min(md, 4096)
+
+
+def test_pipeline_recovers_from_nms_capacity_overflow():
+    """More candidates per page than the graph's fixed pool / n_cap: results() redoes the NMS eagerly."""
+    b, G, imgsz, nc, strides = 2, 20, 320, 1, synth.P2_P5
+    pipe = kzd.PagePipeline(b, synth.level_shapes(imgsz, strides), strides, nc, G, device=DEV, conf_thres=0.25,
+                            iou_thres=0.7, max_det=300, pool=256, n_cap=128)
+    lv = synth.head_outputs(b, nc, imgsz, strides, seed=81, device=DEV, sparse_cls=1500)
+    d = synth.assigner_inputs(b, G, imgsz, nc, strides, seed=81, device=DEV)
+    pipe.load(levels=lv, pred_distri=d["pred_distri"], pd_scores=d["pd_scores"], gt_labels=d["gt_labels"],
+              gt_bboxes=d["gt_bboxes"], mask_gt=d["mask_gt"])
+    pipe.step()
+    dets = pipe.detections()
+    y = kzd.decode_inference(lv, strides, nc)
+    _check_nms(dets, O.non_max_suppression(y.clone(), 0.25, 0.7, max_det=300))
