@@ -242,8 +242,11 @@ def run_kzd(args, rank, local_rank, world):
     # one kernel decodes the head maps once for both halves (validation-during-training flow); set
     # KZD_BENCH_FUSE=0 to time the two separate decode kernels of the drop-in signatures instead
     fuse = os.environ.get("KZD_BENCH_FUSE", "1") != "0"
+    # the inference decode also does the NMS filter stage on the values it has just computed (the Detect ->
+    # non_max_suppression flow with a known conf_thres); KZD_BENCH_FILTER=0 keeps the separate filter pass
+    fuse_filter = os.environ.get("KZD_BENCH_FILTER", "1") != "0"
     pipe_kw = dict(device=dev, topk=w["topk"], alpha=w["alpha"], beta=w["beta"], conf_thres=w["conf"],
-                   iou_thres=w["iou"], max_det=w["max_det"])
+                   iou_thres=w["iou"], max_det=w["max_det"], fuse_filter=fuse_filter)
     pipe = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G, fuse_decodes=fuse,
                             **pipe_kw)
     dv_lv = [l.to(dev) for l in host_lv]
@@ -325,20 +328,23 @@ def run_kzd(args, rank, local_rank, world):
 
     def nms_calls():
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(_lib.lib.kzd_nms_filter(y_static.data_ptr(), b, A, nc, w["conf"], 0, None, 0, 0,
-                                           pipe.keys.data_ptr(), pipe.rows.data_ptr(), pipe.counts[0].data_ptr(),
-                                           pipe.pool, st), "kzd_nms_filter")
+        if not fuse_filter:
+            _lib.check(_lib.lib.kzd_nms_filter(y_static.data_ptr(), b, A, nc, w["conf"], 0, None, 0, 0,
+                                               pipe.keys.data_ptr(), pipe.rows.data_ptr(), pipe.counts[0].data_ptr(),
+                                               pipe.pool, st), "kzd_nms_filter")
         _lib.check(_lib.lib.kzd_nms_suppress(pipe.keys.data_ptr(), pipe.rows.data_ptr(), pipe.counts[0].data_ptr(), b,
                                              pipe.pool, pipe.n_cap, w["iou"], 0, w["max_det"], 30000, 7680.0,
                                              pipe.det_rows.data_ptr(), pipe.counts[1].data_ptr(),
                                              pipe.nms_ws.data_ptr(), pipe.ws_bytes, st), "kzd_nms_suppress")
 
+    pool_arg = (w["conf"], pipe.keys, pipe.rows, pipe.counts[0]) if fuse_filter else None
     stage_fns = {
-        "decode_dual": lambda: kzd.decode_inference(pipe.levels, w["strides"], nc, with_train_boxes=True),
+        "decode_dual": lambda: kzd.decode_inference(pipe.levels, w["strides"], nc, with_train_boxes=True,
+                                                    nms_pool=pool_arg),
         "decode_train": lambda: kzd.bbox_decode(pipe.anchor_points, pipe.pred_distri, pipe.stride_tensor),
         "assign": lambda: asg(pipe.pd_scores, px_static, pipe.anc_points, pipe.gt_labels, pipe.gt_bboxes,
                               pipe.mask_gt),
-        "decode_infer": lambda: kzd.decode_inference(pipe.levels, w["strides"], nc),
+        "decode_infer": lambda: kzd.decode_inference(pipe.levels, w["strides"], nc, nms_pool=pool_arg),
         "nms": nms_calls,
     }
     st_ms = {}
@@ -434,8 +440,9 @@ def run_kzd(args, rank, local_rank, world):
     # ---- roofline of the dominant kernel ----
     n_cand = int(sum(pipe.candidate_counts()))
     ab = algorithmic_bytes(b, A, G, nc, n_cand, int(sum(n_keep)))
-    single_kernel = ({"decode_dual": "decode_infer_kernel<4, float, true>"} if fuse else
-                     {"decode_train": "decode_train_kernel", "decode_infer": "decode_infer_kernel<4, float, false>"})
+    ff = "true" if fuse_filter else "false"
+    single_kernel = ({"decode_dual": f"decode_infer_kernel<4, float, true, {ff}>"} if fuse else
+                     {"decode_train": "decode_train_kernel", "decode_infer": f"decode_infer_kernel<4, float, false, {ff}>"})
     dom = max(single_kernel, key=lambda n: st_ms[n])
     peak, peak_src = hbm_peak()
     achieved = ab[dom] / (st_ms[dom] * 1e-3) / 1e9
@@ -481,6 +488,9 @@ def run_kzd(args, rank, local_rank, world):
                    "l2_policy": "inputs larger than L2 (0.6-1.2 GB read per step vs 126 MB L2)",
                    "decodes": ("fused: one kernel reads the head maps once and emits y + the training-side boxes"
                                if fuse else "separate decode_train (b,A,64) and decode_infer (NCHW maps) kernels"),
+                   "nms_filter": ("inside the inference decode kernel (no second pass over y); the kernel's roofline "
+                                  "figure counts the decode's algorithmic bytes only" if fuse_filter else
+                                  "separate nms_filter_kernel pass over y"),
                    "step": "PagePipeline: one CUDA-graph replay of decode_train+assign+decode_infer+NMS per step; "
                            f"{depth} pipelines alternate on {depth} streams (multi-buffering)",
                    "ms_per_step_single_stream": ms_single,

@@ -70,6 +70,18 @@ int kzd_decode_dual(const void* const* h_level_ptrs, int in_dtype, const kzd_lev
                     int n_levels, int b, int nc, float* y, float* out_xyxy, float* out_xyxy_px,
                     void* stream);
 
+/* kzd_decode_infer / kzd_decode_dual (out_xyxy may be NULL) + the first stage of
+ * ops.non_max_suppression (utils/ops.py:234-286, best-class path) in the same kernel: for the
+ * Detect -> non_max_suppression flow (models/yolo/detect/predict.py:25, detect/val.py:94) with a known
+ * conf_thres. y's box rows are written as xyxy - the state ops.py:243-244 (in_place=True) leaves the
+ * caller's tensor in - and every anchor whose best class score exceeds conf_thres is appended to the
+ * candidate pool exactly as kzd_nms_filter would after re-reading y (same keys, same rows; slot order is
+ * unspecified in both). cand_counts is zeroed on the stream first. Follow with kzd_nms_suppress. */
+int kzd_decode_filter(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels,
+                      int n_levels, int b, int nc, float* y, float* out_xyxy, float* out_xyxy_px,
+                      float conf_thres, uint64_t* cand_keys, float* cand_rows, int32_t* cand_counts,
+                      int cand_cap, void* stream);
+
 /* v8DetectionLoss.bbox_decode (utils/loss.py:197-204) + dist2bbox(xywh=False).
  *   pred_dist     : (b, A, 64)  side-major, 16 bins per side; in_dtype 0 fp32, 1 fp16, 2 bf16
  *                   (under AMP the head emits fp16, engine/trainer.py:379); outputs are fp32

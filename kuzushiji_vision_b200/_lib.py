@@ -39,6 +39,8 @@ def _load():
         "kzd_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
         "kzd_decode_infer": (C.c_int, [C.POINTER(vp), i32, C.POINTER(Level), i32, i32, i32, vp, vp]),
         "kzd_decode_dual": (C.c_int, [C.POINTER(vp), i32, C.POINTER(Level), i32, i32, i32, vp, vp, vp, vp]),
+        "kzd_decode_filter": (C.c_int, [C.POINTER(vp), i32, C.POINTER(Level), i32, i32, i32, vp, vp, vp, f32, vp, vp, vp,
+                                        i32, vp]),
         "kzd_decode_train": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp, vp]),
         "kzd_decode_train_bwd": (C.c_int, [vp, vp, i32, i32, vp, vp]),
         "kzd_assign_workspace_bytes": (sz, [i32, i32, i32]),

@@ -5,16 +5,16 @@
 // select_highest_overlaps :264-295) and CIoU utils/metrics.py:96-130.
 //
 // Kernels (one stream, no host sync):
-//   assign_begin_kernel       per-call flags and the device-side epoch of the persistent state
-//   assign_verify_kernel      checks anc_points against the level table (grid accelerator is only
-//                             used when every anchor matches bit-for-bit)
-//   assign_candidates_kernel  one warp per (image, GT): enumerate the anchors inside the GT (separable
-//                             x / y tests), queue them, CIoU + alignment metric 32 pairs at a time,
-//                             per-anchor argmax-overlap via 64-bit atomicMax, warp-shuffle top-k,
-//                             selecting GTs recorded with two atomicMax words
+//   assign_verify_kernel      per-call flags + device-side epoch of the persistent state; checks
+//                             anc_points against the level table (grid accelerator is only used
+//                             when every anchor matches bit-for-bit)
+//   assign_candidates_kernel  one warp per (image, GT): the anchors inside the GT are an exact
+//                             rectangle per level (separable x / y tests); CIoU + alignment metric 32
+//                             pairs at a time, per-anchor argmax-overlap via 64-bit atomicMax, top-k by
+//                             warp-wide redux max, selecting GTs recorded with two atomicMax words
 //   assign_resolve_kernel     one thread per anchor: resolve the owner GT, write labels / boxes /
-//                             fg / gt_idx for every anchor, append foreground anchors to a compact list
-//   assign_fg_metric_kernel   foreground list: recompute the owner pair's metric, per-GT maxima
+//                             fg / gt_idx for every anchor; the CTA's foreground anchors are compacted
+//                             and their owner pair's metric + the per-GT maxima computed in place
 //   assign_normalize_kernel   foreground list: target_scores = align * pos_ov / (pos_align+eps)
 //
 // Bit-exactness: every fp32 operation of the eager reference rounds separately, so the pair
@@ -26,8 +26,6 @@
 #include "kzd_common.cuh"
 
 namespace kzd {
-
-typedef unsigned long long u64;
 
 // Per-anchor state words carry an 8-bit epoch in their top bits, so a persistent workspace never has
 // to be re-zeroed between calls: entries written under an older epoch lose every atomicMax / CAS.
@@ -43,7 +41,7 @@ struct AssignWs {
     uint2* sel;          // (b*A)  smallest / largest GT whose top-k selected the anchor
     uint32_t* pos_align; // (b*G)  per-GT max alignment metric (float bits)
     uint32_t* pos_ov;    // (b*G)  per-GT max overlap (float bits)
-    uint32_t* fg_list;   // (b*A)  compact list of foreground anchors (flat index)
+    uint2* fg_list;      // (b*A)  compact list of foreground anchors: (flat anchor index, flat GT slot)
     int32_t* flags;      // [0] != 0: anc_points does not match the level table; [1] = fg count;
                          // [2] = current epoch (1..255), advanced on the device by assign_begin_kernel
     size_t state_bytes;  // key + sel + flags: the part that must have been zeroed once
@@ -134,30 +132,23 @@ __device__ __forceinline__ float overlap_ciou(const GtBox& g, const float4 p) {
     return fmaxf(ciou, 0.f);
 }
 
-__device__ __forceinline__ u64 shfl64(u64 v, int src) {
-    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
-    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
-    return ((u64)hi << 32) | lo;
-}
-__device__ __forceinline__ u64 shfl_up64(u64 v, int d) {
-    const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
-    const uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
-    return ((u64)hi << 32) | lo;
-}
-
 // ---- begin: per-call flags and the device-side epoch -----------------------------------------
 
-__global__ void assign_begin_kernel(AssignWs ws, int reset_epoch) {
-    ws.flags[0] = 0;
+// flags[0] (grid mismatch) is consumed by the candidates kernel only and cleared again by the resolve
+// kernel, so it is already 0 when a call starts.
+__device__ __forceinline__ void begin_call(const AssignWs& ws, int reset_epoch) {
     ws.flags[1] = 0;
     const int e = reset_epoch ? 0 : ws.flags[2];
     ws.flags[2] = (e % 255) + 1;  // 1..255; at 255 the resolve kernel wipes the state for the wrap to 1
 }
 
-// ---- verify ----------------------------------------------------------------------------------
+__global__ void assign_begin_kernel(AssignWs ws, int reset_epoch) { begin_call(ws, reset_epoch); }
 
-__global__ void assign_verify_kernel(const float* __restrict__ anc, int A, AssignParams p) {
+// ---- verify (+ begin) ------------------------------------------------------------------------
+
+__global__ void assign_verify_kernel(const float* __restrict__ anc, int A, AssignParams p, int reset_epoch) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == 0) begin_call(p.ws, reset_epoch);
     if (a >= A) return;
     int l = 0;
     for (int k = 1; k < p.n_levels; ++k)
@@ -166,7 +157,8 @@ __global__ void assign_verify_kernel(const float* __restrict__ anc, int A, Assig
     const float s = p.lv[l].stride;
     const float ex = __fmul_rn((float)(q % p.lv[l].w) + 0.5f, s);
     const float ey = __fmul_rn((float)(q / p.lv[l].w) + 0.5f, s);
-    if (anc[2 * a] != ex || anc[2 * a + 1] != ey) atomicOr(p.ws.flags, 1);
+    const float2 ap = __ldg(reinterpret_cast<const float2*>(anc) + a);
+    if (ap.x != ex || ap.y != ey) p.ws.flags[0] = 1;
 }
 
 // ---- candidates + top-k ----------------------------------------------------------------------
@@ -176,65 +168,7 @@ constexpr int CAND_THREADS = 256;
 #define KZD_CAND_MINB 4
 #endif
 constexpr int CAND_WARPS = CAND_THREADS / 32;
-
-struct TopK {
-    u64 tk;   // lane i holds the i-th best  metric_bits<<32 | ~anchor  (0 = empty)
-    u64 kth;  // entry topk-1: the bar a new candidate has to clear
-    bool empty;
-};
-
-// 32 keys, one per lane -> descending order across the lanes (bitonic network on shuffles)
-__device__ __forceinline__ u64 warp_sort_desc(u64 v, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, j);
-            const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), j);
-            const u64 o = ((u64)hi << 32) | lo;
-            const bool want_max = (((lane & k) == 0) == ((lane & j) == 0));  // descending overall
-            v = (want_max == (o > v)) ? o : v;
-        }
-    }
-    return v;
-}
-
-// One in-GT pair per lane (a < 0: idle lane): overlap, metric, argmax key, streaming top-k insert.
-__device__ __forceinline__ void eval_pairs(const AssignParams& p, const GtBox& gt, int a, size_t img,
-                                           const float4* __restrict__ pdb, const float* __restrict__ pds, int g,
-                                           int topk, int lane, uint32_t epoch, TopK& st) {
-    u64 key = 0ull;
-    if (a >= 0) {
-        const float4 pb = __ldg(pdb + a);
-        const float sc = __ldg(pds + (size_t)a * p.nc);
-        const float o = overlap_ciou(gt, pb);
-        if (o > 0.f)
-            atomicMax(p.ws.key + img + a, ((u64)epoch << 56) | ((u64)min(__float_as_uint(o), 0x3fffffffu) << KEY_GBITS) |
-                                              (KEY_GMASK - (u64)g));
-        const float al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
-        if (al > 0.f) key = ((u64)__float_as_uint(al) << 32) | (0xffffffffu - (uint32_t)a);
-    }
-    if (st.empty) {  // first batch: one warp sort instead of up to 32 serial insertions
-        st.tk = warp_sort_desc(key, lane);
-        st.kth = shfl64(st.tk, topk - 1);
-        st.empty = false;
-        return;
-    }
-    // The list stays sorted over all 32 lanes, so inserting a key that the k-th entry has meanwhile
-    // overtaken is harmless (it lands at a lane >= topk): the bar is refreshed once per batch.
-    unsigned m = __ballot_sync(0xffffffffu, key > st.kth);
-    if (m == 0u) return;
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const u64 ck = shfl64(key, src);
-        const int pos = __popc(__ballot_sync(0xffffffffu, st.tk > ck));
-        const u64 up = shfl_up64(st.tk, 1);
-        if (lane == pos) st.tk = ck;
-        else if (lane > pos) st.tk = up;
-    }
-    st.kth = shfl64(st.tk, topk - 1);
-}
+constexpr int CAND_CAP = 512;  // in-GT pairs a warp holds at a time (anchor + metric bits in shared memory)
 
 // GT `g` selected the anchor: two fire-and-forget atomicMax (smallest and largest selecting GT).
 __device__ __forceinline__ void mark_selected(uint2* __restrict__ sel, uint32_t epoch, int g) {
@@ -242,8 +176,55 @@ __device__ __forceinline__ void mark_selected(uint2* __restrict__ sel, uint32_t 
     atomicMax(&sel->y, (epoch << 24) | (uint32_t)g);
 }
 
+// One in-GT pair: overlap (+ the per-anchor argmax-overlap key) and the alignment metric's bits (0: not
+// positive; positive floats order like their bit patterns).
+__device__ __forceinline__ uint32_t eval_pair(const AssignParams& p, const GtBox& gt, int a, size_t img,
+                                              const float4* __restrict__ pdb, const float* __restrict__ pds, int g,
+                                              uint32_t epoch) {
+    const float4 pb = __ldg(pdb + a);
+    const float sc = __ldg(pds + (size_t)a * p.nc);
+    const float o = overlap_ciou(gt, pb);
+    if (o > 0.f)
+        atomicMax(p.ws.key + img + a, ((u64)epoch << 56) | ((u64)min(__float_as_uint(o), 0x3fffffffu) << KEY_GBITS) |
+                                          (KEY_GMASK - (u64)g));
+    const float al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
+    return al > 0.f ? __float_as_uint(al) : 0u;
+}
+
+// The columns (or rows) of one level whose centre passes both strict fp32 tests of utils/tal.py:259-262
+// against [lo_edge, hi_edge]. Each test is monotone in the cell index (the centre (i+0.5)*s is), so the
+// passing cells are exactly [first cell passing the low test, last cell passing the high test]; the
+// float estimate is only a starting point and is walked to the exact boundary in either direction.
+__device__ __forceinline__ void cell_range(float lo_edge, float hi_edge, float s, float inv_s, int n_cells, int& first,
+                                           int& last) {
+    auto low_ok = [&](int i) { return __fsub_rn(__fmul_rn((float)i + 0.5f, s), lo_edge) > 1e-9f; };
+    auto high_ok = [&](int i) { return __fsub_rn(hi_edge, __fmul_rn((float)i + 0.5f, s)) > 1e-9f; };
+    int i = (int)fminf(fmaxf(floorf(lo_edge * inv_s - 0.5f), 0.f), (float)(n_cells - 1));
+    while (i > 0 && low_ok(i - 1)) --i;
+    while (i < n_cells && !low_ok(i)) ++i;
+    first = i;  // n_cells: none
+    int j = (int)fminf(fmaxf(ceilf(hi_edge * inv_s - 0.5f), 0.f), (float)(n_cells - 1));
+    while (j < n_cells - 1 && high_ok(j + 1)) ++j;
+    while (j >= 0 && !high_ok(j)) --j;
+    last = j;  // -1: none
+}
+
+// One warp per (image, GT).
+//  1. produce: the anchors inside the GT. The in-GT predicate (utils/tal.py:259-262: min of the four fp32
+//     differences > 1e-9  <=>  each one is) separates into an x test per column and a y test per row, so on
+//     a make_anchors grid the anchors are an exact rectangle per level, written to shared memory 32 per
+//     step in ascending anchor order (only ~108 of 136,000 anchors are ever touched).
+//  2. evaluate: 32 pairs at a time with all lanes busy - CIoU, s^alpha * o^beta, the per-anchor
+//     argmax-overlap key (64-bit atomicMax); metric bits parked next to the anchor.
+//  3. select: topk rounds of warp-wide max (redux.sync) over the lanes' local maxima; ties go to the
+//     lowest anchor index = lowest slot, as torch.topk breaks them on the device. Only the lane that owned
+//     the winner rescans its slots.
+// A GT with more than CAND_CAP pairs is handled in chunks: the chunk's winners are carried into the first
+// slots of the next one (they have the lowest anchor indices, so the tie rule still holds).
 __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates_kernel(const AssignParams p) {
-    __shared__ int queue[CAND_WARPS][64];
+    __shared__ uint32_t s_bits[CAND_WARPS][CAND_CAP];
+    __shared__ int s_anc[CAND_WARPS][CAND_CAP];
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= (long long)p.b * p.G) return;
@@ -262,48 +243,79 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
     const float* __restrict__ pds = p.pd_scores + img * p.nc + label;
     const int topk = p.topk;
-    int* q = queue[wib];
-    int qn = 0;  // queued in-GT anchors (warp-uniform)
-    TopK st{0ull, 0ull, true};
+    uint32_t* bits = s_bits[wib];
+    int* ancs = s_anc[wib];
+    int n = 0, n_eval = 0;        // slots filled / evaluated (warp-uniform)
+    uint32_t sel_bits = 0u;       // lane r < n_sel: the r-th best pair so far
+    int sel_anc = -1, n_sel = 0;
 
-    // In-GT test (utils/tal.py:259-262): min of the four fp32 differences > 1e-9  <=>  each one is,
-    // so it separates into an x test per column and a y test per row of the level's grid.
-    auto flush32 = [&]() {
-        const int a32 = q[lane];
-        const int tail = q[32 + lane];
+    auto evaluate = [&]() {  // slots [n_eval, n): anchors -> metric bits
         __syncwarp();
-        q[lane] = tail;
-        qn -= 32;
+        for (int e = n_eval; e < n; e += 32) {
+            const int t = e + lane;
+            if (t < n) bits[t] = eval_pair(p, gt, ancs[t], img, pdb, pds, g, epoch);
+        }
+        n_eval = n;
         __syncwarp();
-        eval_pairs(p, gt, a32, img, pdb, pds, g, topk, lane, epoch, st);
     };
+    auto select = [&]() {  // top-k of slots [0, n) -> lanes 0..n_sel-1
+        uint32_t lm = 0u, nb = 0u;
+        int lt = 0x7fffffff, na = -1, cnt = 0;
+        for (int t = lane; t < n; t += 32) {
+            const uint32_t v = bits[t];
+            if (v > lm) lm = v, lt = t;  // strict: the lowest slot among equals
+        }
+        for (int r = 0; r < topk; ++r) {
+            const uint32_t mx = __reduce_max_sync(FULL, lm);
+            if (mx == 0u) break;
+            const unsigned who = __ballot_sync(FULL, lm == mx);
+            int owner = __ffs(who) - 1;
+            if (who & (who - 1u)) owner = __reduce_min_sync(FULL, lm == mx ? lt : 0x7fffffff) & 31;  // slot t belongs to lane t % 32
+            const int ts = __shfl_sync(FULL, lt, owner);
+            const int as = ancs[ts];
+            if (lane == r) nb = mx, na = as;
+            ++cnt;
+            if (lane == owner) {
+                bits[ts] = 0u;
+                lm = 0u, lt = 0x7fffffff;
+                for (int t = lane; t < n; t += 32) {
+                    const uint32_t v = bits[t];
+                    if (v > lm) lm = v, lt = t;
+                }
+            }
+        }
+        sel_bits = nb, sel_anc = na, n_sel = cnt;
+    };
+    auto make_room = [&]() {  // chunk full: keep its winners, drop the rest
+        if (n + 32 <= CAND_CAP) return;
+        evaluate();
+        select();
+        __syncwarp();
+        if (lane < n_sel) bits[lane] = sel_bits, ancs[lane] = sel_anc;
+        n = n_eval = n_sel;
+        __syncwarp();
+    };
+
     if (grid_ok) {
         for (int l = 0; l < p.n_levels; ++l) {
-            // superset of the cells whose centre can be inside the GT; the exact fp32 predicates decide.
-            // centres inside need index in (x1/s-0.5, x2/s-0.5); [floor, ceil] of the computed bounds
-            // contains it even when the quotient is off by an ulp
             const float s = p.lv[l].stride, inv_s = 1.f / s;
             const int W = p.lv[l].w, H = p.lv[l].h, off = p.lv[l].offset;
-            int ia = (int)floorf(gt.x1 * inv_s - 0.5f) - 1, ib = (int)ceilf(gt.x2 * inv_s - 0.5f) + 1;
-            int ja = (int)floorf(gt.y1 * inv_s - 0.5f) - 1, jb = (int)ceilf(gt.y2 * inv_s - 0.5f) + 1;
-            ia = max(ia, 0), ja = max(ja, 0), ib = min(ib, W - 1), jb = min(jb, H - 1);
-            if (ia > ib || ja > jb) continue;
-            for (int i0 = ia; i0 <= ib; i0 += 32) {  // 32 columns at a time (one pass unless the GT is huge)
-                const int ii = i0 + lane;
-                // anchor x verified bit-identical to anc_points by assign_verify_kernel
-                const float ax = __fmul_rn((float)ii + 0.5f, s);
-                const bool x_in = ii <= ib && __fsub_rn(ax, gt.x1) > 1e-9f && __fsub_rn(gt.x2, ax) > 1e-9f;
-                const unsigned xm = __ballot_sync(0xffffffffu, x_in);
-                if (xm == 0u) continue;
-                const int nxm = __popc(xm), my_pos = __popc(xm & ((1u << lane) - 1u));
-                for (int jj = ja; jj <= jb; ++jj) {
-                    const float ay = __fmul_rn((float)jj + 0.5f, s);
-                    if (!(__fsub_rn(ay, gt.y1) > 1e-9f && __fsub_rn(gt.y2, ay) > 1e-9f)) continue;  // uniform
-                    if (x_in) q[qn + my_pos] = off + jj * W + ii;
-                    qn += nxm;
-                    __syncwarp();
-                    if (qn >= 32) flush32();
+            int i0, i1, j0, j1;
+            // anchor coordinates verified bit-identical to anc_points by assign_verify_kernel
+            cell_range(gt.x1, gt.x2, s, inv_s, W, i0, i1);
+            if (i0 > i1) continue;
+            cell_range(gt.y1, gt.y2, s, inv_s, H, j0, j1);
+            if (j0 > j1) continue;
+            const unsigned nx = (unsigned)(i1 - i0 + 1), cnt = nx * (unsigned)(j1 - j0 + 1);
+            const int base = off + j0 * W + i0;
+            for (unsigned r = 0; r < cnt; r += 32) {
+                make_room();
+                const unsigned t = r + lane;
+                if (t < cnt) {
+                    const unsigned row = t / nx;
+                    ancs[n + lane] = base + (int)row * W + (int)(t - row * nx);
                 }
+                n += (int)min(32u, cnt - r);
             }
         }
     } else {
@@ -314,24 +326,25 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
                 const float2 ap = __ldg(anc + a);
                 inside = anchor_in_gt(ap.x, ap.y, gt);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, inside);
-            if (inside) q[qn + __popc(m & ((1u << lane) - 1u))] = a;
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) flush32();
+            const unsigned m = __ballot_sync(FULL, inside);
+            if (m == 0u) continue;
+            make_room();
+            if (inside) ancs[n + __popc(m & ((1u << lane) - 1u))] = a;
+            n += __popc(m);
         }
     }
-    if (qn > 0) eval_pairs(p, gt, lane < qn ? q[lane] : -1, img, pdb, pds, g, topk, lane, epoch, st);
+    evaluate();
+    select();
 
-    const bool has = lane < topk && st.tk != 0ull;
-    if (has) mark_selected(p.ws.sel + img + (0xffffffffu - (uint32_t)st.tk), epoch, g);
+    const bool has = lane < n_sel;
+    if (has) mark_selected(p.ws.sel + img + sel_anc, epoch, g);
     if (p.zero_fill) {
         // torch.topk pads a short list with zero-metric entries, lowest anchor index first; a padded
         // pick only matters when that anchor lies inside this GT (utils/tal.py:128).
-        int need = topk - __popc(__ballot_sync(0xffffffffu, has));
+        int need = topk - n_sel;
         for (int a = 0; need > 0 && a < p.A; ++a) {
-            const bool mine = has && (0xffffffffu - (uint32_t)st.tk) == (uint32_t)a;
-            if (__any_sync(0xffffffffu, mine)) continue;  // positive pick, already counted
+            const bool mine = has && sel_anc == a;
+            if (__any_sync(FULL, mine)) continue;  // positive pick, already counted
             --need;
             const float2 ap = __ldg(anc + a);
             if (lane == 0 && anchor_in_gt(ap.x, ap.y, gt)) mark_selected(p.ws.sel + img + a, epoch, g);
@@ -339,19 +352,26 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     }
 }
 
-// ---- resolve -----------------------------------------------------------------------------------
+// ---- resolve + owner metric --------------------------------------------------------------------
 
 constexpr int RES_THREADS = 256;
 constexpr int RES_ITERS = 8;  // anchors per CTA = RES_THREADS * RES_ITERS
 
 // The image's GT table is staged in shared memory: boxes by one TMA bulk copy (always 16 B aligned),
 // labels and mask by plain loads. Each thread then owns RES_ITERS anchors (state words loaded up
-// front so RES_ITERS independent loads are in flight).
+// front so RES_ITERS independent loads are in flight) and writes labels / boxes / fg / gt_idx.
+// The CTA's foreground anchors (a few per cent) are compacted into a shared-memory list and then
+// evaluated with all lanes busy: the alignment metric of each (anchor, owner GT) pair, recomputed with
+// the same instruction sequence as in assign_candidates_kernel (=> identical bits; this also covers
+// anchors owned by a GT that did not top-k them), stored in the owner's target_scores slot, plus the
+// per-GT maxima of utils/tal.py:112-114. The list is also appended to the global one for the normalise
+// pass (one global atomic per CTA).
 __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const AssignParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ int warp_tot[RES_THREADS / 32];
-    __shared__ int block_base;
+    __shared__ int block_base, block_tot;
+    __shared__ uint2 s_fg[RES_THREADS * RES_ITERS];  // (anchor, owner GT) of the CTA's foreground anchors
     float4* s_box = reinterpret_cast<float4*>(smem_raw);
     float* s_lab = reinterpret_cast<float*>(smem_raw + (size_t)p.G * 16);
     float* s_msk = s_lab + p.G;
@@ -366,6 +386,7 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
         const uint32_t bytes = (uint32_t)p.G * 16u;
         mbar_expect_tx(&bar, bytes);
         tma_load_1d(s_box, p.gt_bboxes + (size_t)bi * p.G * 4, bytes, &bar);
+        if (blockIdx.x == 0 && bi == 0) p.ws.flags[0] = 0;  // consumed by the candidates kernel; clean for the next call
     }
     for (int g = tid; g < p.G; g += RES_THREADS) {
         s_lab[g] = p.gt_labels[(size_t)bi * p.G + g];
@@ -384,10 +405,12 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
     mbar_wait(&bar, 0);
 
     unsigned fg_bits = 0u;
+    uint32_t own[RES_ITERS];
 #pragma unroll
     for (int it = 0; it < RES_ITERS; ++it) {
         const int a = a_base + it * RES_THREADS;
-        if (a >= p.A) break;
+        own[it] = 0u;
+        if (a >= p.A) continue;
         const size_t idx = img + a;
         const bool fg = (sel[it].y >> 24) == epoch;
         uint32_t g = 0;
@@ -402,6 +425,7 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
                 g = any ? (uint32_t)(KEY_GMASK - (k & KEY_GMASK)) : 0u;
             }
         }
+        own[it] = g;
         const float4 gb = s_box[g];
         long long lab = (long long)s_lab[g];
         lab = lab < 0 ? 0 : lab;
@@ -409,14 +433,13 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
         p.target_labels[idx] = lab;
         p.fg_mask[idx] = fg ? 1 : 0;
         reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
-        // foreground entries get their alignment metric from assign_fg_metric_kernel (compact list)
-        if (p.nc == 1) p.target_scores[idx] = 0.f;
+        if (p.nc == 1 && !fg) p.target_scores[idx] = 0.f;  // foreground entries are written below
         if (epoch == 255u) {  // last epoch before the wrap: leave the state clean for epoch 1
             p.ws.sel[idx] = make_uint2(0u, 0u);
             p.ws.key[idx] = 0ull;
         }
     }
-    // compact list of foreground anchors for the normalise pass: one global atomic per CTA
+    // compact the CTA's foreground anchors: shared-memory list + one global atomic per CTA
     const int mine = __popc(fg_bits);
     int incl = mine;
 #pragma unroll
@@ -433,44 +456,39 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
             warp_tot[w] = tot;
             tot += t;
         }
+        block_tot = tot;
         block_base = tot ? atomicAdd(p.ws.flags + 1, tot) : 0;
     }
     __syncthreads();
-    int slot = block_base + warp_tot[wib] + incl - mine;
+    int slot = warp_tot[wib] + incl - mine;
 #pragma unroll
     for (int it = 0; it < RES_ITERS; ++it)
-        if (fg_bits & (1u << it)) p.ws.fg_list[slot++] = (uint32_t)(img + a_base + it * RES_THREADS);
-}
-
-// ---- foreground metric -------------------------------------------------------------------------
-
-// Compact foreground list, all lanes busy: alignment metric of each (anchor, owner GT) pair, recomputed
-// with the same instruction sequence as in assign_candidates_kernel (=> identical bits; also covers
-// anchors owned by a GT that did not top-k them), stored in the owner's target_scores slot, and the
-// per-GT maxima of utils/tal.py:112-114.
-__global__ void __launch_bounds__(256) assign_fg_metric_kernel(const AssignParams p) {
-    const int n = p.ws.flags[1];
+        if (fg_bits & (1u << it)) s_fg[slot++] = make_uint2((uint32_t)(a_base + it * RES_THREADS), own[it]);
+    __syncthreads();
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const size_t idx = p.ws.fg_list[i];
-        const int bi = (int)(idx / (size_t)p.A);
-        const int a = (int)(idx - (size_t)bi * p.A);
-        const long long g = p.target_gt_idx[idx];
-        long long lab = p.target_labels[idx];
-        lab = lab >= p.nc ? p.nc - 1 : lab;
+    for (int i = tid; i < block_tot; i += RES_THREADS) {
+        const uint2 e = s_fg[i];
+        const int a = (int)e.x;
+        const uint32_t g = e.y;
+        const size_t idx = img + a;
         const size_t gslot = (size_t)bi * p.G + g;
-        const GtBox gt = make_gt(*reinterpret_cast<const float4*>(p.gt_bboxes + gslot * 4));
-        const float2 ap = __ldg(anc + a);
+        long long lab = (long long)s_lab[g];
+        lab = lab < 0 ? 0 : (lab >= p.nc ? p.nc - 1 : lab);
         float al = 0.f;
-        if (p.mask_gt[gslot] != 0.f && anchor_in_gt(ap.x, ap.y, gt)) {
-            const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
-            const float sc = __ldg(p.pd_scores + idx * p.nc + lab);
-            const float o = overlap_ciou(gt, pb);
-            al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
-            atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
-            atomicMax(p.ws.pos_align + gslot, __float_as_uint(al));
+        if (s_msk[g] != 0.f) {
+            const GtBox gt = make_gt(s_box[g]);
+            const float2 ap = __ldg(anc + a);
+            if (anchor_in_gt(ap.x, ap.y, gt)) {
+                const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
+                const float sc = __ldg(p.pd_scores + idx * p.nc + lab);
+                const float o = overlap_ciou(gt, pb);
+                al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
+                atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
+                atomicMax(p.ws.pos_align + gslot, __float_as_uint(al));
+            }
         }
         p.target_scores[idx * p.nc + lab] = al;
+        p.ws.fg_list[block_base + i] = make_uint2((uint32_t)idx, (uint32_t)gslot);
     }
 }
 
@@ -484,14 +502,16 @@ __global__ void __launch_bounds__(256) assign_normalize_kernel(const AssignParam
     const int n = p.ws.flags[1];
     float local = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const size_t idx = p.ws.fg_list[i];
-        const int bi = (int)(idx / (size_t)p.A);
-        const long long g = p.target_gt_idx[idx];
-        long long lab = p.target_labels[idx];
-        lab = lab >= p.nc ? p.nc - 1 : lab;
+        const uint2 e = p.ws.fg_list[i];
+        const size_t idx = e.x, gslot = e.y;
+        long long lab = 0;
+        if (p.nc > 1) {
+            lab = (long long)p.gt_labels[gslot];
+            lab = lab < 0 ? 0 : (lab >= p.nc ? p.nc - 1 : lab);
+        }
         float* dst = p.target_scores + idx * p.nc + lab;
-        const float ov = __uint_as_float(p.ws.pos_ov[(size_t)bi * p.G + g]);
-        const float pa = __uint_as_float(p.ws.pos_align[(size_t)bi * p.G + g]);
+        const float ov = __uint_as_float(p.ws.pos_ov[gslot]);
+        const float pa = __uint_as_float(p.ws.pos_align[gslot]);
         const float v = __fdiv_rn(__fmul_rn(*dst, ov), __fadd_rn(pa, p.eps));  // utils/tal.py:115
         *dst = v;
         local += v;
@@ -530,7 +550,7 @@ static void split_ws(void* workspace, int b, int A, int G, AssignWs& ws, size_t&
     ws.state_bytes = o;
     ws.pos_align = (uint32_t*)take((size_t)b * G * 4);
     ws.pos_ov = (uint32_t*)take((size_t)b * G * 4);
-    ws.fg_list = (uint32_t*)take(n * 4);
+    ws.fg_list = (uint2*)take(n * 8);
     total = o;
 }
 
@@ -564,6 +584,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     KZD_CHECK_ARG(score_dtype >= 0 && score_dtype <= 2, "kzd_tal_assign: score_dtype=%d not in {0,1,2}", score_dtype);
     KZD_CHECK_ARG((double)b * A < 4294967295.0 && G < (1 << 24) - 2, "kzd_tal_assign: b*A or G too large");
     KZD_CHECK_ARG((size_t)G * 24 <= 200 * 1024, "kzd_tal_assign: G=%d exceeds the shared-memory GT table (8533)", G);
+    KZD_CHECK_ARG((double)b * G < 4294967295.0, "kzd_tal_assign: b*G too large");
     KZD_CHECK_ARG(((uintptr_t)gt_bboxes) % 16 == 0 && ((uintptr_t)pd_bboxes) % 16 == 0 &&
                       ((uintptr_t)target_bboxes) % 16 == 0 && ((uintptr_t)anc_points) % 8 == 0 &&
                       ((uintptr_t)workspace) % 256 == 0,
@@ -594,11 +615,12 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
 
     cudaStream_t st = (cudaStream_t)stream;
     if (!persistent) KZD_CUDA(cudaMemsetAsync(workspace, 0, p.ws.state_bytes, st));  // stateless mode
-    assign_begin_kernel<<<1, 1, 0, st>>>(p.ws, persistent ? 0 : 1);
-    KZD_LAUNCH_CHECK("assign_begin_kernel");
     if (n_levels > 0) {
-        assign_verify_kernel<<<(A + 255) / 256, 256, 0, st>>>(anc_points, A, p);
+        assign_verify_kernel<<<(A + 255) / 256, 256, 0, st>>>(anc_points, A, p, persistent ? 0 : 1);
         KZD_LAUNCH_CHECK("assign_verify_kernel");
+    } else {
+        assign_begin_kernel<<<1, 1, 0, st>>>(p.ws, persistent ? 0 : 1);
+        KZD_LAUNCH_CHECK("assign_begin_kernel");
     }
     if (nc > 1) {  // dense (b,A,nc) target_scores: zero rows now, the owner's entry is written later
         const size_t n = (size_t)b * A * nc;
@@ -630,8 +652,6 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
         KZD_LAUNCH_CHECK("assign_resolve_kernel");
     }
     {
-        assign_fg_metric_kernel<<<(unsigned)sm_count() * 2, 256, 0, st>>>(p);
-        KZD_LAUNCH_CHECK("assign_fg_metric_kernel");
         assign_normalize_kernel<<<(unsigned)sm_count() * 2, 256, 0, st>>>(p);
         KZD_LAUNCH_CHECK("assign_normalize_kernel");
     }

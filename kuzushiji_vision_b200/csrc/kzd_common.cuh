@@ -91,4 +91,37 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
         : "memory");
 }
 
+// ---- NMS candidate pool (shared by nms_filter_kernel and the filtering decode kernel) ---------------
+
+typedef unsigned long long u64;
+
+// key = score_bits<<32 | ~order: a plain 64-bit descending order of the keys reproduces torchvision's
+// stable descending score sort (order = anchor index, or anchor*nc+class for multi-label rows)
+__device__ __forceinline__ void write_candidate(int slot, int cap, float x1, float y1, float x2, float y2, float conf,
+                                                int cls, uint32_t order, unsigned long long* __restrict__ keys,
+                                                float* __restrict__ rows) {
+    if (slot < cap) {
+        keys[slot] = ((unsigned long long)__float_as_uint(conf) << 32) | (unsigned long long)(0xffffffffu - order);
+        float2* r = reinterpret_cast<float2*>(rows + (size_t)slot * 6);  // 24-byte rows are 8-byte aligned
+        r[0] = make_float2(x1, y1), r[1] = make_float2(x2, y2), r[2] = make_float2(conf, (float)cls);
+    }
+}
+
+// Warp-aggregated slot allocation: every lane asks for `want` (0..VEC) consecutive slots.
+__device__ __forceinline__ int warp_alloc(int want, int32_t* __restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    int incl = want;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return 0;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(count, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - want;
+}
+
 }  // namespace kzd

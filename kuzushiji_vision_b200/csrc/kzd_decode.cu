@@ -87,84 +87,132 @@ struct Out<1> {
 // its pixel-space copy (utils/loss.py:197-204,236) - so that validation-during-training
 // (engine/validator.py:180-185: eval-mode Detect, then model.loss on the same maps) reads the head
 // outputs once instead of twice.
-template <int VEC, typename T, bool DUAL>
+// FILTER: additionally do the first stage of non_max_suppression (utils/ops.py:234-286, best-class path)
+// on the values just computed: y's box rows are written as xyxy (the state ops.py:243-244 leaves the
+// caller's tensor in) and every anchor above conf is appended to the candidate pool, exactly as
+// nms_filter_kernel would after re-reading y - which saves that pass (a read of y and the write-back).
+struct FilterArgs {
+    float conf;
+    u64* keys;
+    float* rows;
+    int32_t* counts;
+    int cap;
+};
+
+template <int VEC, typename T, bool DUAL, bool FILTER>
 __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, float* __restrict__ y,
                                                            float* __restrict__ out_xyxy,
-                                                           float* __restrict__ out_px) {
+                                                           float* __restrict__ out_px, const FilterArgs f) {
     const int bi = blockIdx.y;
     const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (a0 >= p.A) return;
-    int l = 0;
+    const bool live = a0 < p.A;
+    if (!FILTER && !live) return;  // FILTER: whole warps stay alive for the slot allocation
+    float ox[VEC], oy[VEC], ow[VEC], oh[VEC], best[VEC];
+    int cls[VEC];
+    if (live) {
+        int l = 0;
 #pragma unroll
-    for (int k = 1; k < KZD_MAX_LEVELS; ++k)
-        if (k < p.n_levels && a0 >= p.off[k]) l = k;
-    const int hw = p.hw[l];
-    const int pos = a0 - p.off[l];
-    const int no = 4 * KZD_REG_MAX + p.nc;
-    const T* __restrict__ src = reinterpret_cast<const T*>(p.ptr[l]) + (size_t)bi * no * hw + pos;
+        for (int k = 1; k < KZD_MAX_LEVELS; ++k)
+            if (k < p.n_levels && a0 >= p.off[k]) l = k;
+        const int hw = p.hw[l];
+        const int pos = a0 - p.off[l];
+        const int no = 4 * KZD_REG_MAX + p.nc;
+        const T* __restrict__ src = reinterpret_cast<const T*>(p.ptr[l]) + (size_t)bi * no * hw + pos;
 
-    float d[4][VEC];
+        float d[4][VEC];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        float v[KZD_REG_MAX][VEC];
+        for (int s = 0; s < 4; ++s) {
+            float v[KZD_REG_MAX][VEC];
 #pragma unroll
-        for (int k = 0; k < KZD_REG_MAX; ++k) In<VEC, T>::load(v[k], src + (size_t)(s * KZD_REG_MAX + k) * hw);
+            for (int k = 0; k < KZD_REG_MAX; ++k) In<VEC, T>::load(v[k], src + (size_t)(s * KZD_REG_MAX + k) * hw);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float m = v[0][i];
+#pragma unroll
+                for (int k = 1; k < KZD_REG_MAX; ++k) m = fmaxf(m, v[k][i]);
+                // exp(v - m) = ex2(v*log2e - m*log2e): one FFMA + one MUFU per bin; weights per 4-bin chunk
+                const float L2E = 1.4426950408889634f;
+                const float ml = -m * L2E;
+                float sum = 0.f, wsum = 0.f;
+#pragma unroll
+                for (int c = 0; c < KZD_REG_MAX; c += 4) {
+                    const float e0 = ex2_approx(fmaf(v[c][i], L2E, ml)), e1 = ex2_approx(fmaf(v[c + 1][i], L2E, ml));
+                    const float e2 = ex2_approx(fmaf(v[c + 2][i], L2E, ml)), e3 = ex2_approx(fmaf(v[c + 3][i], L2E, ml));
+                    const float sc = (e0 + e1) + (e2 + e3);
+                    sum += sc;
+                    wsum += fmaf((float)c, sc, fmaf(3.f, e3, fmaf(2.f, e2, e1)));
+                }
+                d[s][i] = wsum / sum;
+            }
+        }
+        const float st = p.stride[l];
+        const int w = p.w[l];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            float m = v[0][i];
-#pragma unroll
-            for (int k = 1; k < KZD_REG_MAX; ++k) m = fmaxf(m, v[k][i]);
-            // exp(v - m) = ex2(v*log2e - m*log2e): one FFMA + one MUFU per bin; weights per 4-bin chunk
-            const float L2E = 1.4426950408889634f;
-            const float ml = -m * L2E;
-            float sum = 0.f, wsum = 0.f;
-#pragma unroll
-            for (int c = 0; c < KZD_REG_MAX; c += 4) {
-                const float e0 = ex2_approx(fmaf(v[c][i], L2E, ml)), e1 = ex2_approx(fmaf(v[c + 1][i], L2E, ml));
-                const float e2 = ex2_approx(fmaf(v[c + 2][i], L2E, ml)), e3 = ex2_approx(fmaf(v[c + 3][i], L2E, ml));
-                const float sc = (e0 + e1) + (e2 + e3);
-                sum += sc;
-                wsum += fmaf((float)c, sc, fmaf(3.f, e3, fmaf(2.f, e2, e1)));
+            const int q = pos + i;
+            const float ax = (float)(q % w) + 0.5f;
+            const float ay = (float)(q / w) + 0.5f;
+            const float x1 = ax - d[0][i], y1 = ay - d[1][i];
+            const float x2 = ax + d[2][i], y2 = ay + d[3][i];
+            ox[i] = ((x1 + x2) * 0.5f) * st;
+            oy[i] = ((y1 + y2) * 0.5f) * st;
+            ow[i] = (x2 - x1) * st;
+            oh[i] = (y2 - y1) * st;
+            if (DUAL) {
+                const size_t o = ((size_t)bi * p.A + a0 + i) * 4;
+                __stcs(reinterpret_cast<float4*>(out_xyxy + o), make_float4(x1, y1, x2, y2));
+                if (out_px)
+                    __stcs(reinterpret_cast<float4*>(out_px + o),
+                           make_float4(__fmul_rn(x1, st), __fmul_rn(y1, st), __fmul_rn(x2, st), __fmul_rn(y2, st)));
             }
-            d[s][i] = wsum / sum;
         }
-    }
-    const float st = p.stride[l];
-    const int w = p.w[l];
-    float ox[VEC], oy[VEC], ow[VEC], oh[VEC];
+        if (FILTER) {  // xywh -> xyxy from the fp32 values y would have held (utils/ops.py:429-432)
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        const int q = pos + i;
-        const float ax = (float)(q % w) + 0.5f;
-        const float ay = (float)(q / w) + 0.5f;
-        const float x1 = ax - d[0][i], y1 = ay - d[1][i];
-        const float x2 = ax + d[2][i], y2 = ay + d[3][i];
-        ox[i] = ((x1 + x2) * 0.5f) * st;
-        oy[i] = ((y1 + y2) * 0.5f) * st;
-        ow[i] = (x2 - x1) * st;
-        oh[i] = (y2 - y1) * st;
-        if (DUAL) {
-            const size_t o = ((size_t)bi * p.A + a0 + i) * 4;
-            __stcs(reinterpret_cast<float4*>(out_xyxy + o), make_float4(x1, y1, x2, y2));
-            if (out_px)
-                __stcs(reinterpret_cast<float4*>(out_px + o),
-                       make_float4(__fmul_rn(x1, st), __fmul_rn(y1, st), __fmul_rn(x2, st), __fmul_rn(y2, st)));
+            for (int i = 0; i < VEC; ++i) {
+                const float hw2 = ow[i] * 0.5f, hh2 = oh[i] * 0.5f;
+                const float cx = ox[i], cy = oy[i];
+                ox[i] = cx - hw2, oy[i] = cy - hh2, ow[i] = cx + hw2, oh[i] = cy + hh2;
+            }
         }
-    }
-    float* __restrict__ dst = y + (size_t)bi * (4 + p.nc) * p.A + a0;
-    Out<VEC>::store(dst, ox);
-    Out<VEC>::store(dst + (size_t)p.A, oy);
-    Out<VEC>::store(dst + 2 * (size_t)p.A, ow);
-    Out<VEC>::store(dst + 3 * (size_t)p.A, oh);
-    const T* __restrict__ csrc = src + (size_t)(4 * KZD_REG_MAX) * hw;
-    float* __restrict__ cdst = dst + 4 * (size_t)p.A;
+        float* __restrict__ dst = y + (size_t)bi * (4 + p.nc) * p.A + a0;
+        Out<VEC>::store(dst, ox);
+        Out<VEC>::store(dst + (size_t)p.A, oy);
+        Out<VEC>::store(dst + 2 * (size_t)p.A, ow);
+        Out<VEC>::store(dst + 3 * (size_t)p.A, oh);
+        const T* __restrict__ csrc = src + (size_t)(4 * KZD_REG_MAX) * hw;
+        float* __restrict__ cdst = dst + 4 * (size_t)p.A;
 #pragma unroll 4
-    for (int c = 0; c < p.nc; ++c) {
-        float v[VEC], o[VEC];
-        In<VEC, T>::load(v, csrc + (size_t)c * hw);
+        for (int c = 0; c < p.nc; ++c) {
+            float v[VEC], o[VEC];
+            In<VEC, T>::load(v, csrc + (size_t)c * hw);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = 1.f / (1.f + __expf(-v[i]));  // |err| < 2e-7: ex2.approx + IEEE div
-        Out<VEC>::store(cdst + (size_t)c * p.A, o);
+            for (int i = 0; i < VEC; ++i) {
+                o[i] = 1.f / (1.f + __expf(-v[i]));  // |err| < 2e-7: ex2.approx + IEEE div
+                if (FILTER && (c == 0 || o[i] > best[i])) best[i] = o[i], cls[i] = c;  // first maximum wins (ops.py:274)
+            }
+            Out<VEC>::store(cdst + (size_t)c * p.A, o);
+        }
+    }
+    if (FILTER) {
+        int want = 0;
+        bool is_cand[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            is_cand[i] = live && best[i] > f.conf;
+            want += is_cand[i] ? 1 : 0;
+        }
+        int slot = warp_alloc(want, f.counts + bi);
+        if (want) {
+            u64* k_img = f.keys + (size_t)bi * f.cap;
+            float* r_img = f.rows + (size_t)bi * f.cap * 6;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+                if (is_cand[i]) {
+                    write_candidate(slot, f.cap, ox[i], oy[i], ow[i], oh[i], best[i], cls[i], (uint32_t)(a0 + i), k_img,
+                                    r_img);
+                    ++slot;
+                }
+        }
     }
 }
 
@@ -382,26 +430,33 @@ __global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const floa
 
 using namespace kzd;
 
-template <typename T>
-static void launch_infer(const InferParams& p, int total, int b, bool vec4, float* y, float* out_xyxy, float* out_px,
-                         cudaStream_t st) {
-    if (vec4) {
-        dim3 grid((total / 4 + 127) / 128, b);
-        if (out_xyxy) decode_infer_kernel<4, T, true><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px);
-        else decode_infer_kernel<4, T, false><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr);
+template <int VEC, typename T>
+static void launch_infer_vec(const InferParams& p, dim3 grid, float* y, float* out_xyxy, float* out_px,
+                             const FilterArgs* f, cudaStream_t st) {
+    const FilterArgs none{0.f, nullptr, nullptr, nullptr, 0};
+    if (f) {
+        if (out_xyxy) decode_infer_kernel<VEC, T, true, true><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px, *f);
+        else decode_infer_kernel<VEC, T, false, true><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr, *f);
     } else {
-        dim3 grid((total + 127) / 128, b);
-        if (out_xyxy) decode_infer_kernel<1, T, true><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px);
-        else decode_infer_kernel<1, T, false><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr);
+        if (out_xyxy) decode_infer_kernel<VEC, T, true, false><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px, none);
+        else decode_infer_kernel<VEC, T, false, false><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr, none);
     }
 }
 
+template <typename T>
+static void launch_infer(const InferParams& p, int total, int b, bool vec4, float* y, float* out_xyxy, float* out_px,
+                         const FilterArgs* f, cudaStream_t st) {
+    if (vec4) launch_infer_vec<4, T>(p, dim3((total / 4 + 127) / 128, b), y, out_xyxy, out_px, f, st);
+    else launch_infer_vec<1, T>(p, dim3((total + 127) / 128, b), y, out_xyxy, out_px, f, st);
+}
+
 static int decode_maps(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels, int n_levels, int b,
-                       int nc, float* y, float* out_xyxy, float* out_px, void* stream, const char* who);
+                       int nc, float* y, float* out_xyxy, float* out_px, const FilterArgs* f, void* stream,
+                       const char* who);
 
 extern "C" __attribute__((visibility("default"))) int kzd_decode_infer(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels,
                                 int n_levels, int b, int nc, float* y, void* stream) {
-    return decode_maps(h_level_ptrs, in_dtype, h_levels, n_levels, b, nc, y, nullptr, nullptr, stream,
+    return decode_maps(h_level_ptrs, in_dtype, h_levels, n_levels, b, nc, y, nullptr, nullptr, nullptr, stream,
                        "kzd_decode_infer");
 }
 
@@ -412,12 +467,27 @@ extern "C" __attribute__((visibility("default"))) int kzd_decode_dual(const void
         set_error("kzd_decode_dual: null out_xyxy");
         return KZD_EINVAL;
     }
-    return decode_maps(h_level_ptrs, in_dtype, h_levels, n_levels, b, nc, y, out_xyxy, out_xyxy_px, stream,
+    return decode_maps(h_level_ptrs, in_dtype, h_levels, n_levels, b, nc, y, out_xyxy, out_xyxy_px, nullptr, stream,
                        "kzd_decode_dual");
 }
 
+extern "C" __attribute__((visibility("default"))) int kzd_decode_filter(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels,
+                                 int n_levels, int b, int nc, float* y, float* out_xyxy, float* out_xyxy_px,
+                                 float conf_thres, uint64_t* cand_keys, float* cand_rows, int32_t* cand_counts,
+                                 int cand_cap, void* stream) {
+    KZD_CHECK_ARG(cand_keys && cand_rows && cand_counts, "kzd_decode_filter: null candidate pool");
+    KZD_CHECK_ARG(nc >= 1 && cand_cap >= 1, "kzd_decode_filter: bad sizes nc=%d cap=%d", nc, cand_cap);
+    KZD_CHECK_ARG(out_xyxy || !out_xyxy_px, "kzd_decode_filter: out_xyxy_px without out_xyxy");
+    if (b <= 0) return b == 0 ? 0 : KZD_EINVAL;
+    KZD_CUDA(cudaMemsetAsync(cand_counts, 0, (size_t)b * sizeof(int32_t), (cudaStream_t)stream));
+    const FilterArgs f{conf_thres, (u64*)cand_keys, cand_rows, cand_counts, cand_cap};
+    return decode_maps(h_level_ptrs, in_dtype, h_levels, n_levels, b, nc, y, out_xyxy, out_xyxy_px, &f, stream,
+                       "kzd_decode_filter");
+}
+
 static int decode_maps(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels, int n_levels, int b,
-                       int nc, float* y, float* out_xyxy, float* out_px, void* stream, const char* who) {
+                       int nc, float* y, float* out_xyxy, float* out_px, const FilterArgs* f, void* stream,
+                       const char* who) {
     KZD_CHECK_ARG(h_level_ptrs && h_levels && y, "%s: null pointer", who);
     KZD_CHECK_ARG(n_levels >= 1 && n_levels <= KZD_MAX_LEVELS, "%s: n_levels=%d not in [1,%d]", who, n_levels,
                   KZD_MAX_LEVELS);
@@ -447,9 +517,9 @@ static int decode_maps(const void* const* h_level_ptrs, int in_dtype, const kzd_
     if (b == 0) return 0;
     KZD_CHECK_ARG(b <= 65535, "%s: b=%d > 65535", who, b);
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_dtype == 1) launch_infer<__half>(p, off, b, vec4, y, out_xyxy, out_px, st);
-    else if (in_dtype == 2) launch_infer<__nv_bfloat16>(p, off, b, vec4, y, out_xyxy, out_px, st);
-    else launch_infer<float>(p, off, b, vec4, y, out_xyxy, out_px, st);
+    if (in_dtype == 1) launch_infer<__half>(p, off, b, vec4, y, out_xyxy, out_px, f, st);
+    else if (in_dtype == 2) launch_infer<__nv_bfloat16>(p, off, b, vec4, y, out_xyxy, out_px, f, st);
+    else launch_infer<float>(p, off, b, vec4, y, out_xyxy, out_px, f, st);
     KZD_LAUNCH_CHECK("decode_infer_kernel");
     return 0;
 }

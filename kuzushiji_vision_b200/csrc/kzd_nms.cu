@@ -20,8 +20,6 @@
 
 namespace kzd {
 
-typedef unsigned long long u64;
-
 // ------------------------------------------------------------------------------------------
 // stage 1: filter
 // ------------------------------------------------------------------------------------------
@@ -31,33 +29,6 @@ __device__ __forceinline__ bool class_allowed(int c, const int32_t* __restrict__
     for (int k = 0; k < n_classes; ++k)
         if (classes[k] == c) return true;
     return false;
-}
-
-__device__ __forceinline__ void write_candidate(int slot, int cap, float x1, float y1, float x2, float y2, float conf,
-                                                int cls, uint32_t order, u64* __restrict__ keys,
-                                                float* __restrict__ rows) {
-    if (slot < cap) {
-        keys[slot] = ((u64)__float_as_uint(conf) << 32) | (u64)(0xffffffffu - order);
-        float2* r = reinterpret_cast<float2*>(rows + (size_t)slot * 6);  // 24-byte rows are 8-byte aligned
-        r[0] = make_float2(x1, y1), r[1] = make_float2(x2, y2), r[2] = make_float2(conf, (float)cls);
-    }
-}
-
-// Warp-aggregated slot allocation: every lane asks for `want` (0..VEC) consecutive slots.
-__device__ __forceinline__ int warp_alloc(int want, int32_t* __restrict__ count) {
-    const int lane = threadIdx.x & 31;
-    int incl = want;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return 0;
-    int base = 0;
-    if (lane == 31) base = atomicAdd(count, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    return base + incl - want;
 }
 
 // Best-class path, VEC consecutive anchors per thread (128-bit loads/stores when VEC == 4).
@@ -336,17 +307,21 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
     extern __shared__ int pre[];  // (b+1) prefix of item counts
     __shared__ float4 colbox[MASK_CG * 64];
     static_assert(MASK_CG == 4, "items_before() assumes groups of 4 column tiles");
+    for (int i = threadIdx.x; i < b; i += MASK_THREADS) {  // item counts: the loads of all images in flight together
+        const int n = ws.n_sorted[i];
+        const int done = phase > 0 ? ws.state[i * 4] : 0;
+        int items = 0;
+        if (n > 0 && !done) {
+            const int T = (n + 63) >> 6;
+            items = items_before(T, g_hi) - items_before(T, g_lo);
+        }
+        pre[i + 1] = items;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int i = 0; i < b; ++i) {
-            pre[i] = acc;
-            const int n = ws.n_sorted[i];
-            if (n > 0 && !(phase > 0 && ws.state[i * 4])) {
-                const int T = (n + 63) >> 6;
-                acc += items_before(T, g_hi) - items_before(T, g_lo);
-            }
-        }
-        pre[b] = acc;
+        pre[0] = 0;
+        for (int i = 1; i <= b; ++i) acc += pre[i], pre[i] = acc;
     }
     __syncthreads();
     const int total = pre[b];

@@ -20,7 +20,7 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def decode_inference(levels_x, strides, nc, with_train_boxes=False):
+def decode_inference(levels_x, strides, nc, with_train_boxes=False, nms_pool=None):
     """Fused DFL softmax-expectation + dist2bbox(xywh) + x stride + class sigmoid.
 
     ``levels_x``: list of per-level maps ``(b, 64+nc, H_l, W_l)`` (CUDA), ``strides``: floats.
@@ -30,6 +30,12 @@ def decode_inference(levels_x, strides, nc, with_train_boxes=False):
     decode of these maps - ``v8DetectionLoss.bbox_decode`` (utils/loss.py:197-204) in grid units and its
     ``* stride_tensor`` copy (loss.py:236) - so validation-during-training (engine/validator.py:180-185)
     reads the head outputs once and needs no ``(b,A,64)`` transposed copy for the decode.
+
+    ``nms_pool=(conf_thres, keys, rows, counts)`` (the candidate pool ``ops.nms_batched`` allocates: int64
+    ``(b,cap)``, fp32 ``(b,cap,6)``, int32 ``(b)``) additionally runs the first stage of
+    ``non_max_suppression`` (utils/ops.py:234-286) inside the decode kernel: ``y``'s box rows come back as
+    xyxy (what ``in_place=True`` leaves behind, ops.py:243-244) and the pool is filled, so the NMS that follows
+    skips its filter pass over ``y``.
     """
     x0 = levels_x[0]
     _lib.require_cuda(x0, "Detect input")
@@ -46,6 +52,17 @@ def decode_inference(levels_x, strides, nc, with_train_boxes=False):
     lv, A = _lib.levels_array([(xi.shape[2], xi.shape[3], float(s)) for xi, s in zip(xs, strides)])
     ptrs = (C.c_void_p * len(xs))(*[xi.data_ptr() for xi in xs])
     y = torch.empty((b, 4 + nc, A), dtype=torch.float32, device=x0.device)
+    if nms_pool is not None:
+        conf, keys, rows, counts = nms_pool
+        xyxy = torch.empty((b, A, 4), dtype=torch.float32, device=x0.device) if with_train_boxes else None
+        px = torch.empty_like(xyxy) if with_train_boxes else None
+        with torch.cuda.device(x0.device):
+            rc = _lib.lib.kzd_decode_filter(ptrs, code, lv, len(xs), b, nc, y.data_ptr(),
+                                            xyxy.data_ptr() if with_train_boxes else None,
+                                            px.data_ptr() if with_train_boxes else None, float(conf), keys.data_ptr(),
+                                            rows.data_ptr(), counts.data_ptr(), keys.shape[1], _stream(x0.device))
+        _lib.check(rc, "kzd_decode_filter")
+        return (y, xyxy, px) if with_train_boxes else y
     if with_train_boxes:
         xyxy = torch.empty((b, A, 4), dtype=torch.float32, device=x0.device)
         px = torch.empty_like(xyxy)

@@ -28,7 +28,7 @@ from .tal import TaskAlignedAssigner, make_anchors
 class PagePipeline:
     def __init__(self, batch, level_hw, strides, nc, n_max_boxes, device="cuda:0", topk=10, alpha=0.5, beta=6.0,
                  conf_thres=0.25, iou_thres=0.7, max_det=300, max_nms=30000, agnostic=False, max_wh=7680.0,
-                 pool=32768, n_cap=4096, use_graph=True, overlap=True, fuse_decodes=False):
+                 pool=32768, n_cap=4096, use_graph=True, overlap=True, fuse_decodes=False, fuse_filter=False):
         dev = torch.device(device)
         self.device, self.b, self.nc, self.G = dev, int(batch), int(nc), int(n_max_boxes)
         self.level_hw = [(int(h), int(w)) for h, w in level_hw]
@@ -68,15 +68,18 @@ class PagePipeline:
         # one kernel reads the head maps once and emits both y and the training-side boxes (the
         # validation-during-training flow, engine/validator.py:180-185); pred_distri is then not read
         self.fuse_decodes = bool(fuse_decodes)
+        # the inference decode also does the NMS filter stage (conf threshold, xyxy, candidate pool) on the
+        # values it has just computed, so the NMS branch starts at the ordering kernels
+        self.fuse_filter = bool(fuse_filter)
         self._side = torch.cuda.Stream(device=dev, priority=-1)  # the small NMS kernels go first
         self.out = None
         self.graph = None
-        # decode_train, assign x6, decode_infer, nms filter + chunk sort + rank + (mask, scan) per phase
+        # decode_train, assign x4, decode_infer, nms filter + chunk sort + rank + (mask, scan) per phase
         t0 = ((self.max_det + self.max_det // 4 + 127) // 64 + 3) // 4 * 4
         t_cap, phases = (self.n_cap + 63) // 64, 1
         while t0 < t_cap:
             t0, phases = t0 * 4, phases + 1
-        self.kernels_per_step = (1 if self.fuse_decodes else 2) + 6 + 3 + 2 * phases
+        self.kernels_per_step = (1 if self.fuse_decodes else 2) + 4 + (2 if self.fuse_filter else 3) + 2 * phases
         if use_graph:
             self._capture()
 
@@ -89,14 +92,18 @@ class PagePipeline:
         dev = self.device
         lib = _lib.lib
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(lib.kzd_nms_filter(y.data_ptr(), self.b, self.A, self.nc, self.conf, 0, None, 0, 1,
-                                      self.keys.data_ptr(), self.rows.data_ptr(), self.counts[0].data_ptr(), self.pool,
-                                      st), "kzd_nms_filter")
+        if not self.fuse_filter:
+            _lib.check(lib.kzd_nms_filter(y.data_ptr(), self.b, self.A, self.nc, self.conf, 0, None, 0, 1,
+                                          self.keys.data_ptr(), self.rows.data_ptr(), self.counts[0].data_ptr(),
+                                          self.pool, st), "kzd_nms_filter")
         _lib.check(lib.kzd_nms_suppress(self.keys.data_ptr(), self.rows.data_ptr(), self.counts[0].data_ptr(), self.b,
                                         self.pool, self.n_cap, self.iou, int(self.agnostic), self.max_det,
                                         self.max_nms, self.max_wh, self.det_rows.data_ptr(),
                                         self.keep_host.data_ptr(), self.nms_ws.data_ptr(), self.ws_bytes, st),
                    "kzd_nms_suppress")
+
+    def _pool(self):
+        return (self.conf, self.keys, self.rows, self.counts[0]) if self.fuse_filter else None
 
     # -- the step body: the same libkzd calls as the drop-ins. The training half (decode -> assign) and
     # the inference half (decode -> NMS) do not depend on each other, so they are forked onto two
@@ -109,7 +116,8 @@ class PagePipeline:
         side = self._side if self.overlap else main
         if self.fuse_decodes:
             with torch.no_grad():
-                y, boxes, boxes_px = decode_inference(self.levels, self.strides, self.nc, with_train_boxes=True)
+                y, boxes, boxes_px = decode_inference(self.levels, self.strides, self.nc, with_train_boxes=True,
+                                                      nms_pool=self._pool())
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self._nms(y)
@@ -120,7 +128,7 @@ class PagePipeline:
             decoded = torch.cuda.Event()
             with torch.cuda.stream(side):
                 with torch.no_grad():
-                    y = decode_inference(self.levels, self.strides, self.nc)
+                    y = decode_inference(self.levels, self.strides, self.nc, nms_pool=self._pool())
                 decoded.record(side)
                 self._nms(y)
             main.wait_event(decoded)

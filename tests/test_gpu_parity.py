@@ -414,14 +414,16 @@ def test_chained_path_page_batch():
     _check_nms(m, r)
 
 
-@pytest.mark.parametrize("fuse", [False, True])
+@pytest.mark.parametrize("fuse", [False, True, "filter", "dual+filter"])
 def test_pipeline_graph_matches_eager(fuse):
     """PagePipeline (one CUDA graph for decode -> assign and decode -> NMS) returns the same bits as the
     eager drop-in calls and the oracle, across several replays with different inputs. With fuse_decodes
     both decodes come from one read of the head maps."""
     b, G, imgsz, nc, strides = 4, 200, 640, 1, synth.P2_P5
     pipe = kzd.PagePipeline(b, synth.level_shapes(imgsz, strides), strides, nc, G, device=DEV,
-                            conf_thres=0.25, iou_thres=0.7, max_det=300, fuse_decodes=fuse)
+                            conf_thres=0.25, iou_thres=0.7, max_det=300, fuse_decodes=fuse in (True, "dual+filter"),
+                            fuse_filter=fuse in ("filter", "dual+filter"))
+    fuse = pipe.fuse_decodes
     anchor_points, stride_tensor = O.make_anchors(synth.level_shapes(imgsz, strides), strides, device=DEV)
     for seed in (1, 2, 3):
         lv = synth.head_outputs(b, nc, imgsz, strides, seed=seed + 50, device=DEV, sparse_cls=800)
@@ -445,6 +447,7 @@ def test_pipeline_graph_matches_eager(fuse):
                        out["target_gt_idx"]), ref)
         y = kzd.decode_inference(lv, strides, nc)
         assert torch.equal(out["y"][:, 4:], y[:, 4:])
+        assert torch.equal(out["y"][:, :4].transpose(1, 2), O.xywh2xyxy(y[:, :4].transpose(1, 2)))  # ops.py:243-244
         _check_nms(pipe.detections(), O.non_max_suppression(y.clone(), 0.25, 0.7, max_det=300))
         assert pipe.counters()[1] == float(ref[3].sum())
 
@@ -691,6 +694,42 @@ def test_decode_dual_matches_both_single_decodes():
         ref = O.decode_train(d["pred_distri"], d["anchor_points"])
         assert ((xyxy - ref).abs() / ref.abs().clamp(min=1.0)).max() < RTOL
         assert torch.equal(px, xyxy * d["stride_tensor"])
+
+
+def test_decode_filter_fills_the_same_pool_as_nms_filter():
+    """kzd_decode_filter = decode (+ training-side boxes) + the NMS filter stage in one kernel: same y apart
+    from the box rows coming back as xyxy (ops.py:243-244), same candidate keys and rows as kzd_nms_filter
+    on the separately decoded y (slot order is unspecified in both, so pools are compared sorted by key)."""
+    import ctypes as C
+
+    from kuzushiji_vision_b200 import _lib
+
+    for b, nc, imgsz, strides, dt in [(2, 1, 640, synth.P2_P5, torch.float32), (1, 3, 200, synth.P3_P5, torch.float32),
+                                      (2, 2, 320, synth.P2_P5, torch.float16)]:
+        lv = [x.to(dt) for x in synth.head_outputs(b, nc, imgsz, strides, seed=91, device=DEV, sparse_cls=400)]
+        A = sum(x.shape[2] * x.shape[3] for x in lv)
+        y_ref, xyxy_ref, px_ref = kzd.decode_inference(lv, strides, nc, with_train_boxes=True)
+        pools = []
+        for fused in (False, True):
+            keys = torch.zeros((b, A), dtype=torch.int64, device=DEV)
+            rows = torch.zeros((b, A, 6), device=DEV)
+            counts = torch.zeros(b, dtype=torch.int32, device=DEV)
+            if fused:
+                y, xyxy, px = kzd.decode_inference(lv, strides, nc, with_train_boxes=True, nms_pool=(0.3, keys, rows, counts))
+                y2 = kzd.decode_inference(lv, strides, nc, nms_pool=(0.3, keys.clone(), rows.clone(), counts.clone()))
+                assert torch.equal(y, y2) and torch.equal(xyxy, xyxy_ref) and torch.equal(px, px_ref)
+            else:
+                y = y_ref.clone()
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                _lib.check(_lib.lib.kzd_nms_filter(y.data_ptr(), b, A, nc, 0.3, 0, None, 0, 1, keys.data_ptr(),
+                                                   rows.data_ptr(), counts.data_ptr(), A, st), "kzd_nms_filter")
+            pools.append((y, keys, rows, counts))
+        (ya, ka, ra, ca), (yb, kb, rb, cb) = pools
+        assert torch.equal(ya, yb) and torch.equal(ca, cb) and int(ca.min()) > 0
+        for i in range(b):
+            n = int(ca[i])
+            oa, ob = torch.argsort(ka[i, :n]), torch.argsort(kb[i, :n])
+            assert torch.equal(ka[i, :n][oa], kb[i, :n][ob]) and torch.equal(ra[i, :n][oa], rb[i, :n][ob])
 
 
 def test_extreme_shapes():
