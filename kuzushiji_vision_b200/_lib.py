@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkzd.so")
+LIB_PATH = os.environ.get("KZD_LIB_PATH") or os.path.join(_HERE, "libkzd.so")  # override: A/B builds of the same ABI
 
 KZD_MAX_LEVELS = 8
 KZD_MAX_TOPK = 32

@@ -52,6 +52,7 @@ struct AssignParams {
     int b, A, G, nc, topk;
     float alpha, beta, eps;
     kzd_level lv[KZD_MAX_LEVELS];
+    float inv_stride[KZD_MAX_LEVELS];
     int n_levels, zero_fill;
     int score_dtype;  // dtype pd_scores had at the call site: 0 fp32, 1 fp16, 2 bf16 (AMP, utils/tal.py:137)
     long long* target_labels;
@@ -163,10 +164,13 @@ __global__ void assign_verify_kernel(const float* __restrict__ anc, int A, Assig
 
 // ---- candidates + top-k ----------------------------------------------------------------------
 
-constexpr int CAND_THREADS = 256;
-#ifndef KZD_CAND_MINB
-#define KZD_CAND_MINB 4
+#ifndef KZD_CAND_THREADS
+#define KZD_CAND_THREADS 256
 #endif
+#ifndef KZD_CAND_MINB
+#define KZD_CAND_MINB (1024 / KZD_CAND_THREADS)
+#endif
+constexpr int CAND_THREADS = KZD_CAND_THREADS;
 constexpr int CAND_WARPS = CAND_THREADS / 32;
 constexpr int CAND_CAP = 512;  // in-GT pairs a warp holds at a time (anchor + metric bits in shared memory)
 
@@ -226,12 +230,16 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     __shared__ int s_anc[CAND_WARPS][CAND_CAP];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wid >= (long long)p.b * p.G) return;
+    const long long total = (long long)p.b * p.G;
+    // (a device-side work queue - warps pulling GTs from an atomic counter - was measured 16 us slower
+    // than this fixed assignment: the queue's round trips sit on every warp's critical path)
+    for (long long it = 0;; ++it) {
+    const long long wid = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + it * (((long long)gridDim.x * blockDim.x) >> 5);
+    if (wid >= total) return;
     const int bi = (int)(wid / p.G), g = (int)(wid % p.G);
     if (lane == 0) p.ws.pos_align[wid] = 0u, p.ws.pos_ov[wid] = 0u;
     if (wid == 0 && lane == 0 && p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
-    if (p.mask_gt[wid] == 0.f) return;  // padded GT: claims nothing, contributes zero overlap
+    if (p.mask_gt[wid] == 0.f) continue;  // padded GT: claims nothing, contributes zero overlap
 
     const GtBox gt = make_gt(*reinterpret_cast<const float4*>(p.gt_bboxes + wid * 4));
     int label = (int)p.gt_labels[wid];
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     };
     auto select = [&]() {  // top-k of slots [0, n) -> lanes 0..n_sel-1
         uint32_t lm = 0u, nb = 0u;
-        int lt = 0x7fffffff, na = -1, cnt = 0;
+        int lt = 0x7fffffff, nt = 0, cnt = 0;
         for (int t = lane; t < n; t += 32) {
             const uint32_t v = bits[t];
             if (v > lm) lm = v, lt = t;  // strict: the lowest slot among equals
@@ -272,19 +280,21 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             int owner = __ffs(who) - 1;
             if (who & (who - 1u)) owner = __reduce_min_sync(FULL, lm == mx ? lt : 0x7fffffff) & 31;  // slot t belongs to lane t % 32
             const int ts = __shfl_sync(FULL, lt, owner);
-            const int as = ancs[ts];
-            if (lane == r) nb = mx, na = as;
+            if (lane == r) nb = mx, nt = ts;
             ++cnt;
             if (lane == owner) {
                 bits[ts] = 0u;
                 lm = 0u, lt = 0x7fffffff;
+#pragma unroll 1
                 for (int t = lane; t < n; t += 32) {
                     const uint32_t v = bits[t];
                     if (v > lm) lm = v, lt = t;
                 }
             }
+            __syncwarp();
         }
-        sel_bits = nb, sel_anc = na, n_sel = cnt;
+        sel_bits = nb, n_sel = cnt;
+        sel_anc = lane < cnt ? ancs[nt] : -1;
     };
     auto make_room = [&]() {  // chunk full: keep its winners, drop the rest
         if (n + 32 <= CAND_CAP) return;
@@ -297,22 +307,56 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     };
 
     if (grid_ok) {
+        // Exact cell ranges, one ballot per level: lanes 0-7 probe 8 columns around the estimate of the first
+        // column inside, lanes 8-15 around the last column, lanes 16-23 / 24-31 the same for rows. Each probe is
+        // the reference's own fp32 test on the (verified) anchor coordinate; the tests are monotone in the cell
+        // index, so the boundary is where the probe pattern flips. A window that does not show the flip (a GT
+        // edge outside the page; otherwise the fp32 estimate is off by one cell at most) falls back to the
+        // scalar walk.
+        const int grp = lane >> 3, k = lane & 7;
+        const bool is_hi = grp & 1, is_y = grp >= 2;
+        const float edge = is_y ? (is_hi ? gt.y2 : gt.y1) : (is_hi ? gt.x2 : gt.x1);
         for (int l = 0; l < p.n_levels; ++l) {
-            const float s = p.lv[l].stride, inv_s = 1.f / s;
+            const float s = p.lv[l].stride, inv_s = p.inv_stride[l];
             const int W = p.lv[l].w, H = p.lv[l].h, off = p.lv[l].offset;
+            const int ncell = is_y ? H : W;
+            const float est = fminf(fmaxf(floorf(edge * inv_s - 0.5f), -8.f), (float)ncell + 8.f);
+            const int w0 = (int)est - 3;  // first probed cell of this lane's group
+            const int c = w0 + k;
+            const float ctr = __fmul_rn((float)c + 0.5f, s);
+            const bool ok = c >= 0 && c < ncell && (is_hi ? (__fsub_rn(edge, ctr) > 1e-9f) : (__fsub_rn(ctr, edge) > 1e-9f));
+            const unsigned m = __ballot_sync(FULL, ok);
+            const int wx0 = __shfl_sync(FULL, w0, 0), wx1 = __shfl_sync(FULL, w0, 8);
+            const int wy0 = __shfl_sync(FULL, w0, 16), wy1 = __shfl_sync(FULL, w0, 24);
             int i0, i1, j0, j1;
-            // anchor coordinates verified bit-identical to anc_points by assign_verify_kernel
-            cell_range(gt.x1, gt.x2, s, inv_s, W, i0, i1);
-            if (i0 > i1) continue;
-            cell_range(gt.y1, gt.y2, s, inv_s, H, j0, j1);
-            if (j0 > j1) continue;
+            {   // low edges: first passing cell; trusted when the cell before it was probed (or is cell 0)
+                const unsigned bx = m & 0xffu, by = (m >> 16) & 0xffu;
+                const int qx = __ffs(bx) - 1, qy = __ffs(by) - 1;
+                const bool okx = bx ? (qx > 0 || wx0 <= 0) : (wx0 <= W - 1 && wx0 + 7 >= W - 1);
+                const bool oky = by ? (qy > 0 || wy0 <= 0) : (wy0 <= H - 1 && wy0 + 7 >= H - 1);
+                i0 = bx ? wx0 + qx : W;
+                j0 = by ? wy0 + qy : H;
+                // high edges: last passing cell; trusted when the cell after it was probed (or is the last cell)
+                const unsigned cx = (m >> 8) & 0xffu, cy = m >> 24;
+                const int rx = 31 - __clz(cx), ry = 31 - __clz(cy);
+                const bool okx1 = cx ? (rx < 7 || wx1 + 7 >= W - 1) : (wx1 <= 0 && wx1 + 7 >= 0);
+                const bool oky1 = cy ? (ry < 7 || wy1 + 7 >= H - 1) : (wy1 <= 0 && wy1 + 7 >= 0);
+                i1 = cx ? wx1 + rx : -1;
+                j1 = cy ? wy1 + ry : -1;
+                if (!(okx && okx1)) cell_range(gt.x1, gt.x2, s, inv_s, W, i0, i1);  // uniform
+                if (!(oky && oky1)) cell_range(gt.y1, gt.y2, s, inv_s, H, j0, j1);
+            }
+            if (i0 > i1 || j0 > j1) continue;
             const unsigned nx = (unsigned)(i1 - i0 + 1), cnt = nx * (unsigned)(j1 - j0 + 1);
             const int base = off + j0 * W + i0;
+            // t / nx by multiplication: exact for t < 2^16 (magic = ceil(2^32 / nx), nx >= 2)
+            const bool use_magic = cnt <= 65536u && nx >= 2u;
+            const unsigned magic = use_magic ? 0xffffffffu / nx + 1u : 0u;
             for (unsigned r = 0; r < cnt; r += 32) {
                 make_room();
                 const unsigned t = r + lane;
                 if (t < cnt) {
-                    const unsigned row = t / nx;
+                    const unsigned row = use_magic ? __umulhi(t, magic) : t / nx;
                     ancs[n + lane] = base + (int)row * W + (int)(t - row * nx);
                 }
                 n += (int)min(32u, cnt - r);
@@ -350,6 +394,8 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             if (lane == 0 && anchor_in_gt(ap.x, ap.y, gt)) mark_selected(p.ws.sel + img + a, epoch, g);
         }
     }
+    __syncwarp();
+    }  // next GT
 }
 
 // ---- resolve + owner metric --------------------------------------------------------------------
@@ -602,6 +648,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
         KZD_CHECK_ARG(h_levels[l].h > 0 && h_levels[l].w > 0 && h_levels[l].offset == off && h_levels[l].stride > 0.f,
                       "kzd_tal_assign: level %d inconsistent", l);
         p.lv[l] = h_levels[l];
+        p.inv_stride[l] = 1.f / h_levels[l].stride;
         off += h_levels[l].h * h_levels[l].w;
     }
     KZD_CHECK_ARG(n_levels == 0 || off == A, "kzd_tal_assign: levels cover %d anchors, A=%d", off, A);
@@ -640,7 +687,8 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     }
     {
         const long long warps = (long long)b * G;
-        const long long blocks = (warps * 32 + CAND_THREADS - 1) / CAND_THREADS;
+        long long blocks = (warps * 32 + CAND_THREADS - 1) / CAND_THREADS;
+        if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;  // the kernel strides over the rest
         assign_candidates_kernel<<<(unsigned)blocks, CAND_THREADS, 0, st>>>(p);
         KZD_LAUNCH_CHECK("assign_candidates_kernel");
     }

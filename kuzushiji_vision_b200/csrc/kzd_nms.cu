@@ -16,7 +16,11 @@
 //                      loads two chunks ahead; the first max_det kept rows are gathered in score order
 //   mask + scan run in phases of growing column ranges: the walk stops once max_det boxes are kept,
 //   so finished images skip the later phases on the device (kzd_nms_suppress)
+#include <cooperative_groups.h>
+
 #include "kzd_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace kzd {
 
@@ -267,6 +271,121 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_rank_kernel(const float* __
     emit(k1, r1, cv[t1]);
 }
 
+// One thread-block cluster per image does the whole ordering when the candidate pool is at most 8 chunks
+// (the PagePipeline / first-try case): CTA c sorts chunk c (compare-exchange distances < 32 by warp
+// shuffles, 32..128 through shared memory, 256 inside the thread), the cluster synchronises, and every CTA
+// ranks its keys against the other CTAs' sorted chunks read through distributed shared memory - no
+// round trip through global memory and one launch instead of two.
+constexpr int ORDER_CL = 8;
+
+__device__ __forceinline__ void order_cx_shfl(u64& key, uint32_t& val, int i, int k, int j) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)key, j);
+    const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(key >> 32), j);
+    const uint32_t pv = __shfl_xor_sync(0xffffffffu, val, j);
+    const u64 pk = ((u64)hi << 32) | lo;
+    const bool want_max = (((i & k) == 0) == ((i & j) == 0));  // descending overall: the lower index keeps the larger key
+    if (want_max ? (pk > key) : (pk < key)) key = pk, val = pv;
+}
+
+__global__ void __cluster_dims__(ORDER_CL, 1, 1) __launch_bounds__(CHUNK_THREADS)
+    nms_order_cluster_kernel(const u64* __restrict__ cand_keys, const float* __restrict__ cand_rows,
+                             const int32_t* __restrict__ cand_counts, int cand_cap, int n_cap, int max_nms, int agnostic,
+                             float max_wh, SuppressWs ws) {
+    __shared__ u64 keys[CHUNK];
+    __shared__ uint32_t vals[CHUNK];
+    __shared__ u64 other[ORDER_CL - 1][CHUNK];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int bi = blockIdx.y, chunk = (int)cluster.block_rank();
+    const int t = threadIdx.x;
+    const int count = cand_counts[bi];
+    const int n = count < max_nms ? count : max_nms;
+    const bool overflow = count > cand_cap || n > n_cap;  // pool or suppression stage too small
+    if (chunk == 0 && t == 0) ws.n_sorted[bi] = overflow ? -1 : n;
+    if (overflow || count <= 0) return;  // uniform over the cluster
+    const bool active = chunk * CHUNK < count;
+    const int i0 = t, i1 = t + CHUNK_THREADS;
+    u64 k0 = 0ull, k1 = 0ull;
+    uint32_t v0 = (uint32_t)(chunk * CHUNK + i0), v1 = (uint32_t)(chunk * CHUNK + i1);
+    if (active) {
+        const u64* __restrict__ src = cand_keys + (size_t)bi * cand_cap;
+        if ((int)v0 < count) k0 = src[v0];
+        if ((int)v1 < count) k1 = src[v1];
+        for (int k = 2; k <= CHUNK; k <<= 1) {
+            int j = k >> 1;
+            if (j == CHUNK_THREADS) {  // distance 256: both elements live in this thread (only k == 512: descending)
+                if (k0 < k1) {
+                    const u64 tk = k0; k0 = k1, k1 = tk;
+                    const uint32_t tv = v0; v0 = v1, v1 = tv;
+                }
+                j >>= 1;
+            }
+            if (j >= 32) {  // distances 128, 64, 32 through shared memory
+                __syncthreads();
+                keys[i0] = k0, keys[i1] = k1, vals[i0] = v0, vals[i1] = v1;
+                for (; j >= 32; j >>= 1) {
+                    __syncthreads();
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), q = i | j;
+                    const u64 ki = keys[i], kq = keys[q];
+                    if ((ki < kq) == ((i & k) == 0)) {
+                        keys[i] = kq, keys[q] = ki;
+                        const uint32_t vi = vals[i];
+                        vals[i] = vals[q], vals[q] = vi;
+                    }
+                }
+                __syncthreads();
+                k0 = keys[i0], k1 = keys[i1], v0 = vals[i0], v1 = vals[i1];
+            }
+            for (; j > 0; j >>= 1) {  // distances 16..1 inside the warp
+                order_cx_shfl(k0, v0, i0, k, j);
+                order_cx_shfl(k1, v1, i1, k, j);
+            }
+        }
+        __syncthreads();
+        keys[i0] = k0, keys[i1] = k1, vals[i0] = v0, vals[i1] = v1;
+    }
+    cluster.sync();  // every chunk of the image is sorted and visible cluster-wide
+    if (active) {
+        const int n_chunks = (count + CHUNK - 1) / CHUNK;
+        int slot = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            if (c == chunk) continue;
+            const u64* remote = cluster.map_shared_rank(keys, c);
+            other[slot][i0] = remote[i0], other[slot][i1] = remote[i1];
+            ++slot;
+        }
+        __syncthreads();
+        int r0 = i0, r1 = i1;
+        for (int sidx = 0; sidx < slot; ++sidx) {
+            const u64* __restrict__ oc = other[sidx];
+            int lo0 = 0, hi0 = CHUNK, lo1 = 0, hi1 = CHUNK;
+#pragma unroll
+            for (int step = 0; step < 10; ++step) {  // 2^9 = 512: 10 halvings always converge
+                const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+                const bool g0 = lo0 < hi0 && oc[m0 < CHUNK ? m0 : CHUNK - 1] > k0;
+                const bool g1 = lo1 < hi1 && oc[m1 < CHUNK ? m1 : CHUNK - 1] > k1;
+                if (lo0 < hi0) { if (g0) lo0 = m0 + 1; else hi0 = m0; }
+                if (lo1 < hi1) { if (g1) lo1 = m1 + 1; else hi1 = m1; }
+            }
+            r0 += lo0, r1 += lo1;
+        }
+        const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
+        float4* __restrict__ sbox = ws.sbox + (size_t)bi * n_cap;
+        uint32_t* __restrict__ sslot = ws.sslot + (size_t)bi * n_cap;
+        auto emit = [&](u64 key, int rank, uint32_t slot_) {
+            if (key == 0ull || rank >= n) return;
+            const float2* r = reinterpret_cast<const float2*>(rows + (size_t)slot_ * 6);
+            const float2 p0 = r[0], p1 = r[1], p2 = r[2];
+            const float off = agnostic ? 0.f : __fmul_rn(p2.y, max_wh);                      // utils/ops.py:289
+            sbox[rank] = make_float4(__fadd_rn(p0.x, off), __fadd_rn(p0.y, off), __fadd_rn(p1.x, off),
+                                     __fadd_rn(p1.y, off));                                   // utils/ops.py:295
+            sslot[rank] = slot_;
+        };
+        emit(k0, r0, v0);
+        emit(k1, r1, v1);
+    }
+    cluster.sync();  // no CTA leaves while its shared memory may still be read by the others
+}
+
 // ------------------------------------------------------------------------------------------
 // stage 2b: IoU bitmask
 // ------------------------------------------------------------------------------------------
@@ -290,14 +409,17 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float sa, const flo
 // (4 compares; a superset of the true intersections). Pass 2 (rare): exact IoU > thr only for those.
 // Mask layout: [image][r*T_cap + c][i]  (64 consecutive words per tile => coalesced 512 B stores,
 // and the scan reads whole tiles).
-constexpr int MASK_CG = 4;
+#ifndef KZD_MASK_CG
+#define KZD_MASK_CG 1
+#endif
+constexpr int MASK_CG = KZD_MASK_CG;
 
-// items of column groups [0, g) for an image of T tiles: group k holds rows 0..min(T, 4k+4)-1
+// items of column groups [0, g) for an image of T tiles: group k holds rows 0..min(T, CG*(k+1))-1
 __device__ __forceinline__ int items_before(int T, int g) {
     const int Gc = (T + MASK_CG - 1) / MASK_CG;
     if (g <= 0 || T <= 0) return 0;
-    if (g >= Gc) return 2 * (Gc - 1) * Gc + T;  // MASK_CG * (1 + ... + (Gc-1)) + T, MASK_CG == 4
-    return 2 * g * (g + 1);
+    if (g >= Gc) return MASK_CG * (Gc - 1) * Gc / 2 + T;  // CG * (1 + ... + (Gc-1)) + T
+    return MASK_CG * g * (g + 1) / 2;
 }
 
 // Phase = column groups [g_lo, g_hi) of every image that is not finished yet (the greedy walk stops as
@@ -306,7 +428,6 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
                                                                 int g_lo, int g_hi, SuppressWs ws) {
     extern __shared__ int pre[];  // (b+1) prefix of item counts
     __shared__ float4 colbox[MASK_CG * 64];
-    static_assert(MASK_CG == 4, "items_before() assumes groups of 4 column tiles");
     for (int i = threadIdx.x; i < b; i += MASK_THREADS) {  // item counts: the loads of all images in flight together
         const int n = ws.n_sorted[i];
         const int done = phase > 0 ? ws.state[i * 4] : 0;
@@ -332,12 +453,12 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
         const int n = ws.n_sorted[bi];
         const int T = (n + 63) >> 6;
         const int q = w - pre[bi] + items_before(T, g_lo);
-        // items are ordered by column group g, then row r:  offset(g) = 2 g (g+1)
-        int g = (int)((sqrtf(1.f + 2.f * (float)q) - 1.f) * 0.5f);
+        // items are ordered by column group g, then row r:  offset(g) = CG g (g+1) / 2
+        int g = (int)((sqrtf(1.f + (8.f / MASK_CG) * (float)q) - 1.f) * 0.5f);
         g = max(g, 0);
-        while (2 * g * (g + 1) > q) --g;
-        while (2 * (g + 1) * (g + 2) <= q) ++g;
-        const int r = q - 2 * g * (g + 1);
+        while (MASK_CG * g * (g + 1) / 2 > q) --g;
+        while (MASK_CG * (g + 1) * (g + 2) / 2 <= q) ++g;
+        const int r = q - MASK_CG * g * (g + 1) / 2;
         const int c_first = g * MASK_CG;
         const float4* __restrict__ sbox = ws.sbox + (size_t)bi * n_cap;
         const int row = r * 64 + i;
@@ -641,16 +762,28 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
         return KZD_ENOSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 cgrid(ws.C_cap, b);
-    nms_chunk_sort_kernel<<<cgrid, CHUNK_THREADS, 0, st>>>((const u64*)cand_keys, cand_counts, cand_cap, n_cap, max_nms,
-                                                           ws);
-    KZD_LAUNCH_CHECK("nms_chunk_sort_kernel");
-    nms_rank_kernel<<<cgrid, CHUNK_THREADS, 0, st>>>(cand_rows, cand_counts, cand_cap, n_cap, agnostic, max_wh, ws);
-    KZD_LAUNCH_CHECK("nms_rank_kernel");
+#ifndef KZD_NO_CLUSTER
+#define KZD_NO_CLUSTER 0
+#endif
+    if (!KZD_NO_CLUSTER && ws.C_cap <= ORDER_CL) {  // pool of at most 8 chunks: one cluster per image orders it in one launch
+        nms_order_cluster_kernel<<<dim3(ORDER_CL, b), CHUNK_THREADS, 0, st>>>((const u64*)cand_keys, cand_rows, cand_counts,
+                                                                            cand_cap, n_cap, max_nms, agnostic, max_wh, ws);
+        KZD_LAUNCH_CHECK("nms_order_cluster_kernel");
+    } else {
+        dim3 cgrid(ws.C_cap, b);
+        nms_chunk_sort_kernel<<<cgrid, CHUNK_THREADS, 0, st>>>((const u64*)cand_keys, cand_counts, cand_cap, n_cap,
+                                                               max_nms, ws);
+        KZD_LAUNCH_CHECK("nms_chunk_sort_kernel");
+        nms_rank_kernel<<<cgrid, CHUNK_THREADS, 0, st>>>(cand_rows, cand_counts, cand_cap, n_cap, agnostic, max_wh, ws);
+        KZD_LAUNCH_CHECK("nms_rank_kernel");
+    }
     // The greedy walk stops as soon as max_det boxes are kept, so the mask is built and walked in phases
     // of growing column ranges: first enough tiles for max_det kept boxes plus 25 %, then 4x more per
     // phase. Finished images skip the later phases on the device (no host round trip).
-    const int grid = sm_count() * 16;
+#ifndef KZD_MASK_GRID
+#define KZD_MASK_GRID 16
+#endif
+    const int grid = sm_count() * KZD_MASK_GRID;
     int t_prev = 0;
     int t_next = ((max_det + max_det / 4 + 64 + 63) / 64 + MASK_CG - 1) / MASK_CG * MASK_CG;
     for (int phase = 0; t_prev < ws.T_cap; ++phase) {

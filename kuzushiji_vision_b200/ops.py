@@ -39,7 +39,14 @@ def nms_batched(prediction, conf_thres, iou_thres, classes=None, agnostic=False,
     dev = prediction.device
     multi_label = bool(multi_label) and nc > 1
     max_cand = A * nc if multi_label else A
-    pool = min(max_cand, pool or DEFAULT_POOL)
+    if pool is None:
+        # Typical prediction settings leave a few thousand candidates per page: a first-try pool of n_cap lets
+        # one thread-block cluster per image order them in a single launch (more candidates than n_cap would
+        # overflow the suppression stage anyway). Validation settings (conf 0.001, multi_label:
+        # models/yolo/detect/val.py:92-102) produce tens of thousands, so they start with the big pool.
+        small = max_nms >= DEFAULT_N_CAP and conf_thres >= 0.01 and not multi_label
+        pool = (n_cap or DEFAULT_N_CAP) if small else DEFAULT_POOL
+    pool = min(max_cand, pool)
     cls_t, n_cls = None, 0
     if classes is not None:
         cls_t = torch.as_tensor(list(classes), dtype=torch.int32, device=dev)
@@ -50,6 +57,7 @@ def nms_batched(prediction, conf_thres, iou_thres, classes=None, agnostic=False,
     counts = torch.empty((2, b), dtype=torch.int32, device=dev)  # [0] candidates, [1] kept
     lib = _lib.lib
     mode = 2 if xyxy_input else (1 if in_place else 0)
+    cap_hint = None  # suppression capacity learned from a failed first try
     with torch.cuda.device(dev):
         while True:
             keys = torch.empty((b, pool), dtype=torch.int64, device=dev)
@@ -60,7 +68,7 @@ def nms_batched(prediction, conf_thres, iou_thres, classes=None, agnostic=False,
                        "kzd_nms_filter")
             if mode == 1:
                 mode = 2  # boxes are xyxy from now on
-            cap = min(n_cap or DEFAULT_N_CAP, max_nms, pool)
+            cap = min(cap_hint or n_cap or DEFAULT_N_CAP, max_nms, pool)
             cap = _round_up(max(cap, 64), 64)
             while True:
                 ws_bytes = lib.kzd_nms_workspace_bytes(b, pool, cap)
@@ -75,9 +83,9 @@ def nms_batched(prediction, conf_thres, iou_thres, classes=None, agnostic=False,
                 if min(n_keep) >= 0:
                     return out_rows, n_keep
                 worst = max(n_cand)
+                cap = cap_hint = _round_up(min(worst, max_nms), 64)
                 if worst > pool:
                     break  # pool overflow: redo the filter with room for everything
-                cap = _round_up(min(worst, max_nms), 64)
             pool = max_cand
 
 

@@ -28,7 +28,8 @@ from .tal import TaskAlignedAssigner, make_anchors
 class PagePipeline:
     def __init__(self, batch, level_hw, strides, nc, n_max_boxes, device="cuda:0", topk=10, alpha=0.5, beta=6.0,
                  conf_thres=0.25, iou_thres=0.7, max_det=300, max_nms=30000, agnostic=False, max_wh=7680.0,
-                 pool=32768, n_cap=4096, use_graph=True, overlap=True, fuse_decodes=False, fuse_filter=False):
+                 pool=32768, n_cap=4096, use_graph=True, overlap=True, fuse_decodes=False, fuse_filter=False,
+                 cluster_order=False):
         dev = torch.device(device)
         self.device, self.b, self.nc, self.G = dev, int(batch), int(nc), int(n_max_boxes)
         self.level_hw = [(int(h), int(w)) for h, w in level_hw]
@@ -52,6 +53,13 @@ class PagePipeline:
         # NMS buffers (fixed capacities; an overflow is reported by results())
         self.pool = min(A, int(pool))
         self.n_cap = max(64, (min(int(n_cap), self.max_nms, self.pool) + 63) // 64 * 64)
+        if cluster_order and self.max_nms >= self.n_cap:
+            # A pool of at most 4096 lets one thread-block cluster per image order the candidates in a single
+            # launch (more candidates than n_cap overflow the suppression stage anyway): ~4 us less latency
+            # for a single pipeline, but the gang-scheduled clusters cost ~10 us per step when several
+            # pipelines are in flight and the decode kernels of the others fill the SMs (measured), so it is
+            # opt-in here; the eager drop-in (ops.nms_batched) uses it by default.
+            self.pool = min(self.pool, self.n_cap)
         self.keys = torch.empty((b, self.pool), dtype=torch.int64, device=dev)
         self.rows = torch.empty((b, self.pool, 6), dtype=f32, device=dev)
         self.counts = torch.zeros((2, b), dtype=torch.int32, device=dev)
@@ -72,6 +80,8 @@ class PagePipeline:
         # values it has just computed, so the NMS branch starts at the ordering kernels
         self.fuse_filter = bool(fuse_filter)
         self._side = torch.cuda.Stream(device=dev, priority=-1)  # the small NMS kernels go first
+        import os
+        self._side2 = torch.cuda.Stream(device=dev, priority=-1) if os.environ.get("KZD_ASSIGN_PRIO") == "1" else None
         self.out = None
         self.graph = None
         # decode_train, assign x4, decode_infer, nms filter + chunk sort + rank + (mask, scan) per phase
@@ -121,7 +131,13 @@ class PagePipeline:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self._nms(y)
-            tgt = self._assign(boxes_px)
+            if self._side2 is not None:
+                self._side2.wait_stream(main)
+                with torch.cuda.stream(self._side2):
+                    tgt = self._assign(boxes_px)
+                main.wait_stream(self._side2)
+            else:
+                tgt = self._assign(boxes_px)
             main.wait_stream(side)
         else:
             side.wait_stream(main)

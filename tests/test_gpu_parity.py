@@ -732,6 +732,51 @@ def test_decode_filter_fills_the_same_pool_as_nms_filter():
             assert torch.equal(ka[i, :n][oa], kb[i, :n][ob]) and torch.equal(ra[i, :n][oa], rb[i, :n][ob])
 
 
+def test_assign_gt_edge_geometry():
+    """GT boxes the grid accelerator has to get exactly right: covering the whole page (tens of thousands of
+    in-GT anchors: the chunked top-k with carried winners), hanging over each border, entirely off the page,
+    degenerate (zero width), thinner than one cell, with edges exactly on anchor centres (strict > 1e-9), and
+    the same with anchors that are not a make_anchors grid (scan-all fallback)."""
+    b, G, imgsz, nc, strides = 2, 16, 320, 2, synth.P2_P5
+    d = synth.assigner_inputs(b, G, imgsz, nc, strides, seed=93, device=DEV, layout="uniform")
+    boxes = torch.tensor([
+        [0.0, 0.0, 320.0, 320.0],        # whole page
+        [-50.0, 40.0, 30.0, 90.0],       # over the left border
+        [300.0, 100.0, 400.0, 180.0],    # over the right border
+        [100.0, -80.0, 180.0, 20.0],     # over the top
+        [60.0, 290.0, 140.0, 500.0],     # over the bottom
+        [-200.0, -200.0, -10.0, -10.0],  # off the page
+        [400.0, 400.0, 500.0, 500.0],    # off the page
+        [50.0, 50.0, 50.0, 120.0],       # zero width
+        [64.5, 64.5, 65.5, 65.5],        # thinner than a cell, between P2 centres (66 is one: excluded? 65.5 < 66)
+        [62.0, 62.0, 66.0, 66.0],        # edges exactly on P2 centres (strict test excludes them)
+        [10.0, 10.0, 310.0, 30.0],       # wide and flat
+        [150.0, 5.0, 170.0, 315.0],      # tall and thin
+        [2.0, 2.0, 6.0, 6.0],            # contains exactly one P2 centre, corner of the page
+        [0.0, 0.0, 2.0, 2.0],            # contains no centre
+        [314.0, 314.0, 320.0, 320.0],    # last P2 cell
+        [-1e4, -1e4, 1e4, 1e4],          # far larger than the page
+    ], device=DEV)
+    d["gt_bboxes"][:] = boxes
+    d["mask_gt"][:] = 1
+    d["mask_gt"][1, 3] = 0
+    mine, ref, _ = _assign_both(d, nc)
+    _check_assign(mine, ref)
+    assert int(ref[3].sum()) > 0
+    # anchors that are not a make_anchors grid -> every GT scans all anchors
+    d2 = dict(d)
+    d2["anc_points"] = d["anc_points"] + 0.25
+    mine, ref, _ = _assign_both(d2, nc)
+    _check_assign(mine, ref)
+    # only the whole-page GT (b*G pairs ~ A each), topk larger than usual
+    d3 = dict(d)
+    d3["gt_bboxes"] = d["gt_bboxes"][:, :1].contiguous()
+    d3["gt_labels"] = d["gt_labels"][:, :1].contiguous()
+    d3["mask_gt"] = d["mask_gt"][:, :1].contiguous()
+    mine, ref, _ = _assign_both(d3, nc, topk=32)
+    _check_assign(mine, ref)
+
+
 def test_extreme_shapes():
     """Corners of the size envelope: thousands of GT slots (shared-memory GT table of 72 KB), 80 classes,
     a single tiny level, and an NMS input where every candidate is the same box (one survivor, the longest
