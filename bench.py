@@ -260,7 +260,7 @@ def run_kzd(args, rank, local_rank, world):
     # ---- device-resident timing: inputs already in HBM; a step is one CUDA-graph replay. Two pipelines
     # (two input/output buffer sets, same page batch) are stepped alternately on two streams, so batch
     # i+1's HBM-bound decodes overlap batch i's issue-bound assign / NMS kernels (double buffering). ----
-    depth = max(1, int(os.environ.get("KZD_BENCH_DEPTH", "3")))
+    depth = max(1, int(os.environ.get("KZD_BENCH_DEPTH", "4")))
     pipes = [pipe]
     for _ in range(depth - 1):
         pn = kzd.PagePipeline(b, synth.level_shapes(w["imgsz"], w["strides"]), w["strides"], nc, G,

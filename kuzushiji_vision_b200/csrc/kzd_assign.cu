@@ -5,16 +5,17 @@
 // select_highest_overlaps :264-295) and CIoU utils/metrics.py:96-130.
 //
 // Kernels (one stream, no host sync):
-//   assign_verify_kernel      per-call flags + device-side epoch of the persistent state; checks
+//   assign_begin_kernel       per-call flags + device-side epoch of the persistent state; checks
 //                             anc_points against the level table (grid accelerator is only used
 //                             when every anchor matches bit-for-bit)
 //   assign_candidates_kernel  one warp per (image, GT): the anchors inside the GT are an exact
 //                             rectangle per level (separable x / y tests); CIoU + alignment metric 32
 //                             pairs at a time, per-anchor argmax-overlap via 64-bit atomicMax, top-k by
-//                             warp-wide redux max, selecting GTs recorded with two atomicMax words
-//   assign_resolve_kernel     one thread per anchor: resolve the owner GT, write labels / boxes /
-//                             fg / gt_idx for every anchor; the CTA's foreground anchors are compacted
-//                             and their owner pair's metric + the per-GT maxima computed in place
+//                             warp-wide redux max, selecting GTs recorded with two atomicMax words and
+//                             in a pick list; each warp also stores the background targets of a
+//                             slice of the image's anchors (no dense pass over the anchors remains)
+//   assign_patch_kernel       pick list (~10 per GT): resolve each picked anchor's owner GT, overwrite
+//                             its targets, owner pair's metric + per-GT maxima, compact fg list
 //   assign_normalize_kernel   foreground list: target_scores = align * pos_ov / (pos_align+eps)
 //
 // Bit-exactness: every fp32 operation of the eager reference rounds separately, so the pair
@@ -42,8 +43,10 @@ struct AssignWs {
     uint32_t* pos_align; // (b*G)  per-GT max alignment metric (float bits)
     uint32_t* pos_ov;    // (b*G)  per-GT max overlap (float bits)
     uint2* fg_list;      // (b*A)  compact list of foreground anchors: (flat anchor index, flat GT slot)
+    uint2* picks;        // (b*G*topk)  every GT's selected anchors: (flat anchor index, g); x = ~0: empty slot
     int32_t* flags;      // [0] != 0: anc_points does not match the level table; [1] = fg count;
-                         // [2] = current epoch (1..255), advanced on the device by assign_begin_kernel
+                         // [2] = current epoch (1..255), advanced on the device by assign_begin_kernel;
+                         // [4] != 0: the previous call ran under epoch 255, wipe the state before this one
     size_t state_bytes;  // key + sel + flags: the part that must have been zeroed once
 };
 
@@ -54,6 +57,7 @@ struct AssignParams {
     kzd_level lv[KZD_MAX_LEVELS];
     float inv_stride[KZD_MAX_LEVELS];
     int n_levels, zero_fill;
+    int fill_vec;     // A % 16 == 0 and 16-byte aligned outputs: background targets are stored as 16 B words
     int score_dtype;  // dtype pd_scores had at the call site: 0 fp32, 1 fp16, 2 bf16 (AMP, utils/tal.py:137)
     long long* target_labels;
     float* target_bboxes;
@@ -64,7 +68,7 @@ struct AssignParams {
     AssignWs ws;
 };
 
-// ---- arithmetic shared by the candidates and resolve kernels (must be one instruction sequence) ----
+// ---- arithmetic shared by the candidates and patch kernels (must be one instruction sequence) ----
 
 // aten pow(tensor, scalar) dispatch: 0.5 -> sqrt, 2 -> x*x, 3 -> x*x*x, 1 -> x, 0 -> 1, -0.5 -> rsqrt,
 // -1 -> 1/x, -2 -> 1/(x*x), else ::pow  (ATen/native/cuda/PowKernel.cu)
@@ -133,24 +137,28 @@ __device__ __forceinline__ float overlap_ciou(const GtBox& g, const float4 p) {
     return fmaxf(ciou, 0.f);
 }
 
-// ---- begin: per-call flags and the device-side epoch -----------------------------------------
+// ---- begin: per-call flags, device-side epoch, anchor check -----------------------------------
 
-// flags[0] (grid mismatch) is consumed by the candidates kernel only and cleared again by the resolve
-// kernel, so it is already 0 when a call starts.
-__device__ __forceinline__ void begin_call(const AssignWs& ws, int reset_epoch) {
-    ws.flags[1] = 0;
-    const int e = reset_epoch ? 0 : ws.flags[2];
-    ws.flags[2] = (e % 255) + 1;  // 1..255; at 255 the resolve kernel wipes the state for the wrap to 1
-}
-
-__global__ void assign_begin_kernel(AssignWs ws, int reset_epoch) { begin_call(ws, reset_epoch); }
-
-// ---- verify (+ begin) ------------------------------------------------------------------------
-
-__global__ void assign_verify_kernel(const float* __restrict__ anc, int A, AssignParams p, int reset_epoch) {
+// One thread per anchor. Thread 0 resets the per-call counters and advances the epoch of the persistent
+// per-anchor state (flags[0], the grid-mismatch flag, is consumed by the candidates kernel only and
+// cleared again by the patch kernel, so it is already 0 when a call starts). The others check
+// anc_points against the level table bit for bit (the grid accelerator is used only when every anchor
+// matches) and, once every 255 calls, wipe the state so that the epoch can wrap.
+__global__ void assign_begin_kernel(const float* __restrict__ anc, int A, AssignParams p, int reset_epoch) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a == 0) begin_call(p.ws, reset_epoch);
+    const bool wipe = p.ws.flags[4] != 0;  // written by the previous call's patch kernel
+    if (a == 0) {
+        p.ws.flags[1] = 0;
+        const int e = reset_epoch ? 0 : p.ws.flags[2];
+        p.ws.flags[2] = (e % 255) + 1;  // 1..255
+    }
     if (a >= A) return;
+    if (wipe)
+        for (int bi = 0; bi < p.b; ++bi) {
+            p.ws.sel[(size_t)bi * A + a] = make_uint2(0u, 0u);
+            p.ws.key[(size_t)bi * A + a] = 0ull;
+        }
+    if (p.n_levels == 0) return;
     int l = 0;
     for (int k = 1; k < p.n_levels; ++k)
         if (a >= p.lv[k].offset) l = k;
@@ -239,14 +247,56 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     const int bi = (int)(wid / p.G), g = (int)(wid % p.G);
     if (lane == 0) p.ws.pos_align[wid] = 0u, p.ws.pos_ov[wid] = 0u;
     if (wid == 0 && lane == 0 && p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
-    if (p.mask_gt[wid] == 0.f) continue;  // padded GT: claims nothing, contributes zero overlap
+    const size_t img = (size_t)bi * p.A;
+    uint2* __restrict__ picks = p.ws.picks + wid * p.topk;
+    auto fill_background = [&]() {
+        // Background targets for this warp's slice of the image's anchors (every anchor that nobody
+        // selects takes GT 0's label and box, target_gt_idx 0, utils/tal.py:215-233): plain streaming
+        // stores that ride along with the latency-bound pair work instead of a separate dense pass (issued
+        // when the warp has finished its GT, so they are spread over the kernel's lifetime).
+        int per = (p.A + p.G - 1) / p.G;
+        if (p.fill_vec) per = (per + 15) & ~15;  // 16-anchor granules: every array's slice is a whole number of 16 B words
+        const int a_lo = min(p.A, g * per), a_hi = min(p.A, a_lo + per);
+        const float4 box0 = *reinterpret_cast<const float4*>(p.gt_bboxes + (size_t)bi * p.G * 4);
+        long long lab0 = (long long)p.gt_labels[(size_t)bi * p.G];
+        lab0 = lab0 < 0 ? 0 : lab0;
+        if (p.fill_vec) {
+            const size_t first = img + a_lo;
+            const int len = a_hi - a_lo;
+            auto fill16 = [&](void* base, int elem_bytes, uint4 pat) {
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + first * elem_bytes);
+                for (int i = lane; i < (len * elem_bytes) >> 4; i += 32) dst[i] = pat;
+            };
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t l_lo = (uint32_t)lab0, l_hi = (uint32_t)((unsigned long long)lab0 >> 32);
+            fill16(p.target_bboxes, 16, make_uint4(__float_as_uint(box0.x), __float_as_uint(box0.y),
+                                                   __float_as_uint(box0.z), __float_as_uint(box0.w)));
+            fill16(p.target_labels, 8, make_uint4(l_lo, l_hi, l_lo, l_hi));
+            fill16(p.target_gt_idx, 8, zero);
+            fill16(p.fg_mask, 1, zero);
+            if (p.nc == 1) fill16(p.target_scores, 4, zero);
+        } else {
+            for (int a = a_lo + lane; a < a_hi; a += 32) {
+                const size_t idx = img + a;
+                p.target_gt_idx[idx] = 0;
+                p.target_labels[idx] = lab0;
+                p.fg_mask[idx] = 0;
+                reinterpret_cast<float4*>(p.target_bboxes)[idx] = box0;
+                if (p.nc == 1) p.target_scores[idx] = 0.f;
+            }
+        }
+    };
+    if (p.mask_gt[wid] == 0.f) {  // padded GT: claims nothing, contributes zero overlap
+        if (lane < p.topk) picks[lane] = make_uint2(0xffffffffu, 0u);
+        fill_background();
+        continue;
+    }
 
     const GtBox gt = make_gt(*reinterpret_cast<const float4*>(p.gt_bboxes + wid * 4));
     int label = (int)p.gt_labels[wid];
     label = label < 0 ? 0 : (label >= p.nc ? p.nc - 1 : label);
     const bool grid_ok = p.n_levels > 0 && p.ws.flags[0] == 0;
     const uint32_t epoch = (uint32_t)p.ws.flags[2];
-    const size_t img = (size_t)bi * p.A;
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
     const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
     const float* __restrict__ pds = p.pd_scores + img * p.nc + label;
@@ -382,147 +432,90 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
 
     const bool has = lane < n_sel;
     if (has) mark_selected(p.ws.sel + img + sel_anc, epoch, g);
+    uint32_t pick = has ? (uint32_t)(img + sel_anc) : 0xffffffffu;  // lane r: the r-th entry of this GT's pick list
     if (p.zero_fill) {
         // torch.topk pads a short list with zero-metric entries, lowest anchor index first; a padded
         // pick only matters when that anchor lies inside this GT (utils/tal.py:128).
-        int need = topk - n_sel;
+        int need = topk - n_sel, n_pick = n_sel;
         for (int a = 0; need > 0 && a < p.A; ++a) {
             const bool mine = has && sel_anc == a;
             if (__any_sync(FULL, mine)) continue;  // positive pick, already counted
             --need;
             const float2 ap = __ldg(anc + a);
-            if (lane == 0 && anchor_in_gt(ap.x, ap.y, gt)) mark_selected(p.ws.sel + img + a, epoch, g);
+            if (anchor_in_gt(ap.x, ap.y, gt)) {  // uniform
+                if (lane == 0) mark_selected(p.ws.sel + img + a, epoch, g);
+                if (lane == n_pick) pick = (uint32_t)(img + a);
+                ++n_pick;
+            }
         }
     }
+    if (lane < topk) picks[lane] = make_uint2(pick, (uint32_t)g);
+    fill_background();  // last: the stores never sit in front of this warp's latency-critical loads
     __syncwarp();
     }  // next GT
 }
 
-// ---- resolve + owner metric --------------------------------------------------------------------
+// ---- patch: foreground anchors --------------------------------------------------------------------
 
-constexpr int RES_THREADS = 256;
-constexpr int RES_ITERS = 8;  // anchors per CTA = RES_THREADS * RES_ITERS
-
-// The image's GT table is staged in shared memory: boxes by one TMA bulk copy (always 16 B aligned),
-// labels and mask by plain loads. Each thread then owns RES_ITERS anchors (state words loaded up
-// front so RES_ITERS independent loads are in flight) and writes labels / boxes / fg / gt_idx.
-// The CTA's foreground anchors (a few per cent) are compacted into a shared-memory list and then
-// evaluated with all lanes busy: the alignment metric of each (anchor, owner GT) pair, recomputed with
-// the same instruction sequence as in assign_candidates_kernel (=> identical bits; this also covers
-// anchors owned by a GT that did not top-k them), stored in the owner's target_scores slot, plus the
-// per-GT maxima of utils/tal.py:112-114. The list is also appended to the global one for the normalise
-// pass (one global atomic per CTA).
-__global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const AssignParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    __shared__ int warp_tot[RES_THREADS / 32];
-    __shared__ int block_base, block_tot;
-    __shared__ uint2 s_fg[RES_THREADS * RES_ITERS];  // (anchor, owner GT) of the CTA's foreground anchors
-    float4* s_box = reinterpret_cast<float4*>(smem_raw);
-    float* s_lab = reinterpret_cast<float*>(smem_raw + (size_t)p.G * 16);
-    float* s_msk = s_lab + p.G;
-    const int bi = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t bytes = (uint32_t)p.G * 16u;
-        mbar_expect_tx(&bar, bytes);
-        tma_load_1d(s_box, p.gt_bboxes + (size_t)bi * p.G * 4, bytes, &bar);
-        if (blockIdx.x == 0 && bi == 0) p.ws.flags[0] = 0;  // consumed by the candidates kernel; clean for the next call
-    }
-    for (int g = tid; g < p.G; g += RES_THREADS) {
-        s_lab[g] = p.gt_labels[(size_t)bi * p.G + g];
-        s_msk[g] = p.mask_gt[(size_t)bi * p.G + g];
-    }
+// One thread per pick-list slot (b*G*topk, ~85 % filled). An anchor picked by several GTs appears once
+// per GT; the entry of the smallest selecting GT represents it. The representative resolves the owner
+// (one selector -> it; several -> the first-max argmax of overlaps over ALL GTs, utils/tal.py:286, kept in
+// the key word by the candidates kernel), overwrites the background targets the candidates kernel
+// stored for that anchor, recomputes the (anchor, owner) pair's alignment metric with the same
+// instruction sequence as the candidates kernel (=> identical bits; this also covers anchors owned by a
+// GT that did not top-k them), records the per-GT maxima of utils/tal.py:112-114 and appends the anchor
+// to the compact foreground list of the normalise pass.
+__global__ void __launch_bounds__(256) assign_patch_kernel(const AssignParams p) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     const uint32_t epoch = (uint32_t)p.ws.flags[2];
-    const size_t img = (size_t)bi * p.A;
-    const int a_base = blockIdx.x * RES_ITERS * RES_THREADS + tid;
-    uint2 sel[RES_ITERS];
-#pragma unroll
-    for (int it = 0; it < RES_ITERS; ++it) {
-        const int a = a_base + it * RES_THREADS;
-        sel[it] = a < p.A ? p.ws.sel[img + a] : make_uint2(0u, 0u);
+    const long long n_slots = (long long)p.b * p.G * p.topk;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.ws.flags[0] = 0;                // consumed by the candidates kernel; clean for the next call
+        p.ws.flags[4] = epoch == 255u;    // last epoch before the wrap: the next call wipes the state first
     }
-    __syncthreads();
-    mbar_wait(&bar, 0);
-
-    unsigned fg_bits = 0u;
-    uint32_t own[RES_ITERS];
-#pragma unroll
-    for (int it = 0; it < RES_ITERS; ++it) {
-        const int a = a_base + it * RES_THREADS;
-        own[it] = 0u;
-        if (a >= p.A) continue;
-        const size_t idx = img + a;
-        const bool fg = (sel[it].y >> 24) == epoch;
+    const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
+    for (long long s0 = (long long)blockIdx.x * blockDim.x; s0 < n_slots; s0 += stride) {  // whole warps iterate together
+        const long long s = s0 + threadIdx.x;
+        bool rep = false;
+        size_t idx = 0;
         uint32_t g = 0;
-        if (fg) {
-            fg_bits |= 1u << it;
-            const uint32_t g_min = SEL_GMASK - (sel[it].x & SEL_GMASK), g_max = sel[it].y & SEL_GMASK;
-            if (g_min == g_max) {
+        if (s < n_slots) {
+            const uint2 e = p.ws.picks[s];
+            if (e.x != 0xffffffffu) {
+                idx = e.x;
+                const uint2 sel = p.ws.sel[idx];
+                const uint32_t g_min = SEL_GMASK - (sel.x & SEL_GMASK), g_max = sel.y & SEL_GMASK;
+                rep = e.y == g_min;
                 g = g_min;
-            } else {  // contested: first-max argmax of overlaps over ALL GTs (utils/tal.py:286)
-                const u64 k = p.ws.key[idx];
-                const bool any = (k >> 56) == epoch && ((k >> KEY_GBITS) & 0x3fffffffull) != 0ull;
-                g = any ? (uint32_t)(KEY_GMASK - (k & KEY_GMASK)) : 0u;
+                if (rep && g_min != g_max) {  // contested
+                    const u64 k = p.ws.key[idx];
+                    const bool any = (k >> 56) == epoch && ((k >> KEY_GBITS) & 0x3fffffffull) != 0ull;
+                    g = any ? (uint32_t)(KEY_GMASK - (k & KEY_GMASK)) : 0u;
+                }
             }
         }
-        own[it] = g;
-        const float4 gb = s_box[g];
-        long long lab = (long long)s_lab[g];
+        // compact-list slot: one global atomic per warp
+        const unsigned m = __ballot_sync(FULL, rep);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(p.ws.flags + 1, __popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (!rep) continue;
+        const int bi = (int)(idx / (size_t)p.A);
+        const int a = (int)(idx - (size_t)bi * p.A);
+        const size_t gslot = (size_t)bi * p.G + g;
+        const float4 gb = *reinterpret_cast<const float4*>(p.gt_bboxes + gslot * 4);
+        long long lab = (long long)p.gt_labels[gslot];
         lab = lab < 0 ? 0 : lab;
         p.target_gt_idx[idx] = (long long)g;
         p.target_labels[idx] = lab;
-        p.fg_mask[idx] = fg ? 1 : 0;
+        p.fg_mask[idx] = 1;
         reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
-        if (p.nc == 1 && !fg) p.target_scores[idx] = 0.f;  // foreground entries are written below
-        if (epoch == 255u) {  // last epoch before the wrap: leave the state clean for epoch 1
-            p.ws.sel[idx] = make_uint2(0u, 0u);
-            p.ws.key[idx] = 0ull;
-        }
-    }
-    // compact the CTA's foreground anchors: shared-memory list + one global atomic per CTA
-    const int mine = __popc(fg_bits);
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[wib] = incl;
-    __syncthreads();
-    if (tid == 0) {
-        int tot = 0;
-        for (int w = 0; w < RES_THREADS / 32; ++w) {
-            const int t = warp_tot[w];
-            warp_tot[w] = tot;
-            tot += t;
-        }
-        block_tot = tot;
-        block_base = tot ? atomicAdd(p.ws.flags + 1, tot) : 0;
-    }
-    __syncthreads();
-    int slot = warp_tot[wib] + incl - mine;
-#pragma unroll
-    for (int it = 0; it < RES_ITERS; ++it)
-        if (fg_bits & (1u << it)) s_fg[slot++] = make_uint2((uint32_t)(a_base + it * RES_THREADS), own[it]);
-    __syncthreads();
-    const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
-    for (int i = tid; i < block_tot; i += RES_THREADS) {
-        const uint2 e = s_fg[i];
-        const int a = (int)e.x;
-        const uint32_t g = e.y;
-        const size_t idx = img + a;
-        const size_t gslot = (size_t)bi * p.G + g;
-        long long lab = (long long)s_lab[g];
-        lab = lab < 0 ? 0 : (lab >= p.nc ? p.nc - 1 : lab);
+        lab = lab >= p.nc ? p.nc - 1 : lab;
         float al = 0.f;
-        if (s_msk[g] != 0.f) {
-            const GtBox gt = make_gt(s_box[g]);
+        if (p.mask_gt[gslot] != 0.f) {
+            const GtBox gt = make_gt(gb);
             const float2 ap = __ldg(anc + a);
             if (anchor_in_gt(ap.x, ap.y, gt)) {
                 const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
@@ -534,7 +527,7 @@ __global__ void __launch_bounds__(RES_THREADS) assign_resolve_kernel(const Assig
             }
         }
         p.target_scores[idx * p.nc + lab] = al;
-        p.ws.fg_list[block_base + i] = make_uint2((uint32_t)idx, (uint32_t)gslot);
+        p.ws.fg_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)idx, (uint32_t)gslot);
     }
 }
 
@@ -597,6 +590,7 @@ static void split_ws(void* workspace, int b, int A, int G, AssignWs& ws, size_t&
     ws.pos_align = (uint32_t*)take((size_t)b * G * 4);
     ws.pos_ov = (uint32_t*)take((size_t)b * G * 4);
     ws.fg_list = (uint2*)take(n * 8);
+    ws.picks = (uint2*)take((size_t)b * G * KZD_MAX_TOPK * 8);
     total = o;
 }
 
@@ -629,7 +623,6 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     KZD_CHECK_ARG(b <= 65535, "kzd_tal_assign: b=%d > 65535", b);
     KZD_CHECK_ARG(score_dtype >= 0 && score_dtype <= 2, "kzd_tal_assign: score_dtype=%d not in {0,1,2}", score_dtype);
     KZD_CHECK_ARG((double)b * A < 4294967295.0 && G < (1 << 24) - 2, "kzd_tal_assign: b*A or G too large");
-    KZD_CHECK_ARG((size_t)G * 24 <= 200 * 1024, "kzd_tal_assign: G=%d exceeds the shared-memory GT table (8533)", G);
     KZD_CHECK_ARG((double)b * G < 4294967295.0, "kzd_tal_assign: b*G too large");
     KZD_CHECK_ARG(((uintptr_t)gt_bboxes) % 16 == 0 && ((uintptr_t)pd_bboxes) % 16 == 0 &&
                       ((uintptr_t)target_bboxes) % 16 == 0 && ((uintptr_t)anc_points) % 8 == 0 &&
@@ -657,18 +650,15 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     p.b = b, p.A = A, p.G = G, p.nc = nc, p.topk = topk;
     p.alpha = alpha, p.beta = beta, p.eps = eps;
     p.n_levels = n_levels, p.zero_fill = zero_fill, p.score_dtype = score_dtype;
+    p.fill_vec = A % 16 == 0 && ((uintptr_t)target_labels | (uintptr_t)target_gt_idx | (uintptr_t)fg_mask |
+                                 (uintptr_t)target_scores | (uintptr_t)target_bboxes) % 16 == 0;
     p.target_labels = (long long*)target_labels, p.target_bboxes = target_bboxes, p.target_scores = target_scores;
     p.fg_mask = fg_mask, p.target_gt_idx = (long long*)target_gt_idx, p.counters = counters;
 
     cudaStream_t st = (cudaStream_t)stream;
     if (!persistent) KZD_CUDA(cudaMemsetAsync(workspace, 0, p.ws.state_bytes, st));  // stateless mode
-    if (n_levels > 0) {
-        assign_verify_kernel<<<(A + 255) / 256, 256, 0, st>>>(anc_points, A, p, persistent ? 0 : 1);
-        KZD_LAUNCH_CHECK("assign_verify_kernel");
-    } else {
-        assign_begin_kernel<<<1, 1, 0, st>>>(p.ws, persistent ? 0 : 1);
-        KZD_LAUNCH_CHECK("assign_begin_kernel");
-    }
+    assign_begin_kernel<<<(A + 255) / 256, 256, 0, st>>>(anc_points, A, p, persistent ? 0 : 1);
+    KZD_LAUNCH_CHECK("assign_begin_kernel");
     if (nc > 1) {  // dense (b,A,nc) target_scores: zero rows now, the owner's entry is written later
         const size_t n = (size_t)b * A * nc;
         const size_t n4 = (((uintptr_t)target_scores) % 16 == 0) ? n / 4 : 0;
@@ -693,11 +683,12 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
         KZD_LAUNCH_CHECK("assign_candidates_kernel");
     }
     {
-        const size_t smem = (size_t)G * 24;
-        KZD_CUDA(cudaFuncSetAttribute(assign_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((A + RES_THREADS * RES_ITERS - 1) / (RES_THREADS * RES_ITERS), b);
-        assign_resolve_kernel<<<grid, RES_THREADS, smem, st>>>(p);
-        KZD_LAUNCH_CHECK("assign_resolve_kernel");
+        const long long slots = (long long)b * G * topk;
+        long long blocks = (slots + 255) / 256;
+        const long long cap = (long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        assign_patch_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+        KZD_LAUNCH_CHECK("assign_patch_kernel");
     }
     {
         assign_normalize_kernel<<<(unsigned)sm_count() * 2, 256, 0, st>>>(p);
