@@ -190,11 +190,8 @@ __device__ __forceinline__ void mark_selected(uint2* __restrict__ sel, uint32_t 
 
 // One in-GT pair: overlap (+ the per-anchor argmax-overlap key) and the alignment metric's bits (0: not
 // positive; positive floats order like their bit patterns).
-__device__ __forceinline__ uint32_t eval_pair(const AssignParams& p, const GtBox& gt, int a, size_t img,
-                                              const float4* __restrict__ pdb, const float* __restrict__ pds, int g,
-                                              uint32_t epoch) {
-    const float4 pb = __ldg(pdb + a);
-    const float sc = __ldg(pds + (size_t)a * p.nc);
+__device__ __forceinline__ uint32_t eval_pair(const AssignParams& p, const GtBox& gt, int a, size_t img, const float4 pb,
+                                              const float sc, int g, uint32_t epoch) {
     const float o = overlap_ciou(gt, pb);
     if (o > 0.f)
         atomicMax(p.ws.key + img + a, ((u64)epoch << 56) | ((u64)min(__float_as_uint(o), 0x3fffffffu) << KEY_GBITS) |
@@ -286,17 +283,21 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             }
         }
     };
-    if (p.mask_gt[wid] == 0.f) {  // padded GT: claims nothing, contributes zero overlap
+    // everything the warp needs about its GT, loaded together (one memory round trip instead of three)
+    const float gt_mask = p.mask_gt[wid], gt_label = p.gt_labels[wid];
+    const float4 gt_box = *reinterpret_cast<const float4*>(p.gt_bboxes + wid * 4);
+    const int flag_mismatch = p.ws.flags[0], flag_epoch = p.ws.flags[2];
+    if (gt_mask == 0.f) {  // padded GT: claims nothing, contributes zero overlap
         if (lane < p.topk) picks[lane] = make_uint2(0xffffffffu, 0u);
         fill_background();
         continue;
     }
 
-    const GtBox gt = make_gt(*reinterpret_cast<const float4*>(p.gt_bboxes + wid * 4));
-    int label = (int)p.gt_labels[wid];
+    const GtBox gt = make_gt(gt_box);
+    int label = (int)gt_label;
     label = label < 0 ? 0 : (label >= p.nc ? p.nc - 1 : label);
-    const bool grid_ok = p.n_levels > 0 && p.ws.flags[0] == 0;
-    const uint32_t epoch = (uint32_t)p.ws.flags[2];
+    const bool grid_ok = p.n_levels > 0 && flag_mismatch == 0;
+    const uint32_t epoch = (uint32_t)flag_epoch;
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
     const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
     const float* __restrict__ pds = p.pd_scores + img * p.nc + label;
@@ -309,9 +310,25 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
 
     auto evaluate = [&]() {  // slots [n_eval, n): anchors -> metric bits
         __syncwarp();
+        // the gathers of batch k+1 (predicted box 16 B, score 4 B per pair) are issued before batch k is
+        // evaluated, so only the first batch's memory latency is exposed
+        int a_nx = 0;
+        float4 pb_nx = make_float4(0.f, 0.f, 0.f, 0.f);
+        float sc_nx = 0.f;
+        auto fetch = [&](int t) {
+            if (t < n) {
+                a_nx = ancs[t];
+                pb_nx = __ldg(pdb + a_nx);
+                sc_nx = __ldg(pds + (size_t)a_nx * p.nc);
+            }
+        };
+        fetch(n_eval + lane);
         for (int e = n_eval; e < n; e += 32) {
-            const int t = e + lane;
-            if (t < n) bits[t] = eval_pair(p, gt, ancs[t], img, pdb, pds, g, epoch);
+            const int t = e + lane, a_cur = a_nx;
+            const float4 pb = pb_nx;
+            const float sc = sc_nx;
+            fetch(t + 32);
+            if (t < n) bits[t] = eval_pair(p, gt, a_cur, img, pb, sc, g, epoch);
         }
         n_eval = n;
         __syncwarp();
