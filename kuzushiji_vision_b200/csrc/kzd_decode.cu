@@ -181,16 +181,26 @@ __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, 
         Out<VEC>::store(dst + 3 * (size_t)p.A, oh);
         const T* __restrict__ csrc = src + (size_t)(4 * KZD_REG_MAX) * hw;
         float* __restrict__ cdst = dst + 4 * (size_t)p.A;
-#pragma unroll 4
-        for (int c = 0; c < p.nc; ++c) {
-            float v[VEC], o[VEC];
-            In<VEC, T>::load(v, csrc + (size_t)c * hw);
+        // class rows in groups of CG: all loads of a group are issued before any is used (a multi-class
+        // kuzushiji head has thousands of rows, so this loop then carries almost all of the traffic)
+        constexpr int CG = 8;
+        for (int c0 = 0; c0 < p.nc; c0 += CG) {
+            float v[CG][VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                o[i] = 1.f / (1.f + __expf(-v[i]));  // |err| < 2e-7: ex2.approx + IEEE div
-                if (FILTER && (c == 0 || o[i] > best[i])) best[i] = o[i], cls[i] = c;  // first maximum wins (ops.py:274)
+            for (int k = 0; k < CG; ++k)
+                if (c0 + k < p.nc) In<VEC, T>::load(v[k], csrc + (size_t)(c0 + k) * hw);
+#pragma unroll
+            for (int k = 0; k < CG; ++k) {
+                const int c = c0 + k;
+                if (c >= p.nc) break;
+                float o[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    o[i] = 1.f / (1.f + __expf(-v[k][i]));  // |err| < 2e-7: ex2.approx + IEEE div
+                    if (FILTER && (c == 0 || o[i] > best[i])) best[i] = o[i], cls[i] = c;  // first maximum wins (ops.py:274)
+                }
+                Out<VEC>::store(cdst + (size_t)c * p.A, o);
             }
-            Out<VEC>::store(cdst + (size_t)c * p.A, o);
         }
     }
     if (FILTER) {
