@@ -122,7 +122,7 @@ size_t kzd_assign_workspace_bytes(int b, int A, int G);
  *   target_gt_idx int64 (b,A); counters double[2] = { sum(target_scores), count(fg_mask) }
  *   (may be NULL). G must be >= 1 (the G == 0 early-out of tal.py:64-71 is host logic).
  *   persistent: 0 = stateless: the call zeroes the per-anchor state in `workspace` itself (one extra
- *     12 B/anchor memset). 1 = the caller keeps ONE workspace per (b, A, G), zeroed ONCE after
+ *     16 B/anchor memset). 1 = the caller keeps ONE workspace per (b, A, G), zeroed ONCE after
  *     allocation, and passes it unchanged on every call: the state words carry an 8-bit epoch that the
  *     library advances on the device (CUDA-graph friendly), stale entries lose every atomic, and the
  *     state is wiped by the kernels themselves once per 255 calls. */
