@@ -230,6 +230,11 @@ def run_kzd(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device - the kzd arm has no CPU path (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    try:
+        all_cpus = os.sched_getaffinity(0)
+    except Exception:
+        all_cpus = None
+    numa_node = kdist.bind_to_gpu_numa(local_rank) if world > 1 else None  # before the pinned buffers are allocated
     w = WORKLOAD
     b, nc, G = w["batch"], w["nc"], w["G"]
     glo, ghi = kdist.shard_range(b * world, rank, world)  # this rank's pages of the global batch
@@ -465,6 +470,8 @@ def run_kzd(args, rank, local_rank, world):
                               "replay, CUDA events); the timed region replays all four stages as one graph"}
 
     # ---- CPU baseline on a bounded sample (one page, repeated) ----
+    if all_cpus is not None and numa_node is not None:
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm may use every host core again
     threads = cpu_threads()
     torch.set_num_threads(threads)
     page = page_inputs(1, 0)
@@ -494,7 +501,7 @@ def run_kzd(args, rank, local_rank, world):
                    "step": "PagePipeline: one CUDA-graph replay of decode_train+assign+decode_infer+NMS per step; "
                            f"{depth} pipelines alternate on {depth} streams (multi-buffering)",
                    "ms_per_step_single_stream": ms_single,
-                   "parallelism": f"image-sharded x{world}"},
+                   "parallelism": f"image-sharded x{world}", "numa_node_rank0": numa_node},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "path": "pinned host head maps + GT -> H2D -> caller glue (torch) -> PagePipeline graph "

@@ -33,6 +33,47 @@ def init(backend=None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process (and, through first-touch, the pinned host buffers it allocates afterwards) to the
+    CPUs of the NUMA node the GPU hangs off. With one process per GPU feeding page batches from host memory
+    (the end-to-end path: 566 MB of head maps per step and GPU), buffers on the far socket halve the H2D rate
+    when all eight GPUs pull at once. Returns the node, or None when the topology is not exposed
+    (containers without /sys PCI info) - then nothing is changed."""
+    try:
+        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id  # torch >= 2.3
+    except Exception:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            idx = device_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                idx = int(vis.split(",")[device_index])
+            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        except Exception:
+            return None
+    try:
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:  # NVML pads the PCI domain to 8 hex digits, sysfs uses 4
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_range(n_images, rank, world):
     """Contiguous shard [lo, hi) of ``n_images`` for ``rank``; the first ``n % world`` ranks get one more."""
     base, extra = divmod(n_images, world)

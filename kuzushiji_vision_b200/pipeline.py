@@ -41,7 +41,8 @@ class PagePipeline:
         no = 4 * REG_MAX + nc
         # static inputs (fill with load() or write into them directly)
         self.levels = [torch.zeros((b, no, h, w), dtype=f32, device=dev) for h, w in self.level_hw]
-        self.pred_distri = torch.zeros((b, A, 4 * REG_MAX), dtype=f32, device=dev)
+        # the fused decode reads the NCHW maps directly: no (b,A,64) transposed copy is needed then
+        self.pred_distri = None if fuse_decodes else torch.zeros((b, A, 4 * REG_MAX), dtype=f32, device=dev)
         self.pd_scores = torch.zeros((b, A, nc), dtype=f32, device=dev)
         self.gt_labels = torch.zeros((b, G, 1), dtype=f32, device=dev)
         self.gt_bboxes = torch.zeros((b, G, 4), dtype=f32, device=dev)
@@ -179,7 +180,7 @@ class PagePipeline:
                 dst.copy_(src, non_blocking=True)
         for name, src in (("pred_distri", pred_distri), ("pd_scores", pd_scores), ("gt_labels", gt_labels),
                           ("gt_bboxes", gt_bboxes), ("mask_gt", mask_gt)):
-            if src is not None:
+            if src is not None and getattr(self, name) is not None:
                 getattr(self, name).copy_(src.reshape(getattr(self, name).shape), non_blocking=True)
 
     def step(self, stream=None):
