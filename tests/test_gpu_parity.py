@@ -815,11 +815,32 @@ def test_extreme_shapes():
         assert m[0].shape[0] == min(md, 4096)
 
 
-def test_pipeline_recovers_from_nms_capacity_overflow():
+def test_nms_first_try_pool_overflow_is_recovered():
+    """The eager drop-in starts with a 4096-candidate pool (cluster ordering); a page with more candidates
+    overflows it, the filter is redone with room for everything (box rows are already xyxy by then) and the
+    suppression capacity grows: rows and the in-place side effect must still match the reference."""
+    torch.manual_seed(5)
+    b, A = 2, 20000
+    y = torch.zeros(b, 5, A, device=DEV)
+    y[:, 0] = torch.rand(b, A, device=DEV) * 1200 + 40
+    y[:, 1] = torch.rand(b, A, device=DEV) * 1200 + 40
+    y[:, 2:4] = torch.rand(b, 2, A, device=DEV) * 40 + 10
+    y[:, 4] = torch.rand(b, A, device=DEV)
+    y[1, 4] *= 0.3  # image 1 stays under the first-try pool, image 0 has ~15000 candidates
+    for kw in (dict(conf_thres=0.25, iou_thres=0.6, max_det=300), dict(conf_thres=0.25, iou_thres=0.5, max_det=20000),
+               dict(conf_thres=0.25, iou_thres=0.6, max_det=300, max_nms=3000)):
+        m, r, p1, p2 = _nms_both(y, **kw)
+        _check_nms(m, r)
+        assert torch.equal(p1, p2)  # xywh -> xyxy applied exactly once
+
+
+@pytest.mark.parametrize("fuse_filter", [False, True])
+def test_pipeline_recovers_from_nms_capacity_overflow(fuse_filter):
     """More candidates per page than the graph's fixed pool / n_cap: results() redoes the NMS eagerly."""
     b, G, imgsz, nc, strides = 2, 20, 320, 1, synth.P2_P5
     pipe = kzd.PagePipeline(b, synth.level_shapes(imgsz, strides), strides, nc, G, device=DEV, conf_thres=0.25,
-                            iou_thres=0.7, max_det=300, pool=256, n_cap=128)
+                            iou_thres=0.7, max_det=300, pool=256, n_cap=128, fuse_filter=fuse_filter,
+                            fuse_decodes=fuse_filter)
     lv = synth.head_outputs(b, nc, imgsz, strides, seed=81, device=DEV, sparse_cls=1500)
     d = synth.assigner_inputs(b, G, imgsz, nc, strides, seed=81, device=DEV)
     pipe.load(levels=lv, pred_distri=d["pred_distri"], pd_scores=d["pd_scores"], gt_labels=d["gt_labels"],
