@@ -493,58 +493,67 @@ __global__ void __launch_bounds__(256) assign_patch_kernel(const AssignParams p)
         p.ws.flags[4] = epoch == 255u;    // last epoch before the wrap: the next call wipes the state first
     }
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
+    const float4* __restrict__ gtb = reinterpret_cast<const float4*>(p.gt_bboxes);
     for (long long s0 = (long long)blockIdx.x * blockDim.x; s0 < n_slots; s0 += stride) {  // whole warps iterate together
         const long long s = s0 + threadIdx.x;
         bool rep = false;
-        size_t idx = 0;
-        uint32_t g = 0;
+        size_t idx = 0, gslot = 0;
         if (s < n_slots) {
             const uint2 e = p.ws.picks[s];
             if (e.x != 0xffffffffu) {
+                // Everything that depends only on the pick is requested at once: the selection words, the
+                // anchor, its predicted box, and - speculatively - the selecting GT's row (it is the owner
+                // unless the anchor is contested). One memory round trip instead of four.
                 idx = e.x;
+                const int bi = (int)(idx / (size_t)p.A);
+                const int a = (int)(idx - (size_t)bi * p.A);
+                gslot = (size_t)bi * p.G + e.y;
                 const uint2 sel = p.ws.sel[idx];
+                const float2 ap = __ldg(anc + a);
+                const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
+                float4 gb = gtb[gslot];
+                float glab = p.gt_labels[gslot], gmsk = p.mask_gt[gslot];
                 const uint32_t g_min = SEL_GMASK - (sel.x & SEL_GMASK), g_max = sel.y & SEL_GMASK;
-                rep = e.y == g_min;
-                g = g_min;
-                if (rep && g_min != g_max) {  // contested
-                    const u64 k = p.ws.key[idx];
-                    const bool any = (k >> 56) == epoch && ((k >> KEY_GBITS) & 0x3fffffffull) != 0ull;
-                    g = any ? (uint32_t)(KEY_GMASK - (k & KEY_GMASK)) : 0u;
+                rep = e.y == g_min;  // the smallest selecting GT's entry represents the anchor
+                if (rep) {
+                    uint32_t g = g_min;
+                    if (g_min != g_max) {  // contested: first-max argmax of overlaps over ALL GTs (utils/tal.py:286)
+                        const u64 k = p.ws.key[idx];
+                        const bool any = (k >> 56) == epoch && ((k >> KEY_GBITS) & 0x3fffffffull) != 0ull;
+                        g = any ? (uint32_t)(KEY_GMASK - (k & KEY_GMASK)) : 0u;
+                        if (g != e.y) {
+                            gslot = (size_t)bi * p.G + g;
+                            gb = gtb[gslot], glab = p.gt_labels[gslot], gmsk = p.mask_gt[gslot];
+                        }
+                    }
+                    long long lab = (long long)glab;
+                    lab = lab < 0 ? 0 : lab;
+                    p.target_gt_idx[idx] = (long long)g;
+                    p.target_labels[idx] = lab;
+                    p.fg_mask[idx] = 1;
+                    reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
+                    lab = lab >= p.nc ? p.nc - 1 : lab;
+                    float al = 0.f;
+                    if (gmsk != 0.f) {
+                        const GtBox gt = make_gt(gb);
+                        if (anchor_in_gt(ap.x, ap.y, gt)) {
+                            const float sc = __ldg(p.pd_scores + idx * p.nc + lab);
+                            const float o = overlap_ciou(gt, pb);
+                            al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
+                            atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
+                            atomicMax(p.ws.pos_align + gslot, __float_as_uint(al));
+                        }
+                    }
+                    p.target_scores[idx * p.nc + lab] = al;
                 }
             }
         }
-        // compact-list slot: one global atomic per warp
+        // compact foreground list: one global atomic per warp
         const unsigned m = __ballot_sync(FULL, rep);
         int base = 0;
         if (lane == 0 && m) base = atomicAdd(p.ws.flags + 1, __popc(m));
         base = __shfl_sync(FULL, base, 0);
-        if (!rep) continue;
-        const int bi = (int)(idx / (size_t)p.A);
-        const int a = (int)(idx - (size_t)bi * p.A);
-        const size_t gslot = (size_t)bi * p.G + g;
-        const float4 gb = *reinterpret_cast<const float4*>(p.gt_bboxes + gslot * 4);
-        long long lab = (long long)p.gt_labels[gslot];
-        lab = lab < 0 ? 0 : lab;
-        p.target_gt_idx[idx] = (long long)g;
-        p.target_labels[idx] = lab;
-        p.fg_mask[idx] = 1;
-        reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
-        lab = lab >= p.nc ? p.nc - 1 : lab;
-        float al = 0.f;
-        if (p.mask_gt[gslot] != 0.f) {
-            const GtBox gt = make_gt(gb);
-            const float2 ap = __ldg(anc + a);
-            if (anchor_in_gt(ap.x, ap.y, gt)) {
-                const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
-                const float sc = __ldg(p.pd_scores + idx * p.nc + lab);
-                const float o = overlap_ciou(gt, pb);
-                al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
-                atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
-                atomicMax(p.ws.pos_align + gslot, __float_as_uint(al));
-            }
-        }
-        p.target_scores[idx * p.nc + lab] = al;
-        p.ws.fg_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)idx, (uint32_t)gslot);
+        if (rep) p.ws.fg_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)idx, (uint32_t)gslot);
     }
 }
 
