@@ -87,12 +87,15 @@ class PagePipeline:
         self._side2 = torch.cuda.Stream(device=dev, priority=-1) if (assign_priority and overlap) else None
         self.out = None
         self.graph = None
-        # decode_train, assign x4, decode_infer, nms filter + chunk sort + rank + (mask, scan) per phase
-        t0 = ((self.max_det + self.max_det // 4 + 127) // 64 + 3) // 4 * 4
+        # kernels per step: decode(s), assign x4, [nms filter], ordering (chunk sort + rank, or one cluster
+        # kernel), (mask, scan) per phase - the phase schedule mirrors kzd_nms_suppress
+        t0 = (self.max_det + self.max_det // 4 + 127) // 64
         t_cap, phases = (self.n_cap + 63) // 64, 1
         while t0 < t_cap:
             t0, phases = t0 * 4, phases + 1
-        self.kernels_per_step = (1 if self.fuse_decodes else 2) + 4 + (2 if self.fuse_filter else 3) + 2 * phases
+        order = 1 if (self.pool + 511) // 512 <= 8 else 2
+        self.kernels_per_step = ((1 if self.fuse_decodes else 2) + 4 + (0 if self.fuse_filter else 1) + order
+                                 + 2 * phases)
         if use_graph:
             self._capture()
 

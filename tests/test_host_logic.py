@@ -116,6 +116,30 @@ def test_shard_range_partitions_exactly():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_numa_binding_is_a_noop_without_a_gpu():
+    """bind_to_gpu_numa never raises and leaves the affinity alone when there is no device / no topology."""
+    import os
+
+    from kuzushiji_vision_b200 import dist as kdist
+
+    before = os.sched_getaffinity(0)
+    assert kdist.bind_to_gpu_numa(0) is None or isinstance(kdist.bind_to_gpu_numa(0), int)
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
+
+
+def test_decode_filter_argument_validation_without_gpu():
+    """kzd_decode_filter rejects a missing candidate pool / nc == 0 before touching the device."""
+    import ctypes as C
+
+    from kuzushiji_vision_b200 import _lib
+
+    lv, _ = _lib.levels_array([(4, 4, 8.0)])
+    ptrs = (C.c_void_p * 1)(None)
+    rc = _lib.lib.kzd_decode_filter(ptrs, 0, lv, 1, 1, 1, None, None, None, 0.25, None, None, None, 16, None)
+    assert rc != 0 and b"candidate pool" in _lib.lib.kzd_last_error()
+
+
 def test_install_patches_and_restores_reference_attributes():
     from oracle import ref_loader
 
