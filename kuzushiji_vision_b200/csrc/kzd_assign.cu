@@ -334,12 +334,21 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
         __syncwarp();
     };
     auto select = [&]() {  // top-k of slots [0, n) -> lanes 0..n_sel-1
-        uint32_t lm = 0u, nb = 0u;
-        int lt = 0x7fffffff, nt = 0, cnt = 0;
-        for (int t = lane; t < n; t += 32) {
-            const uint32_t v = bits[t];
-            if (v > lm) lm = v, lt = t;  // strict: the lowest slot among equals
-        }
+        // every lane tracks the best TWO of its slots (t = lane, lane + 32, ...), so a lane that wins a round
+        // moves on to its runner-up without touching shared memory; only a lane winning again rescans
+        uint32_t lm = 0u, lm2 = 0u, nb = 0u;
+        int lt = 0x7fffffff, lt2 = 0x7fffffff, nt = 0, cnt = 0;
+        bool have2 = true;
+        auto scan2 = [&]() {
+            lm = lm2 = 0u, lt = lt2 = 0x7fffffff;
+            for (int t = lane; t < n; t += 32) {
+                const uint32_t v = bits[t];
+                if (v > lm) lm2 = lm, lt2 = lt, lm = v, lt = t;  // strict: the lowest slot among equals comes first
+                else if (v > lm2) lm2 = v, lt2 = t;
+            }
+            have2 = true;
+        };
+        scan2();
         for (int r = 0; r < topk; ++r) {
             const uint32_t mx = __reduce_max_sync(FULL, lm);
             if (mx == 0u) break;
@@ -351,12 +360,8 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             ++cnt;
             if (lane == owner) {
                 bits[ts] = 0u;
-                lm = 0u, lt = 0x7fffffff;
-#pragma unroll 1
-                for (int t = lane; t < n; t += 32) {
-                    const uint32_t v = bits[t];
-                    if (v > lm) lm = v, lt = t;
-                }
+                if (have2) lm = lm2, lt = lt2, have2 = false;
+                else scan2();
             }
             __syncwarp();
         }
