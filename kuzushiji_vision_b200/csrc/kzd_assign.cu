@@ -153,6 +153,7 @@ __global__ void assign_begin_kernel(const float* __restrict__ anc, int A, Assign
         p.ws.flags[2] = (e % 255) + 1;  // 1..255
     }
     if (a >= A) return;
+    const float2 ap = __ldg(reinterpret_cast<const float2*>(anc) + a);  // requested together with the wipe flag
     if (wipe)
         for (int bi = 0; bi < p.b; ++bi) {
             p.ws.sel[(size_t)bi * A + a] = make_uint2(0u, 0u);
@@ -166,7 +167,6 @@ __global__ void assign_begin_kernel(const float* __restrict__ anc, int A, Assign
     const float s = p.lv[l].stride;
     const float ex = __fmul_rn((float)(q % p.lv[l].w) + 0.5f, s);
     const float ey = __fmul_rn((float)(q / p.lv[l].w) + 0.5f, s);
-    const float2 ap = __ldg(reinterpret_cast<const float2*>(anc) + a);
     if (ap.x != ex || ap.y != ey) p.ws.flags[0] = 1;
 }
 

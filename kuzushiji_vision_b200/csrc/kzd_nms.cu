@@ -180,7 +180,56 @@ struct SuppressWs {
     int T_cap, C_cap;
 };
 
-// CTA (chunk, image): bitonic sort of 512 keys in shared memory, descending; padding keys are 0.
+// Bitonic sort of one 512-key chunk by 256 threads, descending (keys are unique apart from the zero
+// padding). Thread t holds elements t and t + 256 in registers: compare-exchange distance 256 is inside the
+// thread, distances 16..1 go through warp shuffles, only distances 128, 64, 32 need shared memory and a CTA
+// barrier (9 of the 45 stages). On return the sorted chunk is also in keys[] / vals[].
+__device__ __forceinline__ void order_cx_shfl(u64& key, uint32_t& val, int i, int k, int j) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)key, j);
+    const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(key >> 32), j);
+    const uint32_t pv = __shfl_xor_sync(0xffffffffu, val, j);
+    const u64 pk = ((u64)hi << 32) | lo;
+    const bool want_max = (((i & k) == 0) == ((i & j) == 0));  // descending overall: the lower index keeps the larger key
+    if (want_max ? (pk > key) : (pk < key)) key = pk, val = pv;
+}
+
+__device__ __forceinline__ void chunk_sort_desc(u64& k0, uint32_t& v0, u64& k1, uint32_t& v1, u64* keys, uint32_t* vals) {
+    const int t = threadIdx.x, i0 = t, i1 = t + CHUNK_THREADS;
+    for (int k = 2; k <= CHUNK; k <<= 1) {
+        int j = k >> 1;
+        if (j == CHUNK_THREADS) {  // distance 256: both elements live in this thread (only k == 512: descending)
+            if (k0 < k1) {
+                const u64 tk = k0; k0 = k1, k1 = tk;
+                const uint32_t tv = v0; v0 = v1, v1 = tv;
+            }
+            j >>= 1;
+        }
+        if (j >= 32) {  // distances 128, 64, 32 through shared memory
+            __syncthreads();
+            keys[i0] = k0, keys[i1] = k1, vals[i0] = v0, vals[i1] = v1;
+            for (; j >= 32; j >>= 1) {
+                __syncthreads();
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), q = i | j;
+                const u64 ki = keys[i], kq = keys[q];
+                if ((ki < kq) == ((i & k) == 0)) {
+                    keys[i] = kq, keys[q] = ki;
+                    const uint32_t vi = vals[i];
+                    vals[i] = vals[q], vals[q] = vi;
+                }
+            }
+            __syncthreads();
+            k0 = keys[i0], k1 = keys[i1], v0 = vals[i0], v1 = vals[i1];
+        }
+        for (; j > 0; j >>= 1) {  // distances 16..1 inside the warp
+            order_cx_shfl(k0, v0, i0, k, j);
+            order_cx_shfl(k1, v1, i1, k, j);
+        }
+    }
+    __syncthreads();
+    keys[i0] = k0, keys[i1] = k1, vals[i0] = v0, vals[i1] = v1;
+}
+
+// CTA (chunk, image): sort of the chunk's 512 keys, descending; padding keys are 0.
 __global__ void __launch_bounds__(CHUNK_THREADS) nms_chunk_sort_kernel(const u64* __restrict__ cand_keys,
                                                                        const int32_t* __restrict__ cand_counts,
                                                                        int cand_cap, int n_cap, int max_nms,
@@ -194,29 +243,13 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_chunk_sort_kernel(const u64
     if (chunk == 0 && threadIdx.x == 0) ws.n_sorted[bi] = overflow ? -1 : n;
     if (overflow || chunk * CHUNK >= count) return;
     const u64* __restrict__ src = cand_keys + (size_t)bi * cand_cap;
-    for (int t = threadIdx.x; t < CHUNK; t += CHUNK_THREADS) {
-        const int i = chunk * CHUNK + t;
-        keys[t] = i < count ? src[i] : 0ull;
-        vals[t] = (uint32_t)i;
-    }
-    __syncthreads();
-    for (int k = 2; k <= CHUNK; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const int t = threadIdx.x;  // CHUNK/2 compare-exchanges, one per thread
-            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-            const int p = i | j;
-            const u64 ki = keys[i], kp = keys[p];
-            if ((ki < kp) == ((i & k) == 0)) {
-                keys[i] = kp, keys[p] = ki;
-                const uint32_t vi = vals[i];
-                vals[i] = vals[p], vals[p] = vi;
-            }
-            __syncthreads();
-        }
-    }
+    const int t = threadIdx.x;
+    uint32_t v0 = (uint32_t)(chunk * CHUNK + t), v1 = (uint32_t)(chunk * CHUNK + t + CHUNK_THREADS);
+    u64 k0 = (int)v0 < count ? src[v0] : 0ull, k1 = (int)v1 < count ? src[v1] : 0ull;
+    chunk_sort_desc(k0, v0, k1, v1, keys, vals);
     u64* __restrict__ dk = ws.ckeys + ((size_t)bi * ws.C_cap + chunk) * CHUNK;
     uint32_t* __restrict__ dv = ws.cvals + ((size_t)bi * ws.C_cap + chunk) * CHUNK;
-    for (int t = threadIdx.x; t < CHUNK; t += CHUNK_THREADS) dk[t] = keys[t], dv[t] = vals[t];
+    dk[t] = k0, dk[t + CHUNK_THREADS] = k1, dv[t] = v0, dv[t + CHUNK_THREADS] = v1;
 }
 
 // CTA (chunk, image): global rank of each of the chunk's keys = position inside its own chunk + number of
@@ -272,20 +305,10 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_rank_kernel(const float* __
 }
 
 // One thread-block cluster per image does the whole ordering when the candidate pool is at most 8 chunks
-// (the PagePipeline / first-try case): CTA c sorts chunk c (compare-exchange distances < 32 by warp
-// shuffles, 32..128 through shared memory, 256 inside the thread), the cluster synchronises, and every CTA
-// ranks its keys against the other CTAs' sorted chunks read through distributed shared memory - no
+// (the first-try case of the eager drop-in): CTA c sorts chunk c (chunk_sort_desc), the cluster
+// synchronises, and every CTA ranks its keys against the other CTAs' sorted chunks read through distributed shared memory - no
 // round trip through global memory and one launch instead of two.
 constexpr int ORDER_CL = 8;
-
-__device__ __forceinline__ void order_cx_shfl(u64& key, uint32_t& val, int i, int k, int j) {
-    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)key, j);
-    const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(key >> 32), j);
-    const uint32_t pv = __shfl_xor_sync(0xffffffffu, val, j);
-    const u64 pk = ((u64)hi << 32) | lo;
-    const bool want_max = (((i & k) == 0) == ((i & j) == 0));  // descending overall: the lower index keeps the larger key
-    if (want_max ? (pk > key) : (pk < key)) key = pk, val = pv;
-}
 
 __global__ void __cluster_dims__(ORDER_CL, 1, 1) __launch_bounds__(CHUNK_THREADS)
     nms_order_cluster_kernel(const u64* __restrict__ cand_keys, const float* __restrict__ cand_rows,
@@ -310,38 +333,7 @@ __global__ void __cluster_dims__(ORDER_CL, 1, 1) __launch_bounds__(CHUNK_THREADS
         const u64* __restrict__ src = cand_keys + (size_t)bi * cand_cap;
         if ((int)v0 < count) k0 = src[v0];
         if ((int)v1 < count) k1 = src[v1];
-        for (int k = 2; k <= CHUNK; k <<= 1) {
-            int j = k >> 1;
-            if (j == CHUNK_THREADS) {  // distance 256: both elements live in this thread (only k == 512: descending)
-                if (k0 < k1) {
-                    const u64 tk = k0; k0 = k1, k1 = tk;
-                    const uint32_t tv = v0; v0 = v1, v1 = tv;
-                }
-                j >>= 1;
-            }
-            if (j >= 32) {  // distances 128, 64, 32 through shared memory
-                __syncthreads();
-                keys[i0] = k0, keys[i1] = k1, vals[i0] = v0, vals[i1] = v1;
-                for (; j >= 32; j >>= 1) {
-                    __syncthreads();
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), q = i | j;
-                    const u64 ki = keys[i], kq = keys[q];
-                    if ((ki < kq) == ((i & k) == 0)) {
-                        keys[i] = kq, keys[q] = ki;
-                        const uint32_t vi = vals[i];
-                        vals[i] = vals[q], vals[q] = vi;
-                    }
-                }
-                __syncthreads();
-                k0 = keys[i0], k1 = keys[i1], v0 = vals[i0], v1 = vals[i1];
-            }
-            for (; j > 0; j >>= 1) {  // distances 16..1 inside the warp
-                order_cx_shfl(k0, v0, i0, k, j);
-                order_cx_shfl(k1, v1, i1, k, j);
-            }
-        }
-        __syncthreads();
-        keys[i0] = k0, keys[i1] = k1, vals[i0] = v0, vals[i1] = v1;
+        chunk_sort_desc(k0, v0, k1, v1, keys, vals);
     }
     cluster.sync();  // every chunk of the image is sorted and visible cluster-wide
     if (active) {
