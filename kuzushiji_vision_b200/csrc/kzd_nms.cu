@@ -501,8 +501,18 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
 
 constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
-constexpr int SCAN_HELPERS = SCAN_WARPS - 1;  // warp 0 only resolves diagonal tiles
-constexpr int SCAN_BATCH = 4;  // column tiles per warp whose loads are in flight together
+// Warp 0 walks the diagonal tiles. Warps 4, 8, 12 share its scheduler (warp id mod 4) and only follow the
+// barriers: clock64 traces showed the walker - the critical path - waiting hundreds of cycles for issue
+// slots behind helper warps that the scheduler runs greedily after every barrier release.
+constexpr int SCAN_HELPERS = SCAN_WARPS - SCAN_WARPS / 4;
+#ifndef KZD_SCAN_BATCH
+#define KZD_SCAN_BATCH 4
+#endif
+#ifndef KZD_SCAN_DEPTH
+#define KZD_SCAN_DEPTH 2
+#endif
+constexpr int SCAN_BATCH = KZD_SCAN_BATCH;  // column tiles per helper warp held in registers (48 columns ahead; more: from global)
+constexpr int SCAN_DEPTH = KZD_SCAN_DEPTH;  // chunks a mask load is issued ahead of its use (2, 4 and 6 measured the same)
 
 __device__ __forceinline__ u64 shfl64(u64 v, int src) {
     const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
@@ -512,22 +522,25 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src) {
 
 // One CTA per image walks the 64-row chunks in score order. Per chunk the only serial work is the
 // diagonal tile (warp 0: ballot of the rows that suppress anything inside the chunk, shuffle their
-// words, test/OR). All global loads are issued TWO chunks ahead into a rotating set of three register
-// buffers and are independent of the keep mask (it is applied afterwards), so no memory round trip
-// sits on the chunk-to-chunk critical path. The keep masks are parked in shared memory and the kept
-// rows are gathered by all threads after the walk.
-struct ScanRow {
-    u64 v_lo[SCAN_BATCH], v_hi[SCAN_BATCH];  // every warp: its later tiles of the row
-    u64 d_lo, d_hi;                          // warp 0: the diagonal tile
-};
+// words, test/OR); the helper warps then OR the kept rows into the removed words of the later chunks.
+// A chunk costs what the slowest warp's instruction stream costs (a lone warp issues one dependent
+// instruction every ~4 cycles; clock64 traces showed ~350 instructions per chunk in the first version of
+// this kernel), so the two roles run separate, minimal loops: every tile pointer advances by the same
+// stride per chunk (row and column both move by one tile), tile validity is one compare against a
+// per-warp constant, keep masks and kept counts stay in shared memory until the walk is over, and all
+// global loads are issued SCAN_DEPTH chunks ahead into rotating registers (they do not depend on the keep mask).
+// Both loops meet at two named barriers per chunk and leave together (the exit tests are CTA-uniform).
+__device__ __forceinline__ void scan_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SCAN_THREADS) : "memory"); }
 
 __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __restrict__ cand_rows, int cand_cap,
                                                                 int n_cap, int max_det, int phase, int t_lo,
                                                                 int t_hi, SuppressWs ws,
                                                                 float* __restrict__ out_rows,
                                                                 int32_t* __restrict__ out_counts) {
-    extern __shared__ u64 removed[];  // T_cap words
-    __shared__ u64 keep_sh;
+    extern __shared__ u64 scan_smem[];
+    u64* removed = scan_smem;                                               // T_cap: bits suppressed by a kept row
+    u64* keep_s = scan_smem + ws.T_cap;                                     // T_cap: keep mask of every chunk walked here
+    int* kb_s = reinterpret_cast<int*>(scan_smem + 2 * (size_t)ws.T_cap);   // T_cap: boxes kept before the chunk
     const int bi = blockIdx.x;
     const int n = ws.n_sorted[bi];
     int32_t* state = ws.state + bi * 4;  // [0] done, [1] kept, [2] chunks walked
@@ -560,88 +573,125 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
         }
         __syncthreads();
     }
-    // warp 0 loads only diagonal tiles; warps 1.. load the later tiles of the row, helper w taking
-    // c = r + 1 + (w-1), + SCAN_HELPERS, ...
-    const int hw = warp - 1;
-    auto load_row = [&](int r, ScanRow& row) {
-        row.d_lo = row.d_hi = 0ull;
-#pragma unroll
-        for (int k = 0; k < SCAN_BATCH; ++k) row.v_lo[k] = row.v_hi[k] = 0ull;
-        if (r >= hi) return;
-        const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
-        if (warp == 0) {
-            row.d_lo = tile_row[(size_t)r * 64 + lane], row.d_hi = tile_row[(size_t)r * 64 + lane + 32];
-        } else {
-            const u64* __restrict__ t = tile_row + (size_t)(r + 1 + hw) * 64 + lane;
-#pragma unroll
-            for (int k = 0; k < SCAN_BATCH; ++k)
-                if (r + 1 + hw + k * SCAN_HELPERS < hi)
-                    row.v_lo[k] = t[(size_t)k * SCAN_HELPERS * 64], row.v_hi[k] = t[(size_t)k * SCAN_HELPERS * 64 + 32];
-        }
-    };
     bool finished = (hi <= t_lo);  // nothing new to walk: the image ended in an earlier phase's range
-    // one chunk; returns true when this phase's walk is over
-    auto step = [&](int r, ScanRow& cur, ScanRow& fut) -> bool {
-        load_row(r + 2, fut);  // in flight for two chunks
-        if (warp == 0) {       // (a) resolve the diagonal tile
-            u64 rem = removed[r];
-            const int valid = n - r * 64;  // rows of this chunk that exist
-            if (valid < 64) rem |= ~0ull << valid;
-            u64 nz = (u64)__ballot_sync(0xffffffffu, cur.d_lo != 0ull) |
-                     ((u64)__ballot_sync(0xffffffffu, cur.d_hi != 0ull) << 32);
-            while (nz) {  // only rows that suppress something inside the chunk need the serial step
-                const int i = __ffsll((long long)nz) - 1;
-                nz &= nz - 1;
-                const u64 di = (i < 32) ? shfl64(cur.d_lo, i) : shfl64(cur.d_hi, i - 32);
-                if (!((rem >> i) & 1ull)) rem |= di;
-            }
-            if (lane == 0) keep_sh = ~rem, keepmask[r] = ~rem, kept_before[r] = kept;
-        }
-        __syncthreads();
-        const u64 keep = keep_sh;
-        kept += __popcll(keep);
-        chunks = r + 1;
-        if (kept >= max_det || r + 1 == T) {  // uniform: later boxes cannot enter the first max_det
-            finished = true;
-            return true;
-        }
-        if (r + 1 == hi) return true;  // end of this phase's columns
-        // (b) helpers OR the kept rows into the removed words of the later chunks (data loaded two chunks ago)
-        if (warp > 0) {
-            const bool k_lo = (keep >> lane) & 1ull, k_hi = (keep >> (lane + 32)) & 1ull;
-#pragma unroll
-            for (int k = 0; k < SCAN_BATCH; ++k) {
-                const int c = r + 1 + hw + k * SCAN_HELPERS;
-                if (c < hi) {
-                    const u64 v = (k_lo ? cur.v_lo[k] : 0ull) | (k_hi ? cur.v_hi[k] : 0ull);
-                    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
-                    const uint32_t hi32 = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
-                    if (lane == 0 && (lo | hi32)) removed[c] |= ((u64)hi32 << 32) | lo;
-                }
-            }
-            const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
-            for (int c = r + 1 + hw + SCAN_BATCH * SCAN_HELPERS; c < hi; c += SCAN_HELPERS) {  // very long rows
-                const u64* t = tile_row + (size_t)c * 64;
-                const u64 v = (k_lo ? t[lane] : 0ull) | (k_hi ? t[lane + 32] : 0ull);
-                const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
-                const uint32_t hi32 = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
-                if (lane == 0 && (lo | hi32)) removed[c] |= ((u64)hi32 << 32) | lo;
-            }
-        }
-        __syncthreads();
-        return false;
-    };
+    const size_t stride = ((size_t)ws.T_cap + 1) * 64;  // tile (r, c) -> tile (r+1, c+1)
     if (!finished) {
-        ScanRow b0, b1, b2;
-        load_row(t_lo, b0);
-        load_row(t_lo + 1, b1);
-        for (int r = t_lo; r < hi; r += 3) {
-            if (step(r, b0, b2)) break;
-            if (step(r + 1, b1, b0)) break;
-            if (step(r + 2, b2, b1)) break;
+        if (warp == 0) {
+            // ---- walker: diagonal tiles ----
+            const u64* dp = mask + ((size_t)t_lo * ws.T_cap + t_lo) * 64 + lane;  // this lane's words of tile (r, r)
+            u64 q_lo[SCAN_DEPTH + 1], q_hi[SCAN_DEPTH + 1];  // [0]: chunk r ... [SCAN_DEPTH]: chunk r + SCAN_DEPTH
+#pragma unroll
+            for (int d = 0; d < SCAN_DEPTH; ++d) {
+                q_lo[d] = q_hi[d] = 0ull;
+                if (t_lo + d < hi) q_lo[d] = dp[d * stride], q_hi[d] = dp[d * stride + 32];
+            }
+            q_lo[SCAN_DEPTH] = q_hi[SCAN_DEPTH] = 0ull;
+            dp += SCAN_DEPTH * stride;  // next tile to fetch
+            for (int r = t_lo;; ++r) {
+                if (r + SCAN_DEPTH < hi) q_lo[SCAN_DEPTH] = dp[0], q_hi[SCAN_DEPTH] = dp[32];  // in flight for SCAN_DEPTH chunks
+                dp += stride;
+                const u64 a_lo = q_lo[0], a_hi = q_hi[0];
+                u64 rem = removed[r];
+                const int valid = n - r * 64;  // rows of this chunk that exist
+                if (valid < 64) rem |= ~0ull << valid;
+                u64 nz = (u64)__ballot_sync(0xffffffffu, a_lo != 0ull) | ((u64)__ballot_sync(0xffffffffu, a_hi != 0ull) << 32);
+                while (nz) {  // only rows that suppress something inside the chunk need the serial step
+                    const int i = __ffsll((long long)nz) - 1;
+                    nz &= nz - 1;
+                    const u64 di = (i < 32) ? shfl64(a_lo, i) : shfl64(a_hi, i - 32);
+                    if (!((rem >> i) & 1ull)) rem |= di;
+                }
+                const u64 keep = ~rem;
+                if (lane == 0) keep_s[r] = keep, kb_s[r] = kept;
+                kept += __popcll(keep);
+                chunks = r + 1;
+                scan_bar();  // keep_s[r] is published
+                if (kept >= max_det || r + 1 == T) {  // later boxes cannot enter the first max_det
+                    finished = true;
+                    break;
+                }
+                if (r + 1 == hi) break;  // end of this phase's columns
+#pragma unroll
+                for (int d = 0; d < SCAN_DEPTH; ++d) q_lo[d] = q_lo[d + 1], q_hi[d] = q_hi[d + 1];
+                scan_bar();  // the helpers have applied chunk r's kept rows
+            }
+        } else if ((warp & 3) == 0) {
+            // ---- warps on the walker's scheduler: follow the barriers and the exit test, nothing else ----
+            for (int r = t_lo;; ++r) {
+                scan_bar();
+                kept += __popcll(keep_s[r]);
+                chunks = r + 1;
+                if (kept >= max_det || r + 1 == T) {
+                    finished = true;
+                    break;
+                }
+                if (r + 1 == hi) break;
+                scan_bar();
+            }
+        } else {
+            // ---- helpers: tiles (r, r + 1 + hw + k * SCAN_HELPERS), k < SCAN_BATCH, and the rare columns beyond ----
+            const int hw = warp - 1 - (warp >> 2);  // 0..11 over the warps with warp % 4 != 0
+            const u64* hp = mask + ((size_t)t_lo * ws.T_cap + (t_lo + 1 + hw)) * 64 + lane;
+            // tile k of chunk r exists while r < hi - 1 - hw - 15 k
+            int rmax[SCAN_BATCH];
+#pragma unroll
+            for (int k = 0; k < SCAN_BATCH; ++k) rmax[k] = hi - 1 - hw - k * SCAN_HELPERS;
+            u64 q_lo[SCAN_DEPTH + 1][SCAN_BATCH], q_hi[SCAN_DEPTH + 1][SCAN_BATCH];  // [d]: this warp's tiles of chunk r + d
+#pragma unroll
+            for (int d = 0; d <= SCAN_DEPTH; ++d)
+#pragma unroll
+                for (int k = 0; k < SCAN_BATCH; ++k) {
+                    q_lo[d][k] = q_hi[d][k] = 0ull;
+                    if (d < SCAN_DEPTH && t_lo + d < rmax[k])
+                        q_lo[d][k] = hp[d * stride + (size_t)k * SCAN_HELPERS * 64],
+                        q_hi[d][k] = hp[d * stride + (size_t)k * SCAN_HELPERS * 64 + 32];
+                }
+            hp += SCAN_DEPTH * stride;
+            for (int r = t_lo;; ++r) {
+#pragma unroll
+                for (int k = 0; k < SCAN_BATCH; ++k)
+                    if (r + SCAN_DEPTH < rmax[k])
+                        q_lo[SCAN_DEPTH][k] = hp[(size_t)k * SCAN_HELPERS * 64], q_hi[SCAN_DEPTH][k] = hp[(size_t)k * SCAN_HELPERS * 64 + 32];
+                hp += stride;
+                scan_bar();  // keep_s[r] is published
+                const u64 keep = keep_s[r];
+                kept += __popcll(keep);
+                chunks = r + 1;
+                if (kept >= max_det || r + 1 == T) {
+                    finished = true;
+                    break;
+                }
+                if (r + 1 == hi) break;
+                const bool k_lo = (keep >> lane) & 1ull, k_hi = (keep >> (lane + 32)) & 1ull;
+#pragma unroll
+                for (int k = 0; k < SCAN_BATCH; ++k)
+                    if (r < rmax[k]) {
+                        // suppression words are sparse: the few lanes that hold a non-zero word of a kept row OR
+                        // it in with a shared-memory atomic; no warp-wide reduction sits on the chunk's path
+                        const u64 v = (k_lo ? q_lo[0][k] : 0ull) | (k_hi ? q_hi[0][k] : 0ull);
+                        if (v) atomicOr(reinterpret_cast<unsigned long long*>(removed + r + 1 + hw + k * SCAN_HELPERS), v);
+                    }
+                if (r + 1 + hw + SCAN_BATCH * SCAN_HELPERS < hi) {  // very long rows: straight from global memory
+                    const u64* __restrict__ tile_row = mask + (size_t)r * ws.T_cap * 64;
+                    for (int c = r + 1 + hw + SCAN_BATCH * SCAN_HELPERS; c < hi; c += SCAN_HELPERS) {
+                        const u64* t = tile_row + (size_t)c * 64;
+                        const u64 v = (k_lo ? t[lane] : 0ull) | (k_hi ? t[lane + 32] : 0ull);
+                        if (v) atomicOr(reinterpret_cast<unsigned long long*>(removed + c), v);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < SCAN_DEPTH; ++d)
+#pragma unroll
+                    for (int k = 0; k < SCAN_BATCH; ++k) q_lo[d][k] = q_lo[d + 1][k], q_hi[d][k] = q_hi[d + 1][k];
+                scan_bar();  // chunk r's kept rows are applied
+            }
         }
     }
     __syncthreads();
+    if (hi > t_lo) {  // park the walked chunks' keep masks for the gather and for later phases
+        for (int c = t_lo + threadIdx.x; c < chunks; c += SCAN_THREADS) keepmask[c] = keep_s[c], kept_before[c] = kb_s[c];
+        __syncthreads();
+    }
     if (n == 0) finished = true;
     if (!finished) {  // more columns are needed: the next phase continues from here
         if (threadIdx.x == 0) state[0] = 0, state[1] = kept, state[2] = chunks;
@@ -784,7 +834,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
         nms_mask_kernel<<<grid, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(b, n_cap, iou_thres, phase, g_lo,
                                                                                  g_hi, ws);
         KZD_LAUNCH_CHECK("nms_mask_kernel");
-        nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * sizeof(u64), st>>>(cand_rows, cand_cap, n_cap, max_det,
+        nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * 20, st>>>(cand_rows, cand_cap, n_cap, max_det,
                                                                                 phase, t_prev, t_next, ws, out_rows,
                                                                                 out_counts);
         KZD_LAUNCH_CHECK("nms_scan_kernel");
