@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
 // GT that did not top-k them), records the per-GT maxima of utils/tal.py:112-114 and appends the anchor
 // to the compact foreground list of the normalise pass.
 __global__ void __launch_bounds__(256) assign_patch_kernel(const AssignParams p) {
+    __shared__ int warp_cnt[8], cta_base;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t epoch = (uint32_t)p.ws.flags[2];
@@ -553,12 +554,25 @@ __global__ void __launch_bounds__(256) assign_patch_kernel(const AssignParams p)
                 }
             }
         }
-        // compact foreground list: one global atomic per warp
+        // compact foreground list: one global atomic per CTA (thousands of returning atomics on one address
+        // would serialise in L2)
         const unsigned m = __ballot_sync(FULL, rep);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(p.ws.flags + 1, __popc(m));
-        base = __shfl_sync(FULL, base, 0);
-        if (rep) p.ws.fg_list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)idx, (uint32_t)gslot);
+        if (lane == 0) warp_cnt[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) {
+                const int c = warp_cnt[w];
+                warp_cnt[w] = tot;
+                tot += c;
+            }
+            cta_base = tot ? atomicAdd(p.ws.flags + 1, tot) : 0;
+        }
+        __syncthreads();
+        if (rep)
+            p.ws.fg_list[cta_base + warp_cnt[threadIdx.x >> 5] + __popc(m & ((1u << lane) - 1u))] =
+                make_uint2((uint32_t)idx, (uint32_t)gslot);
+        __syncthreads();  // warp_cnt / cta_base are reused by the next round
     }
 }
 
