@@ -253,14 +253,15 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_chunk_sort_kernel(const u64
 }
 
 // CTA (chunk, image): global rank of each of the chunk's keys = position inside its own chunk + number of
-// larger keys in every other chunk (binary search; keys are unique). The rank is the box's position in
+// larger keys in every other chunk (binary search; keys are unique; one 4 KB staging buffer - staging all
+// other chunks at once, 28 KB per CTA, was 2 us faster alone and 20 us per step slower with several
+// pipelines in flight: the fat CTAs no longer fit next to the assigner's). The rank is the box's position in
 // torchvision's stable descending score order; the first n boxes are emitted with their class offset.
 __global__ void __launch_bounds__(CHUNK_THREADS) nms_rank_kernel(const float* __restrict__ cand_rows,
                                                                  const int32_t* __restrict__ cand_counts,
                                                                  int cand_cap, int n_cap, int agnostic, float max_wh,
                                                                  SuppressWs ws) {
-    constexpr int GROUP = 7;  // other chunks staged per round: all their loads are in flight together
-    __shared__ u64 other[GROUP][CHUNK];
+    __shared__ u64 other[CHUNK];
     const int bi = blockIdx.y, chunk = blockIdx.x;
     const int n = ws.n_sorted[bi];
     if (n <= 0) return;
@@ -269,36 +270,26 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_rank_kernel(const float* __
     const int n_chunks = (count + CHUNK - 1) / CHUNK;
     const u64* __restrict__ ck = ws.ckeys + (size_t)bi * ws.C_cap * CHUNK;
     const int t0 = threadIdx.x, t1 = threadIdx.x + CHUNK_THREADS;
-    // the pool slot and the candidate row do not depend on the rank: request them before the searches
-    const uint32_t* __restrict__ cv = ws.cvals + ((size_t)bi * ws.C_cap + chunk) * CHUNK;
     const u64 k0 = ck[(size_t)chunk * CHUNK + t0], k1 = ck[(size_t)chunk * CHUNK + t1];
-    const uint32_t s0 = cv[t0], s1 = cv[t1];
     int r0 = t0, r1 = t1;
-    for (int c = 0; c < n_chunks;) {
-        // the next chunks except this CTA's own, up to GROUP of them
+    for (int c = 0; c < n_chunks; ++c) {
+        if (c == chunk) continue;  // uniform
         __syncthreads();
-        int cnt = 0;
-        for (; c < n_chunks && cnt < GROUP; ++c) {
-            if (c == chunk) continue;  // uniform
-            other[cnt][t0] = ck[(size_t)c * CHUNK + t0];
-            other[cnt][t1] = ck[(size_t)c * CHUNK + t1];
-            ++cnt;
-        }
+        other[t0] = ck[(size_t)c * CHUNK + t0];
+        other[t1] = ck[(size_t)c * CHUNK + t1];
         __syncthreads();
-        for (int g = 0; g < cnt; ++g) {
-            const u64* __restrict__ oc = other[g];
-            int lo0 = 0, hi0 = CHUNK, lo1 = 0, hi1 = CHUNK;
+        int lo0 = 0, hi0 = CHUNK, lo1 = 0, hi1 = CHUNK;
 #pragma unroll
-            for (int s_ = 0; s_ < 10; ++s_) {  // 2^9 = 512: 10 halvings always converge
-                const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
-                const bool g0 = lo0 < hi0 && oc[m0 < CHUNK ? m0 : CHUNK - 1] > k0;
-                const bool g1 = lo1 < hi1 && oc[m1 < CHUNK ? m1 : CHUNK - 1] > k1;
-                if (lo0 < hi0) { if (g0) lo0 = m0 + 1; else hi0 = m0; }
-                if (lo1 < hi1) { if (g1) lo1 = m1 + 1; else hi1 = m1; }
-            }
-            r0 += lo0, r1 += lo1;
+        for (int s = 0; s < 10; ++s) {  // 2^9 = 512: 10 halvings always converge
+            const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+            const bool g0 = lo0 < hi0 && other[m0 < CHUNK ? m0 : CHUNK - 1] > k0;
+            const bool g1 = lo1 < hi1 && other[m1 < CHUNK ? m1 : CHUNK - 1] > k1;
+            if (lo0 < hi0) { if (g0) lo0 = m0 + 1; else hi0 = m0; }
+            if (lo1 < hi1) { if (g1) lo1 = m1 + 1; else hi1 = m1; }
         }
+        r0 += lo0, r1 += lo1;
     }
+    const uint32_t* __restrict__ cv = ws.cvals + ((size_t)bi * ws.C_cap + chunk) * CHUNK;
     const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
     float4* __restrict__ sbox = ws.sbox + (size_t)bi * n_cap;
     uint32_t* __restrict__ sslot = ws.sslot + (size_t)bi * n_cap;
@@ -311,8 +302,8 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_rank_kernel(const float* __
                                  __fadd_rn(p1.y, off));                                   // utils/ops.py:295
         sslot[rank] = slot;
     };
-    emit(k0, r0, s0);
-    emit(k1, r1, s1);
+    emit(k0, r0, cv[t0]);
+    emit(k1, r1, cv[t1]);
 }
 
 // One thread-block cluster per image does the whole ordering when the candidate pool is at most 8 chunks
