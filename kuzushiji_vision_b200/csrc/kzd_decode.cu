@@ -3,6 +3,8 @@
 //  * decode_infer : Detect._inference + DFL.forward + dist2bbox(xywh) + sigmoid, reading the
 //                   per-level NCHW maps directly (reference: nn/modules/head.py:100-131,
 //                   nn/modules/block.py:71-74, utils/tal.py:348-357).
+//                   Optional extras from the same read of the maps: the training-side boxes (DUAL) and
+//                   the filter stage of non_max_suppression, utils/ops.py:234-286 (FILTER).
 //  * decode_train : v8DetectionLoss.bbox_decode + dist2bbox(xyxy) on the anchor-major (b,A,64)
 //                   layout (reference: utils/loss.py:197-204), and its backward.
 //

@@ -7,13 +7,16 @@
 // Pipeline (no host synchronisation inside; candidate counts live on the device):
 //   nms_filter_kernel  conf filter + best class / multi-label + xywh->xyxy, candidates appended to
 //                      a per-image pool with a 64-bit key  score_bits<<32 | ~order
-//   nms_chunk_sort / nms_rank   512-key chunk sorts + rank by binary search = torchvision's stable
-//                      descending score sort; writes score-ordered, class-offset boxes
+//   nms_chunk_sort / nms_rank   512-key chunk sorts (registers + warp shuffles + shared memory) + rank by
+//                      binary search = torchvision's stable descending score sort; writes score-ordered,
+//                      class-offset boxes. nms_order_cluster_kernel does both in one launch (one 8-CTA
+//                      thread-block cluster per image, rank through distributed shared memory) when the
+//                      candidate pool is at most 4096 per image
 //   nms_mask_kernel    persistent CTAs over 64x64 tiles of the upper triangle: bit (i,j) = IoU > thr
 //                      (4-compare superset test for all pairs, exact IoU only for intersecting ones)
-//   nms_scan_kernel    per image: greedy walk in 64-row chunks; the diagonal chunk is resolved by
-//                      one warp with ballot/shuffle, the rest of the row OR-reduced by helper warps,
-//                      loads two chunks ahead; the first max_det kept rows are gathered in score order
+//   nms_scan_kernel    per image: greedy walk in 64-row chunks; the diagonal tile is resolved by one
+//                      warp with ballot/shuffle, helper warps OR the kept rows into later chunks with
+//                      sparse shared-memory atomics; the first max_det kept rows are gathered in score order
 //   mask + scan run in phases of growing column ranges: the walk stops once max_det boxes are kept,
 //   so finished images skip the later phases on the device (kzd_nms_suppress)
 #include <cooperative_groups.h>
