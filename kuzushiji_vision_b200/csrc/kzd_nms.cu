@@ -836,8 +836,10 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
     for (int phase = 0; t_prev < ws.T_cap; ++phase) {
         if (t_next > ws.T_cap) t_next = ws.T_cap;
         const int g_lo = t_prev / MASK_CG, g_hi = (t_next + MASK_CG - 1) / MASK_CG;
-        nms_mask_kernel<<<grid, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(b, n_cap, iou_thres, phase, g_lo,
-                                                                                 g_hi, ws);
+        // later phases usually find every image finished: a quarter of the CTAs keeps that exit cheap (the
+        // kernel strides over its items, so a phase with real work is only spread over fewer, longer CTAs)
+        nms_mask_kernel<<<phase == 0 ? grid : grid / 4, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(
+            b, n_cap, iou_thres, phase, g_lo, g_hi, ws);
         KZD_LAUNCH_CHECK("nms_mask_kernel");
         nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * 20, st>>>(cand_rows, cand_cap, n_cap, max_det,
                                                                                 phase, t_prev, t_next, ws, out_rows,
