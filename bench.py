@@ -428,12 +428,16 @@ def run_kzd(args, rank, local_rank, world):
     torch.cuda.synchronize()
     kdist.barrier()
     e2e_steps = max(4, min(args.steps, 20))
-    t0, t1 = ev(), ev()
-    t0.record()
-    e2e_last = e2e_run(e2e_steps)
-    t1.record()
-    torch.cuda.synchronize()
-    e2e_ms = kdist.max_over_ranks(t0.elapsed_time(t1), dev)
+    e2e_reps = []  # two timed repetitions, the faster one is reported (host-side hiccups on a shared box)
+    for _ in range(2):
+        kdist.barrier()
+        t0, t1 = ev(), ev()
+        t0.record()
+        e2e_last = e2e_run(e2e_steps)
+        t1.record()
+        torch.cuda.synchronize()
+        e2e_reps.append(kdist.max_over_ranks(t0.elapsed_time(t1), dev))
+    e2e_ms = min(e2e_reps)
     e2e_value = pages * e2e_steps / (e2e_ms * 1e-3)
     h2d = sum(l.numel() * 4 for l in host_lv) + sum(t.numel() * 4 for t in host_gt)
     d2h = det_host[0].numel() * 4 + 2 * 8 + b * 4
@@ -504,8 +508,9 @@ def run_kzd(args, rank, local_rank, world):
                    "parallelism": f"image-sharded x{world}", "numa_node_rank0": numa_node},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "path": "pinned host head maps + GT -> H2D -> caller glue (torch) -> PagePipeline graph "
-                                            "-> detections + counters D2H; two buffer sets / streams"},
+                "steps": e2e_steps, "ms_per_step_repetitions": [round(v / e2e_steps, 3) for v in e2e_reps],
+                "path": "pinned host head maps + GT -> H2D -> caller glue (torch) -> PagePipeline graph "
+                                            "-> detections + counters D2H; two buffer sets / streams; faster of two repetitions"},
         "gpu_launches": pipe.kernels_per_step * args.steps,
         "per_rank_ms_per_step": per_rank_ms,
         "roofline": roofline,
