@@ -86,12 +86,53 @@ def micro_case(R):
     print("assign_micro fg", int(out[3].sum()), "max score", float(out[2].max()))
 
 
+EDGE_BOXES = [
+    [0.0, 0.0, 320.0, 320.0],        # whole page (tens of thousands of in-GT anchors)
+    [-50.0, 40.0, 30.0, 90.0],       # over the left border
+    [300.0, 100.0, 400.0, 180.0],    # over the right border
+    [100.0, -80.0, 180.0, 20.0],     # over the top
+    [60.0, 290.0, 140.0, 500.0],     # over the bottom
+    [-200.0, -200.0, -10.0, -10.0],  # off the page
+    [400.0, 400.0, 500.0, 500.0],    # off the page
+    [50.0, 50.0, 50.0, 120.0],       # zero width
+    [64.5, 64.5, 65.5, 65.5],        # thinner than a cell
+    [62.0, 62.0, 66.0, 66.0],        # edges exactly on P2 centres (strict test excludes them)
+    [10.0, 10.0, 310.0, 30.0],       # wide and flat
+    [150.0, 5.0, 170.0, 315.0],      # tall and thin
+    [2.0, 2.0, 6.0, 6.0],            # exactly one P2 centre, corner of the page
+    [0.0, 0.0, 2.0, 2.0],            # contains no centre
+    [314.0, 314.0, 320.0, 320.0],    # last P2 cell
+    [-1e4, -1e4, 1e4, 1e4],          # far larger than the page
+]
+
+
+def edge_case(R):
+    """GT boxes at the corners of the in-GT geometry (same set as tests/test_gpu_parity.py::
+    test_assign_gt_edge_geometry): what the reference's own assigner returns for them."""
+    b, G, imgsz, nc, strides = 2, 16, 320, 2, synth.P2_P5
+    d = synth.assigner_inputs(b, G, imgsz, nc, strides, seed=93, layout="uniform")
+    d["gt_bboxes"][:] = torch.tensor(EDGE_BOXES)
+    d["mask_gt"][:] = 1
+    d["mask_gt"][1, 3] = 0
+    out = R.TaskAlignedAssigner(topk=10, num_classes=nc, alpha=0.5, beta=6.0)(
+        d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+    np.savez_compressed(
+        os.path.join(OUT, "assign_edge.npz"), meta=np.array([b, G, imgsz, nc, 10], dtype=np.int64),
+        hyp=np.array([0.5, 6.0]), pd_scores=np_(d["pd_scores"]), pd_bboxes=np_(d["pd_bboxes"]),
+        anc_points=np_(d["anc_points"]), gt_labels=np_(d["gt_labels"]), gt_bboxes=np_(d["gt_bboxes"]),
+        mask_gt=np_(d["mask_gt"]), target_labels=np_(out[0]), target_bboxes=np_(out[1]), target_scores=np_(out[2]),
+        fg_mask=np_(out[3]), target_gt_idx=np_(out[4]),
+    )
+    print("assign_edge fg", int(out[3].sum()))
+
+
 def main():
     R = ref_loader.load()
     y1 = assign_case(R, "path_p3p5_nc1", 2, 40, 320, 1, synth.P3_P5, "columns", seed=11)
     y2 = assign_case(R, "path_p2p5_nc5", 1, 30, 256, 5, synth.P2_P5, "uniform", seed=12)
     assign_case(R, "path_p2p5_topk13", 1, 24, 256, 3, synth.P2_P5, "columns", seed=13, topk=13, alpha=1.0)
     micro_case(R)
+    edge_case(R)
     nms_case(R, "nms_nc1", y1, conf_thres=0.5, iou_thres=0.7, max_det=300)
     nms_case(R, "nms_nc5", y2, conf_thres=0.6, iou_thres=0.45, max_det=100)
     nms_case(R, "nms_nc5_agnostic", y2, conf_thres=0.7, iou_thres=0.5, max_det=1000, agnostic=True)

@@ -178,7 +178,7 @@ def test_assign_tie_heavy_micro_case():
     _check_assign(kzd.TaskAlignedAssigner(10, 2, 0.5, 6.0)(*args), O.tal_assign(*args, 10, 2, 0.5, 6.0))
 
 
-@pytest.mark.parametrize("name", ["path_p3p5_nc1", "path_p2p5_nc5", "path_p2p5_topk13"])
+@pytest.mark.parametrize("name", ["path_p3p5_nc1", "path_p2p5_nc5", "path_p2p5_topk13", "assign_edge"])
 def test_assign_against_reference_golden(name):
     """Golden outputs come from the reference on CPU; CPU and CUDA libm may differ in the last bit of
     atan/pow, so indices are required to agree on >= 99.9 % of anchors here (they are bit-exact against

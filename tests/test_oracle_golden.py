@@ -10,7 +10,7 @@ from oracle import torch_oracle as O
 PATH_CASES = ["path_p3p5_nc1", "path_p2p5_nc5", "path_p2p5_topk13"]
 
 
-@pytest.mark.parametrize("name", PATH_CASES + ["assign_micro"])
+@pytest.mark.parametrize("name", PATH_CASES + ["assign_micro", "assign_edge"])
 def test_assign_matches_reference_golden(name):
     g = load_golden(name)
     b, G, imgsz, nc, topk = (int(v) for v in g["meta"])
