@@ -104,6 +104,10 @@ int kzd_decode_train_bwd(const float* pred_dist, const float* grad_xyxy, int b, 
  * ------------------------------------------------------------------------------------------ */
 
 size_t kzd_assign_workspace_bytes(int b, int A, int G);
+/* Byte offset inside the workspace of an int32 the last kzd_tal_assign call on it left behind: non-zero
+ * when that call's device check found anc_points different from h_levels (it then used the slow
+ * all-anchors scan). A host shim may copy it out asynchronously and rebuild its level table. */
+size_t kzd_assign_report_offset(int b, int A);
 
 /* TaskAlignedAssigner.forward (utils/tal.py:39-118, helpers :120-295; CIoU utils/metrics.py:96-130).
  *   pd_scores (b,A,nc) sigmoided, pd_bboxes (b,A,4) xyxy px, anc_points (A,2) px,
@@ -121,18 +125,24 @@ size_t kzd_assign_workspace_bytes(int b, int A, int G);
  *   target_labels int64 (b,A), target_bboxes (b,A,4), target_scores (b,A,nc), fg_mask uint8 (b,A),
  *   target_gt_idx int64 (b,A); counters double[2] = { sum(target_scores), count(fg_mask) }
  *   (may be NULL). G must be >= 1 (the G == 0 early-out of tal.py:64-71 is host logic).
- *   persistent: 0 = stateless: the call zeroes the per-anchor state in `workspace` itself (one extra
- *     16 B/anchor memset). 1 = the caller keeps ONE workspace per (b, A, G), zeroed ONCE after
- *     allocation, and passes it unchanged on every call: the state words carry an 8-bit epoch that the
- *     library advances on the device (CUDA-graph friendly), stale entries lose every atomic, and the
- *     state is wiped by the kernels themselves once per 255 calls. */
+ *   flags: bit mask.
+ *     KZD_ASSIGN_PERSISTENT      the caller keeps ONE workspace per (b, A) - sized for the largest G it
+ *       will pass - zeroed ONCE after allocation, and passes it unchanged on every call (one call at a time
+ *       per workspace). Every call leaves the per-anchor state all-zero again (the last CTA of each image
+ *       clears what the call set), so no per-call memset is needed (CUDA-graph friendly). Without this
+ *       bit the call zeroes the state itself first (one extra 8 B/anchor memset).
+ *     KZD_ASSIGN_TRUSTED_ANCHORS the caller vouches that anc_points equals the grid described by h_levels
+ *       bit for bit (e.g. it built both, or checked them once on the host); the per-call device check is
+ *       skipped. */
+#define KZD_ASSIGN_PERSISTENT 1
+#define KZD_ASSIGN_TRUSTED_ANCHORS 2
 int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
                    const float* gt_labels, const float* gt_bboxes, const float* mask_gt,
                    int b, int A, int G, int nc, int topk, float alpha, float beta, float eps,
                    const kzd_level* h_levels, int n_levels, int zero_fill, int score_dtype,
                    int64_t* target_labels, float* target_bboxes, float* target_scores,
                    uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
-                   void* workspace, size_t workspace_bytes, int persistent, void* stream);
+                   void* workspace, size_t workspace_bytes, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * NMS

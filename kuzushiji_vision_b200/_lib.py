@@ -13,6 +13,8 @@ LIB_PATH = os.environ.get("KZD_LIB_PATH") or os.path.join(_HERE, "libkzd.so")  #
 
 KZD_MAX_LEVELS = 8
 KZD_MAX_TOPK = 32
+KZD_ASSIGN_PERSISTENT = 1        # include/kzd.h: flags of kzd_tal_assign
+KZD_ASSIGN_TRUSTED_ANCHORS = 2
 
 
 class KzdError(RuntimeError):
@@ -44,6 +46,7 @@ def _load():
         "kzd_decode_train": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp, vp]),
         "kzd_decode_train_bwd": (C.c_int, [vp, vp, i32, i32, vp, vp]),
         "kzd_assign_workspace_bytes": (sz, [i32, i32, i32]),
+        "kzd_assign_report_offset": (sz, [i32, i32]),
         "kzd_tal_assign": (C.c_int, [vp] * 6 + [i32] * 5 + [f32] * 3 + [C.POINTER(Level), i32, i32, i32] + [vp] * 6 + [vp, sz, i32, vp]),
         "kzd_nms_filter": (C.c_int, [vp, i32, i32, i32, f32, i32, vp, i32, i32, vp, vp, vp, i32, vp]),
         "kzd_nms_workspace_bytes": (sz, [i32, i32, i32]),

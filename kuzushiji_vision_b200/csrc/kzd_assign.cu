@@ -4,19 +4,24 @@
 // :132-151, select_topk_candidates :157-190, get_targets :192-238, select_candidates_in_gts :241-262,
 // select_highest_overlaps :264-295) and CIoU utils/metrics.py:96-130.
 //
-// Kernels (one stream, no host sync):
-//   assign_begin_kernel       per-call flags + device-side epoch of the persistent state; checks
-//                             anc_points against the level table (grid accelerator is only used
-//                             when every anchor matches bit-for-bit)
+// Kernels (one stream, no host sync; two launches in the steady state):
+//   assign_verify_kernel      only when the caller does not vouch for anc_points: checks them against the
+//                             level table bit for bit (the grid accelerator is used only when every anchor
+//                             matches)
 //   assign_candidates_kernel  one warp per (image, GT): the anchors inside the GT are an exact
 //                             rectangle per level (separable x / y tests); CIoU + alignment metric 32
-//                             pairs at a time, per-anchor argmax-overlap via 64-bit atomicMax, top-k by
-//                             warp-wide redux max, selecting GTs recorded with two atomicMax words and
-//                             in a pick list; each warp also stores the background targets of a
-//                             slice of the image's anchors (no dense pass over the anchors remains)
-//   assign_patch_kernel       pick list (~10 per GT): resolve each picked anchor's owner GT, overwrite
-//                             its targets, owner pair's metric + per-GT maxima, compact fg list
-//   assign_normalize_kernel   foreground list: target_scores = align * pos_ov / (pos_align+eps)
+//                             pairs at a time, top-k by warp-wide redux max, selecting GTs recorded with two
+//                             atomicMax words per picked anchor and in a pick list; each warp also stores the
+//                             background targets of a slice of the image's anchors (no dense pass over the
+//                             anchors remains)
+//   assign_patch_kernel       pick list (~10 per GT): resolve each picked anchor's owner GT (a contested
+//                             anchor - picked by several GTs - takes the first-max argmax of overlaps over
+//                             ALL GTs of the image, found by one warp scanning the image's GT rows), overwrite
+//                             its targets, owner pair's metric + per-GT maxima, compact per-image fg list.
+//                             The LAST CTA of every image (ticket) then normalises that image's foreground
+//                             scores (target_scores = align * pos_ov / (pos_align + eps)) and clears the
+//                             selection words its picks set, so the persistent state is all-zero again when
+//                             the call ends: no begin kernel, no epoch, no per-call memset.
 //
 // Bit-exactness: every fp32 operation of the eager reference rounds separately, so the pair
 // arithmetic below uses __fadd_rn/__fmul_rn/__fdiv_rn (never contracted into FMAs) and the same
@@ -28,26 +33,22 @@
 
 namespace kzd {
 
-// Per-anchor state words carry an 8-bit epoch in their top bits, so a persistent workspace never has
-// to be re-zeroed between calls: entries written under an older epoch lose every atomicMax / CAS.
-//   key  = epoch:8 | overlap_bits:30 | (KEY_GMASK - g):26     (overlap <= 1.0f  =>  bits < 2^30)
-//   sel  = { epoch:8 | (SEL_GMASK - g):24 ,  epoch:8 | g:24 }  both updated with atomicMax (no return
-//          value needed): smallest and largest selecting GT; equal => exactly one selector
-constexpr int KEY_GBITS = 26;
-constexpr u64 KEY_GMASK = (1ull << KEY_GBITS) - 1ull;
-constexpr uint32_t SEL_GMASK = 0xffffffu;
-
+// Persistent per-anchor state: two words per anchor, all-zero between calls.
+//   sel = { max over selecting GTs of (0xffffffff - g),  max over selecting GTs of (g + 1) }
+//   => smallest and largest GT whose top-k selected the anchor; equal => exactly one selector.
 struct AssignWs {
-    u64* key;            // (b*A)  max over in-GT pairs of the packed (overlap, ~g) key
-    uint2* sel;          // (b*A)  smallest / largest GT whose top-k selected the anchor
+    uint2* sel;          // (b*A)  see above; set by the candidates kernel, cleared by the patch kernel's tail
+    int32_t* flags;      // [0] != 0: anc_points does not match the level table (set by assign_verify_kernel,
+                         //           consumed by the candidates kernel, cleared by the patch kernel's tail);
+                         // [1] images finished (ticket of the patch kernel's tail, self-resetting);
+                         // [2] copy of [0] as the last call left it (the host may poll it, kzd_assign_report_offset)
+    int32_t* img;        // (b*2)  per image: [0] foreground count, [1] CTA ticket; both self-resetting
     uint32_t* pos_align; // (b*G)  per-GT max alignment metric (float bits)
     uint32_t* pos_ov;    // (b*G)  per-GT max overlap (float bits)
-    uint2* fg_list;      // (b*A)  compact list of foreground anchors: (flat anchor index, flat GT slot)
+    uint4* fg_list;      // (b*A)  per-image compact list of foreground anchors, image i at i*A:
+                         //        (flat anchor index, flat GT slot, alignment metric bits, class)
     uint2* picks;        // (b*G*topk)  every GT's selected anchors: (flat anchor index, g); x = ~0: empty slot
-    int32_t* flags;      // [0] != 0: anc_points does not match the level table; [1] = fg count;
-                         // [2] = current epoch (1..255), advanced on the device by assign_begin_kernel;
-                         // [4] != 0: the previous call ran under epoch 255, wipe the state before this one
-    size_t state_bytes;  // key + sel + flags: the part that must have been zeroed once
+    size_t state_bytes;  // sel + flags + img: the part that must be zero when a call starts
 };
 
 struct AssignParams {
@@ -137,29 +138,15 @@ __device__ __forceinline__ float overlap_ciou(const GtBox& g, const float4 p) {
     return fmaxf(ciou, 0.f);
 }
 
-// ---- begin: per-call flags, device-side epoch, anchor check -----------------------------------
+// ---- verify: anchor check (only when the caller does not vouch for anc_points) ----------------------
 
-// One thread per anchor. Thread 0 resets the per-call counters and advances the epoch of the persistent
-// per-anchor state (flags[0], the grid-mismatch flag, is consumed by the candidates kernel only and
-// cleared again by the patch kernel, so it is already 0 when a call starts). The others check
-// anc_points against the level table bit for bit (the grid accelerator is used only when every anchor
-// matches) and, once every 255 calls, wipe the state so that the epoch can wrap.
-__global__ void assign_begin_kernel(const float* __restrict__ anc, int A, AssignParams p, int reset_epoch) {
+// One thread per anchor: anc_points against the level table, bit for bit. Any mismatch raises flags[0]; the
+// candidates kernel then scans all anchors per GT instead of enumerating grid rectangles, and the patch
+// kernel's tail clears the flag again.
+__global__ void assign_verify_kernel(const float* __restrict__ anc, int A, AssignParams p) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool wipe = p.ws.flags[4] != 0;  // written by the previous call's patch kernel
-    if (a == 0) {
-        p.ws.flags[1] = 0;
-        const int e = reset_epoch ? 0 : p.ws.flags[2];
-        p.ws.flags[2] = (e % 255) + 1;  // 1..255
-    }
     if (a >= A) return;
-    const float2 ap = __ldg(reinterpret_cast<const float2*>(anc) + a);  // requested together with the wipe flag
-    if (wipe)
-        for (int bi = 0; bi < p.b; ++bi) {
-            p.ws.sel[(size_t)bi * A + a] = make_uint2(0u, 0u);
-            p.ws.key[(size_t)bi * A + a] = 0ull;
-        }
-    if (p.n_levels == 0) return;
+    const float2 ap = __ldg(reinterpret_cast<const float2*>(anc) + a);
     int l = 0;
     for (int k = 1; k < p.n_levels; ++k)
         if (a >= p.lv[k].offset) l = k;
@@ -183,19 +170,14 @@ constexpr int CAND_WARPS = CAND_THREADS / 32;
 constexpr int CAND_CAP = 512;  // in-GT pairs a warp holds at a time (anchor + metric bits in shared memory)
 
 // GT `g` selected the anchor: two fire-and-forget atomicMax (smallest and largest selecting GT).
-__device__ __forceinline__ void mark_selected(uint2* __restrict__ sel, uint32_t epoch, int g) {
-    atomicMax(&sel->x, (epoch << 24) | (SEL_GMASK - (uint32_t)g));
-    atomicMax(&sel->y, (epoch << 24) | (uint32_t)g);
+__device__ __forceinline__ void mark_selected(uint2* __restrict__ sel, int g) {
+    atomicMax(&sel->x, 0xffffffffu - (uint32_t)g);
+    atomicMax(&sel->y, (uint32_t)g + 1u);
 }
 
-// One in-GT pair: overlap (+ the per-anchor argmax-overlap key) and the alignment metric's bits (0: not
-// positive; positive floats order like their bit patterns).
-__device__ __forceinline__ uint32_t eval_pair(const AssignParams& p, const GtBox& gt, int a, size_t img, const float4 pb,
-                                              const float sc, int g, uint32_t epoch) {
+// One in-GT pair: the alignment metric's bits (0: not positive; positive floats order like their bit patterns).
+__device__ __forceinline__ uint32_t eval_pair(const AssignParams& p, const GtBox& gt, const float4 pb, const float sc) {
     const float o = overlap_ciou(gt, pb);
-    if (o > 0.f)
-        atomicMax(p.ws.key + img + a, ((u64)epoch << 56) | ((u64)min(__float_as_uint(o), 0x3fffffffu) << KEY_GBITS) |
-                                          (KEY_GMASK - (u64)g));
     const float al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
     return al > 0.f ? __float_as_uint(al) : 0u;
 }
@@ -286,7 +268,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     // everything the warp needs about its GT, loaded together (one memory round trip instead of three)
     const float gt_mask = p.mask_gt[wid], gt_label = p.gt_labels[wid];
     const float4 gt_box = *reinterpret_cast<const float4*>(p.gt_bboxes + wid * 4);
-    const int flag_mismatch = p.ws.flags[0], flag_epoch = p.ws.flags[2];
+    const int flag_mismatch = p.ws.flags[0];
     if (gt_mask == 0.f) {  // padded GT: claims nothing, contributes zero overlap
         if (lane < p.topk) picks[lane] = make_uint2(0xffffffffu, 0u);
         fill_background();
@@ -297,7 +279,6 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     int label = (int)gt_label;
     label = label < 0 ? 0 : (label >= p.nc ? p.nc - 1 : label);
     const bool grid_ok = p.n_levels > 0 && flag_mismatch == 0;
-    const uint32_t epoch = (uint32_t)flag_epoch;
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
     const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
     const float* __restrict__ pds = p.pd_scores + img * p.nc + label;
@@ -324,11 +305,11 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
         };
         fetch(n_eval + lane);
         for (int e = n_eval; e < n; e += 32) {
-            const int t = e + lane, a_cur = a_nx;
+            const int t = e + lane;
             const float4 pb = pb_nx;
             const float sc = sc_nx;
             fetch(t + 32);
-            if (t < n) bits[t] = eval_pair(p, gt, a_cur, img, pb, sc, g, epoch);
+            if (t < n) bits[t] = eval_pair(p, gt, pb, sc);
         }
         n_eval = n;
         __syncwarp();
@@ -453,7 +434,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     select();
 
     const bool has = lane < n_sel;
-    if (has) mark_selected(p.ws.sel + img + sel_anc, epoch, g);
+    if (has) mark_selected(p.ws.sel + img + sel_anc, g);
     uint32_t pick = has ? (uint32_t)(img + sel_anc) : 0xffffffffu;  // lane r: the r-th entry of this GT's pick list
     if (p.zero_fill) {
         // torch.topk pads a short list with zero-metric entries, lowest anchor index first; a padded
@@ -465,7 +446,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             --need;
             const float2 ap = __ldg(anc + a);
             if (anchor_in_gt(ap.x, ap.y, gt)) {  // uniform
-                if (lane == 0) mark_selected(p.ws.sel + img + a, epoch, g);
+                if (lane == 0) mark_selected(p.ws.sel + img + a, g);
                 if (lane == n_pick) pick = (uint32_t)(img + a);
                 ++n_pick;
             }
@@ -477,136 +458,176 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     }  // next GT
 }
 
-// ---- patch: foreground anchors --------------------------------------------------------------------
+// ---- patch: foreground anchors, normalisation, state clean-up ---------------------------------------
 
-// One thread per pick-list slot (b*G*topk, ~85 % filled). An anchor picked by several GTs appears once
-// per GT; the entry of the smallest selecting GT represents it. The representative resolves the owner
-// (one selector -> it; several -> the first-max argmax of overlaps over ALL GTs, utils/tal.py:286, kept in
-// the key word by the candidates kernel), overwrites the background targets the candidates kernel
-// stored for that anchor, recomputes the (anchor, owner) pair's alignment metric with the same
-// instruction sequence as the candidates kernel (=> identical bits; this also covers anchors owned by a
-// GT that did not top-k them), records the per-GT maxima of utils/tal.py:112-114 and appends the anchor
-// to the compact foreground list of the normalise pass.
-__global__ void __launch_bounds__(256) assign_patch_kernel(const AssignParams p) {
-    __shared__ int warp_cnt[8], cta_base;
+constexpr int PATCH_THREADS = 256;
+constexpr int PATCH_WARPS = PATCH_THREADS / 32;
+
+// Grid (x, image): the CTAs of one image stride over that image's pick-list slots (G*topk, ~85 % filled),
+// one thread per slot. An anchor picked by several GTs appears once per GT; the entry of the smallest
+// selecting GT represents it. The representative resolves the owner - one selector -> it; several
+// (contested) -> the first-max argmax of overlaps over ALL GTs of the image (utils/tal.py:283-289; all-zero
+// column -> GT 0), found by the whole warp scanning the image's GT rows: contested anchors are rare, so
+// this replaces one 64-bit atomicMax per in-GT pair of the whole batch. It then overwrites the background
+// targets the candidates kernel stored for that anchor, recomputes the (anchor, owner) pair's alignment
+// metric with the same instruction sequence as the candidates kernel (=> identical bits; this also covers
+// anchors owned by a GT that did not top-k them), records the per-GT maxima of utils/tal.py:112-114 and
+// appends the anchor to the image's compact foreground list.
+// Tail: the last CTA of an image to get here (ticket) normalises that image's foreground scores
+// (utils/tal.py:111-116), clears the selection words of the image's picks and resets the per-image
+// counters, so the next call finds the state all-zero.
+__global__ void __launch_bounds__(PATCH_THREADS) assign_patch_kernel(const AssignParams p) {
+    __shared__ int warp_cnt[PATCH_WARPS], cta_base, s_last;
+    __shared__ double s_sum;
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const uint32_t epoch = (uint32_t)p.ws.flags[2];
-    const long long n_slots = (long long)p.b * p.G * p.topk;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        p.ws.flags[0] = 0;                // consumed by the candidates kernel; clean for the next call
-        p.ws.flags[4] = epoch == 255u;    // last epoch before the wrap: the next call wipes the state first
-    }
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int bi = blockIdx.y;
+    const int n_slots = p.G * p.topk;  // of this image
+    const size_t slot0 = (size_t)bi * n_slots;
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
-    const float4* __restrict__ gtb = reinterpret_cast<const float4*>(p.gt_bboxes);
-    for (long long s0 = (long long)blockIdx.x * blockDim.x; s0 < n_slots; s0 += stride) {  // whole warps iterate together
-        const long long s = s0 + threadIdx.x;
-        bool rep = false;
-        size_t idx = 0, gslot = 0;
+    const float4* __restrict__ gtb = reinterpret_cast<const float4*>(p.gt_bboxes) + (size_t)bi * p.G;
+    const float* __restrict__ gtl = p.gt_labels + (size_t)bi * p.G;
+    const float* __restrict__ gtm = p.mask_gt + (size_t)bi * p.G;
+    uint4* __restrict__ fg_list = p.ws.fg_list + (size_t)bi * p.A;
+    int32_t* __restrict__ img_state = p.ws.img + 2 * bi;
+    for (int s0 = blockIdx.x * PATCH_THREADS; s0 < n_slots; s0 += gridDim.x * PATCH_THREADS) {  // whole warps iterate together
+        const int s = s0 + threadIdx.x;
+        bool rep = false, contested = false;
+        size_t idx = 0;
+        uint32_t g = 0u;
+        float2 ap = make_float2(0.f, 0.f);
+        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f), gb = pb;
+        float glab = 0.f, gmsk = 0.f;
         if (s < n_slots) {
-            const uint2 e = p.ws.picks[s];
+            const uint2 e = p.ws.picks[slot0 + s];
             if (e.x != 0xffffffffu) {
                 // Everything that depends only on the pick is requested at once: the selection words, the
                 // anchor, its predicted box, and - speculatively - the selecting GT's row (it is the owner
                 // unless the anchor is contested). One memory round trip instead of four.
                 idx = e.x;
-                const int bi = (int)(idx / (size_t)p.A);
                 const int a = (int)(idx - (size_t)bi * p.A);
-                gslot = (size_t)bi * p.G + e.y;
-                const uint2 sel = p.ws.sel[idx];
-                const float2 ap = __ldg(anc + a);
-                const float4 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
-                float4 gb = gtb[gslot];
-                float glab = p.gt_labels[gslot], gmsk = p.mask_gt[gslot];
-                const uint32_t g_min = SEL_GMASK - (sel.x & SEL_GMASK), g_max = sel.y & SEL_GMASK;
+                const uint2 sel = __ldcg(p.ws.sel + idx);
+                ap = __ldg(anc + a);
+                pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
+                gb = gtb[e.y], glab = gtl[e.y], gmsk = gtm[e.y];
+                const uint32_t g_min = 0xffffffffu - sel.x, g_max = sel.y - 1u;
                 rep = e.y == g_min;  // the smallest selecting GT's entry represents the anchor
-                if (rep) {
-                    uint32_t g = g_min;
-                    if (g_min != g_max) {  // contested: first-max argmax of overlaps over ALL GTs (utils/tal.py:286)
-                        const u64 k = p.ws.key[idx];
-                        const bool any = (k >> 56) == epoch && ((k >> KEY_GBITS) & 0x3fffffffull) != 0ull;
-                        g = any ? (uint32_t)(KEY_GMASK - (k & KEY_GMASK)) : 0u;
-                        if (g != e.y) {
-                            gslot = (size_t)bi * p.G + g;
-                            gb = gtb[gslot], glab = p.gt_labels[gslot], gmsk = p.mask_gt[gslot];
-                        }
-                    }
-                    long long lab = (long long)glab;
-                    lab = lab < 0 ? 0 : lab;
-                    p.target_gt_idx[idx] = (long long)g;
-                    p.target_labels[idx] = lab;
-                    p.fg_mask[idx] = 1;
-                    reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
-                    lab = lab >= p.nc ? p.nc - 1 : lab;
-                    float al = 0.f;
-                    if (gmsk != 0.f) {
-                        const GtBox gt = make_gt(gb);
-                        if (anchor_in_gt(ap.x, ap.y, gt)) {
-                            const float sc = __ldg(p.pd_scores + idx * p.nc + lab);
-                            const float o = overlap_ciou(gt, pb);
-                            al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
-                            atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
-                            atomicMax(p.ws.pos_align + gslot, __float_as_uint(al));
-                        }
-                    }
-                    p.target_scores[idx * p.nc + lab] = al;
+                contested = rep && g_min != g_max;
+                g = g_min;
+            }
+        }
+        // contested anchors, one at a time, all lanes: argmax over the image's GTs of clamp(CIoU, 0) restricted to
+        // valid GTs that contain the anchor (everything else is 0 in the reference's overlaps tensor)
+        unsigned cm = __ballot_sync(FULL, contested);
+        while (cm) {
+            const int src = __ffs(cm) - 1;
+            cm &= cm - 1u;
+            const float ax = __shfl_sync(FULL, ap.x, src), ay = __shfl_sync(FULL, ap.y, src);
+            const float4 q = make_float4(__shfl_sync(FULL, pb.x, src), __shfl_sync(FULL, pb.y, src),
+                                         __shfl_sync(FULL, pb.z, src), __shfl_sync(FULL, pb.w, src));
+            uint32_t best_o = 0u, best_g = 0xffffffffu;
+            for (int gg = lane; gg < p.G; gg += 32) {
+                if (gtm[gg] == 0.f) continue;
+                const float4 box = gtb[gg];
+                GtBox corners;
+                corners.x1 = box.x, corners.y1 = box.y, corners.x2 = box.z, corners.y2 = box.w;
+                if (!anchor_in_gt(ax, ay, corners)) continue;
+                const uint32_t ob = __float_as_uint(overlap_ciou(make_gt(box), q));
+                if (ob > best_o) best_o = ob, best_g = (uint32_t)gg;  // strict: the lowest GT among equals (gg ascends)
+            }
+            const uint32_t mo = __reduce_max_sync(FULL, best_o);
+            const uint32_t mg = __reduce_min_sync(FULL, (best_o == mo && mo != 0u) ? best_g : 0xffffffffu);
+            const uint32_t owner = mo != 0u ? mg : 0u;
+            if (lane == src && owner != g) {
+                g = owner;
+                gb = gtb[g], glab = gtl[g], gmsk = gtm[g];
+            }
+        }
+        uint32_t al_bits = 0u;
+        long long lab = 0;
+        const size_t gslot = (size_t)bi * p.G + g;
+        if (rep) {
+            lab = (long long)glab;
+            lab = lab < 0 ? 0 : lab;
+            p.target_gt_idx[idx] = (long long)g;
+            p.target_labels[idx] = lab;
+            p.fg_mask[idx] = 1;
+            reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
+            lab = lab >= p.nc ? p.nc - 1 : lab;
+            float al = 0.f;
+            if (gmsk != 0.f) {
+                const GtBox gt = make_gt(gb);
+                if (anchor_in_gt(ap.x, ap.y, gt)) {
+                    const float sc = __ldg(p.pd_scores + idx * p.nc + lab);
+                    const float o = overlap_ciou(gt, pb);
+                    al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
+                    atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
+                    atomicMax(p.ws.pos_align + gslot, __float_as_uint(al));
                 }
             }
+            al_bits = __float_as_uint(al);
         }
         // compact foreground list: one global atomic per CTA (thousands of returning atomics on one address
         // would serialise in L2)
-        const unsigned m = __ballot_sync(FULL, rep);
-        if (lane == 0) warp_cnt[threadIdx.x >> 5] = __popc(m);
+        const bool listed = rep;
+        const unsigned m = __ballot_sync(FULL, listed);
+        if (lane == 0) warp_cnt[wib] = __popc(m);
         __syncthreads();
         if (threadIdx.x == 0) {
             int tot = 0;
-            for (int w = 0; w < 8; ++w) {
+            for (int w = 0; w < PATCH_WARPS; ++w) {
                 const int c = warp_cnt[w];
                 warp_cnt[w] = tot;
                 tot += c;
             }
-            cta_base = tot ? atomicAdd(p.ws.flags + 1, tot) : 0;
+            cta_base = tot ? atomicAdd(img_state, tot) : 0;
         }
         __syncthreads();
-        if (rep)
-            p.ws.fg_list[cta_base + warp_cnt[threadIdx.x >> 5] + __popc(m & ((1u << lane) - 1u))] =
-                make_uint2((uint32_t)idx, (uint32_t)gslot);
+        if (listed)
+            fg_list[cta_base + warp_cnt[wib] + __popc(m & ((1u << lane) - 1u))] =
+                make_uint4((uint32_t)idx, (uint32_t)gslot, al_bits, (uint32_t)lab);
         __syncthreads();  // warp_cnt / cta_base are reused by the next round
     }
-}
 
-// ---- normalise ---------------------------------------------------------------------------------
-
-// Foreground anchors only (compact list): target_scores = align * pos_ov / (pos_align + eps).
-__global__ void __launch_bounds__(256) assign_normalize_kernel(const AssignParams p) {
-    __shared__ double s_sum;
-    if (threadIdx.x == 0) s_sum = 0.0;
+    // ---- tail: the image's last CTA -----------------------------------------------------------------
+    __threadfence();  // this CTA's target / list / maxima writes are visible device-wide before its ticket
     __syncthreads();
-    const int n = p.ws.flags[1];
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(img_state + 1, 1) == (int)gridDim.x - 1;
+        s_sum = 0.0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int n_fg = __ldcg(img_state);
     float local = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint2 e = p.ws.fg_list[i];
-        const size_t idx = e.x, gslot = e.y;
-        long long lab = 0;
-        if (p.nc > 1) {
-            lab = (long long)p.gt_labels[gslot];
-            lab = lab < 0 ? 0 : (lab >= p.nc ? p.nc - 1 : lab);
-        }
-        float* dst = p.target_scores + idx * p.nc + lab;
-        const float ov = __uint_as_float(p.ws.pos_ov[gslot]);
-        const float pa = __uint_as_float(p.ws.pos_align[gslot]);
-        const float v = __fdiv_rn(__fmul_rn(*dst, ov), __fadd_rn(pa, p.eps));  // utils/tal.py:115
-        *dst = v;
+    for (int i = threadIdx.x; i < n_fg; i += PATCH_THREADS) {
+        const uint4 e = __ldcg(fg_list + i);
+        const float ov = __uint_as_float(__ldcg(p.ws.pos_ov + e.y));
+        const float pa = __uint_as_float(__ldcg(p.ws.pos_align + e.y));
+        const float v = __fdiv_rn(__fmul_rn(__uint_as_float(e.z), ov), __fadd_rn(pa, p.eps));  // utils/tal.py:115
+        p.target_scores[(size_t)e.x * p.nc + e.w] = v;
         local += v;
     }
+    // the image's picks: clear the selection words they set (all readers of this image are done)
+    for (int s = threadIdx.x; s < n_slots; s += PATCH_THREADS) {
+        const uint2 e = p.ws.picks[slot0 + s];
+        if (e.x != 0xffffffffu) p.ws.sel[e.x] = make_uint2(0u, 0u);
+    }
     if (p.counters) {
-        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-        if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(&s_sum, (double)local);
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
+        if (lane == 0 && local != 0.f) atomicAdd(&s_sum, (double)local);
         __syncthreads();
         if (threadIdx.x == 0) {
             if (s_sum != 0.0) atomicAdd(p.counters, s_sum);
-            if (blockIdx.x == 0) p.counters[1] = (double)n;
+            if (n_fg) atomicAdd(p.counters + 1, (double)n_fg);
+        }
+    }
+    if (threadIdx.x == 0) {
+        img_state[0] = 0, img_state[1] = 0;
+        if (atomicAdd(p.ws.flags + 1, 1) == (int)gridDim.y - 1) {  // the call's last image
+            p.ws.flags[2] = p.ws.flags[0];  // sticky report for the host: this call's level table did not match
+            p.ws.flags[1] = 0, p.ws.flags[0] = 0;
         }
     }
 }
@@ -628,13 +649,15 @@ static void split_ws(void* workspace, int b, int A, int G, AssignWs& ws, size_t&
         return r;
     };
     const size_t n = (size_t)b * A;
-    ws.key = (u64*)take(n * 8);
+    // state first: its layout does not depend on G, so one workspace sized for the largest G seen serves
+    // every smaller G with the same (b, A)
     ws.sel = (uint2*)take(n * 8);
     ws.flags = (int32_t*)take(256);
+    ws.img = (int32_t*)take((size_t)b * 2 * 4);
     ws.state_bytes = o;
     ws.pos_align = (uint32_t*)take((size_t)b * G * 4);
     ws.pos_ov = (uint32_t*)take((size_t)b * G * 4);
-    ws.fg_list = (uint2*)take(n * 8);
+    ws.fg_list = (uint4*)take(n * 16);
     ws.picks = (uint2*)take((size_t)b * G * KZD_MAX_TOPK * 8);
     total = o;
 }
@@ -651,12 +674,17 @@ extern "C" __attribute__((visibility("default"))) size_t kzd_assign_workspace_by
     return total;
 }
 
+extern "C" __attribute__((visibility("default"))) size_t kzd_assign_report_offset(int b, int A) {
+    if (b < 0 || A < 0) return 0;
+    return align_up((size_t)b * A * 8, 256) + 2 * sizeof(int32_t);
+}
+
 extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
                               const float* gt_labels, const float* gt_bboxes, const float* mask_gt, int b, int A,
                               int G, int nc, int topk, float alpha, float beta, float eps, const kzd_level* h_levels,
                               int n_levels, int zero_fill, int score_dtype, int64_t* target_labels, float* target_bboxes,
                               float* target_scores, uint8_t* fg_mask, int64_t* target_gt_idx, double* counters,
-                              void* workspace, size_t workspace_bytes, int persistent, void* stream) {
+                              void* workspace, size_t workspace_bytes, int flags, void* stream) {
     KZD_CHECK_ARG(pd_scores && pd_bboxes && anc_points && gt_labels && gt_bboxes && mask_gt,
                   "kzd_tal_assign: null input");
     KZD_CHECK_ARG(target_labels && target_bboxes && target_scores && fg_mask && target_gt_idx && workspace,
@@ -667,6 +695,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
                   "kzd_tal_assign: bad level table");
     KZD_CHECK_ARG(b <= 65535, "kzd_tal_assign: b=%d > 65535", b);
     KZD_CHECK_ARG(score_dtype >= 0 && score_dtype <= 2, "kzd_tal_assign: score_dtype=%d not in {0,1,2}", score_dtype);
+    KZD_CHECK_ARG((flags & ~(KZD_ASSIGN_PERSISTENT | KZD_ASSIGN_TRUSTED_ANCHORS)) == 0, "kzd_tal_assign: unknown flags 0x%x", flags);
     KZD_CHECK_ARG((double)b * A < 4294967295.0 && G < (1 << 24) - 2, "kzd_tal_assign: b*A or G too large");
     KZD_CHECK_ARG((double)b * G < 4294967295.0, "kzd_tal_assign: b*G too large");
     KZD_CHECK_ARG(((uintptr_t)gt_bboxes) % 16 == 0 && ((uintptr_t)pd_bboxes) % 16 == 0 &&
@@ -701,9 +730,11 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     p.fg_mask = fg_mask, p.target_gt_idx = (long long*)target_gt_idx, p.counters = counters;
 
     cudaStream_t st = (cudaStream_t)stream;
-    if (!persistent) KZD_CUDA(cudaMemsetAsync(workspace, 0, p.ws.state_bytes, st));  // stateless mode
-    assign_begin_kernel<<<(A + 255) / 256, 256, 0, st>>>(anc_points, A, p, persistent ? 0 : 1);
-    KZD_LAUNCH_CHECK("assign_begin_kernel");
+    if (!(flags & KZD_ASSIGN_PERSISTENT)) KZD_CUDA(cudaMemsetAsync(workspace, 0, p.ws.state_bytes, st));  // stateless mode
+    if (n_levels > 0 && !(flags & KZD_ASSIGN_TRUSTED_ANCHORS)) {
+        assign_verify_kernel<<<(A + 255) / 256, 256, 0, st>>>(anc_points, A, p);
+        KZD_LAUNCH_CHECK("assign_verify_kernel");
+    }
     if (nc > 1) {  // dense (b,A,nc) target_scores: zero rows now, the owner's entry is written later
         const size_t n = (size_t)b * A * nc;
         const size_t n4 = (((uintptr_t)target_scores) % 16 == 0) ? n / 4 : 0;
@@ -728,16 +759,14 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
         KZD_LAUNCH_CHECK("assign_candidates_kernel");
     }
     {
-        const long long slots = (long long)b * G * topk;
-        long long blocks = (slots + 255) / 256;
-        const long long cap = (long long)sm_count() * 8;
-        if (blocks > cap) blocks = cap;
-        assign_patch_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+        // the CTAs of an image stride over its G*topk pick slots; enough of them to cover the slots once, but
+        // not more than a few waves of the machine in total (the image's last CTA runs the serial tail)
+        long long per_img = ((long long)G * topk + PATCH_THREADS - 1) / PATCH_THREADS;
+        const long long cap = ((long long)sm_count() * 8 + b - 1) / b;
+        if (per_img > cap) per_img = cap;
+        if (per_img < 1) per_img = 1;
+        assign_patch_kernel<<<dim3((unsigned)per_img, (unsigned)b), PATCH_THREADS, 0, st>>>(p);
         KZD_LAUNCH_CHECK("assign_patch_kernel");
-    }
-    {
-        assign_normalize_kernel<<<(unsigned)sm_count() * 2, 256, 0, st>>>(p);
-        KZD_LAUNCH_CHECK("assign_normalize_kernel");
     }
     return 0;
 }

@@ -34,6 +34,22 @@ def _is_cuda(x):
     return bool(getattr(x, "is_cuda", False))
 
 
+def detect_in_scope(module, detect_cls):
+    """True when ``module``'s ``_inference`` is the plain ``Detect`` decode that libkzd implements
+    (nn/modules/head.py:100-131 with ``decode_bboxes`` :146-148 = ``dist2bbox(xywh=True)``, 16 DFL bins).
+    ``Detect._inference`` is a class attribute, so every subclass inherits the patch: heads that decode
+    differently - ``OBB`` (``decode_bboxes`` overridden with ``dist2rbox`` and ``self.angle``), end-to-end
+    heads (``v10Detect``: ``xywh=False``, head.py:148), other ``reg_max``, export formats - keep the
+    reference's own function."""
+    if getattr(module, "export", False) or getattr(module, "format", None) == "imx":
+        return False
+    if getattr(module, "end2end", False) or getattr(module, "reg_max", 16) != _head.REG_MAX:
+        return False
+    if type(module).decode_bboxes is not detect_cls.decode_bboxes:
+        return False
+    return getattr(module, "no", None) == getattr(module, "nc", 0) + 4 * _head.REG_MAX
+
+
 def install(patch_decode_train=True, patch_preprocess=True):
     """Patch the importable ``ultralytics``; returns the list of patched attribute names."""
     if _saved:
@@ -69,7 +85,7 @@ def install(patch_decode_train=True, patch_preprocess=True):
         return ref_nms(prediction, *args, **kwargs)
 
     def _inference(self, x):
-        if self.export or not _is_cuda(x):
+        if not (_is_cuda(x) and detect_in_scope(self, u_head.Detect)):
             return ref_inference(self, x)
         return _head.detect_inference(self, x)
 

@@ -51,6 +51,7 @@ class PagePipeline:
         self.anchor_points, self.stride_tensor = make_anchors(feats, self.strides, 0.5)
         self.anc_points = self.anchor_points * self.stride_tensor
         self.assigner = TaskAlignedAssigner(topk, nc, alpha, beta)
+        self.assigner.per_stream = False  # one graph = one call in flight: warm-up and capture share the workspace
         # NMS buffers (fixed capacities; an overflow is reported by results())
         self.pool = min(A, int(pool))
         self.n_cap = max(64, (min(int(n_cap), self.max_nms, self.pool) + 63) // 64 * 64)
@@ -87,14 +88,14 @@ class PagePipeline:
         self._side2 = torch.cuda.Stream(device=dev, priority=-1) if (assign_priority and overlap) else None
         self.out = None
         self.graph = None
-        # kernels per step: decode(s), assign x4, [nms filter], ordering (chunk sort + rank, or one cluster
+        # kernels per step: decode(s), assign x2 (candidates, patch), [nms filter], ordering (chunk sort + rank, or one cluster
         # kernel), (mask, scan) per phase - the phase schedule mirrors kzd_nms_suppress
         t0 = (self.max_det + self.max_det // 4 + 127) // 64
         t_cap, phases = (self.n_cap + 63) // 64, 1
         while t0 < t_cap:
             t0, phases = t0 * 4, phases + 1
         order = 1 if (self.pool + 511) // 512 <= 8 else 2
-        self.kernels_per_step = ((1 if self.fuse_decodes else 2) + 4 + (0 if self.fuse_filter else 1) + order
+        self.kernels_per_step = ((1 if self.fuse_decodes else 2) + 2 + (0 if self.fuse_filter else 1) + order
                                  + 2 * phases)
         if use_graph:
             self._capture()

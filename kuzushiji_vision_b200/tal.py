@@ -62,6 +62,16 @@ class TaskAlignedAssigner(nn.Module):
     ``(target_labels int64 (b,A), target_bboxes (b,A,4), target_scores (b,A,nc), fg_mask bool (b,A),
     target_gt_idx int64 (b,A))``. After a call ``self.counters`` holds a device ``float64[2]`` =
     ``[target_scores.sum(), fg_mask.sum()]`` (what utils/loss.py:243,250 reduce again).
+
+    Host-side state (none of it changes results):
+      * one persistent libkzd workspace per ``(b, A, device, stream)``, grown to the largest ``G`` seen - the
+        reference's ``G`` is the batch's largest label count (utils/loss.py:188) and changes every
+        iteration. Calls on different streams get different workspaces, so one instance may be used from
+        several streams; calls on ONE stream are ordered by the stream.
+      * the level table of the anchor grid, inferred on the host from ``anc_points`` once per anchor tensor.
+        The same tensor object (same storage, same version counter) is vouched for on later calls, so the
+        device-side check is skipped; any other tensor is checked on the device against the cached table and,
+        should it not match (same A, different H x W), the next call rebuilds the table.
     """
 
     def __init__(self, topk=13, num_classes=80, alpha=1.0, beta=6.0, eps=1e-9):
@@ -73,26 +83,52 @@ class TaskAlignedAssigner(nn.Module):
         self.beta = beta
         self.eps = eps
         self.zero_fill = ZERO_FILL_DEFAULT
-        self.stateless = False  # True: persistent=0 (libkzd zeroes the per-anchor state on every call)
+        self.stateless = False  # True: libkzd zeroes the per-anchor state on every call (no persistent workspace)
+        self.per_stream = True  # False: one workspace per (b, A, device) whatever the stream (PagePipeline: one graph)
         self.counters = None
-        self._levels = {}  # (A, device) -> (ctypes level array, n_levels)
-        self._ws = {}      # (b, A, G, device) -> zeroed-once uint8 workspace
+        self._levels = {}    # (A, device) -> (ctypes level array, n_levels)
+        self._vouched = {}   # (A, device) -> (anchor tensor, its version): verified against the table on the host
+        self._ws = {}        # (b, A, device, stream) -> [zeroed-once uint8 workspace, G it was sized for]
+        self._report = {}    # (A, device) -> (pinned int32[1], event): did the last device check fail?
 
     def _level_table(self, anc_points):
+        """-> (ctypes level array, n_levels, trusted). ``trusted``: this very tensor was checked on the host."""
         key = (anc_points.shape[0], str(anc_points.device))
         hit = self._levels.get(key)
+        v = self._vouched.get(key)
+        if hit is not None and v is not None and v[0] is anc_points and v[1] == anc_points._version:
+            return hit[0], hit[1], True
+        rep = self._report.pop(key, None)
+        if rep is not None and rep[1].query() and int(rep[0][0]) != 0:
+            hit = None  # the cached table did not describe the previous call's anchors: rebuild it
         if hit is None:
-            lv = infer_levels(anc_points)
+            lv = infer_levels(anc_points)  # one D2H of A*8 bytes; checks every anchor against the grid
             arr, _ = _lib.levels_array(lv or [])
             hit = (arr, len(lv) if lv else 0)
             self._levels[key] = hit
-        return hit
+            # holding the tensor keeps its storage from being recycled under the same address
+            self._vouched[key] = (anc_points, anc_points._version)
+            return hit[0], hit[1], hit[1] > 0
+        return hit[0], hit[1], False
+
+    def _workspace(self, b, A, G, dev, stream):
+        key = (b, A, str(dev), stream if self.per_stream else 0)
+        ent = self._ws.get(key)
+        if ent is None or ent[1] < G:
+            if ent is None and len(self._ws) >= 8:  # train / val batch shapes alternate: keep a few, drop the oldest
+                self._ws.pop(next(iter(self._ws)))
+            g_cap = G if ent is None else max(G, ent[1] * 2)
+            ws = torch.zeros(_lib.lib.kzd_assign_workspace_bytes(b, A, g_cap), dtype=torch.uint8, device=dev)
+            ent = [ws, g_cap]
+            self._ws[key] = ent
+        return ent[0]
 
     @torch.no_grad()
     def forward(self, pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, mask_gt):
         self.bs = pd_scores.shape[0]
         self.n_max_boxes = gt_bboxes.shape[1]
         if self.n_max_boxes == 0:  # utils/tal.py:64-71 (all float, labels = background index)
+            self.counters = torch.zeros(2, dtype=torch.float64, device=pd_scores.device)
             return (
                 torch.full_like(pd_scores[..., 0], self.bg_idx),
                 torch.zeros_like(pd_bboxes),
@@ -112,11 +148,11 @@ class TaskAlignedAssigner(nn.Module):
         score_dtype = _lib.dtype_code(pd_scores.dtype)
         pd_scores_c = pd_scores.to(f32).contiguous()
         pd_bboxes_c = pd_bboxes.to(f32).contiguous()
-        anc_c = anc_points.to(f32).contiguous()
+        anc_c = anc_points if (anc_points.dtype == f32 and anc_points.is_contiguous()) else anc_points.to(f32).contiguous()
         gl = gt_labels.reshape(b, G).to(f32).contiguous()
         gb = gt_bboxes.to(f32).contiguous()
         mg = mask_gt.reshape(b, G).to(f32).contiguous()
-        levels, n_levels = self._level_table(anc_c)
+        levels, n_levels, trusted = self._level_table(anc_c)
 
         target_labels = torch.empty((b, A), dtype=torch.int64, device=dev)
         target_bboxes = torch.empty((b, A, 4), dtype=f32, device=dev)
@@ -124,26 +160,32 @@ class TaskAlignedAssigner(nn.Module):
         fg_u8 = torch.empty((b, A), dtype=torch.uint8, device=dev)
         target_gt_idx = torch.empty((b, A), dtype=torch.int64, device=dev)
         counters = torch.empty(2, dtype=torch.float64, device=dev)
-        # persistent, zeroed-once workspace: the per-anchor state carries an epoch that libkzd advances
-        # on the device, so no per-call memset is needed (include/kzd.h, `persistent`)
-        ws_key = (b, A, G, str(dev))
-        ws = self._ws.get(ws_key)
-        if ws is None:
-            if len(self._ws) >= 4:  # train / val batch shapes alternate: keep a few, drop the oldest
-                self._ws.pop(next(iter(self._ws)))
-            ws = torch.zeros(_lib.lib.kzd_assign_workspace_bytes(b, A, G), dtype=torch.uint8, device=dev)
-            self._ws[ws_key] = ws
-        persistent = 0 if self.stateless else 1
+        stream = torch.cuda.current_stream(dev)
+        # persistent, zeroed-once workspace: every call leaves the per-anchor state all-zero again, so no
+        # per-call memset is needed (include/kzd.h, KZD_ASSIGN_PERSISTENT)
+        if self.stateless:
+            ws = torch.empty(_lib.lib.kzd_assign_workspace_bytes(b, A, G), dtype=torch.uint8, device=dev)
+        else:
+            ws = self._workspace(b, A, G, dev, stream.cuda_stream)
+        flags = (0 if self.stateless else _lib.KZD_ASSIGN_PERSISTENT) | (_lib.KZD_ASSIGN_TRUSTED_ANCHORS if trusted else 0)
         with torch.cuda.device(dev):
             rc = _lib.lib.kzd_tal_assign(
                 pd_scores_c.data_ptr(), pd_bboxes_c.data_ptr(), anc_c.data_ptr(), gl.data_ptr(), gb.data_ptr(),
                 mg.data_ptr(), b, A, G, nc, int(self.topk), float(self.alpha), float(self.beta), float(self.eps),
                 levels, n_levels, int(self.zero_fill), score_dtype,
                 target_labels.data_ptr(), target_bboxes.data_ptr(), target_scores.data_ptr(), fg_u8.data_ptr(),
-                target_gt_idx.data_ptr(), counters.data_ptr(), ws.data_ptr(), ws.numel(), persistent,
-                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream),
+                target_gt_idx.data_ptr(), counters.data_ptr(), ws.data_ptr(), ws.numel(), flags,
+                C.c_void_p(stream.cuda_stream),
             )
         _lib.check(rc, "kzd_tal_assign")
+        if not trusted and n_levels > 0 and not torch.cuda.is_current_stream_capturing():
+            # asynchronous report of the device-side anchor check, looked at by the next call
+            off = _lib.lib.kzd_assign_report_offset(b, A)
+            host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            host.copy_(ws[off:off + 4].view(torch.int32), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self._report[(A, str(dev))] = (host, ev)
         self.counters = counters
         return target_labels, target_bboxes, target_scores, fg_u8.view(torch.bool), target_gt_idx
 

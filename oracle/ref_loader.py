@@ -1,8 +1,10 @@
 """TEST INFRASTRUCTURE ONLY - loader for the unmodified reference (vendored Ultralytics 8.3.63).
 
-The reference is plain Python, so it is imported where it lies (``/root/reference/yolov12``);
-nothing is copied. It only exists in the build container: ``available()`` is False on the GPU
-box and every caller must then fall back to ``oracle.torch_oracle`` + ``tests/golden``.
+The reference is plain Python. In the build container it is imported where it lies
+(``/root/reference/yolov12``); ``oracle/make_ref.py`` (run by ``__graft_entry__.build()``) stages a
+byte-identical copy under the git-ignored ``oracle/_ref/yolov12`` that travels to the GPU box, so the
+unmodified reference is importable there too (CPU and CUDA). ``available()`` is False only when
+neither exists; callers then fall back to ``oracle.torch_oracle`` + ``tests/golden``.
 
 Import recipe: three modules the reference imports at top level are
 absent from this image (``matplotlib``, ``matplotlib.pyplot`` - ultralytics/utils/__init__.py:23,
@@ -16,7 +18,8 @@ import os
 import sys
 import types
 
-REF_ROOTS = (os.environ.get("KZD_REF", ""), "/root/reference/yolov12")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOTS = (os.environ.get("KZD_REF", ""), "/root/reference/yolov12", os.path.join(_HERE, "_ref", "yolov12"))
 
 
 def ref_root() -> str | None:
@@ -57,7 +60,7 @@ def load():
         return _loaded
     root = ref_root()
     if root is None:
-        raise RuntimeError("reference tree not present (expected /root/reference/yolov12)")
+        raise RuntimeError("reference tree not present (expected /root/reference/yolov12 or oracle/_ref/yolov12)")
     os.environ.setdefault("YOLO_CONFIG_DIR", "/tmp/ultra_cfg")
     keep_omp = os.environ.get("OMP_NUM_THREADS")
     for name in ("matplotlib", "matplotlib.pyplot", "thop"):
@@ -81,7 +84,7 @@ def load():
         os.environ.pop("OMP_NUM_THREADS", None)
     torch.set_num_threads(nthreads)
     ns = types.SimpleNamespace(
-        tal=tal, ops=ops, loss=loss, metrics=metrics, head=head, block=block,
+        root=root, tal=tal, ops=ops, loss=loss, metrics=metrics, head=head, block=block,
         TaskAlignedAssigner=tal.TaskAlignedAssigner, make_anchors=tal.make_anchors,
         dist2bbox=tal.dist2bbox, bbox_iou=metrics.bbox_iou, Detect=head.Detect, DFL=block.DFL,
         non_max_suppression=ops.non_max_suppression, v8DetectionLoss=loss.v8DetectionLoss,
