@@ -29,7 +29,7 @@ class PagePipeline:
     def __init__(self, batch, level_hw, strides, nc, n_max_boxes, device="cuda:0", topk=10, alpha=0.5, beta=6.0,
                  conf_thres=0.25, iou_thres=0.7, max_det=300, max_nms=30000, agnostic=False, max_wh=7680.0,
                  pool=32768, n_cap=4096, use_graph=True, overlap=True, fuse_decodes=False, fuse_filter=False,
-                 cluster_order=False, assign_priority=True):
+                 cluster_order=False, assign_priority=True, levels_dtype=torch.float32):
         dev = torch.device(device)
         self.device, self.b, self.nc, self.G = dev, int(batch), int(nc), int(n_max_boxes)
         self.level_hw = [(int(h), int(w)) for h, w in level_hw]
@@ -40,10 +40,13 @@ class PagePipeline:
         b, A, G, f32 = self.b, self.A, self.G, torch.float32
         no = 4 * REG_MAX + nc
         # static inputs (fill with load() or write into them directly)
-        self.levels = [torch.zeros((b, no, h, w), dtype=f32, device=dev) for h, w in self.level_hw]
+        # levels_dtype fp16 / bf16: the AMP / half-inference flow (engine/trainer.py:379, engine/validator.py:115-117):
+        # the decode kernels read the half maps natively and pd_scores keeps the half dtype, so the assigner
+        # reproduces the reference's half-precision rounding of pd_scores.pow(alpha) (utils/tal.py:137,150)
+        self.levels = [torch.zeros((b, no, h, w), dtype=levels_dtype, device=dev) for h, w in self.level_hw]
         # the fused decode reads the NCHW maps directly: no (b,A,64) transposed copy is needed then
         self.pred_distri = None if fuse_decodes else torch.zeros((b, A, 4 * REG_MAX), dtype=f32, device=dev)
-        self.pd_scores = torch.zeros((b, A, nc), dtype=f32, device=dev)
+        self.pd_scores = torch.zeros((b, A, nc), dtype=levels_dtype, device=dev)
         self.gt_labels = torch.zeros((b, G, 1), dtype=f32, device=dev)
         self.gt_bboxes = torch.zeros((b, G, 4), dtype=f32, device=dev)
         self.mask_gt = torch.zeros((b, G, 1), dtype=f32, device=dev)

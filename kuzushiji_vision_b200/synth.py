@@ -22,25 +22,29 @@ def num_anchors(imgsz, strides):
     return sum(h * w for h, w in level_shapes(imgsz, strides))
 
 
-def head_outputs(b, nc, imgsz, strides=P2_P5, seed=0, device="cpu", sparse_cls=None):
+def head_outputs(b, nc, imgsz, strides=P2_P5, seed=0, device="cpu", sparse_cls=None, on_device=False):
     """Per-level raw Detect maps ``(b, 64+nc, H_l, W_l)`` ~ N(0,1), as ``Detect.forward`` emits
     them in training (nn/modules/head.py:69-72 of the reference).
 
     ``sparse_cls = n`` switches the class logits to the inference-like distribution of
     SURVEY.md section 8d: background logit -6 and, per page, ``n`` uniformly chosen anchors with
     logit N(1,1) on one random class (about 0.98 n candidates above conf 0.25).
+
+    ``on_device=True`` draws the numbers with a generator on ``device`` (seconds faster for the bench's
+    hundreds of megabytes per batch; the values then depend on the device type, not only on the seed).
     """
-    g = torch.Generator().manual_seed(seed)
+    gdev = device if on_device else "cpu"
+    g = torch.Generator(device=gdev).manual_seed(seed)
     no = 4 * REG_MAX + nc
     shapes = level_shapes(imgsz, strides)
     A = sum(h * w for h, w in shapes)
-    flat = torch.randn((b, no, A), generator=g)
+    flat = torch.randn((b, no, A), generator=g, device=gdev)
     if sparse_cls is not None:
         flat[:, 4 * REG_MAX:] = -6.0
         for i in range(b):
-            idx = torch.randperm(A, generator=g)[:sparse_cls]
-            c = torch.randint(0, nc, (sparse_cls,), generator=g)
-            flat[i, 4 * REG_MAX + c, idx] = 1.0 + torch.randn(sparse_cls, generator=g)
+            idx = torch.randperm(A, generator=g, device=gdev)[:sparse_cls]
+            c = torch.randint(0, nc, (sparse_cls,), generator=g, device=gdev)
+            flat[i, 4 * REG_MAX + c, idx] = 1.0 + torch.randn(sparse_cls, generator=g, device=gdev)
     out, o = [], 0
     for h, w in shapes:
         out.append(flat[:, :, o:o + h * w].reshape(b, no, h, w).contiguous().to(device))

@@ -895,3 +895,66 @@ def test_pipeline_recovers_from_nms_capacity_overflow(fuse_filter):
     dets = pipe.detections()
     y = kzd.decode_inference(lv, strides, nc)
     _check_nms(dets, O.non_max_suppression(y.clone(), 0.25, 0.7, max_det=300))
+
+
+# ---------------------------------------------------------------------------------------------
+# the benchmarked configurations at their own size, in their own (fused, graph-captured) form
+# ---------------------------------------------------------------------------------------------
+
+def _oracle_assign_chunked(args, topk, nc, alpha, beta, chunk=4):
+    """The oracle materialises dense (b,G,A) tensors (8.7 GB each at b=16, G=1000): images are independent,
+    so it runs on a few images at a time."""
+    outs = []
+    b = args[0].shape[0]
+    for i in range(0, b, chunk):
+        sl = slice(i, i + chunk)
+        outs.append(O.tal_assign(args[0][sl], args[1][sl], args[2], args[3][sl], args[4][sl], args[5][sl], topk, nc, alpha, beta))
+        torch.cuda.empty_cache()
+    return tuple(torch.cat([o[k] for o in outs]) for k in range(5))
+
+
+@pytest.mark.parametrize("G,name", [(600, "BASELINE configs[1]"), (1000, "BASELINE configs[4] micro-batch")])
+def test_bench_workload_fused_pipeline_full_size(G, name):
+    """The exact step bench.py times - fused decode+filter, assign and NMS of 16 pages at 1280x1280 P2-P5 as one
+    CUDA graph, max_det 1000, candidate pool 32768 (chunk-sort + rank ordering), n_cap 4096 - against the oracle
+    on the same inputs: all five assigner outputs and every NMS row of every page."""
+    b, imgsz, nc, strides = 16, 1280, 1, synth.P2_P5
+    pipe = kzd.PagePipeline(b, synth.level_shapes(imgsz, strides), strides, nc, G, device=DEV, topk=10, alpha=0.5,
+                            beta=6.0, conf_thres=0.25, iou_thres=0.7, max_det=1000, fuse_decodes=True, fuse_filter=True)
+    assert pipe.pool == 32768 and pipe.n_cap == 4096
+    lv = synth.head_outputs(b, nc, imgsz, strides, seed=0, device=DEV, sparse_cls=3000)
+    gl, gb, mg = synth.gt_pages(b, G, imgsz, nc, seed=0, device=DEV)
+    cat = torch.cat([x.view(b, 64 + nc, -1) for x in lv], 2)
+    pred_distri = cat[:, :64].permute(0, 2, 1).contiguous()
+    pd_scores = cat[:, 64:].permute(0, 2, 1).contiguous().sigmoid()
+    del cat
+    pipe.load(levels=lv, pd_scores=pd_scores, gt_labels=gl, gt_bboxes=gb, mask_gt=mg)
+    for _ in range(3):  # replays: the persistent assigner state must come back clean every time
+        pipe.step()
+    out, n_keep = pipe.results()
+    assert min(n_keep) >= 0
+    anchor_points, stride_tensor = O.make_anchors(synth.level_shapes(imgsz, strides), strides, device=DEV)
+    ref_boxes = O.decode_train(pred_distri, anchor_points)
+    assert ((out["pred_bboxes"] - ref_boxes).abs() / ref_boxes.abs().clamp(min=1.0)).max() < RTOL
+    del ref_boxes, pred_distri
+    args = (pd_scores, out["pd_bboxes"], anchor_points * stride_tensor, gl, gb, mg)
+    ref = _oracle_assign_chunked(args, 10, nc, 0.5, 6.0)
+    _check_assign((out["target_labels"], out["target_bboxes"], out["target_scores"], out["fg_mask"], out["target_gt_idx"]), ref)
+    assert pipe.counters()[1] == float(ref[3].sum())
+    del ref
+    y = kzd.decode_inference(lv, strides, nc)
+    det_ref = O.non_max_suppression(y, 0.25, 0.7, max_det=1000)
+    _check_nms(pipe.detections(), det_ref)
+    assert sum(n_keep) == sum(int(t.shape[0]) for t in det_ref)
+
+
+def test_assign_config3_multiclass_at_1280():
+    """BASELINE configs[2]: ~4,300 classes at 1280x1280 P2-P5 (A = 136,000), two pages: class-aware metric, dense
+    (b,A,nc) target_scores (4.7 GB)."""
+    b, G, imgsz, nc = 2, 600, 1280, 4300
+    d = synth.assigner_inputs(b, G, imgsz, nc, synth.P2_P5, seed=8, device=DEV)
+    args = (d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+    mine = kzd.TaskAlignedAssigner(10, nc, 0.5, 6.0)(*args)
+    ref = _oracle_assign_chunked(args, 10, nc, 0.5, 6.0, chunk=1)
+    _check_assign(mine, ref)
+    assert int(mine[2].count_nonzero()) == int(mine[3].sum())  # one non-zero class score per foreground anchor

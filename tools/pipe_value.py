@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import kuzushiji_vision_b200 as kzd
 from kuzushiji_vision_b200 import synth
 dev = torch.device("cuda:0")
-b, G, imgsz, nc, strides = 16, 600, 1280, 1, synth.P2_P5
+b, G, imgsz, nc, strides = 16, int(os.environ.get('KZD_PV_G', '600')), 1280, 1, synth.P2_P5
 depth = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 fuse_filter = os.environ.get("KZD_BENCH_FILTER", "1") != "0"
 lv = synth.head_outputs(b, nc, imgsz, strides, seed=0, device=dev, sparse_cls=3000)
