@@ -17,11 +17,12 @@
 //   assign_patch_kernel       pick list (~10 per GT): resolve each picked anchor's owner GT (a contested
 //                             anchor - picked by several GTs - takes the first-max argmax of overlaps over
 //                             ALL GTs of the image, found by one warp scanning the image's GT rows), overwrite
-//                             its targets, owner pair's metric + per-GT maxima, compact per-image fg list.
-//                             The LAST CTA of every image (ticket) then normalises that image's foreground
-//                             scores (target_scores = align * pos_ov / (pos_align + eps)) and clears the
-//                             selection words its picks set, so the persistent state is all-zero again when
-//                             the call ends: no begin kernel, no epoch, no per-call memset.
+//                             its targets, owner pair's metric + per-GT maxima; the entry that swaps the
+//                             anchor's selection words for zero represents it, so the persistent state is
+//                             all-zero again when the call ends: no begin kernel, no epoch, no per-call
+//                             memset. The LAST CTA of every image (ticket) then normalises that image's
+//                             foreground scores (target_scores = align * pos_ov / (pos_align + eps)), one
+//                             thread per pick slot.
 //
 // Bit-exactness: every fp32 operation of the eager reference rounds separately, so the pair
 // arithmetic below uses __fadd_rn/__fmul_rn/__fdiv_rn (never contracted into FMAs) and the same
@@ -42,12 +43,13 @@ struct AssignWs {
                          //           consumed by the candidates kernel, cleared by the patch kernel's tail);
                          // [1] images finished (ticket of the patch kernel's tail, self-resetting);
                          // [2] copy of [0] as the last call left it (the host may poll it, kzd_assign_report_offset)
-    int32_t* img;        // (b*2)  per image: [0] foreground count, [1] CTA ticket; both self-resetting
+    int32_t* img;        // (b*2)  per image: [0] side-list length, [1] CTA ticket; both self-resetting
     uint32_t* pos_align; // (b*G)  per-GT max alignment metric (float bits)
     uint32_t* pos_ov;    // (b*G)  per-GT max overlap (float bits)
-    uint4* fg_list;      // (b*A)  per-image compact list of foreground anchors, image i at i*A:
-                         //        (flat anchor index, flat GT slot, alignment metric bits, class)
-    uint2* picks;        // (b*G*topk)  every GT's selected anchors: (flat anchor index, g); x = ~0: empty slot
+    uint4* fg_list;      // (b*A)  per-image side list (image i at i*A) of foreground anchors owned by another GT
+                         //        than the pick slot's: (flat anchor index, flat GT slot, metric bits, class)
+    uint2* picks;        // (b*G*topk)  every GT's selected anchors: (flat anchor index, g); x = ~0: empty slot.
+                         //        The patch kernel rewrites a slot as (anchor, metric bits) when its GT owns the anchor
     size_t state_bytes;  // sel + flags + img: the part that must be zero when a call starts
 };
 
@@ -460,100 +462,139 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
 
 // ---- patch: foreground anchors, normalisation, state clean-up ---------------------------------------
 
-constexpr int PATCH_THREADS = 256;
-constexpr int PATCH_WARPS = PATCH_THREADS / 32;
+constexpr int PATCH_THREADS = 512;
+constexpr int SCAN_ILP = 4;  // GT rows per lane requested together by the contested-anchor scan
+constexpr int TAIL_ILP = 4;  // pick slots per thread in flight in the normalisation tail
 
 // Grid (x, image): the CTAs of one image stride over that image's pick-list slots (G*topk, ~85 % filled),
-// one thread per slot. An anchor picked by several GTs appears once per GT; the entry of the smallest
-// selecting GT represents it. The representative resolves the owner - one selector -> it; several
-// (contested) -> the first-max argmax of overlaps over ALL GTs of the image (utils/tal.py:283-289; all-zero
-// column -> GT 0), found by the whole warp scanning the image's GT rows: contested anchors are rare, so
-// this replaces one 64-bit atomicMax per in-GT pair of the whole batch. It then overwrites the background
-// targets the candidates kernel stored for that anchor, recomputes the (anchor, owner) pair's alignment
-// metric with the same instruction sequence as the candidates kernel (=> identical bits; this also covers
-// anchors owned by a GT that did not top-k them), records the per-GT maxima of utils/tal.py:112-114 and
-// appends the anchor to the image's compact foreground list.
+// one thread per slot. An anchor picked by several GTs appears once per GT; the first entry to swap the
+// anchor's selection words for zero (one 64-bit atomicExch: it reads both words and leaves the persistent
+// state clean for the next call) represents it. The representative resolves the owner - one selector -> it;
+// several (contested) -> the first-max argmax of overlaps over ALL GTs of the image (utils/tal.py:283-289;
+// all-zero column -> GT 0), found by the whole CTA scanning the image's GT rows once for all contested
+// anchors of the round: they are rare (tens per image), so this replaces one 64-bit atomicMax per in-GT
+// pair of the whole batch. It then overwrites the
+// background targets the candidates kernel stored for that anchor, recomputes the (anchor, owner) pair's
+// alignment metric with the same instruction sequence as the candidates kernel (=> identical bits; this
+// also covers anchors owned by a GT that did not top-k them) and records the per-GT maxima of
+// utils/tal.py:112-114. The slot is rewritten as (anchor, metric bits) when the slot's own GT is the owner
+// (the usual case), else the anchor goes to the image's short side list.
 // Tail: the last CTA of an image to get here (ticket) normalises that image's foreground scores
-// (utils/tal.py:111-116), clears the selection words of the image's picks and resets the per-image
-// counters, so the next call finds the state all-zero.
-__global__ void __launch_bounds__(PATCH_THREADS) assign_patch_kernel(const AssignParams p) {
-    __shared__ int warp_cnt[PATCH_WARPS], cta_base, s_last;
+// (utils/tal.py:111-116), one thread per pick slot: the slot and its GT's maxima are at computable
+// addresses, so every load of the pass is independent of the others (no pointer chasing).
+__global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const AssignParams p) {
+    __shared__ int s_last, s_fg, c_n;
     __shared__ double s_sum;
+    __shared__ float2 c_ap[PATCH_THREADS];              // contested anchors of the current round: centre,
+    __shared__ float4 c_pb[PATCH_THREADS];              // predicted box,
+    __shared__ unsigned long long c_key[PATCH_THREADS]; // best (overlap bits, ~g) found so far
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int bi = blockIdx.y;
+    if (threadIdx.x == 0) c_n = 0;
+    __syncthreads();
     const int n_slots = p.G * p.topk;  // of this image
-    const size_t slot0 = (size_t)bi * n_slots;
+    uint2* __restrict__ picks = p.ws.picks + (size_t)bi * n_slots;
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
     const float4* __restrict__ gtb = reinterpret_cast<const float4*>(p.gt_bboxes) + (size_t)bi * p.G;
     const float* __restrict__ gtl = p.gt_labels + (size_t)bi * p.G;
     const float* __restrict__ gtm = p.mask_gt + (size_t)bi * p.G;
-    uint4* __restrict__ fg_list = p.ws.fg_list + (size_t)bi * p.A;
-    int32_t* __restrict__ img_state = p.ws.img + 2 * bi;
+    uint4* __restrict__ side = p.ws.fg_list + (size_t)bi * p.A;
+    int32_t* __restrict__ img_state = p.ws.img + 2 * bi;  // [0] side-list length, [1] CTA ticket
     for (int s0 = blockIdx.x * PATCH_THREADS; s0 < n_slots; s0 += gridDim.x * PATCH_THREADS) {  // whole warps iterate together
         const int s = s0 + threadIdx.x;
         bool rep = false, contested = false;
         size_t idx = 0;
-        uint32_t g = 0u;
+        uint32_t g = 0u, g_own = 0u;
         float2 ap = make_float2(0.f, 0.f);
         float4 pb = make_float4(0.f, 0.f, 0.f, 0.f), gb = pb;
         float glab = 0.f, gmsk = 0.f;
         if (s < n_slots) {
-            const uint2 e = p.ws.picks[slot0 + s];
+            const uint2 e = picks[s];
             if (e.x != 0xffffffffu) {
                 // Everything that depends only on the pick is requested at once: the selection words, the
                 // anchor, its predicted box, and - speculatively - the selecting GT's row (it is the owner
                 // unless the anchor is contested). One memory round trip instead of four.
-                idx = e.x;
+                idx = e.x, g_own = e.y;
                 const int a = (int)(idx - (size_t)bi * p.A);
-                const uint2 sel = __ldcg(p.ws.sel + idx);
+                const unsigned long long sel = atomicExch(reinterpret_cast<unsigned long long*>(p.ws.sel + idx), 0ull);
                 ap = __ldg(anc + a);
                 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
-                gb = gtb[e.y], glab = gtl[e.y], gmsk = gtm[e.y];
-                const uint32_t g_min = 0xffffffffu - sel.x, g_max = sel.y - 1u;
-                rep = e.y == g_min;  // the smallest selecting GT's entry represents the anchor
+                gb = gtb[g_own], glab = gtl[g_own], gmsk = gtm[g_own];
+                rep = sel != 0ull;  // the other entries of this anchor find zero
+                const uint32_t g_min = 0xffffffffu - (uint32_t)sel, g_max = (uint32_t)(sel >> 32) - 1u;
                 contested = rep && g_min != g_max;
-                g = g_min;
+                g = g_own;  // a single selector is this entry's GT
             }
         }
-        // contested anchors, one at a time, all lanes: argmax over the image's GTs of clamp(CIoU, 0) restricted to
-        // valid GTs that contain the anchor (everything else is 0 in the reference's overlaps tensor)
-        unsigned cm = __ballot_sync(FULL, contested);
-        while (cm) {
-            const int src = __ffs(cm) - 1;
-            cm &= cm - 1u;
-            const float ax = __shfl_sync(FULL, ap.x, src), ay = __shfl_sync(FULL, ap.y, src);
-            const float4 q = make_float4(__shfl_sync(FULL, pb.x, src), __shfl_sync(FULL, pb.y, src),
-                                         __shfl_sync(FULL, pb.z, src), __shfl_sync(FULL, pb.w, src));
-            uint32_t best_o = 0u, best_g = 0xffffffffu;
-            for (int gg = lane; gg < p.G; gg += 32) {
-                if (gtm[gg] == 0.f) continue;
-                const float4 box = gtb[gg];
-                GtBox corners;
-                corners.x1 = box.x, corners.y1 = box.y, corners.x2 = box.z, corners.y2 = box.w;
-                if (!anchor_in_gt(ax, ay, corners)) continue;
-                const uint32_t ob = __float_as_uint(overlap_ciou(make_gt(box), q));
-                if (ob > best_o) best_o = ob, best_g = (uint32_t)gg;  // strict: the lowest GT among equals (gg ascends)
-            }
-            const uint32_t mo = __reduce_max_sync(FULL, best_o);
-            const uint32_t mg = __reduce_min_sync(FULL, (best_o == mo && mo != 0u) ? best_g : 0xffffffffu);
-            const uint32_t owner = mo != 0u ? mg : 0u;
-            if (lane == src && owner != g) {
-                g = owner;
-                gb = gtb[g], glab = gtl[g], gmsk = gtm[g];
-            }
+        // Contested anchors of this round, all of them at once and by the whole CTA: they are listed in shared
+        // memory, every thread takes a few of the image's GT rows (one batch of independent loads) and tests them
+        // against every listed anchor; the argmax over the image's GTs of clamp(CIoU, 0) - restricted to valid
+        // GTs that contain the anchor, everything else is 0 in the reference's overlaps tensor - is a shared-memory
+        // atomicMax on (overlap bits, ~g): highest overlap first, lowest GT among equals.
+        int my_c = -1;
+        if (contested) {
+            my_c = atomicAdd(&c_n, 1);
+            c_ap[my_c] = ap, c_pb[my_c] = pb, c_key[my_c] = 0ull;
         }
-        uint32_t al_bits = 0u;
-        long long lab = 0;
-        const size_t gslot = (size_t)bi * p.G + g;
+        __syncthreads();
+#ifdef KZD_EXP_NOSCAN
+        const int n_c = 0;
+#else
+        const int n_c = c_n;  // CTA-uniform
+#endif
+        if (n_c > 0) {
+            for (int g0 = 0; g0 < p.G; g0 += PATCH_THREADS * SCAN_ILP) {
+                float4 box[SCAN_ILP];
+                float msk[SCAN_ILP];
+#pragma unroll
+                for (int k = 0; k < SCAN_ILP; ++k) {
+                    const int gg = g0 + k * PATCH_THREADS + threadIdx.x;
+                    msk[k] = 0.f;
+                    box[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gg < p.G) msk[k] = gtm[gg], box[k] = gtb[gg];
+                }
+#pragma unroll
+                for (int k = 0; k < SCAN_ILP; ++k) {
+                    if (msk[k] == 0.f) continue;
+                    const uint32_t gg = (uint32_t)(g0 + k * PATCH_THREADS + threadIdx.x);
+                    GtBox corners;
+                    corners.x1 = box[k].x, corners.y1 = box[k].y, corners.x2 = box[k].z, corners.y2 = box[k].w;
+                    bool have_gt = false;
+                    GtBox gt = corners;
+                    for (int j = 0; j < n_c; ++j) {
+                        const float2 a_ = c_ap[j];
+                        if (!anchor_in_gt(a_.x, a_.y, corners)) continue;
+                        if (!have_gt) gt = make_gt(box[k]), have_gt = true;
+                        const uint32_t ob = __float_as_uint(overlap_ciou(gt, c_pb[j]));
+                        if (ob != 0u) atomicMax(c_key + j, ((unsigned long long)ob << 32) | (unsigned long long)(0xffffffffu - gg));
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) c_n = 0;  // n_c is in registers; the next round's entries come after the barrier below
+            if (my_c >= 0) {
+                const unsigned long long k = c_key[my_c];
+                const uint32_t owner = (k >> 32) != 0ull ? 0xffffffffu - (uint32_t)k : 0u;  // all-zero column -> GT 0
+                if (owner != g) {
+                    g = owner;
+                    gb = gtb[g], glab = gtl[g], gmsk = gtm[g];
+                }
+            }
+            __syncthreads();  // every reader of the list is done before the next round refills it
+        }
+#ifdef KZD_EXP_NOREP
+        rep = false;
+#endif
         if (rep) {
-            lab = (long long)glab;
+            long long lab = (long long)glab;
             lab = lab < 0 ? 0 : lab;
             p.target_gt_idx[idx] = (long long)g;
             p.target_labels[idx] = lab;
             p.fg_mask[idx] = 1;
             reinterpret_cast<float4*>(p.target_bboxes)[idx] = gb;
             lab = lab >= p.nc ? p.nc - 1 : lab;
+            const size_t gslot = (size_t)bi * p.G + g;
             float al = 0.f;
             if (gmsk != 0.f) {
                 const GtBox gt = make_gt(gb);
@@ -565,62 +606,89 @@ __global__ void __launch_bounds__(PATCH_THREADS) assign_patch_kernel(const Assig
                     atomicMax(p.ws.pos_align + gslot, __float_as_uint(al));
                 }
             }
-            al_bits = __float_as_uint(al);
-        }
-        // compact foreground list: one global atomic per CTA (thousands of returning atomics on one address
-        // would serialise in L2)
-        const bool listed = rep;
-        const unsigned m = __ballot_sync(FULL, listed);
-        if (lane == 0) warp_cnt[wib] = __popc(m);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int w = 0; w < PATCH_WARPS; ++w) {
-                const int c = warp_cnt[w];
-                warp_cnt[w] = tot;
-                tot += c;
+            if (g == g_own) {
+                picks[s] = make_uint2((uint32_t)idx, __float_as_uint(al));  // normalised by the owner's thread in the tail
+            } else {  // rare: owned by another GT than the slot's
+                picks[s] = make_uint2(0xffffffffu, 0u);
+                side[atomicAdd(img_state, 1)] = make_uint4((uint32_t)idx, (uint32_t)gslot, __float_as_uint(al), (uint32_t)lab);
             }
-            cta_base = tot ? atomicAdd(img_state, tot) : 0;
+        } else if (s < n_slots) {
+            picks[s] = make_uint2(0xffffffffu, 0u);
         }
-        __syncthreads();
-        if (listed)
-            fg_list[cta_base + warp_cnt[wib] + __popc(m & ((1u << lane) - 1u))] =
-                make_uint4((uint32_t)idx, (uint32_t)gslot, al_bits, (uint32_t)lab);
-        __syncthreads();  // warp_cnt / cta_base are reused by the next round
     }
 
     // ---- tail: the image's last CTA -----------------------------------------------------------------
-    __threadfence();  // this CTA's target / list / maxima writes are visible device-wide before its ticket
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();  // this CTA's slot / side-list / maxima writes are visible device-wide before its ticket
         s_last = atomicAdd(img_state + 1, 1) == (int)gridDim.x - 1;
-        s_sum = 0.0;
+        s_sum = 0.0, s_fg = 0;
     }
     __syncthreads();
     if (!s_last) return;
+#ifdef KZD_EXP_NOTAIL
+    if (threadIdx.x == 0) {
+        img_state[0] = 0, img_state[1] = 0;
+        if (atomicAdd(p.ws.flags + 1, 1) == (int)gridDim.y - 1) p.ws.flags[1] = 0, p.ws.flags[0] = 0;
+    }
+    return;
+#endif
     __threadfence();
-    const int n_fg = __ldcg(img_state);
     float local = 0.f;
-    for (int i = threadIdx.x; i < n_fg; i += PATCH_THREADS) {
-        const uint4 e = __ldcg(fg_list + i);
+    int n_fg = 0;
+    const uint32_t* __restrict__ pos_ov = p.ws.pos_ov + (size_t)bi * p.G;
+    const uint32_t* __restrict__ pos_al = p.ws.pos_align + (size_t)bi * p.G;
+    // one thread per pick slot, TAIL_ILP slots at a time: the slot, its GT's two maxima (and label) are
+    // requested together - nothing here waits for an earlier load of the pass
+    for (int s0 = threadIdx.x; s0 < n_slots; s0 += PATCH_THREADS * TAIL_ILP) {
+        uint2 e[TAIL_ILP];
+        uint32_t ov[TAIL_ILP], pa[TAIL_ILP];
+        float gl_[TAIL_ILP];
+#pragma unroll
+        for (int k = 0; k < TAIL_ILP; ++k) {
+            const int s = s0 + k * PATCH_THREADS;
+            e[k] = make_uint2(0xffffffffu, 0u), ov[k] = pa[k] = 0u, gl_[k] = 0.f;
+            if (s < n_slots) {
+                const int g = s / p.topk;
+                e[k] = __ldcg(picks + s), ov[k] = __ldcg(pos_ov + g), pa[k] = __ldcg(pos_al + g);
+                if (p.nc > 1) gl_[k] = gtl[g];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TAIL_ILP; ++k) {
+            if (e[k].x == 0xffffffffu) continue;
+            long long lab = (long long)gl_[k];
+            lab = lab < 0 ? 0 : (lab >= p.nc ? p.nc - 1 : lab);
+            const float v = __fdiv_rn(__fmul_rn(__uint_as_float(e[k].y), __uint_as_float(ov[k])),
+                                      __fadd_rn(__uint_as_float(pa[k]), p.eps));  // utils/tal.py:115
+            p.target_scores[(size_t)e[k].x * p.nc + lab] = v;
+            local += v;
+            ++n_fg;
+        }
+    }
+    const int n_side = __ldcg(img_state);
+    for (int i = threadIdx.x; i < n_side; i += PATCH_THREADS) {
+        const uint4 e = __ldcg(side + i);
         const float ov = __uint_as_float(__ldcg(p.ws.pos_ov + e.y));
         const float pa = __uint_as_float(__ldcg(p.ws.pos_align + e.y));
-        const float v = __fdiv_rn(__fmul_rn(__uint_as_float(e.z), ov), __fadd_rn(pa, p.eps));  // utils/tal.py:115
+        const float v = __fdiv_rn(__fmul_rn(__uint_as_float(e.z), ov), __fadd_rn(pa, p.eps));
         p.target_scores[(size_t)e.x * p.nc + e.w] = v;
         local += v;
-    }
-    // the image's picks: clear the selection words they set (all readers of this image are done)
-    for (int s = threadIdx.x; s < n_slots; s += PATCH_THREADS) {
-        const uint2 e = p.ws.picks[slot0 + s];
-        if (e.x != 0xffffffffu) p.ws.sel[e.x] = make_uint2(0u, 0u);
+        ++n_fg;
     }
     if (p.counters) {
-        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
-        if (lane == 0 && local != 0.f) atomicAdd(&s_sum, (double)local);
+        for (int o = 16; o > 0; o >>= 1) {
+            local += __shfl_xor_sync(FULL, local, o);
+            n_fg += __shfl_xor_sync(FULL, n_fg, o);
+        }
+        if (lane == 0) {
+            if (local != 0.f) atomicAdd(&s_sum, (double)local);
+            if (n_fg) atomicAdd(&s_fg, n_fg);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             if (s_sum != 0.0) atomicAdd(p.counters, s_sum);
-            if (n_fg) atomicAdd(p.counters + 1, (double)n_fg);
+            if (s_fg) atomicAdd(p.counters + 1, (double)s_fg);
         }
     }
     if (threadIdx.x == 0) {

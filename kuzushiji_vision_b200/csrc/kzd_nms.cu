@@ -17,8 +17,9 @@
 //   nms_scan_kernel    per image: greedy walk in 64-row chunks; the diagonal tile is resolved by one
 //                      warp with ballot/shuffle, helper warps OR the kept rows into later chunks with
 //                      sparse shared-memory atomics; the first max_det kept rows are gathered in score order
-//   mask + scan run in phases of growing column ranges: the walk stops once max_det boxes are kept,
-//   so finished images skip the later phases on the device (kzd_nms_suppress)
+//   mask + scan run in two phases of column ranges: the walk stops once max_det boxes are kept, so the
+//   second phase is needed only when some image's walk is not over after the first; inside a captured
+//   CUDA graph it is the body of a conditional node that the first walk switches on (kzd_nms_suppress)
 #include <cooperative_groups.h>
 
 #include "kzd_common.cuh"
@@ -265,34 +266,46 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_rank_kernel(const float* __
                                                                  int cand_cap, int n_cap, int agnostic, float max_wh,
                                                                  SuppressWs ws) {
     __shared__ u64 other[CHUNK];
+    constexpr int STAGE = 7;  // other chunks whose keys are in flight / in registers together
     const int bi = blockIdx.y, chunk = blockIdx.x;
     const int n = ws.n_sorted[bi];
-    if (n <= 0) return;
     const int count = cand_counts[bi];
-    if (chunk * CHUNK >= count) return;
+    if (n <= 0 || chunk * CHUNK >= count) return;
     const int n_chunks = (count + CHUNK - 1) / CHUNK;
     const u64* __restrict__ ck = ws.ckeys + (size_t)bi * ws.C_cap * CHUNK;
     const int t0 = threadIdx.x, t1 = threadIdx.x + CHUNK_THREADS;
     const u64 k0 = ck[(size_t)chunk * CHUNK + t0], k1 = ck[(size_t)chunk * CHUNK + t1];
-    int r0 = t0, r1 = t1;
-    for (int c = 0; c < n_chunks; ++c) {
-        if (c == chunk) continue;  // uniform
-        __syncthreads();
-        other[t0] = ck[(size_t)c * CHUNK + t0];
-        other[t1] = ck[(size_t)c * CHUNK + t1];
-        __syncthreads();
-        int lo0 = 0, hi0 = CHUNK, lo1 = 0, hi1 = CHUNK;
-#pragma unroll
-        for (int s = 0; s < 10; ++s) {  // 2^9 = 512: 10 halvings always converge
-            const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
-            const bool g0 = lo0 < hi0 && other[m0 < CHUNK ? m0 : CHUNK - 1] > k0;
-            const bool g1 = lo1 < hi1 && other[m1 < CHUNK ? m1 : CHUNK - 1] > k1;
-            if (lo0 < hi0) { if (g0) lo0 = m0 + 1; else hi0 = m0; }
-            if (lo1 < hi1) { if (g1) lo1 = m1 + 1; else hi1 = m1; }
-        }
-        r0 += lo0, r1 += lo1;
-    }
+    // own slot / row loads do not depend on the rank: requested now, used at the end
     const uint32_t* __restrict__ cv = ws.cvals + ((size_t)bi * ws.C_cap + chunk) * CHUNK;
+    const uint32_t slot0 = cv[t0], slot1 = cv[t1];
+    int r0 = t0, r1 = t1;
+    for (int base = 0; base < n_chunks; base += STAGE) {
+        u64 st0[STAGE], st1[STAGE];
+#pragma unroll
+        for (int k = 0; k < STAGE; ++k) {  // all loads of the group in flight at once (one memory round trip)
+            const int c = base + k;
+            st0[k] = st1[k] = 0ull;
+            if (c < n_chunks && c != chunk) st0[k] = ck[(size_t)c * CHUNK + t0], st1[k] = ck[(size_t)c * CHUNK + t1];
+        }
+#pragma unroll
+        for (int k = 0; k < STAGE; ++k) {
+            const int c = base + k;
+            if (c >= n_chunks || c == chunk) continue;  // uniform
+            __syncthreads();
+            other[t0] = st0[k], other[t1] = st1[k];
+            __syncthreads();
+            int lo0 = 0, hi0 = CHUNK, lo1 = 0, hi1 = CHUNK;
+#pragma unroll
+            for (int s = 0; s < 10; ++s) {  // 2^9 = 512: 10 halvings always converge
+                const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+                const bool g0 = lo0 < hi0 && other[m0 < CHUNK ? m0 : CHUNK - 1] > k0;
+                const bool g1 = lo1 < hi1 && other[m1 < CHUNK ? m1 : CHUNK - 1] > k1;
+                if (lo0 < hi0) { if (g0) lo0 = m0 + 1; else hi0 = m0; }
+                if (lo1 < hi1) { if (g1) lo1 = m1 + 1; else hi1 = m1; }
+            }
+            r0 += lo0, r1 += lo1;
+        }
+    }
     const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
     float4* __restrict__ sbox = ws.sbox + (size_t)bi * n_cap;
     uint32_t* __restrict__ sslot = ws.sslot + (size_t)bi * n_cap;
@@ -305,8 +318,8 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_rank_kernel(const float* __
                                  __fadd_rn(p1.y, off));                                   // utils/ops.py:295
         sslot[rank] = slot;
     };
-    emit(k0, r0, cv[t0]);
-    emit(k1, r1, cv[t1]);
+    emit(k0, r0, slot0);
+    emit(k1, r1, slot1);
 }
 
 // One thread-block cluster per image does the whole ordering when the candidate pool is at most 8 chunks
@@ -541,7 +554,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
                                                                 int n_cap, int max_det, int phase, int t_lo,
                                                                 int t_hi, SuppressWs ws,
                                                                 float* __restrict__ out_rows,
-                                                                int32_t* __restrict__ out_counts) {
+                                                                int32_t* __restrict__ out_counts,
+                                                                unsigned long long more_handle) {
     extern __shared__ u64 scan_smem[];
     u64* removed = scan_smem;                                               // T_cap: bits suppressed by a kept row
     u64* keep_s = scan_smem + ws.T_cap;                                     // T_cap: keep mask of every chunk walked here
@@ -699,7 +713,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
     }
     if (n == 0) finished = true;
     if (!finished) {  // more columns are needed: the next phase continues from here
-        if (threadIdx.x == 0) state[0] = 0, state[1] = kept, state[2] = chunks;
+        if (threadIdx.x == 0) {
+            state[0] = 0, state[1] = kept, state[2] = chunks;
+            // inside a captured graph the next phase is the body of a conditional node: switch it on
+            if (more_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)more_handle, 1u);
+        }
         return;
     }
     // gather the kept rows in score order, all threads
@@ -824,29 +842,64 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
         nms_rank_kernel<<<cgrid, CHUNK_THREADS, 0, st>>>(cand_rows, cand_counts, cand_cap, n_cap, agnostic, max_wh, ws);
         KZD_LAUNCH_CHECK("nms_rank_kernel");
     }
-    // The greedy walk stops as soon as max_det boxes are kept, so the mask is built and walked in phases
-    // of growing column ranges: first enough tiles for max_det kept boxes plus 25 %, then 4x more per
-    // phase. Finished images skip the later phases on the device (no host round trip).
+    // The greedy walk stops as soon as max_det boxes are kept, so the mask is built and walked in two phases
+    // of column ranges: first enough tiles for max_det kept boxes plus 25 %, then - only if some image's
+    // walk is not over - all the others. Eagerly, phase 1 is launched regardless and finished images skip it
+    // on the device. Under stream capture (CUDA graphs: PagePipeline) phase 1 becomes the body of a
+    // conditional IF node whose handle the phase-0 walk sets when it needs more columns: a step whose images
+    // all finish in phase 0 - the usual case when max_det cuts the walk - pays nothing for it.
 #ifndef KZD_MASK_GRID
 #define KZD_MASK_GRID 16
 #endif
     const int grid = sm_count() * KZD_MASK_GRID;
-    int t_prev = 0;
-    int t_next = ((max_det + max_det / 4 + 64 + 63) / 64 + MASK_CG - 1) / MASK_CG * MASK_CG;
-    for (int phase = 0; t_prev < ws.T_cap; ++phase) {
-        if (t_next > ws.T_cap) t_next = ws.T_cap;
-        const int g_lo = t_prev / MASK_CG, g_hi = (t_next + MASK_CG - 1) / MASK_CG;
-        // later phases usually find every image finished: a quarter of the CTAs keeps that exit cheap (the
+    int t0 = ((max_det + max_det / 4 + 64 + 63) / 64 + MASK_CG - 1) / MASK_CG * MASK_CG;
+    if (t0 > ws.T_cap) t0 = ws.T_cap;
+    const bool two = t0 < ws.T_cap;
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    cudaGraph_t cap_graph = nullptr;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t n_deps = 0;
+    KZD_CUDA(cudaStreamGetCaptureInfo_v2(st, &cap_status, nullptr, &cap_graph, &deps, &n_deps));
+    const bool conditional = two && cap_status == cudaStreamCaptureStatusActive && cap_graph != nullptr;
+    cudaGraphConditionalHandle more = 0;
+    if (conditional) KZD_CUDA(cudaGraphConditionalHandleCreate(&more, cap_graph, 0, cudaGraphCondAssignDefault));
+    auto launch_phase = [&](int phase, int t_lo, int t_hi, cudaStream_t s_, unsigned long long handle) -> int {
+        const int g_lo = t_lo / MASK_CG, g_hi = (t_hi + MASK_CG - 1) / MASK_CG;
+        // a later phase usually finds every image finished: a quarter of the CTAs keeps that exit cheap (the
         // kernel strides over its items, so a phase with real work is only spread over fewer, longer CTAs)
-        nms_mask_kernel<<<phase == 0 ? grid : grid / 4, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(
+        nms_mask_kernel<<<phase == 0 || conditional ? grid : grid / 4, MASK_THREADS, (size_t)(b + 1) * sizeof(int), s_>>>(
             b, n_cap, iou_thres, phase, g_lo, g_hi, ws);
         KZD_LAUNCH_CHECK("nms_mask_kernel");
-        nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * 20, st>>>(cand_rows, cand_cap, n_cap, max_det,
-                                                                                phase, t_prev, t_next, ws, out_rows,
-                                                                                out_counts);
+        nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * 20, s_>>>(cand_rows, cand_cap, n_cap, max_det, phase, t_lo,
+                                                                        t_hi, ws, out_rows, out_counts, handle);
         KZD_LAUNCH_CHECK("nms_scan_kernel");
-        t_prev = t_next;
-        t_next = (t_next * 4 + MASK_CG - 1) / MASK_CG * MASK_CG;
+        return 0;
+    };
+    if (int rc = launch_phase(0, 0, t0, st, (unsigned long long)more)) return rc;
+    if (two && !conditional) {
+        if (int rc = launch_phase(1, t0, ws.T_cap, st, 0ull)) return rc;
+    } else if (two) {
+        KZD_CUDA(cudaStreamGetCaptureInfo_v2(st, &cap_status, nullptr, &cap_graph, &deps, &n_deps));
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = more;
+        np.conditional.type = cudaGraphCondTypeIf;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        KZD_CUDA(cudaGraphAddNode(&node, cap_graph, deps, n_deps, &np));
+        cudaStream_t body_stream;  // exists only while the body is recorded
+        KZD_CUDA(cudaStreamCreateWithFlags(&body_stream, cudaStreamNonBlocking));
+        cudaError_t e = cudaStreamBeginCaptureToGraph(body_stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                                      cudaStreamCaptureModeRelaxed);
+        int rc = 0;
+        if (e == cudaSuccess) {
+            rc = launch_phase(1, t0, ws.T_cap, body_stream, 0ull);
+            e = cudaStreamEndCapture(body_stream, nullptr);
+        }
+        cudaStreamDestroy(body_stream);
+        if (rc) return rc;
+        KZD_CUDA(e);
+        KZD_CUDA(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
     }
     return 0;
 }

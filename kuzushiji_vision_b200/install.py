@@ -45,7 +45,7 @@ def detect_in_scope(module, detect_cls):
         return False
     if getattr(module, "end2end", False) or getattr(module, "reg_max", 16) != _head.REG_MAX:
         return False
-    if type(module).decode_bboxes is not detect_cls.decode_bboxes:
+    if getattr(type(module), "decode_bboxes", None) is not getattr(detect_cls, "decode_bboxes", None):
         return False
     return getattr(module, "no", None) == getattr(module, "nc", 0) + 4 * _head.REG_MAX
 

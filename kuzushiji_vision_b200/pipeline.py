@@ -91,15 +91,11 @@ class PagePipeline:
         self._side2 = torch.cuda.Stream(device=dev, priority=-1) if (assign_priority and overlap) else None
         self.out = None
         self.graph = None
-        # kernels per step: decode(s), assign x2 (candidates, patch), [nms filter], ordering (chunk sort + rank, or one cluster
-        # kernel), (mask, scan) per phase - the phase schedule mirrors kzd_nms_suppress
-        t0 = (self.max_det + self.max_det // 4 + 127) // 64
-        t_cap, phases = (self.n_cap + 63) // 64, 1
-        while t0 < t_cap:
-            t0, phases = t0 * 4, phases + 1
+        # kernels per step: decode(s), assign x2 (candidates, patch), [nms filter], ordering (chunk sort + rank, or one
+        # cluster kernel), mask + walk of the first column range; the second range is a conditional graph node
+        # (two more kernels, only in steps where some image's walk needs it: not counted)
         order = 1 if (self.pool + 511) // 512 <= 8 else 2
-        self.kernels_per_step = ((1 if self.fuse_decodes else 2) + 2 + (0 if self.fuse_filter else 1) + order
-                                 + 2 * phases)
+        self.kernels_per_step = (1 if self.fuse_decodes else 2) + 2 + (0 if self.fuse_filter else 1) + order + 2
         if use_graph:
             self._capture()
 

@@ -72,13 +72,16 @@ def load():
         sys.path.insert(0, root)
     import torch
 
+    import contextlib
+
     nthreads = torch.get_num_threads()
-    tal = importlib.import_module("ultralytics.utils.tal")
-    ops = importlib.import_module("ultralytics.utils.ops")
-    loss = importlib.import_module("ultralytics.utils.loss")
-    metrics = importlib.import_module("ultralytics.utils.metrics")
-    head = importlib.import_module("ultralytics.nn.modules.head")
-    block = importlib.import_module("ultralytics.nn.modules.block")
+    with contextlib.redirect_stdout(sys.stderr):  # the package prints at import time; bench.py's stdout is one JSON line
+        tal = importlib.import_module("ultralytics.utils.tal")
+        ops = importlib.import_module("ultralytics.utils.ops")
+        loss = importlib.import_module("ultralytics.utils.loss")
+        metrics = importlib.import_module("ultralytics.utils.metrics")
+        head = importlib.import_module("ultralytics.nn.modules.head")
+        block = importlib.import_module("ultralytics.nn.modules.block")
     # ultralytics/__init__.py:8-9 forces OMP_NUM_THREADS=1 when unset; undo for our timing.
     if keep_omp is None:
         os.environ.pop("OMP_NUM_THREADS", None)

@@ -958,3 +958,29 @@ def test_assign_config3_multiclass_at_1280():
     ref = _oracle_assign_chunked(args, 10, nc, 0.5, 6.0, chunk=1)
     _check_assign(mine, ref)
     assert int(mine[2].count_nonzero()) == int(mine[3].sum())  # one non-zero class score per foreground anchor
+
+
+def test_pipeline_conditional_second_nms_phase():
+    """Inside the captured graph the second (mask, walk) phase of kzd_nms_suppress is the body of a conditional
+    node. Replays alternate between a batch whose walks end in the first column range (max_det reached) and a
+    batch that needs every column (low IoU threshold: heavy suppression, fewer than max_det kept): every replay
+    must match the oracle, whichever way the node went the time before."""
+    b, G, imgsz, nc, strides = 3, 50, 640, 1, synth.P2_P5
+    pipe = kzd.PagePipeline(b, synth.level_shapes(imgsz, strides), strides, nc, G, device=DEV, conf_thres=0.25,
+                            iou_thres=0.05, max_det=300, fuse_decodes=True, fuse_filter=True)
+    gl, gb, mg = synth.gt_pages(b, G, imgsz, nc, seed=1, device=DEV)
+    seen = set()
+    for seed, n_obj in ((1, 2500), (2, 420), (3, 2500), (4, 2500), (5, 420)):
+        lv = synth.head_outputs(b, nc, imgsz, strides, seed=seed + 70, device=DEV, sparse_cls=n_obj)
+        cat = torch.cat([x.view(b, 64 + nc, -1) for x in lv], 2)
+        pd_scores = cat[:, 64:].permute(0, 2, 1).contiguous().sigmoid()
+        pipe.load(levels=lv, pd_scores=pd_scores, gt_labels=gl, gt_bboxes=gb, mask_gt=mg)
+        pipe.step()
+        det = pipe.detections()
+        y = kzd.decode_inference(lv, strides, nc)
+        ref = O.non_max_suppression(y, 0.25, 0.05, max_det=300)
+        _check_nms(det, ref)
+        n_cand = pipe.candidate_counts()
+        # first column range of this pipeline: (300 + 75 + 127) // 64 = 7 tiles = 448 boxes
+        seen.add(max(n_cand) > 448 and min(int(t.shape[0]) for t in ref) < 300)
+    assert seen == {True, False}, "the test inputs must exercise both directions of the conditional node"

@@ -201,7 +201,9 @@ def test_install_leaves_out_of_scope_heads_to_the_reference(R):
     lv = synth.head_outputs(1, nc, 256, strides, seed=3, device=DEV)
     kzd.install()
     try:
-        from kuzushiji_vision_b200 import install as inst
+        import importlib
+
+        inst = importlib.import_module("kuzushiji_vision_b200.install")  # the package attribute is the function
 
         det = _ref_detect(R, nc, strides)
         assert inst.detect_in_scope(det, R.Detect)
@@ -211,7 +213,7 @@ def test_install_leaves_out_of_scope_heads_to_the_reference(R):
         with torch.no_grad():
             y_e2e = e2e._inference([x.clone() for x in lv])  # reference path: xyxy boxes (head.py:148)
             y_det = det._inference([x.clone() for x in lv])
-        assert not torch.equal(y_e2e[:, :4], y_det[:, :4]) and torch.equal(y_e2e[:, 4:], y_det[:, 4:])
+        assert not torch.equal(y_e2e[:, :4], y_det[:, :4]) and (y_e2e[:, 4:] - y_det[:, 4:]).abs().max() <= 1e-6
         obb = R.head.OBB(nc=nc, ne=1, ch=(64, 64, 64)).to(DEV).eval()
         assert not inst.detect_in_scope(obb, R.Detect)
         seg = R.head.Segment(nc=nc, nm=4, npr=8, ch=(64, 64, 64)).to(DEV).eval()

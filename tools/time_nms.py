@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import kuzushiji_vision_b200 as kzd
 from kuzushiji_vision_b200 import _lib, synth
 dev = torch.device("cuda:0")
-b, nc, cands, max_det, strides = 16, 1, 3000, 1000, synth.P2_P5
+b, nc, cands, max_det, strides = 16, 1, 3000, int(os.environ.get('KZD_TN_MAXDET', '1000')), synth.P2_P5
 lv = synth.head_outputs(b, nc, 1280, strides, seed=100, device=dev, sparse_cls=cands)
 y = kzd.decode_inference(lv, strides, nc)
 A = y.shape[2]
