@@ -204,6 +204,22 @@ int kzd_gt_pack(const float* targets, int n, int b, int G, const float* scale4, 
 int kzd_scale_boxes(float* rows, const int32_t* counts, int b, int max_det, int row_stride,
                     const float* params, void* stream);
 
+/* Validator matching for all images of a batch: DetectionValidator._process_batch (models/yolo/detect/val.py:
+ * 209-228: box_iou of labels x detections, utils/metrics.py:52-71) + BaseValidator.match_predictions
+ * (engine/validator.py:222-260, use_scipy=False). A detection is correct at threshold iouv[i] when its best
+ * equal-class label (highest IoU) has IoU >= iouv[i] and no earlier detection chose the same label at that
+ * threshold (detections come in descending confidence order, as kzd_nms_suppress writes them).
+ *   det_rows (b, max_det, row_stride >= 6) [x1,y1,x2,y2,conf,cls], det_counts int32 (b) or NULL (all rows);
+ *   gt (b, G, 5) [cls, x1,y1,x2,y2] in the same coordinate space, gt_counts int32 (b) labels per image;
+ *   iouv device float[n_iou], n_iou <= 32, every threshold > 0 (the reference uses linspace(0.5, 0.95, 10));
+ *   correct uint8 (b, max_det, n_iou): 0/1, rows beyond det_counts are 0.
+ * Exactly equal IoUs of one detection with several labels are ordered by the reference's unstable argsort;
+ * here the label with the larger index wins. */
+size_t kzd_match_workspace_bytes(int b, int max_det, int G, int n_iou);
+int kzd_match_predictions(const float* det_rows, const int32_t* det_counts, int b, int max_det, int row_stride,
+                          const float* gt, const int32_t* gt_counts, int G, const float* iouv, int n_iou,
+                          uint8_t* correct, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Loss tail on the assigned targets (utils/loss.py:243-258; BboxLoss :91-113, DFLoss :65-88):
  *   loss3[0] = sum_fg (1 - CIoU(pred_box, target_box/stride)) * w / tss   (box, before hyp.box)
  *   loss3[1] = sum BCEWithLogits(pred_scores, target_scores) / tss         (cls)
@@ -221,6 +237,25 @@ int kzd_loss_tail_bwd(const float* pred_scores, const float* pred_dist, const fl
                       const float* stride_tensor, const float* target_bboxes, const float* target_scores,
                       const uint8_t* fg_mask, const float* target_scores_sum, int b, int A, int nc,
                       const float* grad_loss3, float* grad_pred_scores, float* grad_pred_dist, void* stream);
+
+/* Sparse-target form of the same loss tail (utils/loss.py:243-247): the BCE never streams the
+ * dense (b,A,nc) target_scores. BCE(x, t) = softplus(x) - t*x: the first term is one pass over pred_scores,
+ * the second exists only at the foreground (anchor, target_labels[anchor]) elements, because a foreground row
+ * of the assigner's target_scores is one-hot * norm at the anchor's target label and background rows are zero
+ * (utils/tal.py:228-236). target_scores is read at those elements only (also the box / DFL weight, which the
+ * reference takes as target_scores.sum(-1), utils/loss.py:93); target_labels int64 (b,A) is kzd_tal_assign's
+ * first output. score_dtype (0 fp32, 1 fp16, 2 bf16): dtype the reference rounds the BCE target to under AMP
+ * (target_scores.to(dtype), utils/loss.py:247) - the weight keeps the fp32 value. The backward writes
+ * sigmoid(x)*scale everywhere (reads pred_scores only) and subtracts t*scale at the foreground elements. */
+int kzd_loss_tail_sparse_fwd(const float* pred_scores, const float* pred_dist, const float* anchor_points,
+                             const float* stride_tensor, const float* target_bboxes, const float* target_scores,
+                             const int64_t* target_labels, const uint8_t* fg_mask, const float* target_scores_sum,
+                             int b, int A, int nc, int score_dtype, double* sums_ws, float* loss3, void* stream);
+int kzd_loss_tail_sparse_bwd(const float* pred_scores, const float* pred_dist, const float* anchor_points,
+                             const float* stride_tensor, const float* target_bboxes, const float* target_scores,
+                             const int64_t* target_labels, const uint8_t* fg_mask, const float* target_scores_sum,
+                             int b, int A, int nc, int score_dtype, const float* grad_loss3,
+                             float* grad_pred_scores, float* grad_pred_dist, void* stream);
 
 #ifdef __cplusplus
 }

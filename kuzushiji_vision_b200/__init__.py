@@ -18,7 +18,8 @@ from ._lib import KzdError
 from .head import bbox_decode, decode_inference, detect_inference
 from .install import install, installed, uninstall
 from .loss import DetectionLoss, loss_tail, preprocess
-from .ops import nms_batched, non_max_suppression, scale_boxes, scale_boxes_batched, xywh2xyxy
+from .ops import (match_predictions_batched, nms_batched, non_max_suppression, process_batch, scale_boxes,
+                  scale_boxes_batched, xywh2xyxy)
 from .pipeline import PagePipeline
 from .tal import TaskAlignedAssigner, dist2bbox, infer_levels, make_anchors
 
@@ -27,5 +28,6 @@ __all__ = [
     "TaskAlignedAssigner", "make_anchors", "dist2bbox", "infer_levels",
     "detect_inference", "decode_inference", "bbox_decode",
     "non_max_suppression", "nms_batched", "xywh2xyxy", "scale_boxes", "scale_boxes_batched",
+    "match_predictions_batched", "process_batch",
     "DetectionLoss", "loss_tail", "preprocess", "PagePipeline", "install", "uninstall", "installed", "KzdError",
 ]

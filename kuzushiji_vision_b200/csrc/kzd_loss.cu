@@ -12,6 +12,9 @@
 //   w = target_scores.sum(-1) of the anchor, tss = max(target_scores.sum(), 1)
 // The predicted box is re-decoded from pred_dist inside the kernel (softmax expectation), so the
 // backward chains through the decode directly into grad_pred_dist.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "kzd_common.cuh"
 
 namespace kzd {
@@ -21,14 +24,34 @@ struct LossParams {
     const uint8_t* fg_mask;
     const float* tss;  // device scalar: target_scores.sum() (max(., 1) is applied here)
     int b, A, nc;
+    // sparse-target form: the assigner's target_scores row of a foreground anchor is one-hot * norm at its
+    // target label, so target_labels tells where the single non-zero sits and the dense (b,A,nc) tensor is
+    // only read at those (anchor, label) elements
+    const long long* target_labels;  // nullptr: dense form
+    int score_dtype;                 // dtype the BCE target is rounded to (utils/loss.py:247 under AMP): 0 fp32, 1 fp16, 2 bf16
 };
+
+__device__ __forceinline__ float round_to(float v, int dtype) {
+    if (dtype == 1) return __half2float(__float2half_rn(v));
+    if (dtype == 2) return __bfloat162float(__float2bfloat16_rn(v));
+    return v;
+}
 
 // ---- BCE ----------------------------------------------------------------------------------------
 
 __device__ __forceinline__ float bce_logits(float x, float t) {
-    // (1 - t) x + max(-x, 0) + log(exp(-max(-x,0)) + exp(-x - max(-x,0)))   (aten binary_cross_entropy_with_logits)
-    const float mv = fmaxf(-x, 0.f);
-    return (1.f - t) * x + mv + logf(expf(-mv) + expf(-x - mv));
+    // aten binary_cross_entropy_with_logits: (1 - t) x + max(-x, 0) + log(exp(-max(-x,0)) + exp(-x - max(-x,0))),
+    // whose last two terms are softplus(-x) = max(-x, 0) + log1p(exp(-|x|)); the log1p form keeps the tail of
+    // very negative logits that the sum of exponentials rounds away
+    return (1.f - t) * x + fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+
+// BCE(x, 0) = softplus(x) = max(x, 0) + log1p(exp(-|x|)); BCE(x, t) = softplus(x) - t x
+__device__ __forceinline__ float softplus_fast(float x) {
+    const float e = __expf(-fabsf(x));
+    // log1p(e), e in (0, 1]: short series where 1 + e would round the tail away, fast log elsewhere
+    const float l = e < 9.765625e-4f ? e * (1.f - e * (0.5f - e * 0.33333334f)) : __logf(1.f + e);
+    return fmaxf(x, 0.f) + l;
 }
 
 __device__ __forceinline__ void block_add(double v, double* dst, double* s_red) {
@@ -58,6 +81,43 @@ __global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ 
     block_add(total, sums + 1, s_red);
 }
 
+// Sparse-target BCE, forward: sum softplus(x) over ALL logits (the only dense read: pred_scores, 128-bit
+// streaming loads); the -t x terms of the foreground (anchor, label) elements are added by fg_fwd_kernel.
+__global__ void __launch_bounds__(256) softplus_sum_kernel(const float* __restrict__ x, size_t n, size_t n4,
+                                                           double* __restrict__ sums) {
+    __shared__ double s_red[8];
+    float acc = 0.f;
+    double total = 0.0;
+    int k = 0;
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldcs(x4 + i);
+        acc += (softplus_fast(v.x) + softplus_fast(v.y)) + (softplus_fast(v.z) + softplus_fast(v.w));
+        if (++k == 16) total += (double)acc, acc = 0.f, k = 0;  // bound the fp32 partial
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        acc += softplus_fast(__ldcs(x + i));
+    total += (double)acc;
+    block_add(total, sums + 1, s_red);
+}
+
+// Sparse-target BCE, backward: sigmoid(x) * scale everywhere (read x, write the gradient; target_scores is
+// not read); fg_bwd_kernel then subtracts t * scale at the foreground (anchor, label) elements.
+__global__ void __launch_bounds__(256) sigmoid_grad_kernel(const float* __restrict__ x, size_t n, size_t n4,
+                                                           const float* __restrict__ tss, const float* __restrict__ gout,
+                                                           float* __restrict__ gx) {
+    const float scale = gout[1] / fmaxf(*tss, 1.f);
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    float4* __restrict__ g4 = reinterpret_cast<float4*>(gx);
+    auto sg = [&](float v) { return __fdividef(scale, 1.f + __expf(-v)); };
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldcs(x4 + i);
+        __stcs(g4 + i, make_float4(sg(v.x), sg(v.y), sg(v.z), sg(v.w)));
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        __stcs(gx + i, sg(__ldcs(x + i)));
+}
+
 __global__ void __launch_bounds__(256) bce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                                       size_t n, const float* __restrict__ tss,
                                                       const float* __restrict__ gout, float* __restrict__ gx) {
@@ -80,6 +140,7 @@ struct FgTerms {
     float wl, wr;   // DFL weights of this lane's side
     int tl;         // left DFL bin of this lane's side
     float w;        // anchor weight
+    int lab;        // sparse form: class index of the row's non-zero
 };
 
 __device__ __forceinline__ float group8_max(float v) {
@@ -105,10 +166,18 @@ __device__ __forceinline__ FgTerms fg_anchor(const LossParams& p, size_t idx, in
     const float d = wsum / sum;
     const float lse = m + logf(sum);
     r.p0 = e0 / sum, r.p1 = e1 / sum, r.d = d;
-    // anchor weight
+    // anchor weight: target_scores.sum(-1) (utils/loss.py:93) - in the sparse form the row's single non-zero
     float w = 0.f;
-    for (int c = lane; c < p.nc; c += 32) w += p.target_scores[idx * p.nc + c];
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (p.target_labels) {
+        long long lab = p.target_labels[idx];
+        lab = lab < 0 ? 0 : (lab >= p.nc ? p.nc - 1 : lab);
+        w = p.target_scores[idx * p.nc + lab];
+        r.lab = (int)lab;
+    } else {
+        for (int c = lane; c < p.nc; c += 32) w += p.target_scores[idx * p.nc + c];
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        r.lab = 0;
+    }
     r.w = w;
     // boxes in grid units
     const float ax = p.anchor_points[2 * a], ay = p.anchor_points[2 * a + 1], st = p.stride[a];
@@ -184,7 +253,7 @@ __global__ void __launch_bounds__(256) fg_fwd_kernel(const LossParams p, double*
     const long long n = (long long)p.b * p.A;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    double box = 0.0, dfl = 0.0;
+    double box = 0.0, dfl = 0.0, cls = 0.0;
     for (long long base = warp0 * 32; base < n; base += n_warps * 32) {
         const long long mine = base + lane;
         unsigned m = __ballot_sync(0xffffffffu, mine < n && p.fg_mask[mine]);
@@ -193,22 +262,27 @@ __global__ void __launch_bounds__(256) fg_fwd_kernel(const LossParams p, double*
             m &= m - 1;
             const size_t idx = (size_t)(base + k);
             const FgTerms t = fg_anchor<false>(p, idx, (int)(idx % (size_t)p.A), lane);
-            if (lane == 0) box += (double)t.box, dfl += (double)t.dfl;
+            if (lane == 0) {
+                box += (double)t.box, dfl += (double)t.dfl;
+                // sparse-target BCE: BCE(x, t) - BCE(x, 0) = -t x at the row's only non-zero target
+                if (p.target_labels) cls -= (double)(round_to(t.w, p.score_dtype) * p.pred_scores[idx * p.nc + t.lab]);
+            }
         }
     }
     block_add(box, sums + 0, s_red);
     block_add(dfl, sums + 2, s_red);
+    if (p.target_labels) block_add(cls, sums + 1, s_red);
 }
 
 // grad_pred_dist for every anchor: zeros for background rows, decode + CIoU + DFL chain for foreground.
 __global__ void __launch_bounds__(256) fg_bwd_kernel(const LossParams p, const float* __restrict__ gout,
-                                                     float* __restrict__ gdist) {
+                                                     float* __restrict__ gdist, float* gscores) {
     const int lane = threadIdx.x & 31;
     const long long n = (long long)p.b * p.A;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const float inv_tss = 1.f / fmaxf(*p.tss, 1.f);
-    const float g_box = gout[0] * inv_tss, g_dfl = gout[2] * inv_tss;
+    const float g_box = gout[0] * inv_tss, g_dfl = gout[2] * inv_tss, g_cls = gout[1] * inv_tss;
     for (long long base = warp0 * 32; base < n; base += n_warps * 32) {
         const long long mine = base + lane;
         const unsigned m = __ballot_sync(0xffffffffu, mine < n && p.fg_mask[mine]);
@@ -224,6 +298,8 @@ __global__ void __launch_bounds__(256) fg_bwd_kernel(const LossParams p, const f
                 g.x = gd * t.p0 * ((float)j0 - t.d) + gc * (t.p0 - (j0 == t.tl ? t.wl : 0.f) - (j0 == t.tl + 1 ? t.wr : 0.f));
                 g.y = gd * t.p1 * ((float)(j0 + 1) - t.d) +
                       gc * (t.p1 - (j0 + 1 == t.tl ? t.wl : 0.f) - (j0 + 1 == t.tl + 1 ? t.wr : 0.f));
+                // sparse-target BCE: the dense pass wrote sigmoid(x) * scale; the target's share goes in here
+                if (gscores && lane == 0) gscores[idx * p.nc + t.lab] -= round_to(t.w, p.score_dtype) * g_cls;
             }
             __stcs(reinterpret_cast<float2*>(gdist + idx * 64) + lane, g);
         }
@@ -250,26 +326,57 @@ static int check_loss_args(const LossParams& p, const char* who) {
     return 0;
 }
 
+static int loss_fwd(const LossParams& p, double* sums_ws, float* loss3, cudaStream_t st) {
+    KZD_CUDA(cudaMemsetAsync(sums_ws, 0, 3 * sizeof(double), st));
+    const size_t n = (size_t)p.b * p.A * p.nc;
+    const int cap = sm_count() * 8;
+    if (p.target_labels) {
+        const size_t n4 = ((uintptr_t)p.pred_scores) % 16 == 0 ? n / 4 : 0;
+        const size_t work = n4 ? n4 : n;
+        softplus_sum_kernel<<<(unsigned)((work + 255) / 256 < (size_t)cap ? (work + 255) / 256 : cap), 256, 0, st>>>(
+            p.pred_scores, n, n4, sums_ws);
+        KZD_LAUNCH_CHECK("softplus_sum_kernel");
+    } else {
+        bce_fwd_kernel<<<(unsigned)((n + 255) / 256 < (size_t)cap ? (n + 255) / 256 : cap), 256, 0, st>>>(
+            p.pred_scores, p.target_scores, n, sums_ws);
+        KZD_LAUNCH_CHECK("bce_fwd_kernel");
+    }
+    fg_fwd_kernel<<<cap, 256, 0, st>>>(p, sums_ws);
+    KZD_LAUNCH_CHECK("fg_fwd_kernel");
+    loss_finalize_kernel<<<1, 32, 0, st>>>(sums_ws, p.tss, loss3);
+    KZD_LAUNCH_CHECK("loss_finalize_kernel");
+    return 0;
+}
+
+static int loss_bwd(const LossParams& p, const float* grad_loss3, float* grad_pred_scores, float* grad_pred_dist,
+                    cudaStream_t st) {
+    const size_t n = (size_t)p.b * p.A * p.nc;
+    const int cap = sm_count() * 8;
+    if (p.target_labels) {
+        const size_t n4 = (((uintptr_t)p.pred_scores) | ((uintptr_t)grad_pred_scores)) % 16 == 0 ? n / 4 : 0;
+        const size_t work = n4 ? n4 : n;
+        sigmoid_grad_kernel<<<(unsigned)((work + 255) / 256 < (size_t)cap ? (work + 255) / 256 : cap), 256, 0, st>>>(
+            p.pred_scores, n, n4, p.tss, grad_loss3, grad_pred_scores);
+        KZD_LAUNCH_CHECK("sigmoid_grad_kernel");
+    } else {
+        bce_bwd_kernel<<<(unsigned)((n + 255) / 256 < (size_t)cap ? (n + 255) / 256 : cap), 256, 0, st>>>(
+            p.pred_scores, p.target_scores, n, p.tss, grad_loss3, grad_pred_scores);
+        KZD_LAUNCH_CHECK("bce_bwd_kernel");
+    }
+    fg_bwd_kernel<<<cap * 2, 256, 0, st>>>(p, grad_loss3, grad_pred_dist, p.target_labels ? grad_pred_scores : nullptr);
+    KZD_LAUNCH_CHECK("fg_bwd_kernel");
+    return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_fwd(
     const float* pred_scores, const float* pred_dist, const float* anchor_points, const float* stride_tensor,
     const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* target_scores_sum,
     int b, int A, int nc, double* sums_ws, float* loss3, void* stream) {
     LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
-                 target_scores_sum, b, A, nc};
+                 target_scores_sum, b, A, nc, nullptr, 0};
     if (int rc = check_loss_args(p, "kzd_loss_tail_fwd")) return rc;
     KZD_CHECK_ARG(sums_ws && loss3, "kzd_loss_tail_fwd: null output");
-    cudaStream_t st = (cudaStream_t)stream;
-    KZD_CUDA(cudaMemsetAsync(sums_ws, 0, 3 * sizeof(double), st));
-    const size_t n = (size_t)b * A * nc;
-    const int cap = sm_count() * 8;
-    bce_fwd_kernel<<<(unsigned)((n + 255) / 256 < (size_t)cap ? (n + 255) / 256 : cap), 256, 0, st>>>(
-        pred_scores, target_scores, n, sums_ws);
-    KZD_LAUNCH_CHECK("bce_fwd_kernel");
-    fg_fwd_kernel<<<cap, 256, 0, st>>>(p, sums_ws);
-    KZD_LAUNCH_CHECK("fg_fwd_kernel");
-    loss_finalize_kernel<<<1, 32, 0, st>>>(sums_ws, target_scores_sum, loss3);
-    KZD_LAUNCH_CHECK("loss_finalize_kernel");
-    return 0;
+    return loss_fwd(p, sums_ws, loss3, (cudaStream_t)stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_bwd(
@@ -277,17 +384,35 @@ extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_bwd(
     const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* target_scores_sum,
     int b, int A, int nc, const float* grad_loss3, float* grad_pred_scores, float* grad_pred_dist, void* stream) {
     LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
-                 target_scores_sum, b, A, nc};
+                 target_scores_sum, b, A, nc, nullptr, 0};
     if (int rc = check_loss_args(p, "kzd_loss_tail_bwd")) return rc;
     KZD_CHECK_ARG(grad_loss3 && grad_pred_scores && grad_pred_dist, "kzd_loss_tail_bwd: null pointer");
     KZD_CHECK_ARG(((uintptr_t)grad_pred_dist) % 8 == 0, "kzd_loss_tail_bwd: misaligned grad_pred_dist");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)b * A * nc;
-    const int cap = sm_count() * 8;
-    bce_bwd_kernel<<<(unsigned)((n + 255) / 256 < (size_t)cap ? (n + 255) / 256 : cap), 256, 0, st>>>(
-        pred_scores, target_scores, n, target_scores_sum, grad_loss3, grad_pred_scores);
-    KZD_LAUNCH_CHECK("bce_bwd_kernel");
-    fg_bwd_kernel<<<cap * 2, 256, 0, st>>>(p, grad_loss3, grad_pred_dist);
-    KZD_LAUNCH_CHECK("fg_bwd_kernel");
-    return 0;
+    return loss_bwd(p, grad_loss3, grad_pred_scores, grad_pred_dist, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_sparse_fwd(
+    const float* pred_scores, const float* pred_dist, const float* anchor_points, const float* stride_tensor,
+    const float* target_bboxes, const float* target_scores, const int64_t* target_labels, const uint8_t* fg_mask,
+    const float* target_scores_sum, int b, int A, int nc, int score_dtype, double* sums_ws, float* loss3, void* stream) {
+    LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
+                 target_scores_sum, b, A, nc, (const long long*)target_labels, score_dtype};
+    if (int rc = check_loss_args(p, "kzd_loss_tail_sparse_fwd")) return rc;
+    KZD_CHECK_ARG(target_labels && sums_ws && loss3, "kzd_loss_tail_sparse_fwd: null pointer");
+    KZD_CHECK_ARG(score_dtype >= 0 && score_dtype <= 2, "kzd_loss_tail_sparse_fwd: score_dtype=%d not in {0,1,2}", score_dtype);
+    return loss_fwd(p, sums_ws, loss3, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_sparse_bwd(
+    const float* pred_scores, const float* pred_dist, const float* anchor_points, const float* stride_tensor,
+    const float* target_bboxes, const float* target_scores, const int64_t* target_labels, const uint8_t* fg_mask,
+    const float* target_scores_sum, int b, int A, int nc, int score_dtype, const float* grad_loss3,
+    float* grad_pred_scores, float* grad_pred_dist, void* stream) {
+    LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
+                 target_scores_sum, b, A, nc, (const long long*)target_labels, score_dtype};
+    if (int rc = check_loss_args(p, "kzd_loss_tail_sparse_bwd")) return rc;
+    KZD_CHECK_ARG(target_labels && grad_loss3 && grad_pred_scores && grad_pred_dist, "kzd_loss_tail_sparse_bwd: null pointer");
+    KZD_CHECK_ARG(((uintptr_t)grad_pred_dist) % 8 == 0, "kzd_loss_tail_sparse_bwd: misaligned grad_pred_dist");
+    KZD_CHECK_ARG(score_dtype >= 0 && score_dtype <= 2, "kzd_loss_tail_sparse_bwd: score_dtype=%d not in {0,1,2}", score_dtype);
+    return loss_bwd(p, grad_loss3, grad_pred_scores, grad_pred_dist, (cudaStream_t)stream);
 }

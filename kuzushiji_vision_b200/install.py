@@ -10,6 +10,8 @@ attributes, patched here and restored by ``uninstall()``:
   ultralytics.nn.modules.head.Detect._inference      <- head.detect_inference  (nn/modules/head.py:100)
   ultralytics.utils.ops.non_max_suppression    <- ops.non_max_suppression      (utils/ops.py:167)
   ultralytics.utils.loss.v8DetectionLoss.preprocess  <- loss.preprocess         (utils/loss.py:180)
+  ultralytics.models.yolo.detect.val.DetectionValidator._process_batch <- ops.process_batch
+                                                     (models/yolo/detect/val.py:209; only with patch_validator=True)
 
 Calls that are outside this path's scope (CPU tensors, rotated boxes, masks, export formats) are
 handed to the reference's own, unpatched function - they never reach libkzd and libkzd never
@@ -50,7 +52,7 @@ def detect_in_scope(module, detect_cls):
     return getattr(module, "no", None) == getattr(module, "nc", 0) + 4 * _head.REG_MAX
 
 
-def install(patch_decode_train=True, patch_preprocess=True):
+def install(patch_decode_train=True, patch_preprocess=True, patch_validator=False):
     """Patch the importable ``ultralytics``; returns the list of patched attribute names."""
     if _saved:
         return sorted(_saved)
@@ -115,6 +117,22 @@ def install(patch_decode_train=True, patch_preprocess=True):
     if patch_preprocess:
         _saved["loss.v8DetectionLoss.preprocess"] = (u_loss.v8DetectionLoss, "preprocess", ref_preprocess)
         u_loss.v8DetectionLoss.preprocess = preprocess
+    if patch_validator:
+        # the validator module pulls in the whole engine (datasets, cv2, ...): optional, skipped when it does not import
+        try:
+            u_val = importlib.import_module("ultralytics.models.yolo.detect.val")
+        except Exception:
+            u_val = None
+        if u_val is not None:
+            ref_process_batch = u_val.DetectionValidator._process_batch
+
+            def _process_batch(self, detections, gt_bboxes, gt_cls):
+                if not (_is_cuda(detections) and _is_cuda(gt_bboxes)):
+                    return ref_process_batch(self, detections, gt_bboxes, gt_cls)
+                return _ops.process_batch(detections, gt_bboxes, gt_cls, self.iouv)
+
+            _saved["val.DetectionValidator._process_batch"] = (u_val.DetectionValidator, "_process_batch", ref_process_batch)
+            u_val.DetectionValidator._process_batch = _process_batch
     return sorted(_saved)
 
 

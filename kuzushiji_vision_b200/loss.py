@@ -1,6 +1,7 @@
 """Drop-ins for the parts of ``v8DetectionLoss`` next to the hot path.
 
-Reference: ``yolov12/ultralytics/utils/loss.py`` - ``preprocess`` :180-195.
+Reference: ``yolov12/ultralytics/utils/loss.py`` - ``preprocess`` :180-195, the loss tail :243-258
+(``BboxLoss`` :91-113, ``DFLoss`` :65-88).
 """
 from __future__ import annotations
 
@@ -63,7 +64,7 @@ def loss_preprocess(self, targets, batch_size, scale_tensor):
 class _LossTailFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred_scores, pred_distri, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
-                target_scores_sum):
+                target_scores_sum, target_labels, score_dtype):
         b, A, nc = pred_scores.shape
         dev = pred_scores.device
         f32 = torch.float32
@@ -75,43 +76,67 @@ class _LossTailFn(torch.autograd.Function):
         ts = target_scores.to(f32).contiguous()
         fg = fg_mask.contiguous().view(torch.uint8)
         tss = target_scores_sum.to(f32).reshape(1).contiguous()
+        tl = None if target_labels is None else target_labels.to(torch.int64).contiguous()
         sums = torch.empty(3, dtype=torch.float64, device=dev)
         loss3 = torch.empty(3, dtype=f32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib.kzd_loss_tail_fwd(ps.data_ptr(), pd.data_ptr(), anc.data_ptr(), st.data_ptr(),
-                                                  tb.data_ptr(), ts.data_ptr(), fg.data_ptr(), tss.data_ptr(), b, A, nc,
-                                                  sums.data_ptr(), loss3.data_ptr(), _stream(dev)), "kzd_loss_tail_fwd")
-        ctx.save_for_backward(ps, pd, anc, st, tb, ts, fg, tss)
+            if tl is None:
+                _lib.check(_lib.lib.kzd_loss_tail_fwd(ps.data_ptr(), pd.data_ptr(), anc.data_ptr(), st.data_ptr(),
+                                                      tb.data_ptr(), ts.data_ptr(), fg.data_ptr(), tss.data_ptr(), b, A, nc,
+                                                      sums.data_ptr(), loss3.data_ptr(), _stream(dev)), "kzd_loss_tail_fwd")
+            else:
+                _lib.check(_lib.lib.kzd_loss_tail_sparse_fwd(ps.data_ptr(), pd.data_ptr(), anc.data_ptr(), st.data_ptr(),
+                                                             tb.data_ptr(), ts.data_ptr(), tl.data_ptr(), fg.data_ptr(),
+                                                             tss.data_ptr(), b, A, nc, int(score_dtype), sums.data_ptr(),
+                                                             loss3.data_ptr(), _stream(dev)), "kzd_loss_tail_sparse_fwd")
+        ctx.save_for_backward(ps, pd, anc, st, tb, ts, fg, tss, *(() if tl is None else (tl,)))
         ctx.dtypes = (pred_scores.dtype, pred_distri.dtype)
+        ctx.score_dtype = int(score_dtype)
         return loss3
 
     @staticmethod
     def backward(ctx, grad_loss3):
-        ps, pd, anc, st, tb, ts, fg, tss = ctx.saved_tensors
+        ps, pd, anc, st, tb, ts, fg, tss, *rest = ctx.saved_tensors
         b, A, nc = ps.shape
         dev = ps.device
         g = grad_loss3.to(torch.float32).contiguous()
         g_ps, g_pd = torch.empty_like(ps), torch.empty_like(pd)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib.kzd_loss_tail_bwd(ps.data_ptr(), pd.data_ptr(), anc.data_ptr(), st.data_ptr(),
-                                                  tb.data_ptr(), ts.data_ptr(), fg.data_ptr(), tss.data_ptr(), b, A, nc,
-                                                  g.data_ptr(), g_ps.data_ptr(), g_pd.data_ptr(), _stream(dev)),
-                       "kzd_loss_tail_bwd")
-        return g_ps.to(ctx.dtypes[0]), g_pd.to(ctx.dtypes[1]), None, None, None, None, None, None
+            if not rest:
+                _lib.check(_lib.lib.kzd_loss_tail_bwd(ps.data_ptr(), pd.data_ptr(), anc.data_ptr(), st.data_ptr(),
+                                                      tb.data_ptr(), ts.data_ptr(), fg.data_ptr(), tss.data_ptr(), b, A, nc,
+                                                      g.data_ptr(), g_ps.data_ptr(), g_pd.data_ptr(), _stream(dev)),
+                           "kzd_loss_tail_bwd")
+            else:
+                _lib.check(_lib.lib.kzd_loss_tail_sparse_bwd(ps.data_ptr(), pd.data_ptr(), anc.data_ptr(), st.data_ptr(),
+                                                             tb.data_ptr(), ts.data_ptr(), rest[0].data_ptr(), fg.data_ptr(),
+                                                             tss.data_ptr(), b, A, nc, ctx.score_dtype, g.data_ptr(),
+                                                             g_ps.data_ptr(), g_pd.data_ptr(), _stream(dev)),
+                           "kzd_loss_tail_sparse_bwd")
+        return g_ps.to(ctx.dtypes[0]), g_pd.to(ctx.dtypes[1]), None, None, None, None, None, None, None, None
 
 
 def loss_tail(pred_scores, pred_distri, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
-              target_scores_sum=None):
+              target_scores_sum=None, target_labels=None, score_dtype=None):
     """Fused BCE + CIoU + DFL losses on assigned targets (utils/loss.py:243-254): returns a ``(3,)`` tensor
     ``[box, cls, dfl]`` before the ``hyp`` gains, differentiable wrt ``pred_scores`` (logits, (b,A,nc)) and
     ``pred_distri`` ((b,A,64)). ``target_bboxes`` are the assigner's pixel-space boxes (divided by
     ``stride_tensor`` inside); ``target_scores_sum`` defaults to ``target_scores.sum()`` (a device scalar -
-    e.g. ``assigner.counters[0]`` - avoids that extra pass; ``max(., 1)`` is applied in the kernel)."""
+    e.g. ``assigner.counters[0]`` - avoids that extra pass; ``max(., 1)`` is applied in the kernel).
+
+    Sparse-target form: with ``target_labels`` (the assigner's first output) the BCE never reads the dense
+    ``(b,A,nc)`` ``target_scores``: ``BCE(x, t) = softplus(x) - t x``, the first term is one streaming pass over
+    ``pred_scores`` and the second only exists at the foreground ``(anchor, target_labels[anchor])`` elements.
+    It relies on what ``TaskAlignedAssigner`` guarantees (utils/tal.py:228-236): a foreground row of
+    ``target_scores`` is one-hot at the anchor's target label, background rows are zero. ``score_dtype``: dtype
+    the reference rounds the BCE target to under AMP (``target_scores.to(dtype)``, utils/loss.py:247; the box /
+    DFL weight keeps the fp32 scores, :93) - default ``pred_scores.dtype``; pass fp32 ``target_scores``."""
     _lib.require_cuda(pred_scores, "pred_scores")
     if target_scores_sum is None:
         target_scores_sum = target_scores.sum()
+    code = _lib.dtype_code(pred_scores.dtype if score_dtype is None else score_dtype)
     return _LossTailFn.apply(pred_scores, pred_distri, anchor_points, stride_tensor, target_bboxes, target_scores,
-                             fg_mask, target_scores_sum)
+                             fg_mask, target_scores_sum, target_labels, code)
 
 
 class DetectionLoss:
@@ -168,10 +193,13 @@ class DetectionLoss:
         mask_gt = gt_bboxes.sum(2, keepdim=True).gt_(0.0)
 
         pred_bboxes, pd_bboxes_px = bbox_decode(anchor_points, pred_distri, stride_tensor)
-        _, target_bboxes, target_scores, fg_mask, _ = self.assigner(
+        target_labels, target_bboxes, target_scores, fg_mask, _ = self.assigner(
             pred_scores.detach().sigmoid(), pd_bboxes_px, anc_px, gt_labels, gt_bboxes, mask_gt)
-        tss = self.assigner.counters[0] if gt_bboxes.shape[1] else target_scores.sum()
-        loss3 = loss_tail(pred_scores, pred_distri, anchor_points, stride_tensor, target_bboxes,
-                          target_scores.to(dtype), fg_mask.bool() if fg_mask.dtype != torch.bool else fg_mask, tss)
+        tss = self.assigner.counters[0]
+        # sparse-target BCE: the dense target_scores is never read (only its foreground (anchor, label) elements);
+        # under AMP the BCE target is rounded to the logits' dtype inside the kernel, the box / DFL weight is not
+        loss3 = loss_tail(pred_scores, pred_distri, anchor_points, stride_tensor, target_bboxes, target_scores,
+                          fg_mask.bool() if fg_mask.dtype != torch.bool else fg_mask, tss,
+                          target_labels=target_labels.long(), score_dtype=dtype)
         loss = loss3 * torch.tensor([self.box, self.cls, self.dfl], device=dev, dtype=loss3.dtype)
         return loss.sum() * bs, loss.detach()

@@ -172,3 +172,46 @@ def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None, padding=True, xyw
         _lib.check(_lib.lib.kzd_scale_boxes(boxes.data_ptr(), None, 1, boxes.shape[0], boxes.stride(0),
                                             params.data_ptr(), _stream(dev)), "kzd_scale_boxes")
     return boxes
+
+
+# ------------------------------------------------------------------------------------------------
+# validator matching (models/yolo/detect/val.py:209-228, engine/validator.py:222-260)
+# ------------------------------------------------------------------------------------------------
+
+def match_predictions_batched(det_rows, n_keep, gt, n_gt, iouv):
+    """True-positive flags of a whole batch's kept detections: ``det_rows (b, max_det, >=6)`` as ``nms_batched``
+    returns them (descending confidence; already in the labels' coordinate space, e.g. after
+    ``scale_boxes_batched``), ``n_keep`` kept counts (list / tensor / None = all rows), ``gt (b, G, 5)``
+    ``[cls, x1,y1,x2,y2]`` zero-padded labels with ``n_gt`` labels per image, ``iouv`` the IoU thresholds
+    (``torch.linspace(0.5, 0.95, 10)`` in the reference, engine/validator.py:97). Returns bool ``(b, max_det,
+    n_iou)`` - row ``d`` of image ``i`` is what ``DetectionValidator._process_batch`` gives for that detection."""
+    _lib.require_cuda(det_rows, "det_rows")
+    b, max_det, stride = det_rows.shape
+    dev = det_rows.device
+    det = det_rows if (det_rows.dtype == torch.float32 and det_rows.is_contiguous()) else det_rows.float().contiguous()
+    gt = gt.to(device=dev, dtype=torch.float32).contiguous()
+    G = gt.shape[1]
+    cnt = None if n_keep is None else torch.as_tensor(n_keep, dtype=torch.int32).to(dev)
+    gcnt = torch.as_tensor(n_gt, dtype=torch.int32).to(dev)
+    thr = torch.as_tensor(iouv, dtype=torch.float32).to(dev).contiguous()
+    n_iou = thr.numel()
+    correct = torch.empty((b, max_det, n_iou), dtype=torch.uint8, device=dev)
+    ws_bytes = _lib.lib.kzd_match_workspace_bytes(b, max_det, G, n_iou)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.kzd_match_predictions(det.data_ptr(), cnt.data_ptr() if cnt is not None else None, b, max_det,
+                                                  stride, gt.data_ptr() if G else None, gcnt.data_ptr(), G, thr.data_ptr(),
+                                                  n_iou, correct.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev)),
+                   "kzd_match_predictions")
+    return correct.view(torch.bool)
+
+
+def process_batch(detections, gt_bboxes, gt_cls, iouv):
+    """Drop-in body for ``DetectionValidator._process_batch(self, detections, gt_bboxes, gt_cls)`` on one image's
+    CUDA tensors (models/yolo/detect/val.py:209-228): ``detections (N, 6)``, ``gt_bboxes (M, 4)``, ``gt_cls (M,)``
+    -> bool ``(N, len(iouv))``."""
+    n, m = detections.shape[0], gt_bboxes.shape[0]
+    if n == 0:
+        return torch.zeros((0, len(iouv)), dtype=torch.bool, device=detections.device)
+    gt = torch.cat((gt_cls.reshape(m, 1).float(), gt_bboxes.reshape(m, 4).float()), 1).unsqueeze(0)
+    return match_predictions_batched(detections[:, :6].unsqueeze(0), None, gt, [m], iouv)[0]

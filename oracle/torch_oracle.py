@@ -372,14 +372,17 @@ def ciou_generic(box1, box2):
     return iou - (rho2 / c2 + v * alpha)
 
 
-def loss_tail(pred_scores, pred_distri, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask):
+def loss_tail(pred_scores, pred_distri, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
+              target_scores_sum=None):
     """[box, cls, dfl] before the hyp gains, restating utils/loss.py:243-254 with BboxLoss.forward
-    (:99-113), DFLoss (:72-88) and bbox2dist (utils/tal.py:360-363). ``target_bboxes`` in pixels."""
+    (:99-113), DFLoss (:72-88) and bbox2dist (utils/tal.py:360-363). ``target_bboxes`` in pixels.
+    ``target_scores_sum``: the normaliser when it is not ``target_scores.sum()`` (under AMP the reference sums
+    the fp32 scores, utils/loss.py:243, but feeds the BCE their rounded copy, :247)."""
     import torch.nn.functional as F
 
     reg_max = REG_MAX
     pred_bboxes = decode_train(pred_distri, anchor_points)
-    tss = target_scores.sum().clamp(min=1)
+    tss = (target_scores.sum() if target_scores_sum is None else target_scores_sum).clamp(min=1)
     cls = F.binary_cross_entropy_with_logits(pred_scores, target_scores, reduction="none").sum() / tss
     box = pred_scores.new_zeros(())
     dfl = pred_scores.new_zeros(())
@@ -422,3 +425,47 @@ def scale_boxes(img1_shape, boxes, img0_shape):
     boxes[..., 2] = boxes[..., 2].clamp(0, img0_shape[1])
     boxes[..., 3] = boxes[..., 3].clamp(0, img0_shape[0])
     return boxes
+
+
+# --------------------------------------------------------------------------------------
+# validator matching  (utils/metrics.py:52-71, models/yolo/detect/val.py:209-228,
+# engine/validator.py:222-260 with use_scipy=False)
+# --------------------------------------------------------------------------------------
+
+
+def box_iou(box1, box2, eps=1e-7):
+    """Pairwise IoU (N,4) x (M,4) -> (N,M), every op its own fp32 rounding (utils/metrics.py:67-71)."""
+    a1, a2 = box1.float().unsqueeze(1).chunk(2, 2)
+    b1, b2 = box2.float().unsqueeze(0).chunk(2, 2)
+    inter = (torch.min(a2, b2) - torch.max(a1, b1)).clamp_(0).prod(2)
+    return inter / ((a2 - a1).prod(2) + (b2 - b1).prod(2) - inter + eps)
+
+
+def match_predictions(pred_classes, true_classes, iou, iouv):
+    """(N, n_iou) bool: engine/validator.py:236-260 restated. ``iou`` is (labels, detections). Per threshold:
+    matches = pairs of equal class with IoU >= threshold, ordered by IoU descending; each detection keeps its
+    first match, then - in ascending detection order - each label keeps its first detection."""
+    import numpy as np
+
+    correct = np.zeros((pred_classes.shape[0], len(iouv)), dtype=bool)
+    correct_class = true_classes[:, None] == pred_classes
+    iou = (iou * correct_class).cpu().numpy()
+    for i, threshold in enumerate(torch.as_tensor(iouv).cpu().tolist()):
+        lab, det = np.nonzero(iou >= threshold)
+        if lab.shape[0] == 0:
+            continue
+        if lab.shape[0] > 1:
+            order = iou[lab, det].argsort()[::-1]                    # IoU descending
+            lab, det = lab[order], det[order]
+            keep = np.unique(det, return_index=True)[1]              # first (= best) match of every detection
+            lab, det = lab[keep], det[keep]                          # now in ascending detection order
+            keep = np.unique(lab, return_index=True)[1]              # first detection of every label
+            lab, det = lab[keep], det[keep]
+        correct[det.astype(int), i] = True
+    return torch.tensor(correct, dtype=torch.bool, device=pred_classes.device)
+
+
+def process_batch(detections, gt_bboxes, gt_cls, iouv):
+    """DetectionValidator._process_batch (models/yolo/detect/val.py:226-228)."""
+    iou = box_iou(gt_bboxes, detections[:, :4])
+    return match_predictions(detections[:, 5], gt_cls, iou, iouv)

@@ -7,6 +7,8 @@ reference's own functions return on CPU, fp32, torch 2.11.0 / torchvision 0.26.0
   v8DetectionLoss.bbox_decode  (utils/loss.py:197)  - called as an unbound function on a stub
   Detect._inference            (nn/modules/head.py:100)
   ops.non_max_suppression      (utils/ops.py:167)
+  DetectionValidator._process_batch (models/yolo/detect/val.py:209) + BaseValidator.match_predictions
+                               (engine/validator.py:222)
 Inputs are stored next to the outputs so the fixtures do not depend on the generator staying fixed.
 """
 import os
@@ -126,13 +128,57 @@ def edge_case(R):
     print("assign_edge fg", int(out[3].sum()))
 
 
+def match_case(R, name="match_val", seed=5):
+    """DetectionValidator._process_batch (models/yolo/detect/val.py:209-228) = box_iou + BaseValidator.
+    match_predictions (engine/validator.py:222-260) of the unmodified reference, called as unbound functions on a
+    stub that carries ``iouv``. Images with jittered copies of the labels as detections (descending confidence),
+    duplicates competing for one label, wrong-class detections, images without labels / without detections."""
+    import importlib
+
+    val = importlib.import_module("ultralytics.models.yolo.detect.val")
+    iouv = torch.linspace(0.5, 0.95, 10)
+    stub = types.SimpleNamespace(iouv=iouv)
+    stub.match_predictions = types.MethodType(val.DetectionValidator.match_predictions, stub)
+    g = torch.Generator().manual_seed(seed)
+    out = {"iouv": np_(iouv)}
+    cases = [(40, 90, 3), (120, 300, 1), (0, 25, 2), (30, 0, 2), (7, 7, 5), (200, 260, 8)]
+    for k, (m, n, nc) in enumerate(cases):
+        xy = torch.rand(m, 2, generator=g) * 900 + 20
+        wh = torch.rand(m, 2, generator=g) * 80 + 12
+        gt = torch.cat((xy, xy + wh), 1)
+        gcls = torch.randint(0, nc, (m,), generator=g).float()
+        if m and n:
+            src = torch.randint(0, m, (n,), generator=g)
+            jit = (torch.rand(n, 4, generator=g) - 0.5) * wh[src].repeat(1, 2) * 0.35
+            box = gt[src] + jit
+            cls = torch.where(torch.rand(n, generator=g) < 0.85, gcls[src], torch.randint(0, nc, (n,), generator=g).float())
+        else:
+            bx = torch.rand(n, 2, generator=g) * 900
+            box = torch.cat((bx, bx + 40), 1)
+            cls = torch.zeros(n)
+        conf = torch.rand(n, generator=g).sort(descending=True).values
+        det = torch.cat((box, conf[:, None], cls[:, None]), 1)
+        if n and m:
+            correct = val.DetectionValidator._process_batch(stub, det, gt, gcls)
+        else:
+            correct = torch.zeros((n, 10), dtype=torch.bool)  # update_metrics skips the call (detect/val.py:135-158)
+        out[f"det{k}"], out[f"gt{k}"], out[f"gcls{k}"], out[f"correct{k}"] = np_(det), np_(gt), np_(gcls), np_(correct)
+        print(name, k, "labels", m, "detections", n, "tp@0.5", int(correct[:, 0].sum()) if n else 0)
+    out["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+
+
 def main():
     R = ref_loader.load()
+    if "--match-only" in sys.argv:
+        match_case(R)
+        return
     y1 = assign_case(R, "path_p3p5_nc1", 2, 40, 320, 1, synth.P3_P5, "columns", seed=11)
     y2 = assign_case(R, "path_p2p5_nc5", 1, 30, 256, 5, synth.P2_P5, "uniform", seed=12)
     assign_case(R, "path_p2p5_topk13", 1, 24, 256, 3, synth.P2_P5, "columns", seed=13, topk=13, alpha=1.0)
     micro_case(R)
     edge_case(R)
+    match_case(R)
     nms_case(R, "nms_nc1", y1, conf_thres=0.5, iou_thres=0.7, max_det=300)
     nms_case(R, "nms_nc5", y2, conf_thres=0.6, iou_thres=0.45, max_det=100)
     nms_case(R, "nms_nc5_agnostic", y2, conf_thres=0.7, iou_thres=0.5, max_det=1000, agnostic=True)

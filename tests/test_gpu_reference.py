@@ -220,3 +220,33 @@ def test_install_leaves_out_of_scope_heads_to_the_reference(R):
         assert inst.detect_in_scope(seg, R.Detect)  # Segment / Pose use the plain Detect decode
     finally:
         kzd.uninstall()
+
+
+def test_validator_process_batch_patched_on_the_real_package(R):
+    """install(patch_validator=True) replaces DetectionValidator._process_batch (models/yolo/detect/val.py:209):
+    same (N, 10) bool matrix as the reference's own numpy matching, on CUDA detections."""
+    import importlib
+
+    val = importlib.import_module("ultralytics.models.yolo.detect.val")
+    iouv = torch.linspace(0.5, 0.95, 10, device=DEV)
+    stub = types.SimpleNamespace(iouv=iouv)
+    stub.match_predictions = types.MethodType(val.DetectionValidator.match_predictions, stub)
+    b, nc, imgsz, strides = 2, 2, 640, synth.P2_P5
+    lv = synth.head_outputs(b, nc, imgsz, strides, seed=92, device=DEV, sparse_cls=400)
+    dets = kzd.non_max_suppression(kzd.decode_inference(lv, strides, nc), 0.25, 0.6, max_det=300)
+    g = torch.Generator().manual_seed(4)
+    cases = []
+    for det in dets:
+        pick = torch.randint(0, det.shape[0], (60,), generator=g).to(DEV)
+        gt = det[pick, :4] + ((torch.rand(60, 4, generator=g) - 0.5) * 16).to(DEV)
+        cases.append((det, gt, det[pick, 5].clone()))
+    ref = [val.DetectionValidator._process_batch(stub, *c) for c in cases]
+    names = kzd.install(patch_validator=True)
+    try:
+        assert len(names) == 7
+        got = [val.DetectionValidator._process_batch(stub, *c) for c in cases]
+    finally:
+        kzd.uninstall()
+    for a, r in zip(got, ref):
+        assert a.dtype == torch.bool and a.device == r.device and torch.equal(a, r)
+    assert any(r.any() for r in ref)

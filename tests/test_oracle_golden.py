@@ -90,3 +90,17 @@ def test_assign_g0_branch():
                        torch.zeros(2, 0, 4), torch.zeros(2, 0, 1), 10, 3)
     assert all(o.dtype == torch.float32 for o in out)
     assert (out[0] == 3).all() and out[2].shape == (2, 50, 3)
+
+
+def test_validator_matching_matches_reference_golden():
+    """oracle.process_batch (box_iou + match_predictions restated) against what the unmodified reference's
+    DetectionValidator._process_batch returned (tests/golden/make_golden.py::match_case)."""
+    g = load_golden("match_val")
+    iouv = g["iouv"]
+    for k in range(int(g["n_cases"])):
+        det, gt, gcls, want = g[f"det{k}"], g[f"gt{k}"], g[f"gcls{k}"], g[f"correct{k}"]
+        if det.shape[0] == 0 or gt.shape[0] == 0:
+            assert not want.any()
+            continue
+        got = O.process_batch(det, gt, gcls, iouv)
+        assert got.dtype == torch.bool and torch.equal(got, want), k

@@ -102,3 +102,26 @@ def test_scale_boxes_live(R):
     for img1, img0 in [((640, 640), (1080, 1920, 3)), ((320, 512), (700, 500)), ((1280, 1280), (333, 333))]:
         ref = R.ops.scale_boxes(img1, boxes.clone(), img0)
         assert torch.equal(ref, O.scale_boxes(img1, boxes.clone(), img0))
+
+
+def test_validator_matching_live(R):
+    """box_iou / match_predictions restatement against the reference's own functions on random cases."""
+    import importlib
+    import types
+
+    val = importlib.import_module("ultralytics.models.yolo.detect.val")
+    iouv = torch.linspace(0.5, 0.95, 10)
+    stub = types.SimpleNamespace(iouv=iouv)
+    stub.match_predictions = types.MethodType(val.DetectionValidator.match_predictions, stub)
+    g = torch.Generator().manual_seed(21)
+    for m, n, nc in ((25, 60, 2), (80, 200, 1), (3, 1, 1)):
+        xy = torch.rand(m, 2, generator=g) * 500
+        wh = torch.rand(m, 2, generator=g) * 60 + 10
+        gt = torch.cat((xy, xy + wh), 1)
+        gcls = torch.randint(0, nc, (m,), generator=g).float()
+        src = torch.randint(0, m, (n,), generator=g)
+        box = gt[src] + (torch.rand(n, 4, generator=g) - 0.5) * 12
+        det = torch.cat((box, torch.rand(n, 1, generator=g).sort(0, descending=True).values,
+                         torch.randint(0, nc, (n, 1), generator=g).float()), 1)
+        assert torch.equal(O.box_iou(gt, det[:, :4]), R.metrics.box_iou(gt, det[:, :4]))
+        assert torch.equal(O.process_batch(det, gt, gcls, iouv), val.DetectionValidator._process_batch(stub, det, gt, gcls))

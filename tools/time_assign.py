@@ -21,3 +21,16 @@ for i in range(22):
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     if i>=2: tot+=e0.elapsed_time(e1)
 print(sys.argv[1] if len(sys.argv)>1 else "", "assign graph us:", round(tot/20*1e3,1), "fg", int(out[3].sum()))
+# per-kernel device times of the same graph replays (CUPTI), L2 flushed before each replay
+import collections
+from torch.profiler import ProfilerActivity, profile
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for i in range(10):
+        flush.zero_(); g.replay()
+    torch.cuda.synchronize()
+agg = collections.OrderedDict()
+for e in prof.events():
+    if e.device_type.name != "CUDA" or "Memset" in e.name or "Memcpy" in e.name or "fill" in e.name.lower() or "zero" in e.name.lower():
+        continue
+    agg.setdefault(e.name.replace("kzd::", "").split("(")[0], []).append(e.device_time if hasattr(e, "device_time") else e.cuda_time)
+print(sys.argv[1] if len(sys.argv) > 1 else "", "kernels:", {k[-28:]: round(sum(v) / len(v), 1) for k, v in agg.items()})
