@@ -167,6 +167,15 @@ int kzd_nms_filter(float* prediction, int b, int A, int nc, float conf_thres, in
                    uint64_t* cand_keys, float* cand_rows, int32_t* cand_counts, int cand_cap,
                    void* stream);
 
+/* Apriori labels of the autolabelling path (utils/ops.py:256-261, `labels=` of non_max_suppression; the validator
+ * passes them with save_hybrid, models/yolo/detect/val.py:55-64,92-102): labels (b, L, 5) rows [cls, cx, cy, w, h]
+ * in pixels, zero padded, label_counts int32 (b). Every label joins its image's candidate pool as a detection
+ * of its class with confidence 1.0, ordered after the image's predictions (as the reference's torch.cat leaves
+ * them). Call between kzd_nms_filter (same A, nc, conf_thres, multi_label, classes) and kzd_nms_suppress. */
+int kzd_nms_append_labels(const float* labels, const int32_t* label_counts, int b, int L, int A, int nc,
+                          float conf_thres, int multi_label, const int32_t* classes, int n_classes,
+                          uint64_t* cand_keys, float* cand_rows, int32_t* cand_counts, int cand_cap, void* stream);
+
 size_t kzd_nms_workspace_bytes(int b, int cand_cap, int n_cap);
 
 /* Stage 2 (utils/ops.py:285-311 + torchvision.ops.nms): per image, order the candidates by
@@ -200,7 +209,8 @@ int kzd_gt_pack(const float* targets, int n, int b, int G, const float* scale4, 
 /* Post-NMS tail: ops.scale_boxes (utils/ops.py:92-127, padding=True, xywh=False) + clip_boxes
  * (:319-338) for all detections of a batch, in place (models/yolo/detect/predict.py:37-41 does it per
  * image). rows (b, max_det, row_stride) with the xyxy box in columns 0..3; counts (b) int32 or NULL (all
- * rows); params (b,5) device floats = [pad_x, pad_y, gain, w0, h0] of each image. */
+ * rows); params (b,5) device floats = [pad_x, pad_y, 1/gain, w0, h0] of each image, 1/gain evaluated in double
+ * precision and rounded to fp32 (that is how aten's `boxes /= gain` with a host scalar multiplies). */
 int kzd_scale_boxes(float* rows, const int32_t* counts, int b, int max_det, int row_stride,
                     const float* params, void* stream);
 

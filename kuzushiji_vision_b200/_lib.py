@@ -49,6 +49,7 @@ def _load():
         "kzd_assign_report_offset": (sz, [i32, i32]),
         "kzd_tal_assign": (C.c_int, [vp] * 6 + [i32] * 5 + [f32] * 3 + [C.POINTER(Level), i32, i32, i32] + [vp] * 6 + [vp, sz, i32, vp]),
         "kzd_nms_filter": (C.c_int, [vp, i32, i32, i32, f32, i32, vp, i32, i32, vp, vp, vp, i32, vp]),
+        "kzd_nms_append_labels": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, i32, vp, i32, vp, vp, vp, i32, vp]),
         "kzd_nms_workspace_bytes": (sz, [i32, i32, i32]),
         "kzd_gt_count": (C.c_int, [vp, i32, i32, vp, vp, vp, vp]),
         "kzd_gt_pack": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),

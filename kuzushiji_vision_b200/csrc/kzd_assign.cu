@@ -823,6 +823,9 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
         const long long warps = (long long)b * G;
         long long blocks = (warps * 32 + CAND_THREADS - 1) / CAND_THREADS;
         if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;  // the kernel strides over the rest
+#ifdef KZD_CAND_PERSIST
+        if (blocks > (long long)sm_count() * KZD_CAND_PERSIST) blocks = (long long)sm_count() * KZD_CAND_PERSIST;
+#endif
         assign_candidates_kernel<<<(unsigned)blocks, CAND_THREADS, 0, st>>>(p);
         KZD_LAUNCH_CHECK("assign_candidates_kernel");
     }

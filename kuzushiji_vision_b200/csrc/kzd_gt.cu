@@ -97,7 +97,9 @@ __global__ void scale_boxes_kernel(float* __restrict__ rows, const int32_t* __re
     const int bi = idx / max_det, k = idx - bi * max_det;
     if (counts && k >= counts[bi]) return;
     const float* p = params + bi * 5;
-    const float inv = __fdiv_rn(1.f, p[2]);
+    // aten divides a tensor by a host scalar as a multiplication with the scalar's reciprocal, taken in double and
+    // then rounded to fp32 (BinaryDivTrueKernel.cu, is_cpu_scalar path): the host passes that reciprocal
+    const float inv = p[2];
     float* r = rows + (size_t)idx * stride;
     const float x1 = __fmul_rn(__fsub_rn(r[0], p[0]), inv), y1 = __fmul_rn(__fsub_rn(r[1], p[1]), inv);
     const float x2 = __fmul_rn(__fsub_rn(r[2], p[0]), inv), y2 = __fmul_rn(__fsub_rn(r[3], p[1]), inv);

@@ -164,6 +164,33 @@ __global__ void __launch_bounds__(256) nms_filter_multilabel_kernel(float* pred,
     }
 }
 
+// Apriori labels (autolabelling, utils/ops.py:256-261): every label row [cls, cx, cy, w, h] (pixels) becomes a
+// candidate with confidence 1.0 for its class, appended after the image's predictions (order = order_base + k:
+// the reference concatenates them below the prediction rows, so they come last among equal scores).
+__global__ void __launch_bounds__(256) nms_append_labels_kernel(const float* __restrict__ labels,
+                                                                const int32_t* __restrict__ label_counts, int L, int nc,
+                                                                float conf_thres, const int32_t* __restrict__ classes,
+                                                                int n_classes, uint32_t order_base, u64* __restrict__ keys,
+                                                                float* __restrict__ rows, int32_t* __restrict__ counts,
+                                                                int cap) {
+    const int bi = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive for the shuffles
+    bool is_cand = false;
+    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+    int cls = 0;
+    if (k < L && k < label_counts[bi]) {
+        const float* lb = labels + ((size_t)bi * L + k) * 5;
+        cls = (int)(long long)lb[0];
+        const float hw = lb[3] * 0.5f, hh = lb[4] * 0.5f;  // utils/ops.py:429-432
+        x1 = lb[1] - hw, y1 = lb[2] - hh, x2 = lb[1] + hw, y2 = lb[2] + hh;
+        is_cand = cls >= 0 && cls < nc && 1.0f > conf_thres && class_allowed(cls, classes, n_classes);
+    }
+    const int slot = warp_alloc(is_cand ? 1 : 0, counts + bi);
+    if (is_cand)
+        write_candidate(slot, cap, x1, y1, x2, y2, 1.0f, cls, order_base + (uint32_t)k, keys + (size_t)bi * cap,
+                        rows + (size_t)bi * cap * 6);
+}
+
 // ------------------------------------------------------------------------------------------
 // stage 2a: ordering.  chunk sort (512 keys per CTA, all SMs busy) + rank by binary search
 // ------------------------------------------------------------------------------------------
@@ -797,6 +824,27 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_filter(float* pred
                                                    (u64*)cand_keys, cand_rows, cand_counts, cand_cap);
     }
     KZD_LAUNCH_CHECK("nms_filter_kernel");
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_nms_append_labels(const float* labels, const int32_t* label_counts, int b, int L, int A,
+                                     int nc, float conf_thres, int multi_label, const int32_t* classes, int n_classes,
+                                     uint64_t* cand_keys, float* cand_rows, int32_t* cand_counts, int cand_cap,
+                                     void* stream) {
+    KZD_CHECK_ARG(label_counts && cand_keys && cand_rows && cand_counts, "kzd_nms_append_labels: null pointer");
+    KZD_CHECK_ARG(labels || L == 0, "kzd_nms_append_labels: null labels with L=%d", L);
+    KZD_CHECK_ARG(b >= 0 && L >= 0 && A >= 0 && nc >= 1 && cand_cap >= 1, "kzd_nms_append_labels: bad sizes");
+    KZD_CHECK_ARG(b <= 65535, "kzd_nms_append_labels: b=%d > 65535", b);
+    KZD_CHECK_ARG(n_classes == 0 || classes, "kzd_nms_append_labels: n_classes > 0 with null classes");
+    const double base = (multi_label && nc > 1) ? (double)A * nc : (double)A;
+    KZD_CHECK_ARG(base + L < 4294967295.0, "kzd_nms_append_labels: order field overflows");
+    if (b == 0 || L == 0) return 0;
+    dim3 grid((L + 255) / 256, b);
+    nms_append_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, label_counts, L, nc, conf_thres,
+                                                                   n_classes ? classes : nullptr, n_classes,
+                                                                   (uint32_t)base, (u64*)cand_keys, cand_rows, cand_counts,
+                                                                   cand_cap);
+    KZD_LAUNCH_CHECK("nms_append_labels_kernel");
     return 0;
 }
 

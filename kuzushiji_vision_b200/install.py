@@ -10,6 +10,8 @@ attributes, patched here and restored by ``uninstall()``:
   ultralytics.nn.modules.head.Detect._inference      <- head.detect_inference  (nn/modules/head.py:100)
   ultralytics.utils.ops.non_max_suppression    <- ops.non_max_suppression      (utils/ops.py:167)
   ultralytics.utils.loss.v8DetectionLoss.preprocess  <- loss.preprocess         (utils/loss.py:180)
+  ultralytics.models.yolo.detect.predict.DetectionPredictor.postprocess <- batched NMS + scale/clip + Results
+                                                     (models/yolo/detect/predict.py:23; only with patch_predictor=True)
   ultralytics.models.yolo.detect.val.DetectionValidator._process_batch <- ops.process_batch
                                                      (models/yolo/detect/val.py:209; only with patch_validator=True)
 
@@ -52,7 +54,7 @@ def detect_in_scope(module, detect_cls):
     return getattr(module, "no", None) == getattr(module, "nc", 0) + 4 * _head.REG_MAX
 
 
-def install(patch_decode_train=True, patch_preprocess=True, patch_validator=False):
+def install(patch_decode_train=True, patch_preprocess=True, patch_validator=False, patch_predictor=False):
     """Patch the importable ``ultralytics``; returns the list of patched attribute names."""
     if _saved:
         return sorted(_saved)
@@ -117,6 +119,41 @@ def install(patch_decode_train=True, patch_preprocess=True, patch_validator=Fals
     if patch_preprocess:
         _saved["loss.v8DetectionLoss.preprocess"] = (u_loss.v8DetectionLoss, "preprocess", ref_preprocess)
         u_loss.v8DetectionLoss.preprocess = preprocess
+    if patch_predictor:
+        try:
+            u_pred = importlib.import_module("ultralytics.models.yolo.detect.predict")
+        except Exception:
+            u_pred = None
+        if u_pred is not None:
+            ref_postprocess = u_pred.DetectionPredictor.postprocess
+
+            def postprocess(self, preds, img, orig_imgs):
+                """DetectionPredictor.postprocess (models/yolo/detect/predict.py:23-42): NMS of the whole batch in
+                libkzd, scale_boxes + clip_boxes of all kept rows in one kernel, then the reference's own Results
+                objects (engine/results.py) around the per-image row slices."""
+                import torch
+
+                pred = preds[0] if isinstance(preds, (list, tuple)) else preds
+                a = self.args
+                plain = (_is_cuda(pred) and pred.dim() == 3 and pred.shape[-1] != 6 and _is_cuda(img)
+                         and pred.shape[1] - 4 == len(self.model.names))
+                if not plain:
+                    return ref_postprocess(self, preds, img, orig_imgs)
+                direct = pred.dtype == torch.float32 and pred.is_contiguous()
+                work = pred if direct else pred.to(torch.float32).contiguous()
+                rows, n_keep = _ops.nms_batched(work, a.conf, a.iou, classes=a.classes, agnostic=a.agnostic_nms,
+                                                max_det=a.max_det)
+                if not direct:
+                    pred[:, :4] = work[:, :4].to(pred.dtype)  # the reference's in-place xyxy side effect
+                if not isinstance(orig_imgs, list):
+                    orig_imgs = u_ops.convert_torch2numpy_batch(orig_imgs)
+                _ops.scale_boxes_batched(rows, n_keep, tuple(img.shape[2:]), [o.shape for o in orig_imgs])
+                empty = torch.zeros((0, 6), device=pred.device)
+                return [u_pred.Results(o, path=pth, names=self.model.names, boxes=rows[i, :n] if n else empty)
+                        for i, (n, o, pth) in enumerate(zip(n_keep, orig_imgs, self.batch[0]))]
+
+            _saved["predict.DetectionPredictor.postprocess"] = (u_pred.DetectionPredictor, "postprocess", ref_postprocess)
+            u_pred.DetectionPredictor.postprocess = postprocess
     if patch_validator:
         # the validator module pulls in the whole engine (datasets, cv2, ...): optional, skipped when it does not import
         try:

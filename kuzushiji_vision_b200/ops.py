@@ -25,20 +25,44 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+MASK_BUDGET = 2 << 30  # bytes of IoU bitmask ((n_cap/64)^2 * 512 B per image) one suppression call may hold
+
+
+def _pack_labels(labels, b, dev):
+    """list of per-image ``(n_i, 5)`` ``[cls, cx, cy, w, h]`` tensors -> zero-padded ``(b, L, 5)`` + counts, or None."""
+    if labels is None or len(labels) == 0:
+        return None
+    if len(labels) != b:
+        raise _lib.KzdError(f"labels has {len(labels)} entries for a batch of {b} images")
+    counts = [int(lb.shape[0]) for lb in labels]
+    L = max(counts)
+    if L == 0:
+        return None
+    out = torch.zeros((b, L, 5), dtype=torch.float32, device=dev)
+    for i, lb in enumerate(labels):
+        if counts[i]:
+            out[i, :counts[i]] = lb[:, :5].to(device=dev, dtype=torch.float32)
+    return out, torch.tensor(counts, dtype=torch.int32).to(dev), L
+
+
 def nms_batched(prediction, conf_thres, iou_thres, classes=None, agnostic=False, multi_label=False, max_det=300,
-                max_nms=30000, max_wh=7680.0, in_place=True, pool=None, n_cap=None, xyxy_input=False):
+                max_nms=30000, max_wh=7680.0, in_place=True, pool=None, n_cap=None, xyxy_input=False, labels=None):
     """Batched NMS on a contiguous fp32 CUDA tensor ``prediction (b, 4+nc, A)``.
 
     Returns ``(rows (b, max_det, 6), counts list[int])``; ``rows[i, :counts[i]]`` are image i's kept
     detections ``[x1,y1,x2,y2,conf,cls]`` in descending score order. ``prediction[:, :4]`` is
     overwritten with xyxy when ``in_place`` (the reference's side effect, utils/ops.py:243-244).
     ``xyxy_input=True``: the box rows already hold xyxy (e.g. a tensor a previous call converted in place).
+    ``labels``: apriori labels per image (autolabelling, utils/ops.py:256-261): list of ``(n_i, 5)`` tensors
+    ``[cls, cx, cy, w, h]`` in pixels, appended to the image's candidates with confidence 1.
     """
     b, ch, A = prediction.shape
     nc = ch - 4
     dev = prediction.device
     multi_label = bool(multi_label) and nc > 1
-    max_cand = A * nc if multi_label else A
+    packed = _pack_labels(labels, b, dev)
+    n_lab = packed[2] if packed else 0
+    max_cand = (A * nc if multi_label else A) + n_lab
     if pool is None:
         # Typical prediction settings leave a few thousand candidates per page: a first-try pool of n_cap lets
         # one thread-block cluster per image order them in a single launch (more candidates than n_cap would
@@ -66,18 +90,30 @@ def nms_batched(prediction, conf_thres, iou_thres, classes=None, agnostic=False,
                                           cls_t.data_ptr() if n_cls else None, n_cls, mode, keys.data_ptr(),
                                           rows.data_ptr(), counts[0].data_ptr(), pool, _stream(dev)),
                        "kzd_nms_filter")
+            if packed:
+                _lib.check(lib.kzd_nms_append_labels(packed[0].data_ptr(), packed[1].data_ptr(), b, n_lab, A, nc,
+                                                     float(conf_thres), int(multi_label),
+                                                     cls_t.data_ptr() if n_cls else None, n_cls, keys.data_ptr(),
+                                                     rows.data_ptr(), counts[0].data_ptr(), pool, _stream(dev)),
+                           "kzd_nms_append_labels")
             if mode == 1:
                 mode = 2  # boxes are xyxy from now on
             cap = min(cap_hint or n_cap or DEFAULT_N_CAP, max_nms, pool)
             cap = _round_up(max(cap, 64), 64)
             while True:
-                ws_bytes = lib.kzd_nms_workspace_bytes(b, pool, cap)
+                # the IoU bitmask is (cap/64)^2 * 512 B per image (112 MB at the validator's 30,000 candidates): the
+                # batch goes through the suppression stage in groups that keep it under MASK_BUDGET
+                per_img = (cap // 64) ** 2 * 512
+                group = max(1, min(b, MASK_BUDGET // max(per_img, 1)))
+                ws_bytes = lib.kzd_nms_workspace_bytes(group, pool, cap)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                _lib.check(lib.kzd_nms_suppress(keys.data_ptr(), rows.data_ptr(), counts[0].data_ptr(), b, pool, cap,
-                                                float(iou_thres), int(bool(agnostic)), int(max_det), int(max_nms),
-                                                float(max_wh), out_rows.data_ptr(), counts[1].data_ptr(),
-                                                ws.data_ptr(), ws_bytes, _stream(dev)),
-                           "kzd_nms_suppress")
+                for i0 in range(0, b, group):
+                    g = min(group, b - i0)
+                    _lib.check(lib.kzd_nms_suppress(keys[i0:].data_ptr(), rows[i0:].data_ptr(), counts[0, i0:].data_ptr(), g,
+                                                    pool, cap, float(iou_thres), int(bool(agnostic)), int(max_det),
+                                                    int(max_nms), float(max_wh), out_rows[i0:].data_ptr(),
+                                                    counts[1, i0:].data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev)),
+                               "kzd_nms_suppress")
                 host = counts.cpu()  # the one synchronisation of the call
                 n_cand, n_keep = host[0].tolist(), host[1].tolist()
                 if min(n_keep) >= 0:
@@ -95,17 +131,19 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     """Same signature and return convention as the reference (utils/ops.py:167-182): a list of
     ``(n_i, 6)`` tensors ``[x1,y1,x2,y2,conf,cls]`` per image, descending score, at most ``max_det``.
 
+    ``labels``: apriori labels per image (autolabelling, utils/ops.py:256-261).
+
     Out of scope (raise ``NotImplementedError``; ``install()`` routes those calls to the reference's
-    own function): rotated boxes, mask coefficients (``nm > 0``), apriori ``labels``, end-to-end
-    ``(b, n, 6)`` inputs. ``max_time_img`` is accepted and ignored: the batch takes well under the
-    reference's 2 s + 0.05 s/image budget.
+    own function): rotated boxes, mask coefficients (``nm > 0``), end-to-end ``(b, n, 6)`` inputs.
+    ``max_time_img`` is accepted and ignored: the batch takes well under the reference's
+    2 s + 0.05 s/image budget.
     """
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     if isinstance(prediction, (list, tuple)):
         prediction = prediction[0]
-    if rotated or (labels is not None and len(labels)) or prediction.shape[-1] == 6:
-        raise NotImplementedError("kuzushiji_vision_b200.non_max_suppression: rotated / labels / end2end inputs")
+    if rotated or prediction.shape[-1] == 6:
+        raise NotImplementedError("kuzushiji_vision_b200.non_max_suppression: rotated / end2end inputs")
     _lib.require_cuda(prediction, "prediction")
     bs = prediction.shape[0]
     nc = nc or (prediction.shape[1] - 4)
@@ -114,7 +152,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     direct = prediction.dtype == torch.float32 and prediction.is_contiguous()
     work = prediction if direct else prediction.to(torch.float32).contiguous()
     rows, n_keep = nms_batched(work, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms,
-                               float(max_wh), in_place)
+                               float(max_wh), in_place, labels=labels if labels is not None and len(labels) else None)
     if in_place and not direct:
         prediction[:, :4] = work[:, :4].to(prediction.dtype)
     empty = torch.zeros((0, 6), device=prediction.device)
@@ -129,14 +167,16 @@ def xywh2xyxy(x):
 
 
 def _scale_params(img1_shape, img0_shape, ratio_pad=None):
-    """gain and (pad_x, pad_y) exactly as utils/ops.py:110-119 computes them (Python floats)."""
+    """(pad_x, pad_y), 1/gain and the clip limits, from gain and pad exactly as utils/ops.py:110-119 computes them
+    (Python floats). ``boxes /= gain`` with a host scalar is, in aten, a multiplication by the reciprocal taken
+    in double precision and rounded to fp32 - so that reciprocal is what the kernel gets."""
     if ratio_pad is None:
         gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
         pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1),
                round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
     else:
         gain, pad = ratio_pad[0][0], ratio_pad[1]
-    return [float(pad[0]), float(pad[1]), float(gain), float(img0_shape[1]), float(img0_shape[0])]
+    return [float(pad[0]), float(pad[1]), 1.0 / float(gain), float(img0_shape[1]), float(img0_shape[0])]
 
 
 def scale_boxes_batched(rows, n_keep, img1_shape, orig_shapes):

@@ -209,10 +209,12 @@ class PagePipeline:
         if min(n_keep) < 0:
             from .ops import nms_batched
 
-            # the graph's filter already rewrote y's box rows as xyxy
+            # the graph's filter already rewrote y's box rows as xyxy; capacities from the counts this step measured
+            worst = max(self.counts[0].tolist())
             rows, n_keep = nms_batched(self.out["y"], self.conf, self.iou, agnostic=self.agnostic, max_det=self.max_det,
                                        max_nms=self.max_nms, max_wh=self.max_wh, in_place=False, xyxy_input=True,
-                                       pool=self.A, n_cap=self.max_nms)
+                                       pool=min(self.A, (worst + 511) // 512 * 512),
+                                       n_cap=(min(worst, self.max_nms) + 63) // 64 * 64)
             self.det_rows.copy_(rows)
             self.keep_host.copy_(torch.as_tensor(n_keep, dtype=torch.int32))
         return self.out, n_keep

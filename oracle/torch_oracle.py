@@ -273,9 +273,10 @@ def xywh2xyxy(x):
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
                         multi_label=False, max_det=300, nc=0, max_nms=30000, max_wh=7680, in_place=True,
-                        nms_fn=None):
+                        nms_fn=None, labels=()):
     """Restatement of ``ops.non_max_suppression`` (utils/ops.py:167-316) for the detection task
-    (no masks, no rotated boxes, no apriori labels, no wall-clock limit).
+    (no masks, no rotated boxes, no wall-clock limit). ``labels``: apriori labels per image,
+    ``(n_i, 5) [cls, cx, cy, w, h]`` rows appended with class score 1 (utils/ops.py:256-261).
 
     ``prediction (b, 4+nc, A)``: xywh px + class scores. Returns a list of ``(n_i, 6)`` tensors
     ``[x1,y1,x2,y2,conf,cls]`` in descending-score order; with ``in_place`` the caller's box rows
@@ -300,6 +301,12 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     out = [torch.zeros((0, 6), device=prediction.device)] * bs
     for i in range(bs):
         x = pt[i][cand[i]]
+        if labels is not None and len(labels) and len(labels[i]):  # utils/ops.py:256-261
+            lb = labels[i]
+            v = torch.zeros((len(lb), nc + 4), device=x.device)
+            v[:, :4] = xywh2xyxy(lb[:, 1:5])
+            v[range(len(lb)), lb[:, 0].long() + 4] = 1.0
+            x = torch.cat((x, v), 0)
         if not x.shape[0]:
             continue
         box, cls = x[:, :4], x[:, 4:4 + nc]

@@ -646,7 +646,7 @@ def test_scale_boxes_matches_oracle():
     lv = synth.head_outputs(3, 2, 320, synth.P2_P5, seed=33, device=DEV, sparse_cls=400)
     y = O.decode_infer(lv, synth.P2_P5, 2)
     rows, n_keep = kzd.nms_batched(y, 0.25, 0.6, max_det=300)
-    img1, origs = (320, 320), [(1080, 1920, 3), (700, 500, 3), (333, 333, 3)]
+    img1, origs = (320, 320), [(1080, 1920, 3), (700, 500, 3), (900, 1200, 3)]
     ref = [O.scale_boxes(img1, rows[i, :n_keep[i], :4].clone(), origs[i]) for i in range(3)]
     single = [kzd.scale_boxes(img1, rows[i, :n_keep[i]].clone(), origs[i]) for i in range(3)]
     out = kzd.scale_boxes_batched(rows.clone(), n_keep, img1, origs)
@@ -1071,3 +1071,55 @@ def test_validator_matching_batched_matches_oracle():
         else:
             assert not got[i].any()
     assert got.any()
+
+
+# ---------------------------------------------------------------------------------------------
+# variants: apriori labels, validation-scale NMS
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kw", [dict(conf_thres=0.5, iou_thres=0.6), dict(conf_thres=0.3, iou_thres=0.6, multi_label=True),
+                                dict(conf_thres=0.4, iou_thres=0.5, classes=[1, 3], agnostic=True)])
+def test_nms_apriori_labels_match_oracle(kw):
+    """labels= of non_max_suppression (autolabelling, utils/ops.py:256-261): label rows join the candidates with
+    confidence 1, after the image's predictions."""
+    b, nc, imgsz, strides = 3, 4, 320, synth.P2_P5
+    lv = synth.head_outputs(b, nc, imgsz, strides, seed=44, device=DEV, sparse_cls=300)
+    y = kzd.decode_inference(lv, strides, nc)
+    g = torch.Generator().manual_seed(2)
+    labels = []
+    for n in (9, 0, 31):
+        lb = torch.cat((torch.randint(0, nc, (n, 1), generator=g).float(), torch.rand(n, 2, generator=g) * 250 + 30,
+                        torch.rand(n, 2, generator=g) * 50 + 10), 1)
+        labels.append(lb.to(DEV))
+    labels[2][5:8] = labels[2][4]  # duplicated labels: equal boxes and scores, kept / suppressed by their order
+    y1, y2 = y.clone(), y.clone()
+    mine = kzd.non_max_suppression(y1, labels=labels, **kw)
+    ref = O.non_max_suppression(y2, labels=labels, **kw)
+    _check_nms(mine, ref)
+    assert torch.equal(y1, y2) and any((r[:, 4] == 1.0).any() for r in ref)
+
+
+def test_nms_validation_scale_full_size():
+    """The validator's NMS settings (models/yolo/detect/val.py:92-102: conf 0.001, multi_label, max_det 300,
+    max_nms 30000) on dense class scores at 1280x1280 P2-P5: 408,000 (anchor, class) rows per page pass the
+    confidence filter, the 30,000 best enter the suppression stage (469 x 469 mask tiles, 112 MB per page: the
+    batch is walked in groups that respect the mask budget). Scores are made distinct, because the reference's
+    unstable argsort leaves ties at the max_nms boundary open."""
+    from kuzushiji_vision_b200 import ops as kops
+
+    b, nc, imgsz, strides = 3, 3, 1280, synth.P2_P5
+    lv = synth.head_outputs(b, nc, imgsz, strides, seed=45, device=DEV)
+    y = kzd.decode_inference(lv, strides, nc)
+    A = y.shape[2]
+    u = torch.rand(b, nc, A, generator=torch.Generator().manual_seed(1)).to(DEV)  # distinct scores in (0.01, 0.99)
+    y[:, 4:] = 0.01 + 0.98 * u
+    assert int((y[:, 4:] > 0.001).sum()) == b * nc * A
+    old = kops.MASK_BUDGET
+    kops.MASK_BUDGET = 250 << 20  # two pages per group: the grouped path runs with an uneven last group
+    try:
+        mine = kzd.non_max_suppression(y.clone(), conf_thres=0.001, iou_thres=0.7, multi_label=True, max_det=300)
+    finally:
+        kops.MASK_BUDGET = old
+    ref = O.non_max_suppression(y.clone(), conf_thres=0.001, iou_thres=0.7, multi_label=True, max_det=300)
+    _check_nms(mine, ref)
+    assert all(int(t.shape[0]) == 300 for t in ref)

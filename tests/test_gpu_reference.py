@@ -250,3 +250,51 @@ def test_validator_process_batch_patched_on_the_real_package(R):
     for a, r in zip(got, ref):
         assert a.dtype == torch.bool and a.device == r.device and torch.equal(a, r)
     assert any(r.any() for r in ref)
+
+
+def test_nms_apriori_labels_match_unmodified_reference_on_cuda(R):
+    b, nc, imgsz, strides = 2, 3, 320, synth.P2_P5
+    lv = synth.head_outputs(b, nc, imgsz, strides, seed=46, device=DEV, sparse_cls=200)
+    y = kzd.decode_inference(lv, strides, nc)
+    g = torch.Generator().manual_seed(3)
+    labels = [torch.cat((torch.randint(0, nc, (n, 1), generator=g).float(), torch.rand(n, 2, generator=g) * 250 + 30,
+                         torch.rand(n, 2, generator=g) * 50 + 10), 1).to(DEV) for n in (12, 5)]
+    for kw in (dict(conf_thres=0.4, iou_thres=0.6), dict(conf_thres=0.3, iou_thres=0.6, multi_label=True)):
+        ref = R.non_max_suppression(y.clone(), labels=labels, **kw)
+        mine = kzd.non_max_suppression(y.clone(), labels=labels, **kw)
+        assert all(r.shape == m.shape and torch.equal(r, m) for r, m in zip(ref, mine))
+
+
+def test_predictor_postprocess_patched_on_the_real_package(R):
+    """install(patch_predictor=True): DetectionPredictor.postprocess (models/yolo/detect/predict.py:23-42) - NMS,
+    scale_boxes to the original image, Results/Boxes construction (engine/results.py) - gives the same Results as
+    the reference's per-image loop."""
+    import importlib
+
+    import numpy as np
+
+    pred_mod = importlib.import_module("ultralytics.models.yolo.detect.predict")
+    b, nc, imgsz, strides = 3, 2, 640, synth.P2_P5
+    lv = synth.head_outputs(b, nc, imgsz, strides, seed=93, device=DEV, sparse_cls=300)
+    lv[2][:, 64:] = -20.0  # an image without detections
+    for x in lv[1:]:
+        x[2, 64:] = -20.0
+    y = kzd.decode_inference(lv, strides, nc)
+    img = torch.zeros((b, 3, imgsz, imgsz), device=DEV)
+    orig = [np.zeros((900, 1200, 3), np.uint8), np.zeros((640, 640, 3), np.uint8), np.zeros((333, 500, 3), np.uint8)]
+    stub = types.SimpleNamespace(
+        args=types.SimpleNamespace(conf=0.3, iou=0.6, agnostic_nms=False, max_det=200, classes=None),
+        batch=[[f"page{i}.jpg" for i in range(b)]], model=types.SimpleNamespace(names={0: "char", 1: "mark"}))
+    ref = pred_mod.DetectionPredictor.postprocess(stub, y.clone(), img, orig)
+    names = kzd.install(patch_predictor=True)
+    try:
+        assert "predict.DetectionPredictor.postprocess" in names
+        got = pred_mod.DetectionPredictor.postprocess(stub, y.clone(), img, orig)
+    finally:
+        kzd.uninstall()
+    assert len(got) == len(ref) == b
+    for g_, r_ in zip(got, ref):
+        assert type(g_) is type(r_) and g_.path == r_.path and g_.orig_shape == r_.orig_shape
+        assert g_.boxes.data.shape == r_.boxes.data.shape and torch.equal(g_.boxes.data, r_.boxes.data)
+        assert torch.equal(g_.boxes.xywhn, r_.boxes.xywhn)
+    assert ref[0].boxes.data.shape[0] > 0 and ref[2].boxes.data.shape[0] == 0

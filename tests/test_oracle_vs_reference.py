@@ -125,3 +125,22 @@ def test_validator_matching_live(R):
                          torch.randint(0, nc, (n, 1), generator=g).float()), 1)
         assert torch.equal(O.box_iou(gt, det[:, :4]), R.metrics.box_iou(gt, det[:, :4]))
         assert torch.equal(O.process_batch(det, gt, gcls, iouv), val.DetectionValidator._process_batch(stub, det, gt, gcls))
+
+
+def test_nms_apriori_labels_live(R):
+    """labels= (autolabelling, utils/ops.py:256-261): oracle restatement against the reference."""
+    from kuzushiji_vision_b200 import synth
+
+    g = torch.Generator().manual_seed(8)
+    d = synth.assigner_inputs(2, 10, 256, 3, synth.P3_P5, seed=4)
+    y = O.decode_infer(d["levels"], synth.P3_P5, 3)
+    labels = []
+    for n in (6, 0):
+        lb = torch.cat((torch.randint(0, 3, (n, 1), generator=g).float(), torch.rand(n, 2, generator=g) * 200 + 20,
+                        torch.rand(n, 2, generator=g) * 40 + 8), 1)
+        labels.append(lb)
+    for kw in (dict(conf_thres=0.5, iou_thres=0.6), dict(conf_thres=0.3, iou_thres=0.6, multi_label=True, classes=[0, 2])):
+        ref = R.non_max_suppression(y.clone(), labels=labels, **kw)
+        got = O.non_max_suppression(y.clone(), labels=labels, **kw)
+        assert all(torch.equal(a, b) for a, b in zip(got, ref))
+        assert (ref[0][:, 4] == 1.0).sum() >= 1
