@@ -429,7 +429,7 @@ class Measure:
         return {"ms_window": per_window[wi], "windows_ms": [round(v, 4) for v in per_window],
                 "per_rank_ms_per_step": [round(float(v) / steps, 5) for v in allr[:, wi].tolist()]}
 
-    def single_stream_ms(self, reps=20):
+    def single_stream_ms(self, reps=200):
         t0, t1 = ev(), ev()
         t0.record()
         for r in range(reps * self.m):
@@ -474,7 +474,10 @@ class Measure:
             "nms": nms_calls,
         }
         st_ms, n_prof = {}, 20
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2: evict between stage replays
+        # L2 flush between stage replays: write a buffer larger than L2, then READ another one, so the cache holds
+        # clean lines only and the timed kernels do not pay for writing the flush pattern back to HBM
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
         for n in names:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -488,6 +491,7 @@ class Measure:
             tot = 0.0
             for i in range(n_prof + 2):
                 flush.zero_()
+                flush_rd.sum()
                 e0, e1 = ev(), ev()
                 e0.record()
                 g.replay()
@@ -497,7 +501,7 @@ class Measure:
                     tot += e0.elapsed_time(e1)
             st_ms[n] = tot / n_prof
             del g, keep_alive
-        del flush
+        del flush, flush_rd
         return names, st_ms
 
     # -- end to end ----------------------------------------------------------------------------------
@@ -629,8 +633,9 @@ def roofline_block(meas, names, st_ms, ms_per_step, n_cand, n_keep):
             "stages": {n: {"ms": st_ms[n], "algorithmic_bytes": ab.get(n),
                            "gbs": (ab[n] / (st_ms[n] * 1e-3) / 1e9) if ab.get(n) else None,
                            "frac": (ab[n] / (st_ms[n] * 1e-3) / 1e9 / peak) if ab.get(n) else None} for n in names},
-            "stage_note": "stage ms = device time of that stage's kernels on one micro-batch (own CUDA graph, L2 "
-                          "flushed before each replay, CUDA events); the timed region replays all stages as one graph"}
+            "stage_note": "stage ms = device time of that stage's kernels on one micro-batch (own CUDA graph; L2 flushed "
+                          "before each replay by writing 256 MB and then reading 256 MB, so no dirty lines are left for "
+                          "the stage to evict; CUDA events); the timed region replays all stages as one graph"}
 
 
 def measure_workload(kzd, kdist, synth, cfg, m, dev, rank, world, steps, warmup, fuse, fuse_filter, clk=None):
@@ -639,9 +644,10 @@ def measure_workload(kzd, kdist, synth, cfg, m, dev, rank, world, steps, warmup,
     glo = rank * pages_rank
     meas = Measure(kzd, synth, cfg, m, dev, seed0=glo, fuse=fuse, fuse_filter=fuse_filter)
     parity = meas.parity_check()
-    if clk is not None:
-        clk.on = True
+    if clk is not None:  # clocks / throttle reasons are sampled while this step loop keeps the device busy: the warm-up,
+        clk.on = True    # the timed windows and the single-stream repetition that follows them (NVML answers in ms)
     win = meas.timed_windows(kdist, steps, warmup, world)
+    single_ms = meas.single_stream_ms()
     if clk is not None:
         clk.on = False
     # the path's only collective: 4 counters (target_scores_sum, n_fg, pages, kept boxes), once per step in a
@@ -668,7 +674,7 @@ def measure_workload(kzd, kdist, synth, cfg, m, dev, rank, world, steps, warmup,
            "windows_ms_per_step": [round(v / steps, 5) for v in win["windows_ms"]],
            "per_rank_ms_per_step": win["per_rank_ms_per_step"], "parity_checked": parity,
            "counter_all_reduce_us": round(coll_us, 2), "launches_per_step": meas.launches_per_step,
-           "ms_per_step_single_stream": meas.single_stream_ms(),
+           "ms_per_step_single_stream": single_ms,
            "counters": {"target_scores_sum": float(counters[0]), "n_fg": float(counters[1]), "kept_boxes": float(counters[3])}}
     names, st_ms = meas.stage_times()
     e2e_steps = max(2, min(steps, 20 if m == 1 else 6))

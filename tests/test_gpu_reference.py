@@ -276,9 +276,8 @@ def test_predictor_postprocess_patched_on_the_real_package(R):
     pred_mod = importlib.import_module("ultralytics.models.yolo.detect.predict")
     b, nc, imgsz, strides = 3, 2, 640, synth.P2_P5
     lv = synth.head_outputs(b, nc, imgsz, strides, seed=93, device=DEV, sparse_cls=300)
-    lv[2][:, 64:] = -20.0  # an image without detections
-    for x in lv[1:]:
-        x[2, 64:] = -20.0
+    for x in lv:
+        x[2, 64:] = -20.0  # an image without detections
     y = kzd.decode_inference(lv, strides, nc)
     img = torch.zeros((b, 3, imgsz, imgsz), device=DEV)
     orig = [np.zeros((900, 1200, 3), np.uint8), np.zeros((640, 640, 3), np.uint8), np.zeros((333, 500, 3), np.uint8)]

@@ -8,6 +8,7 @@ d = synth.assigner_inputs(16, 600, 1280, 1, synth.P2_P5, seed=0, device=dev, lay
 asg = kzd.TaskAlignedAssigner(10, 1, 0.5, 6.0)
 args = (d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev)  # read after the write: L2 ends up clean
 for _ in range(3): asg(*args)
 torch.cuda.synchronize()
 g = torch.cuda.CUDAGraph()
@@ -17,7 +18,7 @@ torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
 with torch.cuda.graph(g): out = asg(*args)
 tot=0
 for i in range(22):
-    flush.zero_(); e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    flush.zero_(); flush_rd.sum(); e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     if i>=2: tot+=e0.elapsed_time(e1)
 print(sys.argv[1] if len(sys.argv)>1 else "", "assign graph us:", round(tot/20*1e3,1), "fg", int(out[3].sum()))
@@ -26,7 +27,7 @@ import collections
 from torch.profiler import ProfilerActivity, profile
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for i in range(10):
-        flush.zero_(); g.replay()
+        flush.zero_(); flush_rd.sum(); g.replay()
     torch.cuda.synchronize()
 agg = collections.OrderedDict()
 for e in prof.events():

@@ -18,6 +18,7 @@ out_rows = torch.zeros((b, max_det, 6), dtype=torch.float32, device=dev)
 ws_bytes = lib.kzd_nms_workspace_bytes(b, pool, cap)
 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev)  # read after the write: L2 ends up clean
 def st(): return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 _lib.check(lib.kzd_nms_filter(y.data_ptr(), b, A, nc, 0.25, 0, None, 0, 0, keys.data_ptr(), rows.data_ptr(), counts[0].data_ptr(), pool, st()), "filter")
 def suppress():
@@ -31,7 +32,7 @@ g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g): suppress()
 tot = 0
 for i in range(22):
-    flush.zero_(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush.zero_(); flush_rd.sum(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     if i >= 2: tot += e0.elapsed_time(e1)
 print(sys.argv[1] if len(sys.argv) > 1 else "", "nms_suppress graph us:", round(tot / 20 * 1e3, 1), "kept", counts[1].tolist()[:4],
