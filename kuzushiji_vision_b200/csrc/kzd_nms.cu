@@ -7,7 +7,9 @@
 // Pipeline (no host synchronisation inside; candidate counts live on the device):
 //   nms_filter_kernel  conf filter + best class / multi-label + xywh->xyxy, candidates appended to
 //                      a per-image pool with a 64-bit key  score_bits<<32 | ~order
-//   nms_chunk_sort / nms_rank   512-key chunk sorts (registers + warp shuffles + shared memory) + rank by
+//   nms_order_bucket_kernel   the usual case (suppression capacity <= 4096): one CTA per image ranks the
+//                      candidates by score buckets in shared memory (histogram + prefix + in-bucket compares)
+//   nms_chunk_sort / nms_rank   larger capacities: 512-key chunk sorts (registers + warp shuffles + shared memory) + rank by
 //                      binary search = torchvision's stable descending score sort; writes score-ordered,
 //                      class-offset boxes. nms_order_cluster_kernel does both in one launch (one 8-CTA
 //                      thread-block cluster per image, rank through distributed shared memory) when the
@@ -18,8 +20,8 @@
 //                      warp with ballot/shuffle, helper warps OR the kept rows into later chunks with
 //                      sparse shared-memory atomics; the first max_det kept rows are gathered in score order
 //   mask + scan run in two phases of column ranges: the walk stops once max_det boxes are kept, so the
-//   second phase is needed only when some image's walk is not over after the first; inside a captured
-//   CUDA graph it is the body of a conditional node that the first walk switches on (kzd_nms_suppress)
+//   second phase is needed only when some image's walk is not over after the first; finished images skip it
+//   on the device (kzd_nms_suppress)
 #include <cooperative_groups.h>
 
 #include "kzd_common.cuh"
@@ -349,6 +351,155 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_rank_kernel(const float* __
     emit(k1, r1, slot1);
 }
 
+// Ordering in ONE launch for the usual suppression capacity (n_cap <= 4096): one CTA per image ranks the
+// image's candidates by bucketing instead of sorting. Scores are floats in a narrow range, so their bit
+// patterns - rebased to the image's smallest score and shifted to 11 bits - spread the candidates over 2048
+// buckets with one or two members each: a shared-memory histogram + one descending prefix sum give every key
+// the number of keys in higher buckets, the keys of the buckets that reach into the first n ranks are
+// scattered bucket by bucket into shared memory, and a key's exact rank is its bucket's start plus the number
+// of larger keys inside its bucket (a handful of compares). No sort stages, no second kernel, no global
+// round trip for the keys: the chunk sort + rank pair takes 22 us on the bench workload, this takes a few.
+// Equal scores (ties) share a bucket and cost compares quadratic in the tie count - still exact.
+constexpr int BR_THREADS = 512;
+constexpr int BR_BUCKETS = 2048;
+constexpr int BR_KEYS = 4096 + 512;  // keys the shared-memory stage holds: n_cap plus the overhang of the last bucket
+constexpr int BR_REG = 8;            // keys per thread kept in registers between the passes
+
+__global__ void __launch_bounds__(BR_THREADS) nms_order_bucket_kernel(const u64* __restrict__ cand_keys,
+                                                                      const float* __restrict__ cand_rows,
+                                                                      const int32_t* __restrict__ cand_counts,
+                                                                      int cand_cap, int n_cap, int max_nms, int agnostic,
+                                                                      float max_wh, SuppressWs ws) {
+    extern __shared__ unsigned char br_smem[];
+    u64* skey = reinterpret_cast<u64*>(br_smem);                         // BR_KEYS
+    uint32_t* fill = reinterpret_cast<uint32_t*>(skey + BR_KEYS);         // BR_BUCKETS: members scattered so far
+    uint16_t* hist = reinterpret_cast<uint16_t*>(fill + BR_BUCKETS);      // BR_BUCKETS: members
+    uint16_t* start = hist + BR_BUCKETS;                                  // BR_BUCKETS: keys in higher buckets
+    uint16_t* sval = start + BR_BUCKETS;                                  // BR_KEYS: pool slot of the key
+    __shared__ uint32_t s_min, s_max, s_warp[BR_THREADS / 32];
+    __shared__ int s_stored, s_over;
+    const int bi = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int count = cand_counts[bi];
+    const int n = count < max_nms ? count : max_nms;
+    const bool overflow = count > cand_cap || n > n_cap;  // pool or suppression stage too small
+    if (t == 0) ws.n_sorted[bi] = overflow ? -1 : n;
+    if (overflow || count <= 0) return;
+    const u64* __restrict__ src = cand_keys + (size_t)bi * cand_cap;
+    u64 kreg[BR_REG];
+#pragma unroll
+    for (int i = 0; i < BR_REG; ++i) {
+        const int q = i * BR_THREADS + t;
+        kreg[i] = q < count ? src[q] : 0ull;
+    }
+    auto for_each_key = [&](auto&& f) {  // f(key, pool slot): the first BR_REG keys of a thread live in registers
+#pragma unroll
+        for (int i = 0; i < BR_REG; ++i) {
+            const int q = i * BR_THREADS + t;
+            if (q < count) f(kreg[i], q);
+        }
+        for (int q = BR_REG * BR_THREADS + t; q < count; q += BR_THREADS) f(src[q], q);
+    };
+    for (int b = t; b < BR_BUCKETS; b += BR_THREADS) hist[b] = 0, fill[b] = 0u;
+    if (t == 0) s_min = 0xffffffffu, s_max = 0u, s_stored = 0, s_over = 0;
+    __syncthreads();
+    // pass 0: score range of the image
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for_each_key([&](u64 key, int) {
+        const uint32_t sb = (uint32_t)(key >> 32);
+        lo = min(lo, sb), hi = max(hi, sb);
+    });
+    lo = __reduce_min_sync(0xffffffffu, lo), hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) atomicMin(&s_min, lo), atomicMax(&s_max, hi);
+    __syncthreads();
+    const uint32_t base = s_min, range = s_max - s_min;
+    const int shift = range < (uint32_t)BR_BUCKETS ? 0 : (32 - __clz(range)) - 11;  // (score - base) >> shift < 2048
+    // pass 1: histogram (bucket 0 = lowest scores)
+    for_each_key([&](u64 key, int) {
+        const uint32_t b = ((uint32_t)(key >> 32) - base) >> shift;
+        atomicAdd(reinterpret_cast<unsigned int*>(fill) + b, 1u);  // 32-bit counters first, narrowed below
+    });
+    __syncthreads();
+    // descending exclusive prefix: start[b] = number of keys in buckets above b. Thread t owns the four buckets
+    // 2047-4t .. 2044-4t, in that (descending) order.
+    uint32_t c4[4], sum = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c4[k] = fill[BR_BUCKETS - 1 - (4 * t + k)];
+        sum += c4[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < BR_THREADS / 32 ? s_warp[lane] : 0u, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        if (lane < BR_THREADS / 32) s_warp[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;  // keys above this thread's first bucket
+    int stored_hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = BR_BUCKETS - 1 - (4 * t + k);
+        start[b] = (uint16_t)min(run, 65535u);
+        hist[b] = (uint16_t)min(c4[k], 65535u);
+        if (run < (uint32_t)n && c4[k]) stored_hi = (int)min(run + c4[k], 0x7fffffffu);  // this bucket reaches into the first n ranks
+        run += c4[k];
+    }
+    __syncthreads();  // everyone has read fill[] as counters
+#pragma unroll
+    for (int k = 0; k < 4; ++k) fill[BR_BUCKETS - 1 - (4 * t + k)] = 0u;
+    stored_hi = __reduce_max_sync(0xffffffffu, stored_hi);
+    if (lane == 0 && stored_hi) atomicMax(&s_stored, stored_hi);
+    __syncthreads();
+    // pass 2: scatter the keys of the buckets that reach into the first n ranks, bucket by bucket
+    for_each_key([&](u64 key, int q) {
+        const uint32_t b = ((uint32_t)(key >> 32) - base) >> shift;
+        const uint32_t st = start[b];
+        if (st < (uint32_t)n) {
+            const uint32_t pos = st + atomicAdd(reinterpret_cast<unsigned int*>(fill) + b, 1u);
+            if (pos < (uint32_t)BR_KEYS) skey[pos] = key, sval[pos] = (uint16_t)q;
+            else s_over = 1;  // a tie group larger than the shared-memory overhang
+        }
+    });
+    __syncthreads();
+    if (s_over || count > 65535) {  // (pool slots are kept as 16-bit values here)
+        if (t == 0) ws.n_sorted[bi] = -1;
+        return;
+    }
+    // pass 3: exact rank inside the bucket, emit the first n in score order with their class offset
+    const int stored = s_stored;
+    const float* __restrict__ rows = cand_rows + (size_t)bi * cand_cap * 6;
+    float4* __restrict__ sbox = ws.sbox + (size_t)bi * n_cap;
+    uint32_t* __restrict__ sslot = ws.sslot + (size_t)bi * n_cap;
+    for (int p = t; p < stored; p += BR_THREADS) {
+        const u64 key = skey[p];
+        const uint32_t b = ((uint32_t)(key >> 32) - base) >> shift;
+        const int s0 = start[b], m = hist[b];
+        int rank = s0;
+        for (int q = s0; q < s0 + m; ++q) rank += skey[q] > key ? 1 : 0;
+        if (rank >= n) continue;
+        const uint32_t slot = sval[p];
+        const float2* r = reinterpret_cast<const float2*>(rows + (size_t)slot * 6);
+        const float2 p0 = r[0], p1 = r[1], p2 = r[2];
+        const float off = agnostic ? 0.f : __fmul_rn(p2.y, max_wh);                      // utils/ops.py:289
+        sbox[rank] = make_float4(__fadd_rn(p0.x, off), __fadd_rn(p0.y, off), __fadd_rn(p1.x, off),
+                                 __fadd_rn(p1.y, off));                                   // utils/ops.py:295
+        sslot[rank] = slot;
+    }
+}
+
+constexpr size_t BR_SMEM = (size_t)BR_KEYS * 8 + (size_t)BR_BUCKETS * 4 + (size_t)BR_BUCKETS * 2 * 2 + (size_t)BR_KEYS * 2;
+
 // One thread-block cluster per image does the whole ordering when the candidate pool is at most 8 chunks
 // (the first-try case of the eager drop-in): CTA c sorts chunk c (chunk_sort_desc), the cluster
 // synchronises, and every CTA ranks its keys against the other CTAs' sorted chunks read through distributed shared memory - no
@@ -581,8 +732,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
                                                                 int n_cap, int max_det, int phase, int t_lo,
                                                                 int t_hi, SuppressWs ws,
                                                                 float* __restrict__ out_rows,
-                                                                int32_t* __restrict__ out_counts,
-                                                                unsigned long long more_handle) {
+                                                                int32_t* __restrict__ out_counts) {
     extern __shared__ u64 scan_smem[];
     u64* removed = scan_smem;                                               // T_cap: bits suppressed by a kept row
     u64* keep_s = scan_smem + ws.T_cap;                                     // T_cap: keep mask of every chunk walked here
@@ -740,11 +890,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
     }
     if (n == 0) finished = true;
     if (!finished) {  // more columns are needed: the next phase continues from here
-        if (threadIdx.x == 0) {
-            state[0] = 0, state[1] = kept, state[2] = chunks;
-            // inside a captured graph the next phase is the body of a conditional node: switch it on
-            if (more_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)more_handle, 1u);
-        }
+        if (threadIdx.x == 0) state[0] = 0, state[1] = kept, state[2] = chunks;
         return;
     }
     // gather the kept rows in score order, all threads
@@ -878,7 +1024,19 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
 #ifndef KZD_NO_CLUSTER
 #define KZD_NO_CLUSTER 0
 #endif
-    if (!KZD_NO_CLUSTER && ws.C_cap <= ORDER_CL) {  // pool of at most 8 chunks: one cluster per image orders it in one launch
+#ifndef KZD_NO_BUCKET
+#define KZD_NO_BUCKET 0
+#endif
+    if (!KZD_NO_BUCKET && n_cap <= 4096 && cand_cap <= 65535) {  // the usual capacity: one CTA per image ranks by buckets
+        static thread_local bool raised = false;
+        if (!raised) {
+            KZD_CUDA(cudaFuncSetAttribute(nms_order_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BR_SMEM));
+            raised = true;
+        }
+        nms_order_bucket_kernel<<<b, BR_THREADS, BR_SMEM, st>>>((const u64*)cand_keys, cand_rows, cand_counts, cand_cap, n_cap,
+                                                               max_nms, agnostic, max_wh, ws);
+        KZD_LAUNCH_CHECK("nms_order_bucket_kernel");
+    } else if (!KZD_NO_CLUSTER && ws.C_cap <= ORDER_CL) {  // pool of at most 8 chunks: one cluster per image orders it in one launch
         nms_order_cluster_kernel<<<dim3(ORDER_CL, b), CHUNK_THREADS, 0, st>>>((const u64*)cand_keys, cand_rows, cand_counts,
                                                                             cand_cap, n_cap, max_nms, agnostic, max_wh, ws);
         KZD_LAUNCH_CHECK("nms_order_cluster_kernel");
@@ -891,63 +1049,27 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
         KZD_LAUNCH_CHECK("nms_rank_kernel");
     }
     // The greedy walk stops as soon as max_det boxes are kept, so the mask is built and walked in two phases
-    // of column ranges: first enough tiles for max_det kept boxes plus 25 %, then - only if some image's
-    // walk is not over - all the others. Eagerly, phase 1 is launched regardless and finished images skip it
-    // on the device. Under stream capture (CUDA graphs: PagePipeline) phase 1 becomes the body of a
-    // conditional IF node whose handle the phase-0 walk sets when it needs more columns: a step whose images
-    // all finish in phase 0 - the usual case when max_det cuts the walk - pays nothing for it.
+    // of column ranges: first enough tiles for max_det kept boxes plus 25 %, then all the others. Images
+    // whose walk ended in the first range skip the second on the device (no host round trip): when every
+    // image did - the usual case when max_det cuts the walk - the second pair of launches costs ~4.5 us.
+    // (A CUDA-graph conditional node around the second phase was measured: correct, but evaluating the node
+    // costs ~14 us per replay, three times what the two idle launches do. Not kept.)
 #ifndef KZD_MASK_GRID
 #define KZD_MASK_GRID 16
 #endif
     const int grid = sm_count() * KZD_MASK_GRID;
     int t0 = ((max_det + max_det / 4 + 64 + 63) / 64 + MASK_CG - 1) / MASK_CG * MASK_CG;
     if (t0 > ws.T_cap) t0 = ws.T_cap;
-    const bool two = t0 < ws.T_cap;
-    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
-    cudaGraph_t cap_graph = nullptr;
-    const cudaGraphNode_t* deps = nullptr;
-    size_t n_deps = 0;
-    KZD_CUDA(cudaStreamGetCaptureInfo_v2(st, &cap_status, nullptr, &cap_graph, &deps, &n_deps));
-    const bool conditional = two && cap_status == cudaStreamCaptureStatusActive && cap_graph != nullptr;
-    cudaGraphConditionalHandle more = 0;
-    if (conditional) KZD_CUDA(cudaGraphConditionalHandleCreate(&more, cap_graph, 0, cudaGraphCondAssignDefault));
-    auto launch_phase = [&](int phase, int t_lo, int t_hi, cudaStream_t s_, unsigned long long handle) -> int {
+    for (int phase = 0, t_lo = 0, t_hi = t0; t_lo < ws.T_cap; ++phase, t_lo = t_hi, t_hi = ws.T_cap) {
         const int g_lo = t_lo / MASK_CG, g_hi = (t_hi + MASK_CG - 1) / MASK_CG;
-        // a later phase usually finds every image finished: a quarter of the CTAs keeps that exit cheap (the
+        // the second phase usually finds every image finished: a quarter of the CTAs keeps that exit cheap (the
         // kernel strides over its items, so a phase with real work is only spread over fewer, longer CTAs)
-        nms_mask_kernel<<<phase == 0 || conditional ? grid : grid / 4, MASK_THREADS, (size_t)(b + 1) * sizeof(int), s_>>>(
+        nms_mask_kernel<<<phase == 0 ? grid : grid / 4, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(
             b, n_cap, iou_thres, phase, g_lo, g_hi, ws);
         KZD_LAUNCH_CHECK("nms_mask_kernel");
-        nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * 20, s_>>>(cand_rows, cand_cap, n_cap, max_det, phase, t_lo,
-                                                                        t_hi, ws, out_rows, out_counts, handle);
+        nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * 20, st>>>(cand_rows, cand_cap, n_cap, max_det, phase, t_lo, t_hi,
+                                                                        ws, out_rows, out_counts);
         KZD_LAUNCH_CHECK("nms_scan_kernel");
-        return 0;
-    };
-    if (int rc = launch_phase(0, 0, t0, st, (unsigned long long)more)) return rc;
-    if (two && !conditional) {
-        if (int rc = launch_phase(1, t0, ws.T_cap, st, 0ull)) return rc;
-    } else if (two) {
-        KZD_CUDA(cudaStreamGetCaptureInfo_v2(st, &cap_status, nullptr, &cap_graph, &deps, &n_deps));
-        cudaGraphNodeParams np = {};
-        np.type = cudaGraphNodeTypeConditional;
-        np.conditional.handle = more;
-        np.conditional.type = cudaGraphCondTypeIf;
-        np.conditional.size = 1;
-        cudaGraphNode_t node;
-        KZD_CUDA(cudaGraphAddNode(&node, cap_graph, deps, n_deps, &np));
-        cudaStream_t body_stream;  // exists only while the body is recorded
-        KZD_CUDA(cudaStreamCreateWithFlags(&body_stream, cudaStreamNonBlocking));
-        cudaError_t e = cudaStreamBeginCaptureToGraph(body_stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
-                                                      cudaStreamCaptureModeRelaxed);
-        int rc = 0;
-        if (e == cudaSuccess) {
-            rc = launch_phase(1, t0, ws.T_cap, body_stream, 0ull);
-            e = cudaStreamEndCapture(body_stream, nullptr);
-        }
-        cudaStreamDestroy(body_stream);
-        if (rc) return rc;
-        KZD_CUDA(e);
-        KZD_CUDA(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
     }
     return 0;
 }

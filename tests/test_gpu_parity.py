@@ -968,11 +968,11 @@ def test_assign_config3_multiclass_at_1280():
     assert int(mine[2].count_nonzero()) == int(mine[3].sum())  # one non-zero class score per foreground anchor
 
 
-def test_pipeline_conditional_second_nms_phase():
-    """Inside the captured graph the second (mask, walk) phase of kzd_nms_suppress is the body of a conditional
-    node. Replays alternate between a batch whose walks end in the first column range (max_det reached) and a
-    batch that needs every column (low IoU threshold: heavy suppression, fewer than max_det kept): every replay
-    must match the oracle, whichever way the node went the time before."""
+def test_pipeline_second_nms_phase_both_ways():
+    """The second (mask, walk) phase of kzd_nms_suppress only does work for images whose walk did not end in the
+    first column range. Replays of one captured graph alternate between a batch whose walks end there (few
+    candidates) and a batch that needs every column (low IoU threshold: heavy suppression, fewer than max_det
+    kept): every replay must match the oracle, whichever way the previous one went."""
     b, G, imgsz, nc, strides = 3, 50, 640, 1, synth.P2_P5
     pipe = kzd.PagePipeline(b, synth.level_shapes(imgsz, strides), strides, nc, G, device=DEV, conf_thres=0.25,
                             iou_thres=0.05, max_det=300, fuse_decodes=True, fuse_filter=True)
@@ -991,7 +991,7 @@ def test_pipeline_conditional_second_nms_phase():
         n_cand = pipe.candidate_counts()
         # first column range of this pipeline: (300 + 75 + 127) // 64 = 7 tiles = 448 boxes
         seen.add(max(n_cand) > 448 and min(int(t.shape[0]) for t in ref) < 300)
-    assert seen == {True, False}, "the test inputs must exercise both directions of the conditional node"
+    assert seen == {True, False}, "the test inputs must exercise both outcomes of the first phase"
 
 
 @pytest.mark.parametrize("cfg", [(2, 60, 320, 1, "columns", torch.float32), (2, 80, 320, 5, "uniform", torch.float32),

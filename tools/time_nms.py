@@ -37,3 +37,22 @@ for i in range(22):
     if i >= 2: tot += e0.elapsed_time(e1)
 print(sys.argv[1] if len(sys.argv) > 1 else "", "nms_suppress graph us:", round(tot / 20 * 1e3, 1), "kept", counts[1].tolist()[:4],
       "checksum", float(out_rows.double().sum()))
+import collections
+from torch.profiler import ProfilerActivity, profile
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for i in range(10):
+        flush.zero_(); flush_rd.sum(); g.replay()
+    torch.cuda.synchronize()
+agg = collections.OrderedDict()
+evs = sorted([e for e in prof.events() if e.device_type.name == "CUDA" and "nms_" in e.name], key=lambda e: e.time_range.start)
+for e in evs:
+    agg.setdefault(e.name.replace("kzd::", "").split("(")[0], []).append(e.device_time if hasattr(e, "device_time") else e.cuda_time)
+print(sys.argv[1] if len(sys.argv) > 1 else "", "kernels:", {k[-24:]: round(sum(v) / len(v), 1) for k, v in agg.items()})
+# gaps between consecutive nms kernels of one replay (start of next - end of previous)
+per = len(evs) // 10
+if per >= 2:
+    gaps = []
+    for r in range(10):
+        seq = evs[r * per:(r + 1) * per]
+        gaps.append([round(seq[j + 1].time_range.start - seq[j].time_range.end, 1) for j in range(per - 1)])
+    print("gaps us (replay 5):", gaps[5], "span us:", round(evs[6 * per - 1].time_range.end - evs[5 * per].time_range.start, 1))
