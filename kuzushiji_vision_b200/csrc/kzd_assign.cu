@@ -8,7 +8,7 @@
 //   assign_verify_kernel      only when the caller does not vouch for anc_points: checks them against the
 //                             level table bit for bit (the grid accelerator is used only when every anchor
 //                             matches)
-//   assign_candidates_kernel  one warp per (image, GT): the anchors inside the GT are an exact
+//   assign_candidates_kernel  one half warp (topk <= 16) or warp per (image, GT): the anchors inside the GT are an exact
 //                             rectangle per level (separable x / y tests); CIoU + alignment metric 32
 //                             pairs at a time, top-k by warp-wide redux max, selecting GTs recorded with two
 //                             atomicMax words per picked anchor and in a pick list; each warp also stores the
@@ -61,6 +61,7 @@ struct AssignParams {
     float inv_stride[KZD_MAX_LEVELS];
     int n_levels, zero_fill;
     int fill_vec;     // A % 16 == 0 and 16-byte aligned outputs: background targets are stored as 16 B words
+    int fill_per;     // anchors whose background targets one GT's warp stores
     int score_dtype;  // dtype pd_scores had at the call site: 0 fp32, 1 fp16, 2 bf16 (AMP, utils/tal.py:137)
     long long* target_labels;
     float* target_bboxes;
@@ -202,41 +203,52 @@ __device__ __forceinline__ void cell_range(float lo_edge, float hi_edge, float s
     last = j;  // -1: none
 }
 
-// One warp per (image, GT).
+// One GROUP of GW lanes per (image, GT): GW = 32 (a warp per GT) or GW = 16 (two GTs per warp).
 //  1. produce: the anchors inside the GT. The in-GT predicate (utils/tal.py:259-262: min of the four fp32
 //     differences > 1e-9  <=>  each one is) separates into an x test per column and a y test per row, so on
-//     a make_anchors grid the anchors are an exact rectangle per level, written to shared memory 32 per
+//     a make_anchors grid the anchors are an exact rectangle per level, written to shared memory GW per
 //     step in ascending anchor order (only ~108 of 136,000 anchors are ever touched).
-//  2. evaluate: 32 pairs at a time with all lanes busy - CIoU, s^alpha * o^beta, the per-anchor
-//     argmax-overlap key (64-bit atomicMax); metric bits parked next to the anchor.
-//  3. select: topk rounds of warp-wide max (redux.sync) over the lanes' local maxima; ties go to the
+//  2. evaluate: GW pairs at a time with all lanes busy - CIoU, s^alpha * o^beta; metric bits parked next to
+//     the anchor.
+//  3. select: topk rounds of group-wide max (redux.sync) over the lanes' local maxima; ties go to the
 //     lowest anchor index = lowest slot, as torch.topk breaks them on the device. Only the lane that owned
 //     the winner rescans its slots.
-// A GT with more than CAND_CAP pairs is handled in chunks: the chunk's winners are carried into the first
-// slots of the next one (they have the lowest anchor indices, so the tie rule still holds).
+// A GT with more than the group's slot capacity is handled in chunks: the chunk's winners are carried into the
+// first slots of the next one (they have the lowest anchor indices, so the tie rule still holds).
+// Why two GTs per warp: the kernel is a chain of dependent steps per GT and the register budget allows 32
+// resident warps per SM, so 9,600 GTs on a warp each take two "waves" of that chain. Kuzushiji boxes hold
+// ~100 anchors: 16 lanes keep the pair batches as full as 32 do, the group-uniform steps (cell ranges,
+// top-k rounds) now serve two GTs per issued instruction, and one wave is enough.
+template <int GW>
 __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates_kernel(const AssignParams p) {
+    constexpr int GROUPS = 32 / GW;          // GTs per warp
+    constexpr int CAP = CAND_CAP / GROUPS;   // slots per group
+    constexpr int LV = GW / 8;               // level slots one ballot settles: lane = level slot x edge (4) x probe (2)
     __shared__ uint32_t s_bits[CAND_WARPS][CAND_CAP];
     __shared__ int s_anc[CAND_WARPS][CAND_CAP];
-    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long total = (long long)p.b * p.G;
-    // (a device-side work queue - warps pulling GTs from an atomic counter - was measured 16 us slower
-    // than this fixed assignment: the queue's round trips sit on every warp's critical path)
-    for (long long it = 0;; ++it) {
-    const long long wid = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + it * (((long long)gridDim.x * blockDim.x) >> 5);
-    if (wid >= total) return;
-    const int bi = (int)(wid / p.G), g = (int)(wid % p.G);
-    if (lane == 0) p.ws.pos_align[wid] = 0u, p.ws.pos_ov[wid] = 0u;
-    if (wid == 0 && lane == 0 && p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
+    const int gl = lane & (GW - 1), grp = lane / GW, gbase = grp * GW;  // lane inside the group, group inside the warp
+    const unsigned GM = GW == 32 ? 0xffffffffu : (0xffffu << gbase);    // the group's lanes: every sync below is group-wide
+    const uint32_t total = (uint32_t)p.b * (uint32_t)p.G;  // b * G < 2^32 is checked by the host
+    auto gballot = [&](bool pred) { return (__ballot_sync(GM, pred) >> gbase) & (GW == 32 ? 0xffffffffu : 0xffffu); };
+    // (a device-side work queue - groups pulling GTs from an atomic counter - was measured 16 us slower
+    // than this fixed assignment: the queue's round trips sit on every group's critical path)
+    for (unsigned long long it = 0;; ++it) {
+    const unsigned long long wid64 =
+        ((unsigned long long)blockIdx.x * CAND_WARPS + wib) * GROUPS + grp + it * ((unsigned long long)gridDim.x * CAND_WARPS * GROUPS);
+    if (wid64 >= total) return;
+    const uint32_t wid = (uint32_t)wid64;
+    const int bi = (int)(wid / (uint32_t)p.G), g = (int)(wid - (uint32_t)bi * (uint32_t)p.G);  // 32-bit division
+    if (gl == 0) p.ws.pos_align[wid] = 0u, p.ws.pos_ov[wid] = 0u;
+    if (wid == 0 && gl == 0 && p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
     const size_t img = (size_t)bi * p.A;
-    uint2* __restrict__ picks = p.ws.picks + wid * p.topk;
+    uint2* __restrict__ picks = p.ws.picks + (size_t)wid * p.topk;
     auto fill_background = [&]() {
-        // Background targets for this warp's slice of the image's anchors (every anchor that nobody
+        // Background targets for this group's slice of the image's anchors (every anchor that nobody
         // selects takes GT 0's label and box, target_gt_idx 0, utils/tal.py:215-233): plain streaming
         // stores that ride along with the latency-bound pair work instead of a separate dense pass (issued
-        // when the warp has finished its GT, so they are spread over the kernel's lifetime).
-        int per = (p.A + p.G - 1) / p.G;
-        if (p.fill_vec) per = (per + 15) & ~15;  // 16-anchor granules: every array's slice is a whole number of 16 B words
+        // when the group has finished its GT, so they are spread over the kernel's lifetime).
+        const int per = p.fill_per;  // ceil(A / G), in 16-anchor granules when fill_vec: every array's slice is whole 16 B words
         const int a_lo = min(p.A, g * per), a_hi = min(p.A, a_lo + per);
         const float4 box0 = *reinterpret_cast<const float4*>(p.gt_bboxes + (size_t)bi * p.G * 4);
         long long lab0 = (long long)p.gt_labels[(size_t)bi * p.G];
@@ -246,7 +258,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             const int len = a_hi - a_lo;
             auto fill16 = [&](void* base, int elem_bytes, uint4 pat) {
                 uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + first * elem_bytes);
-                for (int i = lane; i < (len * elem_bytes) >> 4; i += 32) dst[i] = pat;
+                for (int i = gl; i < (len * elem_bytes) >> 4; i += GW) dst[i] = pat;
             };
             const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
             const uint32_t l_lo = (uint32_t)lab0, l_hi = (uint32_t)((unsigned long long)lab0 >> 32);
@@ -257,7 +269,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             fill16(p.fg_mask, 1, zero);
             if (p.nc == 1) fill16(p.target_scores, 4, zero);
         } else {
-            for (int a = a_lo + lane; a < a_hi; a += 32) {
+            for (int a = a_lo + gl; a < a_hi; a += GW) {
                 const size_t idx = img + a;
                 p.target_gt_idx[idx] = 0;
                 p.target_labels[idx] = lab0;
@@ -267,12 +279,12 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             }
         }
     };
-    // everything the warp needs about its GT, loaded together (one memory round trip instead of three)
+    // everything the group needs about its GT, loaded together (one memory round trip instead of three)
     const float gt_mask = p.mask_gt[wid], gt_label = p.gt_labels[wid];
-    const float4 gt_box = *reinterpret_cast<const float4*>(p.gt_bboxes + wid * 4);
+    const float4 gt_box = *reinterpret_cast<const float4*>(p.gt_bboxes + (size_t)wid * 4);
     const int flag_mismatch = p.ws.flags[0];
     if (gt_mask == 0.f) {  // padded GT: claims nothing, contributes zero overlap
-        if (lane < p.topk) picks[lane] = make_uint2(0xffffffffu, 0u);
+        if (gl < p.topk) picks[gl] = make_uint2(0xffffffffu, 0u);
         fill_background();
         continue;
     }
@@ -285,14 +297,14 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
     const float* __restrict__ pds = p.pd_scores + img * p.nc + label;
     const int topk = p.topk;
-    uint32_t* bits = s_bits[wib];
-    int* ancs = s_anc[wib];
-    int n = 0, n_eval = 0;        // slots filled / evaluated (warp-uniform)
+    uint32_t* bits = s_bits[wib] + grp * CAP;
+    int* ancs = s_anc[wib] + grp * CAP;
+    int n = 0, n_eval = 0;        // slots filled / evaluated (group-uniform)
     uint32_t sel_bits = 0u;       // lane r < n_sel: the r-th best pair so far
     int sel_anc = -1, n_sel = 0;
 
     auto evaluate = [&]() {  // slots [n_eval, n): anchors -> metric bits
-        __syncwarp();
+        __syncwarp(GM);
         // the gathers of batch k+1 (predicted box 16 B, score 4 B per pair) are issued before batch k is
         // evaluated, so only the first batch's memory latency is exposed
         int a_nx = 0;
@@ -305,26 +317,26 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
                 sc_nx = __ldg(pds + (size_t)a_nx * p.nc);
             }
         };
-        fetch(n_eval + lane);
-        for (int e = n_eval; e < n; e += 32) {
-            const int t = e + lane;
+        fetch(n_eval + gl);
+        for (int e = n_eval; e < n; e += GW) {
+            const int t = e + gl;
             const float4 pb = pb_nx;
             const float sc = sc_nx;
-            fetch(t + 32);
+            fetch(t + GW);
             if (t < n) bits[t] = eval_pair(p, gt, pb, sc);
         }
         n_eval = n;
-        __syncwarp();
+        __syncwarp(GM);
     };
-    auto select = [&]() {  // top-k of slots [0, n) -> lanes 0..n_sel-1
-        // every lane tracks the best TWO of its slots (t = lane, lane + 32, ...), so a lane that wins a round
+    auto select = [&]() {  // top-k of slots [0, n) -> lanes 0..n_sel-1 of the group
+        // every lane tracks the best TWO of its slots (t = gl, gl + GW, ...), so a lane that wins a round
         // moves on to its runner-up without touching shared memory; only a lane winning again rescans
         uint32_t lm = 0u, lm2 = 0u, nb = 0u;
         int lt = 0x7fffffff, lt2 = 0x7fffffff, nt = 0, cnt = 0;
         bool have2 = true;
         auto scan2 = [&]() {
             lm = lm2 = 0u, lt = lt2 = 0x7fffffff;
-            for (int t = lane; t < n; t += 32) {
+            for (int t = gl; t < n; t += GW) {
                 const uint32_t v = bits[t];
                 if (v > lm) lm2 = lm, lt2 = lt, lm = v, lt = t;  // strict: the lowest slot among equals comes first
                 else if (v > lm2) lm2 = v, lt2 = t;
@@ -333,73 +345,86 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
         };
         scan2();
         for (int r = 0; r < topk; ++r) {
-            const uint32_t mx = __reduce_max_sync(FULL, lm);
+            const uint32_t mx = __reduce_max_sync(GM, lm);
             if (mx == 0u) break;
-            const unsigned who = __ballot_sync(FULL, lm == mx);
+            const unsigned who = gballot(lm == mx);
             int owner = __ffs(who) - 1;
-            if (who & (who - 1u)) owner = __reduce_min_sync(FULL, lm == mx ? lt : 0x7fffffff) & 31;  // slot t belongs to lane t % 32
-            const int ts = __shfl_sync(FULL, lt, owner);
-            if (lane == r) nb = mx, nt = ts;
+            if (who & (who - 1u)) owner = __reduce_min_sync(GM, lm == mx ? lt : 0x7fffffff) & (GW - 1);  // slot t belongs to lane t % GW
+            const int ts = __shfl_sync(GM, lt, owner, GW);
+            if (gl == r) nb = mx, nt = ts;
             ++cnt;
-            if (lane == owner) {
+            if (gl == owner) {
                 bits[ts] = 0u;
                 if (have2) lm = lm2, lt = lt2, have2 = false;
                 else scan2();
             }
-            __syncwarp();
+            __syncwarp(GM);
         }
         sel_bits = nb, n_sel = cnt;
-        sel_anc = lane < cnt ? ancs[nt] : -1;
+        sel_anc = gl < cnt ? ancs[nt] : -1;
     };
     auto make_room = [&]() {  // chunk full: keep its winners, drop the rest
-        if (n + 32 <= CAND_CAP) return;
+        if (n + GW <= CAP) return;
         evaluate();
         select();
-        __syncwarp();
-        if (lane < n_sel) bits[lane] = sel_bits, ancs[lane] = sel_anc;
+        __syncwarp(GM);
+        if (gl < n_sel) bits[gl] = sel_bits, ancs[gl] = sel_anc;
         n = n_eval = n_sel;
-        __syncwarp();
+        __syncwarp(GM);
     };
 
     if (grid_ok) {
-        // Exact cell ranges, one ballot per level: lanes 0-7 probe 8 columns around the estimate of the first
-        // column inside, lanes 8-15 around the last column, lanes 16-23 / 24-31 the same for rows. Each probe is
-        // the reference's own fp32 test on the (verified) anchor coordinate; the tests are monotone in the cell
-        // index, so the boundary is where the probe pattern flips. A window that does not show the flip (a GT
-        // edge outside the page; otherwise the fp32 estimate is off by one cell at most) falls back to the
-        // scalar walk.
-        const int grp = lane >> 3, k = lane & 7;
-        const bool is_hi = grp & 1, is_y = grp >= 2;
+        // Exact cell ranges, one ballot for LV levels: lane = level slot x edge (x-low, x-high, y-low, y-high) x
+        // probe (2). Each probe is the reference's own fp32 test on the (verified) anchor coordinate and the tests
+        // are monotone in the cell index, so an edge is settled when its two probes - the cells the fp32 estimate
+        // puts on either side of the boundary - come out (fail, pass) for a low edge or (pass, fail) for a high
+        // one, or when the page border settles it. Anything else (the estimate off by a cell, about one edge in
+        // 10^5) falls back to the scalar walk for that axis.
+        const int q_lane = gl >> 3, e_lane = (gl >> 1) & 3, k_lane = gl & 1;
+        const bool is_hi = e_lane & 1, is_y = e_lane >> 1;
         const float edge = is_y ? (is_hi ? gt.y2 : gt.y1) : (is_hi ? gt.x2 : gt.x1);
-        for (int l = 0; l < p.n_levels; ++l) {
+        for (int l0 = 0; l0 < p.n_levels; l0 += LV) {
+            int c0 = 0;
+            bool ok = false;
+            if (l0 + q_lane < p.n_levels) {
+                const int l = l0 + q_lane;
+                const float s = p.lv[l].stride, x = edge * p.inv_stride[l] - 0.5f;
+                const int ncell = is_y ? p.lv[l].h : p.lv[l].w;
+                // low edge: last failing cell = floor(x); high edge: last passing cell = ceil(x) - 1
+                const float est = is_hi ? ceilf(x) - 1.f : floorf(x);
+                c0 = (int)fminf(fmaxf(est, -1.f), (float)(ncell - 1));
+                const int c = c0 + k_lane;
+                const float ctr = __fmul_rn((float)c + 0.5f, s);
+                ok = c >= 0 && c < ncell && (is_hi ? (__fsub_rn(edge, ctr) > 1e-9f) : (__fsub_rn(ctr, edge) > 1e-9f));
+            }
+            const unsigned m_all = gballot(ok);
+            for (int q = 0; q < LV && l0 + q < p.n_levels; ++q) {
+            const int l = l0 + q;
             const float s = p.lv[l].stride, inv_s = p.inv_stride[l];
             const int W = p.lv[l].w, H = p.lv[l].h, off = p.lv[l].offset;
-            const int ncell = is_y ? H : W;
-            const float est = fminf(fmaxf(floorf(edge * inv_s - 0.5f), -8.f), (float)ncell + 8.f);
-            const int w0 = (int)est - 3;  // first probed cell of this lane's group
-            const int c = w0 + k;
-            const float ctr = __fmul_rn((float)c + 0.5f, s);
-            const bool ok = c >= 0 && c < ncell && (is_hi ? (__fsub_rn(edge, ctr) > 1e-9f) : (__fsub_rn(ctr, edge) > 1e-9f));
-            const unsigned m = __ballot_sync(FULL, ok);
-            const int wx0 = __shfl_sync(FULL, w0, 0), wx1 = __shfl_sync(FULL, w0, 8);
-            const int wy0 = __shfl_sync(FULL, w0, 16), wy1 = __shfl_sync(FULL, w0, 24);
+            const unsigned m = (m_all >> (8 * q)) & 0xffu;  // bits: x-low {0,1}, x-high {2,3}, y-low {4,5}, y-high {6,7}
+            const int cx0 = __shfl_sync(GM, c0, 8 * q, GW), cx1 = __shfl_sync(GM, c0, 8 * q + 2, GW);
+            const int cy0 = __shfl_sync(GM, c0, 8 * q + 4, GW), cy1 = __shfl_sync(GM, c0, 8 * q + 6, GW);
             int i0, i1, j0, j1;
-            {   // low edges: first passing cell; trusted when the cell before it was probed (or is cell 0)
-                const unsigned bx = m & 0xffu, by = (m >> 16) & 0xffu;
-                const int qx = __ffs(bx) - 1, qy = __ffs(by) - 1;
-                const bool okx = bx ? (qx > 0 || wx0 <= 0) : (wx0 <= W - 1 && wx0 + 7 >= W - 1);
-                const bool oky = by ? (qy > 0 || wy0 <= 0) : (wy0 <= H - 1 && wy0 + 7 >= H - 1);
-                i0 = bx ? wx0 + qx : W;
-                j0 = by ? wy0 + qy : H;
-                // high edges: last passing cell; trusted when the cell after it was probed (or is the last cell)
-                const unsigned cx = (m >> 8) & 0xffu, cy = m >> 24;
-                const int rx = 31 - __clz(cx), ry = 31 - __clz(cy);
-                const bool okx1 = cx ? (rx < 7 || wx1 + 7 >= W - 1) : (wx1 <= 0 && wx1 + 7 >= 0);
-                const bool oky1 = cy ? (ry < 7 || wy1 + 7 >= H - 1) : (wy1 <= 0 && wy1 + 7 >= 0);
-                i1 = cx ? wx1 + rx : -1;
-                j1 = cy ? wy1 + ry : -1;
-                if (!(okx && okx1)) cell_range(gt.x1, gt.x2, s, inv_s, W, i0, i1);  // uniform
-                if (!(oky && oky1)) cell_range(gt.y1, gt.y2, s, inv_s, H, j0, j1);
+            {
+                // low edge, probes (c0, c0+1): first passing cell
+                auto low = [](unsigned pr, int c, int ncell, int& first) {
+                    if (pr == 2u) { first = c + 1; return true; }                        // (fail, pass)
+                    if (pr & 1u) { first = c; return c == 0; }                            // c passes: settled only at the border
+                    first = ncell;                                                        // (fail, fail): none, if the last cell was probed
+                    return c + 1 >= ncell - 1;
+                };
+                // high edge, probes (c0, c0+1): last passing cell
+                auto high = [](unsigned pr, int c, int ncell, int& last) {
+                    if (pr == 1u) { last = c; return true; }                              // (pass, fail)
+                    if (pr & 2u) { last = c + 1; return c + 1 == ncell - 1; }             // c+1 passes: settled only at the border
+                    last = -1;                                                            // (fail, fail): none, if cell 0 was probed
+                    return c <= 0;
+                };
+                const bool okx = low(m & 3u, cx0, W, i0) & high((m >> 2) & 3u, cx1, W, i1);
+                const bool oky = low((m >> 4) & 3u, cy0, H, j0) & high((m >> 6) & 3u, cy1, H, j1);
+                if (!okx) cell_range(gt.x1, gt.x2, s, inv_s, W, i0, i1);  // group-uniform
+                if (!oky) cell_range(gt.y1, gt.y2, s, inv_s, H, j0, j1);
             }
             if (i0 > i1 || j0 > j1) continue;
             const unsigned nx = (unsigned)(i1 - i0 + 1), cnt = nx * (unsigned)(j1 - j0 + 1);
@@ -407,35 +432,36 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             // t / nx by multiplication: exact for t < 2^16 (magic = ceil(2^32 / nx), nx >= 2)
             const bool use_magic = cnt <= 65536u && nx >= 2u;
             const unsigned magic = use_magic ? 0xffffffffu / nx + 1u : 0u;
-            for (unsigned r = 0; r < cnt; r += 32) {
+            for (unsigned r = 0; r < cnt; r += GW) {
                 make_room();
-                const unsigned t = r + lane;
+                const unsigned t = r + gl;
                 if (t < cnt) {
                     const unsigned row = use_magic ? __umulhi(t, magic) : t / nx;
-                    ancs[n + lane] = base + (int)row * W + (int)(t - row * nx);
+                    ancs[n + gl] = base + (int)row * W + (int)(t - row * nx);
                 }
-                n += (int)min(32u, cnt - r);
+                n += (int)min((unsigned)GW, cnt - r);
             }
+            }  // level slot
         }
     } else {
-        for (int t0 = 0; t0 < p.A; t0 += 32) {  // anchors are not a make_anchors grid: test them all
-            const int a = t0 + lane;
+        for (int t0 = 0; t0 < p.A; t0 += GW) {  // anchors are not a make_anchors grid: test them all
+            const int a = t0 + gl;
             bool inside = false;
             if (a < p.A) {
                 const float2 ap = __ldg(anc + a);
                 inside = anchor_in_gt(ap.x, ap.y, gt);
             }
-            const unsigned m = __ballot_sync(FULL, inside);
+            const unsigned m = gballot(inside);
             if (m == 0u) continue;
             make_room();
-            if (inside) ancs[n + __popc(m & ((1u << lane) - 1u))] = a;
+            if (inside) ancs[n + __popc(m & ((1u << gl) - 1u))] = a;
             n += __popc(m);
         }
     }
     evaluate();
     select();
 
-    const bool has = lane < n_sel;
+    const bool has = gl < n_sel;
     if (has) mark_selected(p.ws.sel + img + sel_anc, g);
     uint32_t pick = has ? (uint32_t)(img + sel_anc) : 0xffffffffu;  // lane r: the r-th entry of this GT's pick list
     if (p.zero_fill) {
@@ -444,19 +470,19 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
         int need = topk - n_sel, n_pick = n_sel;
         for (int a = 0; need > 0 && a < p.A; ++a) {
             const bool mine = has && sel_anc == a;
-            if (__any_sync(FULL, mine)) continue;  // positive pick, already counted
+            if (__any_sync(GM, mine)) continue;  // positive pick, already counted
             --need;
             const float2 ap = __ldg(anc + a);
-            if (anchor_in_gt(ap.x, ap.y, gt)) {  // uniform
-                if (lane == 0) mark_selected(p.ws.sel + img + a, g);
-                if (lane == n_pick) pick = (uint32_t)(img + a);
+            if (anchor_in_gt(ap.x, ap.y, gt)) {  // group-uniform
+                if (gl == 0) mark_selected(p.ws.sel + img + a, g);
+                if (gl == n_pick) pick = (uint32_t)(img + a);
                 ++n_pick;
             }
         }
     }
-    if (lane < topk) picks[lane] = make_uint2(pick, (uint32_t)g);
-    fill_background();  // last: the stores never sit in front of this warp's latency-critical loads
-    __syncwarp();
+    if (gl < topk) picks[gl] = make_uint2(pick, (uint32_t)g);
+    fill_background();  // last: the stores never sit in front of this group's latency-critical loads
+    __syncwarp(GM);
     }  // next GT
 }
 
@@ -538,11 +564,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
             c_ap[my_c] = ap, c_pb[my_c] = pb, c_key[my_c] = 0ull;
         }
         __syncthreads();
-#ifdef KZD_EXP_NOSCAN
-        const int n_c = 0;
-#else
         const int n_c = c_n;  // CTA-uniform
-#endif
         if (n_c > 0) {
             for (int g0 = 0; g0 < p.G; g0 += PATCH_THREADS * SCAN_ILP) {
                 float4 box[SCAN_ILP];
@@ -583,9 +605,6 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
             }
             __syncthreads();  // every reader of the list is done before the next round refills it
         }
-#ifdef KZD_EXP_NOREP
-        rep = false;
-#endif
         if (rep) {
             long long lab = (long long)glab;
             lab = lab < 0 ? 0 : lab;
@@ -626,13 +645,6 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
     }
     __syncthreads();
     if (!s_last) return;
-#ifdef KZD_EXP_NOTAIL
-    if (threadIdx.x == 0) {
-        img_state[0] = 0, img_state[1] = 0;
-        if (atomicAdd(p.ws.flags + 1, 1) == (int)gridDim.y - 1) p.ws.flags[1] = 0, p.ws.flags[0] = 0;
-    }
-    return;
-#endif
     __threadfence();
     float local = 0.f;
     int n_fg = 0;
@@ -794,6 +806,8 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     p.n_levels = n_levels, p.zero_fill = zero_fill, p.score_dtype = score_dtype;
     p.fill_vec = A % 16 == 0 && ((uintptr_t)target_labels | (uintptr_t)target_gt_idx | (uintptr_t)fg_mask |
                                  (uintptr_t)target_scores | (uintptr_t)target_bboxes) % 16 == 0;
+    p.fill_per = (A + G - 1) / G;
+    if (p.fill_vec) p.fill_per = (p.fill_per + 15) & ~15;
     p.target_labels = (long long*)target_labels, p.target_bboxes = target_bboxes, p.target_scores = target_scores;
     p.fg_mask = fg_mask, p.target_gt_idx = (long long*)target_gt_idx, p.counters = counters;
 
@@ -820,13 +834,23 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
         }
     }
     {
-        const long long warps = (long long)b * G;
-        long long blocks = (warps * 32 + CAND_THREADS - 1) / CAND_THREADS;
-        if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;  // the kernel strides over the rest
-#ifdef KZD_CAND_PERSIST
-        if (blocks > (long long)sm_count() * KZD_CAND_PERSIST) blocks = (long long)sm_count() * KZD_CAND_PERSIST;
+        // two GTs per warp (16 lanes each) whenever the pick list fits the half warp; a warp per GT otherwise
+#ifndef KZD_CAND_GW
+#define KZD_CAND_GW 16
 #endif
-        assign_candidates_kernel<<<(unsigned)blocks, CAND_THREADS, 0, st>>>(p);
+        const int gw = (topk <= 16 && KZD_CAND_GW == 16) ? 16 : 32;
+        const long long warps = ((long long)b * G + (32 / gw) - 1) / (32 / gw);
+        long long blocks = (warps + CAND_WARPS - 1) / CAND_WARPS;
+        if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;  // the kernel strides over the rest
+        // persistent grid: no more CTAs than the SMs hold at once (4 per SM); their groups stride over the GTs.
+        // Measured with four page batches in flight (tools/pipe_value.py, G = 600 / 1000): 150.7 / 180.4 us per step
+        // against 150.4 / 186.3 with one CTA per eight groups, and 159.3 / 182.8 with a warp per GT.
+#ifndef KZD_CAND_PERSIST
+#define KZD_CAND_PERSIST 4
+#endif
+        if (KZD_CAND_PERSIST > 0 && blocks > (long long)sm_count() * KZD_CAND_PERSIST) blocks = (long long)sm_count() * KZD_CAND_PERSIST;
+        if (gw == 16) assign_candidates_kernel<16><<<(unsigned)blocks, CAND_THREADS, 0, st>>>(p);
+        else assign_candidates_kernel<32><<<(unsigned)blocks, CAND_THREADS, 0, st>>>(p);
         KZD_LAUNCH_CHECK("assign_candidates_kernel");
     }
     {

@@ -587,6 +587,14 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float sa, const flo
     const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
     const float inter = __fmul_rn(w, h);
     const float u = __fsub_rn(__fmaf_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y), sa), inter);
+    // inter / u > thr, decided without the division whenever the quotient is not within a few ulps of thr (the
+    // product thr * u carries one rounding, the quotient another: 2^-20 of slack covers both many times over);
+    // only the rare borderline pair pays for the IEEE division that fixes torchvision's exact answer
+    if (u > 0.f && thr > 0.f) {
+        const float tu = __fmul_rn(thr, u);
+        if (inter > __fmul_rn(tu, 1.000001f)) return true;
+        if (inter < __fmul_rn(tu, 0.999999f)) return false;
+    }
     return __fdiv_rn(inter, u) > thr;
 }
 
@@ -608,6 +616,13 @@ __device__ __forceinline__ int items_before(int T, int g) {
     if (g <= 0 || T <= 0) return 0;
     if (g >= Gc) return MASK_CG * (Gc - 1) * Gc / 2 + T;  // CG * (1 + ... + (Gc-1)) + T
     return MASK_CG * g * (g + 1) / 2;
+}
+
+static long long items_before_host(int T, int g) {  // host twin of items_before
+    const int Gc = (T + MASK_CG - 1) / MASK_CG;
+    if (g <= 0 || T <= 0) return 0;
+    if (g >= Gc) return (long long)MASK_CG * (Gc - 1) * Gc / 2 + T;
+    return (long long)MASK_CG * g * (g + 1) / 2;
 }
 
 // Phase = column groups [g_lo, g_hi) of every image that is not finished yet (the greedy walk stops as
@@ -1057,14 +1072,22 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
 #ifndef KZD_MASK_GRID
 #define KZD_MASK_GRID 16
 #endif
+#ifndef KZD_MASK_GRID0
+#define KZD_MASK_GRID0 16
+#endif
     const int grid = sm_count() * KZD_MASK_GRID;
     int t0 = ((max_det + max_det / 4 + 64 + 63) / 64 + MASK_CG - 1) / MASK_CG * MASK_CG;
     if (t0 > ws.T_cap) t0 = ws.T_cap;
     for (int phase = 0, t_lo = 0, t_hi = t0; t_lo < ws.T_cap; ++phase, t_lo = t_hi, t_hi = ws.T_cap) {
         const int g_lo = t_lo / MASK_CG, g_hi = (t_hi + MASK_CG - 1) / MASK_CG;
-        // the second phase usually finds every image finished: a quarter of the CTAs keeps that exit cheap (the
-        // kernel strides over its items, so a phase with real work is only spread over fewer, longer CTAs)
-        nms_mask_kernel<<<phase == 0 ? grid : grid / 4, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(
+        // First phase: one CTA per tile when the machine can hold them all at once (32 resident 64-thread CTAs per
+        // SM), so no CTA builds two tiles while others are done. The second phase usually finds every image
+        // finished: a quarter of the persistent grid keeps that exit cheap (the kernel strides over its items, so a
+        // phase with real work is only spread over fewer, longer CTAs).
+        long long items0 = (long long)b * items_before_host(t_hi, g_hi);
+        const long long cap0 = (long long)sm_count() * KZD_MASK_GRID0;
+        const int grid0 = (int)(items0 < cap0 ? (items0 > grid ? items0 : grid) : cap0);
+        nms_mask_kernel<<<phase == 0 ? grid0 : grid / 4, MASK_THREADS, (size_t)(b + 1) * sizeof(int), st>>>(
             b, n_cap, iou_thres, phase, g_lo, g_hi, ws);
         KZD_LAUNCH_CHECK("nms_mask_kernel");
         nms_scan_kernel<<<b, SCAN_THREADS, (size_t)ws.T_cap * 20, st>>>(cand_rows, cand_cap, n_cap, max_det, phase, t_lo, t_hi,
