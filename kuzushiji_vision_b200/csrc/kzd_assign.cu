@@ -43,7 +43,7 @@ struct AssignWs {
                          //           consumed by the candidates kernel, cleared by the patch kernel's tail);
                          // [1] images finished (ticket of the patch kernel's tail, self-resetting);
                          // [2] copy of [0] as the last call left it (the host may poll it, kzd_assign_report_offset)
-    int32_t* img;        // (b*2)  per image: [0] side-list length, [1] CTA ticket; both self-resetting
+    int32_t* img;        // (b*2)  per image: [0] side-list length, [1] CTA ticket of the normalise kernel; both self-resetting
     uint32_t* pos_align; // (b*G)  per-GT max alignment metric (float bits)
     uint32_t* pos_ov;    // (b*G)  per-GT max overlap (float bits)
     uint4* fg_list;      // (b*A)  per-image side list (image i at i*A) of foreground anchors owned by another GT
@@ -63,6 +63,8 @@ struct AssignParams {
     int fill_vec;     // A % 16 == 0 and 16-byte aligned outputs: background targets are stored as 16 B words
     int fill_per;     // anchors whose background targets one GT's warp stores
     int score_dtype;  // dtype pd_scores had at the call site: 0 fp32, 1 fp16, 2 bf16 (AMP, utils/tal.py:137)
+    int strip_words;  // 32-bit words of one strip's GT mask in the patch kernel's index (0: index not used)
+    float inv_strip;  // strips per pixel
     long long* target_labels;
     float* target_bboxes;
     float* target_scores;
@@ -179,9 +181,20 @@ __device__ __forceinline__ void mark_selected(uint2* __restrict__ sel, int g) {
 }
 
 // One in-GT pair: the alignment metric's bits (0: not positive; positive floats order like their bit patterns).
+// STD: alpha = 0.5, beta = 6 as literals, so the compiler specialises the inlined powf for the constant exponent
+// (same libdevice algorithm, same bits, fewer instructions than the generic call).
+template <bool STD>
 __device__ __forceinline__ uint32_t eval_pair(const AssignParams& p, const GtBox& gt, const float4 pb, const float sc) {
     const float o = overlap_ciou(gt, pb);
-    const float al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
+    float al;
+    if (STD) {
+        float v = sqrtf(sc);
+        if (p.score_dtype == 1) v = __half2float(__float2half_rn(v));
+        else if (p.score_dtype == 2) v = __bfloat162float(__float2bfloat16_rn(v));
+        al = __fmul_rn(v, powf(o, 6.0f));
+    } else {
+        al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
+    }
     return al > 0.f ? __float_as_uint(al) : 0u;
 }
 
@@ -210,36 +223,77 @@ __device__ __forceinline__ void cell_range(float lo_edge, float hi_edge, float s
 //     step in ascending anchor order (only ~108 of 136,000 anchors are ever touched).
 //  2. evaluate: GW pairs at a time with all lanes busy - CIoU, s^alpha * o^beta; metric bits parked next to
 //     the anchor.
-//  3. select: topk rounds of group-wide max (redux.sync) over the lanes' local maxima; ties go to the
+//  3. select: topk rounds of group-wide max over the lanes' local maxima; ties go to the
 //     lowest anchor index = lowest slot, as torch.topk breaks them on the device. Only the lane that owned
 //     the winner rescans its slots.
 // A GT with more than the group's slot capacity is handled in chunks: the chunk's winners are carried into the
 // first slots of the next one (they have the lowest anchor indices, so the tie rule still holds).
 // Why two GTs per warp: the kernel is a chain of dependent steps per GT and the register budget allows 32
 // resident warps per SM, so 9,600 GTs on a warp each take two "waves" of that chain. Kuzushiji boxes hold
-// ~100 anchors: 16 lanes keep the pair batches as full as 32 do, the group-uniform steps (cell ranges,
-// top-k rounds) now serve two GTs per issued instruction, and one wave is enough.
+// ~100 anchors: 16 lanes keep the pair batches as full as 32 do, and every instruction the warp issues now
+// serves two GTs.
+// LOCKSTEP: the two groups of a warp never diverge at a collective. Every vote / shuffle / reduction below is a
+// full-warp instruction whose result is read per group (segmented butterflies, shifted ballots), and every loop
+// that contains one runs to the larger of the two groups' trip counts with the finished group predicated off.
+// (The first two-GTs-per-warp version used half-warp member masks: the compiler then wraps each collective in
+// a divergence protocol - MATCH.ANY / BRA.DIV / WARPSYNC.COLLECTIVE - and the groups drift apart, so each issued
+// instruction served one GT again: 19.9 M warp instructions for 9,600 GTs against 23.9 M with a warp per GT.)
 template <int GW>
 __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates_kernel(const AssignParams p) {
     constexpr int GROUPS = 32 / GW;          // GTs per warp
     constexpr int CAP = CAND_CAP / GROUPS;   // slots per group
     constexpr int LV = GW / 8;               // level slots one ballot settles: lane = level slot x edge (4) x probe (2)
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr unsigned GMASK = GW == 32 ? 0xffffffffu : 0xffffu;
     __shared__ uint32_t s_bits[CAND_WARPS][CAND_CAP];
     __shared__ int s_anc[CAND_WARPS][CAND_CAP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gl = lane & (GW - 1), grp = lane / GW, gbase = grp * GW;  // lane inside the group, group inside the warp
-    const unsigned GM = GW == 32 ? 0xffffffffu : (0xffffu << gbase);    // the group's lanes: every sync below is group-wide
     const uint32_t total = (uint32_t)p.b * (uint32_t)p.G;  // b * G < 2^32 is checked by the host
-    auto gballot = [&](bool pred) { return (__ballot_sync(GM, pred) >> gbase) & (GW == 32 ? 0xffffffffu : 0xffffu); };
+    // segmented collectives: all 32 lanes execute them, each group reads its own half
+    auto gballot = [&](bool pred) -> unsigned { return (__ballot_sync(FULL, pred) >> gbase) & GMASK; };
+    auto gmax = [&](uint32_t v) -> uint32_t {
+        if constexpr (GW == 32) {
+            return __reduce_max_sync(FULL, v);
+        } else {
+#pragma unroll
+            for (int o = GW / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+            return v;
+        }
+    };
+    auto gmin = [&](int v) -> int {
+        if constexpr (GW == 32) {
+            return __reduce_min_sync(FULL, v);
+        } else {
+#pragma unroll
+            for (int o = GW / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+            return v;
+        }
+    };
+    auto gor = [&](unsigned v) -> unsigned {
+        if constexpr (GW == 32) {
+            return __reduce_or_sync(FULL, v);
+        } else {
+#pragma unroll
+            for (int o = GW / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(FULL, v, o);
+            return v;
+        }
+    };
+    auto wmax = [&](int v) -> int {  // group-uniform v -> the larger of the warp's groups
+        if constexpr (GW == 32) return v;
+        else return max(v, __shfl_xor_sync(FULL, v, 16));
+    };
+    const bool std_hyp = p.alpha == 0.5f && p.beta == 6.0f;  // the reference's hyper-parameters (utils/loss.py:168)
     // (a device-side work queue - groups pulling GTs from an atomic counter - was measured 16 us slower
     // than this fixed assignment: the queue's round trips sit on every group's critical path)
     for (unsigned long long it = 0;; ++it) {
-    const unsigned long long wid64 =
-        ((unsigned long long)blockIdx.x * CAND_WARPS + wib) * GROUPS + grp + it * ((unsigned long long)gridDim.x * CAND_WARPS * GROUPS);
-    if (wid64 >= total) return;
-    const uint32_t wid = (uint32_t)wid64;
+    const unsigned long long wid_first =
+        ((unsigned long long)blockIdx.x * CAND_WARPS + wib) * GROUPS + it * ((unsigned long long)gridDim.x * CAND_WARPS * GROUPS);
+    if (wid_first >= total) return;  // warp-uniform
+    const bool in_range = wid_first + grp < total;  // the second group of the very last warp may have no GT: it only follows
+    const uint32_t wid = in_range ? (uint32_t)(wid_first + grp) : total - 1u;
     const int bi = (int)(wid / (uint32_t)p.G), g = (int)(wid - (uint32_t)bi * (uint32_t)p.G);  // 32-bit division
-    if (gl == 0) p.ws.pos_align[wid] = 0u, p.ws.pos_ov[wid] = 0u;
+    if (in_range && gl == 0) p.ws.pos_align[wid] = 0u, p.ws.pos_ov[wid] = 0u;
     if (wid == 0 && gl == 0 && p.counters) p.counters[0] = 0.0, p.counters[1] = 0.0;
     const size_t img = (size_t)bi * p.A;
     uint2* __restrict__ picks = p.ws.picks + (size_t)wid * p.topk;
@@ -249,7 +303,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
         // stores that ride along with the latency-bound pair work instead of a separate dense pass (issued
         // when the group has finished its GT, so they are spread over the kernel's lifetime).
         const int per = p.fill_per;  // ceil(A / G), in 16-anchor granules when fill_vec: every array's slice is whole 16 B words
-        const int a_lo = min(p.A, g * per), a_hi = min(p.A, a_lo + per);
+        const int a_lo = min(p.A, g * per), a_hi = in_range ? min(p.A, a_lo + per) : a_lo;
         const float4 box0 = *reinterpret_cast<const float4*>(p.gt_bboxes + (size_t)bi * p.G * 4);
         long long lab0 = (long long)p.gt_labels[(size_t)bi * p.G];
         lab0 = lab0 < 0 ? 0 : lab0;
@@ -283,16 +337,13 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     const float gt_mask = p.mask_gt[wid], gt_label = p.gt_labels[wid];
     const float4 gt_box = *reinterpret_cast<const float4*>(p.gt_bboxes + (size_t)wid * 4);
     const int flag_mismatch = p.ws.flags[0];
-    if (gt_mask == 0.f) {  // padded GT: claims nothing, contributes zero overlap
-        if (gl < p.topk) picks[gl] = make_uint2(0xffffffffu, 0u);
-        fill_background();
-        continue;
-    }
+    // a padded GT (mask 0) claims nothing and contributes zero overlap: its group produces no pairs and follows
+    const bool valid = in_range && gt_mask != 0.f;
 
     const GtBox gt = make_gt(gt_box);
     int label = (int)gt_label;
     label = label < 0 ? 0 : (label >= p.nc ? p.nc - 1 : label);
-    const bool grid_ok = p.n_levels > 0 && flag_mismatch == 0;
+    const bool grid_ok = p.n_levels > 0 && flag_mismatch == 0;  // warp-uniform
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
     const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
     const float* __restrict__ pds = p.pd_scores + img * p.nc + label;
@@ -304,7 +355,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     int sel_anc = -1, n_sel = 0;
 
     auto evaluate = [&]() {  // slots [n_eval, n): anchors -> metric bits
-        __syncwarp(GM);
+        __syncwarp();
         // the gathers of batch k+1 (predicted box 16 B, score 4 B per pair) are issued before batch k is
         // evaluated, so only the first batch's memory latency is exposed
         int a_nx = 0;
@@ -317,16 +368,18 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
                 sc_nx = __ldg(pds + (size_t)a_nx * p.nc);
             }
         };
-        fetch(n_eval + gl);
-        for (int e = n_eval; e < n; e += GW) {
+        const int trips = wmax((n - n_eval + GW - 1) / GW);
+        int e = n_eval;
+        fetch(e + gl);
+        for (int k = 0; k < trips; ++k, e += GW) {
             const int t = e + gl;
             const float4 pb = pb_nx;
             const float sc = sc_nx;
             fetch(t + GW);
-            if (t < n) bits[t] = eval_pair(p, gt, pb, sc);
+            if (t < n) bits[t] = std_hyp ? eval_pair<true>(p, gt, pb, sc) : eval_pair<false>(p, gt, pb, sc);
         }
         n_eval = n;
-        __syncwarp(GM);
+        __syncwarp();
     };
     auto select = [&]() {  // top-k of slots [0, n) -> lanes 0..n_sel-1 of the group
         // every lane tracks the best TWO of its slots (t = gl, gl + GW, ...), so a lane that wins a round
@@ -344,33 +397,41 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             have2 = true;
         };
         scan2();
+        bool done = false;  // group-uniform: the group's positive pairs are exhausted
         for (int r = 0; r < topk; ++r) {
-            const uint32_t mx = __reduce_max_sync(GM, lm);
-            if (mx == 0u) break;
-            const unsigned who = gballot(lm == mx);
+            const uint32_t mx = gmax(lm);
+            done = done || mx == 0u;
+            if (__all_sync(FULL, done)) break;
+            const unsigned who = gballot(!done && lm == mx);
             int owner = __ffs(who) - 1;
-            if (who & (who - 1u)) owner = __reduce_min_sync(GM, lm == mx ? lt : 0x7fffffff) & (GW - 1);  // slot t belongs to lane t % GW
-            const int ts = __shfl_sync(GM, lt, owner, GW);
-            if (gl == r) nb = mx, nt = ts;
-            ++cnt;
-            if (gl == owner) {
-                bits[ts] = 0u;
-                if (have2) lm = lm2, lt = lt2, have2 = false;
-                else scan2();
+            const bool tie = (who & (who - 1u)) != 0u;
+            if (__any_sync(FULL, tie)) {  // equal metrics in two lanes: the lower slot wins (slot t belongs to lane t % GW)
+                const int m = gmin(!done && lm == mx ? lt : 0x7fffffff);
+                if (tie) owner = m & (GW - 1);
             }
-            __syncwarp(GM);
+            const int ts = __shfl_sync(FULL, lt, gbase + (owner & (GW - 1)));
+            if (!done) {
+                if (gl == r) nb = mx, nt = ts;
+                ++cnt;
+                if (gl == owner) {
+                    bits[ts] = 0u;
+                    if (have2) lm = lm2, lt = lt2, have2 = false;
+                    else scan2();
+                }
+            }
+            __syncwarp();
         }
         sel_bits = nb, n_sel = cnt;
         sel_anc = gl < cnt ? ancs[nt] : -1;
     };
-    auto make_room = [&]() {  // chunk full: keep its winners, drop the rest
-        if (n + GW <= CAP) return;
+    auto make_room = [&]() {  // a chunk is full: keep its winners, drop the rest (both groups, whichever one is full)
+        if (!__any_sync(FULL, n + GW > CAP)) return;
         evaluate();
         select();
-        __syncwarp(GM);
+        __syncwarp();
         if (gl < n_sel) bits[gl] = sel_bits, ancs[gl] = sel_anc;
         n = n_eval = n_sel;
-        __syncwarp(GM);
+        __syncwarp();
     };
 
     if (grid_ok) {
@@ -403,10 +464,10 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             const float s = p.lv[l].stride, inv_s = p.inv_stride[l];
             const int W = p.lv[l].w, H = p.lv[l].h, off = p.lv[l].offset;
             const unsigned m = (m_all >> (8 * q)) & 0xffu;  // bits: x-low {0,1}, x-high {2,3}, y-low {4,5}, y-high {6,7}
-            const int cx0 = __shfl_sync(GM, c0, 8 * q, GW), cx1 = __shfl_sync(GM, c0, 8 * q + 2, GW);
-            const int cy0 = __shfl_sync(GM, c0, 8 * q + 4, GW), cy1 = __shfl_sync(GM, c0, 8 * q + 6, GW);
-            int i0, i1, j0, j1;
-            {
+            const int cx0 = __shfl_sync(FULL, c0, gbase + 8 * q), cx1 = __shfl_sync(FULL, c0, gbase + 8 * q + 2);
+            const int cy0 = __shfl_sync(FULL, c0, gbase + 8 * q + 4), cy1 = __shfl_sync(FULL, c0, gbase + 8 * q + 6);
+            int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+            if (valid) {
                 // low edge, probes (c0, c0+1): first passing cell
                 auto low = [](unsigned pr, int c, int ncell, int& first) {
                     if (pr == 2u) { first = c + 1; return true; }                        // (fail, pass)
@@ -423,23 +484,24 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
                 };
                 const bool okx = low(m & 3u, cx0, W, i0) & high((m >> 2) & 3u, cx1, W, i1);
                 const bool oky = low((m >> 4) & 3u, cy0, H, j0) & high((m >> 6) & 3u, cy1, H, j1);
-                if (!okx) cell_range(gt.x1, gt.x2, s, inv_s, W, i0, i1);  // group-uniform
+                if (!okx) cell_range(gt.x1, gt.x2, s, inv_s, W, i0, i1);  // group-uniform, no collective inside
                 if (!oky) cell_range(gt.y1, gt.y2, s, inv_s, H, j0, j1);
             }
-            if (i0 > i1 || j0 > j1) continue;
-            const unsigned nx = (unsigned)(i1 - i0 + 1), cnt = nx * (unsigned)(j1 - j0 + 1);
+            const bool some = valid && i0 <= i1 && j0 <= j1;
+            const unsigned nx = some ? (unsigned)(i1 - i0 + 1) : 1u, cnt = some ? nx * (unsigned)(j1 - j0 + 1) : 0u;
             const int base = off + j0 * W + i0;
             // t / nx by multiplication: exact for t < 2^16 (magic = ceil(2^32 / nx), nx >= 2)
             const bool use_magic = cnt <= 65536u && nx >= 2u;
             const unsigned magic = use_magic ? 0xffffffffu / nx + 1u : 0u;
-            for (unsigned r = 0; r < cnt; r += GW) {
+            const unsigned cnt_w = (unsigned)wmax((int)cnt);  // cnt < 2^31: a level has fewer cells
+            for (unsigned r = 0; r < cnt_w; r += GW) {
                 make_room();
                 const unsigned t = r + gl;
                 if (t < cnt) {
                     const unsigned row = use_magic ? __umulhi(t, magic) : t / nx;
                     ancs[n + gl] = base + (int)row * W + (int)(t - row * nx);
                 }
-                n += (int)min((unsigned)GW, cnt - r);
+                if (r < cnt) n += (int)min((unsigned)GW, cnt - r);
             }
             }  // level slot
         }
@@ -447,12 +509,12 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
         for (int t0 = 0; t0 < p.A; t0 += GW) {  // anchors are not a make_anchors grid: test them all
             const int a = t0 + gl;
             bool inside = false;
-            if (a < p.A) {
+            if (valid && a < p.A) {
                 const float2 ap = __ldg(anc + a);
                 inside = anchor_in_gt(ap.x, ap.y, gt);
             }
             const unsigned m = gballot(inside);
-            if (m == 0u) continue;
+            if (!__any_sync(FULL, m != 0u)) continue;
             make_room();
             if (inside) ancs[n + __popc(m & ((1u << gl) - 1u))] = a;
             n += __popc(m);
@@ -461,36 +523,48 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     evaluate();
     select();
 
-    const bool has = gl < n_sel;
+    const bool has = valid && gl < n_sel;
     if (has) mark_selected(p.ws.sel + img + sel_anc, g);
     uint32_t pick = has ? (uint32_t)(img + sel_anc) : 0xffffffffu;  // lane r: the r-th entry of this GT's pick list
     if (p.zero_fill) {
         // torch.topk pads a short list with zero-metric entries, lowest anchor index first; a padded
-        // pick only matters when that anchor lies inside this GT (utils/tal.py:128).
-        int need = topk - n_sel, n_pick = n_sel;
-        for (int a = 0; need > 0 && a < p.A; ++a) {
-            const bool mine = has && sel_anc == a;
-            if (__any_sync(GM, mine)) continue;  // positive pick, already counted
-            --need;
-            const float2 ap = __ldg(anc + a);
-            if (anchor_in_gt(ap.x, ap.y, gt)) {  // group-uniform
-                if (gl == 0) mark_selected(p.ws.sel + img + a, g);
-                if (gl == n_pick) pick = (uint32_t)(img + a);
-                ++n_pick;
+        // pick only matters when that anchor lies inside this GT (utils/tal.py:128). The padding takes the
+        // first `need` anchors that are not positive picks; at most n_sel of the anchors below it are, so
+        // every padded anchor has index < need + n_sel = topk: lane a tests anchor a.
+        const int need = valid ? topk - n_sel : 0;
+        if (__any_sync(FULL, need > 0)) {
+            const unsigned posm = gor(has && sel_anc < topk ? 1u << sel_anc : 0u);  // positive picks among anchors [0, topk)
+            bool inside = false;
+            if (need > 0 && gl < topk && gl < p.A && !((posm >> gl) & 1u) && __popc(~posm & ((1u << gl) - 1u)) < need) {
+                const float2 ap = __ldg(anc + gl);
+                inside = anchor_in_gt(ap.x, ap.y, gt);
             }
+            const unsigned im = gballot(inside);  // padded picks that count, ascending anchor index
+            if (inside) mark_selected(p.ws.sel + img + gl, g);
+            const int k = gl - n_sel;  // the k-th of them goes to pick-list entry n_sel + k
+            if (need > 0 && k >= 0 && k < __popc(im)) pick = (uint32_t)(img + __fns(im, 0, k + 1));
         }
     }
-    if (gl < topk) picks[gl] = make_uint2(pick, (uint32_t)g);
+    if (in_range && gl < topk) picks[gl] = make_uint2(pick, (uint32_t)g);
     fill_background();  // last: the stores never sit in front of this group's latency-critical loads
-    __syncwarp(GM);
+    __syncwarp();
     }  // next GT
 }
 
 // ---- patch: foreground anchors, normalisation, state clean-up ---------------------------------------
 
 constexpr int PATCH_THREADS = 512;
+constexpr int PATCH_STRIPS = 64;               // vertical page strips of the contested-anchor index
+#ifndef KZD_PATCH_STRIP_MIN
+#define KZD_PATCH_STRIP_MIN 128
+#endif
+constexpr int PATCH_STRIP_MIN = KZD_PATCH_STRIP_MIN;  // contested anchors in a round from which the index pays
+constexpr size_t PATCH_INDEX_MAX = 64 * 1024;  // bytes of shared memory the index may take (GT boxes + strip masks)
+
+__device__ __forceinline__ int strip_of(float x, float inv_strip) {
+    return (int)fminf(fmaxf(floorf(x * inv_strip), 0.f), (float)(PATCH_STRIPS - 1));
+}
 constexpr int SCAN_ILP = 4;  // GT rows per lane requested together by the contested-anchor scan
-constexpr int TAIL_ILP = 4;  // pick slots per thread in flight in the normalisation tail
 
 // Grid (x, image): the CTAs of one image stride over that image's pick-list slots (G*topk, ~85 % filled),
 // one thread per slot. An anchor picked by several GTs appears once per GT; the first entry to swap the
@@ -505,17 +579,14 @@ constexpr int TAIL_ILP = 4;  // pick slots per thread in flight in the normalisa
 // also covers anchors owned by a GT that did not top-k them) and records the per-GT maxima of
 // utils/tal.py:112-114. The slot is rewritten as (anchor, metric bits) when the slot's own GT is the owner
 // (the usual case), else the anchor goes to the image's short side list.
-// Tail: the last CTA of an image to get here (ticket) normalises that image's foreground scores
-// (utils/tal.py:111-116), one thread per pick slot: the slot and its GT's maxima are at computable
-// addresses, so every load of the pass is independent of the others (no pointer chasing).
+// The normalisation (utils/tal.py:111-116) follows in assign_normalize_kernel.
 __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const AssignParams p) {
-    __shared__ int s_last, s_fg, c_n;
-    __shared__ double s_sum;
+    __shared__ int c_n;
     __shared__ float2 c_ap[PATCH_THREADS];              // contested anchors of the current round: centre,
     __shared__ float4 c_pb[PATCH_THREADS];              // predicted box,
     __shared__ unsigned long long c_key[PATCH_THREADS]; // best (overlap bits, ~g) found so far
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char patch_dyn[];  // contested-anchor index: G boxes, PATCH_STRIPS x strip_words masks
+    bool strips_built = false;
     const int bi = blockIdx.y;
     if (threadIdx.x == 0) c_n = 0;
     __syncthreads();
@@ -534,7 +605,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
         uint32_t g = 0u, g_own = 0u;
         float2 ap = make_float2(0.f, 0.f);
         float4 pb = make_float4(0.f, 0.f, 0.f, 0.f), gb = pb;
-        float glab = 0.f, gmsk = 0.f;
+        float glab = 0.f, gmsk = 0.f, sc_pre = 0.f;
         if (s < n_slots) {
             const uint2 e = picks[s];
             if (e.x != 0xffffffffu) {
@@ -547,6 +618,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
                 ap = __ldg(anc + a);
                 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
                 gb = gtb[g_own], glab = gtl[g_own], gmsk = gtm[g_own];
+                if (p.nc == 1) sc_pre = __ldg(p.pd_scores + idx);  // single class: the score's address does not wait for the label
                 rep = sel != 0ull;  // the other entries of this anchor find zero
                 const uint32_t g_min = 0xffffffffu - (uint32_t)sel, g_max = (uint32_t)(sel >> 32) - 1u;
                 contested = rep && g_min != g_max;
@@ -565,7 +637,65 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
         }
         __syncthreads();
         const int n_c = c_n;  // CTA-uniform
-        if (n_c > 0) {
+        if (n_c >= PATCH_STRIP_MIN && p.strip_words > 0) {
+            // Strip index: the page is cut into PATCH_STRIPS vertical strips; strip s holds a G-bit mask of the valid
+            // GTs whose x-range reaches into it. strip(x) = clamp(floor(x * inv_strip)) is monotone in x, so a GT
+            // that contains an anchor (x1 < ax < x2) is always listed in the anchor's strip: the argmax below tests
+            // ~G * (box width + strip width) / page width GTs per anchor instead of all G (scanning every GT row
+            // for every contested anchor, a CTA with 300 of them took 19 us at G = 1000 and set the kernel's
+            // duration). Masks and a copy of the image's GT boxes live in shared memory; built once per CTA, the
+            // first time a round lists at least PATCH_STRIP_MIN contested anchors (building costs ~4 us: below
+            // that the plain scan of the GT rows is faster - measured 13.3 vs 17.2 us per call at G = 600, where
+            // a CTA lists a few dozen, and 28.6 vs 23.6 us at G = 1000, where it lists hundreds).
+            const int W = p.strip_words;
+            float4* s_box = reinterpret_cast<float4*>(patch_dyn);
+            uint32_t* strips = reinterpret_cast<uint32_t*>(s_box + p.G);
+            if (!strips_built) {
+                for (int i = threadIdx.x; i < PATCH_STRIPS * W; i += PATCH_THREADS) strips[i] = 0u;
+                __syncthreads();
+                for (int gg = threadIdx.x; gg < p.G; gg += PATCH_THREADS) {
+                    const float4 bx = gtb[gg];
+                    s_box[gg] = bx;
+                    if (gtm[gg] == 0.f) continue;
+                    const int s_lo = strip_of(bx.x, p.inv_strip), s_hi = strip_of(bx.z, p.inv_strip);
+                    for (int st = s_lo; st <= s_hi; ++st) atomicOr(strips + st * W + (gg >> 5), 1u << (gg & 31));
+                }
+                strips_built = true;
+                __syncthreads();
+            }
+            // four lanes per contested anchor: lane q takes the words w = q, q + 4, ... of the anchor's strip
+            for (int base = 0; base < n_c; base += PATCH_THREADS / 4) {
+                const int j = base + (threadIdx.x >> 2), q = threadIdx.x & 3;
+                unsigned long long best = 0ull;
+                if (j < n_c) {
+                    const float2 a_ = c_ap[j];
+                    const float4 pb_ = c_pb[j];
+                    const uint32_t* row = strips + strip_of(a_.x, p.inv_strip) * W;
+                    for (int w = q; w < W; w += 4) {
+                        uint32_t bits = row[w];
+                        while (bits) {
+                            const uint32_t gg = (uint32_t)(w * 32 + __ffs(bits) - 1);
+                            bits &= bits - 1u;
+                            const float4 bx = s_box[gg];
+                            GtBox corners;
+                            corners.x1 = bx.x, corners.y1 = bx.y, corners.x2 = bx.z, corners.y2 = bx.w;
+                            if (!anchor_in_gt(a_.x, a_.y, corners)) continue;
+                            const uint32_t ob = __float_as_uint(overlap_ciou(make_gt(bx), pb_));
+                            const unsigned long long k = ((unsigned long long)ob << 32) | (unsigned long long)(0xffffffffu - gg);
+                            if (ob != 0u && k > best) best = k;  // highest overlap, lowest GT among equals
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)best, o);
+                    const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(best >> 32), o);
+                    const unsigned long long other = ((unsigned long long)hi << 32) | lo;
+                    best = other > best ? other : best;
+                }
+                if (j < n_c && q == 0) c_key[j] = best;
+            }
+        } else if (n_c > 0) {  // few contested anchors, no level table (page extent unknown) or no room for the index: every GT row
             for (int g0 = 0; g0 < p.G; g0 += PATCH_THREADS * SCAN_ILP) {
                 float4 box[SCAN_ILP];
                 float msk[SCAN_ILP];
@@ -593,6 +723,8 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
                     }
                 }
             }
+        }
+        if (n_c > 0) {
             __syncthreads();
             if (threadIdx.x == 0) c_n = 0;  // n_c is in registers; the next round's entries come after the barrier below
             if (my_c >= 0) {
@@ -618,7 +750,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
             if (gmsk != 0.f) {
                 const GtBox gt = make_gt(gb);
                 if (anchor_in_gt(ap.x, ap.y, gt)) {
-                    const float sc = __ldg(p.pd_scores + idx * p.nc + lab);
+                    const float sc = p.nc == 1 ? sc_pre : __ldg(p.pd_scores + idx * p.nc + lab);
                     const float o = overlap_ciou(gt, pb);
                     al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
                     atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
@@ -626,7 +758,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
                 }
             }
             if (g == g_own) {
-                picks[s] = make_uint2((uint32_t)idx, __float_as_uint(al));  // normalised by the owner's thread in the tail
+                picks[s] = make_uint2((uint32_t)idx, __float_as_uint(al));  // normalised by assign_normalize_kernel
             } else {  // rare: owned by another GT than the slot's
                 picks[s] = make_uint2(0xffffffffu, 0u);
                 side[atomicAdd(img_state, 1)] = make_uint4((uint32_t)idx, (uint32_t)gslot, __float_as_uint(al), (uint32_t)lab);
@@ -635,58 +767,61 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
             picks[s] = make_uint2(0xffffffffu, 0u);
         }
     }
+}
 
-    // ---- tail: the image's last CTA -----------------------------------------------------------------
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();  // this CTA's slot / side-list / maxima writes are visible device-wide before its ticket
-        s_last = atomicAdd(img_state + 1, 1) == (int)gridDim.x - 1;
-        s_sum = 0.0, s_fg = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    float local = 0.f;
-    int n_fg = 0;
+// ---- normalise: target_scores of the foreground anchors ------------------------------------------------
+
+constexpr int NORM_THREADS = 256;
+
+// Grid (x, image), one thread per pick slot of the image: target_scores = align * pos_ov / (pos_align + eps)
+// (utils/tal.py:111-116) with the per-GT maxima the patch kernel has finished. The slot and its GT's maxima sit
+// at computable addresses, so a thread's loads are all in flight together. CTA 0 of an image also takes the
+// image's short side list; the Sum(target_scores) / n_fg counters are what utils/loss.py:243,250 reduce again.
+// A separate launch on purpose: as the tail of the patch kernel (run by each image's last CTA after a ticket)
+// the same work took 6-9 us of a 20 us kernel on one SM per image; spread over the machine it is one memory round
+// trip. The last CTA of an image to leave (ticket, off the critical path) clears the image's state words, the
+// last image clears the call's flags: the workspace is all-zero again when the call ends.
+__global__ void __launch_bounds__(NORM_THREADS) assign_normalize_kernel(const AssignParams p) {
+    __shared__ double s_sum;
+    __shared__ int s_fg;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int bi = blockIdx.y;
+    const int n_slots = p.G * p.topk;  // of this image
+    const uint2* __restrict__ picks = p.ws.picks + (size_t)bi * n_slots;
+    const float* __restrict__ gtl = p.gt_labels + (size_t)bi * p.G;
     const uint32_t* __restrict__ pos_ov = p.ws.pos_ov + (size_t)bi * p.G;
     const uint32_t* __restrict__ pos_al = p.ws.pos_align + (size_t)bi * p.G;
-    // one thread per pick slot, TAIL_ILP slots at a time: the slot, its GT's two maxima (and label) are
-    // requested together - nothing here waits for an earlier load of the pass
-    for (int s0 = threadIdx.x; s0 < n_slots; s0 += PATCH_THREADS * TAIL_ILP) {
-        uint2 e[TAIL_ILP];
-        uint32_t ov[TAIL_ILP], pa[TAIL_ILP];
-        float gl_[TAIL_ILP];
-#pragma unroll
-        for (int k = 0; k < TAIL_ILP; ++k) {
-            const int s = s0 + k * PATCH_THREADS;
-            e[k] = make_uint2(0xffffffffu, 0u), ov[k] = pa[k] = 0u, gl_[k] = 0.f;
-            if (s < n_slots) {
-                const int g = s / p.topk;
-                e[k] = __ldcg(picks + s), ov[k] = __ldcg(pos_ov + g), pa[k] = __ldcg(pos_al + g);
-                if (p.nc > 1) gl_[k] = gtl[g];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < TAIL_ILP; ++k) {
-            if (e[k].x == 0xffffffffu) continue;
-            long long lab = (long long)gl_[k];
-            lab = lab < 0 ? 0 : (lab >= p.nc ? p.nc - 1 : lab);
-            const float v = __fdiv_rn(__fmul_rn(__uint_as_float(e[k].y), __uint_as_float(ov[k])),
-                                      __fadd_rn(__uint_as_float(pa[k]), p.eps));  // utils/tal.py:115
-            p.target_scores[(size_t)e[k].x * p.nc + lab] = v;
+    int32_t* __restrict__ img_state = p.ws.img + 2 * bi;  // [0] side-list length, [1] CTA ticket
+    if (threadIdx.x == 0) s_sum = 0.0, s_fg = 0;
+    __syncthreads();
+    float local = 0.f;
+    int n_fg = 0;
+    for (int s = blockIdx.x * NORM_THREADS + threadIdx.x; s < n_slots; s += gridDim.x * NORM_THREADS) {
+        const uint2 e = picks[s];
+        const int g = s / p.topk;
+        const uint32_t ov = pos_ov[g], pa = pos_al[g];
+        long long lab = p.nc > 1 ? (long long)gtl[g] : 0;
+        if (e.x == 0xffffffffu) continue;
+        lab = lab < 0 ? 0 : (lab >= p.nc ? p.nc - 1 : lab);
+        const float v = __fdiv_rn(__fmul_rn(__uint_as_float(e.y), __uint_as_float(ov)),
+                                  __fadd_rn(__uint_as_float(pa), p.eps));  // utils/tal.py:115
+        p.target_scores[(size_t)e.x * p.nc + lab] = v;
+        local += v;
+        ++n_fg;
+    }
+    if (blockIdx.x == 0) {  // anchors owned by another GT than the slot's
+        const uint4* __restrict__ side = p.ws.fg_list + (size_t)bi * p.A;
+        const int n_side = img_state[0];
+        for (int i = threadIdx.x; i < n_side; i += NORM_THREADS) {
+            const uint4 e = side[i];
+            const float ov = __uint_as_float(p.ws.pos_ov[e.y]);
+            const float pa = __uint_as_float(p.ws.pos_align[e.y]);
+            const float v = __fdiv_rn(__fmul_rn(__uint_as_float(e.z), ov), __fadd_rn(pa, p.eps));
+            p.target_scores[(size_t)e.x * p.nc + e.w] = v;
             local += v;
             ++n_fg;
         }
-    }
-    const int n_side = __ldcg(img_state);
-    for (int i = threadIdx.x; i < n_side; i += PATCH_THREADS) {
-        const uint4 e = __ldcg(side + i);
-        const float ov = __uint_as_float(__ldcg(p.ws.pos_ov + e.y));
-        const float pa = __uint_as_float(__ldcg(p.ws.pos_align + e.y));
-        const float v = __fdiv_rn(__fmul_rn(__uint_as_float(e.z), ov), __fadd_rn(pa, p.eps));
-        p.target_scores[(size_t)e.x * p.nc + e.w] = v;
-        local += v;
-        ++n_fg;
     }
     if (p.counters) {
         for (int o = 16; o > 0; o >>= 1) {
@@ -697,17 +832,19 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
             if (local != 0.f) atomicAdd(&s_sum, (double)local);
             if (n_fg) atomicAdd(&s_fg, n_fg);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
+    }
+    __syncthreads();  // (also: CTA 0 has read the side-list length before its ticket)
+    if (threadIdx.x == 0) {
+        if (p.counters) {
             if (s_sum != 0.0) atomicAdd(p.counters, s_sum);
             if (s_fg) atomicAdd(p.counters + 1, (double)s_fg);
         }
-    }
-    if (threadIdx.x == 0) {
-        img_state[0] = 0, img_state[1] = 0;
-        if (atomicAdd(p.ws.flags + 1, 1) == (int)gridDim.y - 1) {  // the call's last image
-            p.ws.flags[2] = p.ws.flags[0];  // sticky report for the host: this call's level table did not match
-            p.ws.flags[1] = 0, p.ws.flags[0] = 0;
+        if (atomicAdd(img_state + 1, 1) == (int)gridDim.x - 1) {  // the image's last CTA to leave
+            img_state[0] = 0, img_state[1] = 0;
+            if (atomicAdd(p.ws.flags + 1, 1) == (int)gridDim.y - 1) {  // the call's last image
+                p.ws.flags[2] = p.ws.flags[0];  // sticky report for the host: this call's level table did not match
+                p.ws.flags[1] = 0, p.ws.flags[0] = 0;
+            }
         }
     }
 }
@@ -855,13 +992,34 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     }
     {
         // the CTAs of an image stride over its G*topk pick slots; enough of them to cover the slots once, but
-        // not more than a few waves of the machine in total (the image's last CTA runs the serial tail)
+        // not more than a few waves of the machine in total
         long long per_img = ((long long)G * topk + PATCH_THREADS - 1) / PATCH_THREADS;
         const long long cap = ((long long)sm_count() * 8 + b - 1) / b;
         if (per_img > cap) per_img = cap;
         if (per_img < 1) per_img = 1;
-        assign_patch_kernel<<<dim3((unsigned)per_img, (unsigned)b), PATCH_THREADS, 0, st>>>(p);
+        p.strip_words = 0, p.inv_strip = 0.f;
+        float extent = 0.f;
+        for (int l = 0; l < n_levels; ++l) extent = fmaxf(extent, (float)h_levels[l].w * h_levels[l].stride);
+        const size_t index_bytes = (size_t)G * 16 + (size_t)PATCH_STRIPS * ((G + 31) / 32) * 4;
+#ifndef KZD_NO_STRIPS
+#define KZD_NO_STRIPS 0
+#endif
+        if (!KZD_NO_STRIPS && extent > 0.f && index_bytes <= PATCH_INDEX_MAX) {
+            p.strip_words = (G + 31) / 32, p.inv_strip = (float)PATCH_STRIPS / extent;
+            static thread_local bool raised = false;
+            if (!raised) {
+                KZD_CUDA(cudaFuncSetAttribute(assign_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATCH_INDEX_MAX));
+                raised = true;
+            }
+        }
+        assign_patch_kernel<<<dim3((unsigned)per_img, (unsigned)b), PATCH_THREADS, p.strip_words ? index_bytes : 0, st>>>(p);
         KZD_LAUNCH_CHECK("assign_patch_kernel");
+        long long per_img_n = ((long long)G * topk + NORM_THREADS - 1) / NORM_THREADS;
+        const long long cap_n = ((long long)sm_count() * 8 + b - 1) / b;
+        if (per_img_n > cap_n) per_img_n = cap_n;
+        if (per_img_n < 1) per_img_n = 1;
+        assign_normalize_kernel<<<dim3((unsigned)per_img_n, (unsigned)b), NORM_THREADS, 0, st>>>(p);
+        KZD_LAUNCH_CHECK("assign_normalize_kernel");
     }
     return 0;
 }

@@ -91,12 +91,12 @@ class PagePipeline:
         self._side2 = torch.cuda.Stream(device=dev, priority=-1) if (assign_priority and overlap) else None
         self.out = None
         self.graph = None
-        # kernels per step: decode(s), assign x2 (candidates, patch), [nms filter], ordering (one bucket-rank kernel up to
+        # kernels per step: decode(s), assign x3 (candidates, patch, normalise), [nms filter], ordering (one bucket-rank kernel up to
         # n_cap 4096, else chunk sort + rank), (mask, walk) x column ranges - mirrors kzd_nms_suppress
         order = 1 if (self.n_cap <= 4096 and self.pool <= 65535) or (self.pool + 511) // 512 <= 8 else 2
         t0 = (self.max_det + self.max_det // 4 + 127) // 64
         phases = 1 if t0 >= (self.n_cap + 63) // 64 else 2
-        self.kernels_per_step = (1 if self.fuse_decodes else 2) + 2 + (0 if self.fuse_filter else 1) + order + 2 * phases
+        self.kernels_per_step = (1 if self.fuse_decodes else 2) + 3 + (0 if self.fuse_filter else 1) + order + 2 * phases
         if use_graph:
             self._capture()
 

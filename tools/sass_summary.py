@@ -16,7 +16,7 @@ for line in sass.splitlines():
         counts[cur] = collections.Counter()
         total[cur] = 0
         continue
-    if cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+    if cur and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
         total[cur] += 1
         for k, p in pats.items():
             if re.search(p, line):
