@@ -51,6 +51,10 @@ COMMON = dict(imgsz=1280, nc=1, strides=(4, 8, 16, 32), topk=10, alpha=0.5, beta
               nms_candidates=3000, micro=16)
 CFG5 = dict(COMMON, name="configs[4]", G=1000, global_pages=128, scaling="strong")
 CFG1 = dict(COMMON, name="configs[1]", G=600, pages_per_gpu=16, scaling="weak")
+# context lines at N = 1 (stage times only): the multi-class head of configs[2] (batch 4 of its 16: the dense (b,A,nc)
+# tensors of four pages already total ~70 GB with the timing buffers) and the inference path of configs[3]
+CFG3 = dict(COMMON, name="configs[2]", nc=4300, G=600, micro=4, pages_per_gpu=4, scaling="weak")
+CFG4 = dict(COMMON, name="configs[3]", imgsz=1536, G=600, micro=32, pages_per_gpu=32, max_det=2000, scaling="weak")
 N_STREAMS = 4   # micro-batches in flight per GPU
 N_WINDOWS = 5   # timed windows of exactly --steps steps; the median window is reported
 
@@ -69,12 +73,14 @@ def workload_config(cfg, world):
         pages = f"global batch {cfg['global_pages']} pages image-sharded over the GPUs"
     else:
         pages = f"batch {cfg['pages_per_gpu']} pages per GPU"
+    pages_global = cfg.get("global_pages", cfg.get("pages_per_gpu", 0) * world)
     return {
         "workload": f"BASELINE {cfg['name']}: YOLOv12x P2-P5 head outputs, {cfg['imgsz']}x{cfg['imgsz']} pages, {pages}, "
                     f"~{cfg['G']} GT/page, nc={cfg['nc']}; NMS conf {cfg['conf']} iou {cfg['iou']} max_det {cfg['max_det']} "
                     f"on ~{cfg['nms_candidates']} candidates/page",
         "imgsz": cfg["imgsz"], "gt_slots": cfg["G"], "nc": cfg["nc"], "micro_batch_pages": cfg["micro"],
-        "global_pages": cfg.get("global_pages", cfg.get("pages_per_gpu", 0) * world),
+        "global_pages": pages_global, "pages_per_gpu": pages_global // world, "parallelism": f"image-sharded x{world}",
+        "l2_policy": "inputs larger than L2 (0.6-1.2 GB read per 16-page micro-batch vs 126 MB L2); CPU arm: not applicable",
     }
 
 
@@ -160,7 +166,8 @@ def algorithmic_bytes(b, A, G, nc, n_cand, n_keep):
         # 272*A for the decode + 16*A for the pixel-space copy (x stride, utils/loss.py:236) that the
         # same kernel writes (the reference's separate elementwise pass would read 16*A more)
         "decode_train": (272 + 16) * A * b,
-        "assign": int((57 + 8 / b) * A + 24 * G) * b if nc == 1 else None,
+        # nc > 1: target_scores is a dense (b,A,nc) tensor the call has to write (4*nc instead of 4 bytes per anchor)
+        "assign": int((53 + 4 * nc + 8 / b) * A + 24 * G) * b,
         "decode_infer": (272 + 8 * nc) * A * b,
         # fused: one read of the maps 4(64+nc)A, writes y 4(4+nc)A + grid-unit boxes 16A + pixel boxes 16A
         "decode_dual": (4 * (64 + nc) + 4 * (4 + nc) + 32) * A * b,
@@ -603,6 +610,18 @@ class Measure:
                 "h2d_gbs_achieved_per_gpu": h2d_micro * m * steps / (ms * 1e-3) / 1e9}
 
 
+def stage_entry(name, ms, nbytes, peak, fuse_filter):
+    gbs = nbytes / (ms * 1e-3) / 1e9 if nbytes else None
+    e = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": gbs, "frac": gbs / peak if gbs else None}
+    if name == "nms" and fuse_filter:
+        e["note"] = ("SURVEY 8d bytes of the whole non_max_suppression call, (32+4nc) B per anchor of which belong to the "
+                     "filter pass over y - done inside the decode kernel here; the kernels timed in this stage (order, mask, "
+                     "walk) move ~24 B per candidate and are latency-bound")
+        if e["frac"] and e["frac"] > 1.5:  # multi-class head: the filter pass is nearly all of the call's bytes
+            e["frac"] = None
+    return e
+
+
 def roofline_block(meas, names, st_ms, ms_per_step, n_cand, n_keep):
     b, A, G, nc, m = meas.b, meas.A, meas.G, meas.nc, meas.m
     ab = algorithmic_bytes(b, A, G, nc, n_cand, n_keep)
@@ -630,9 +649,7 @@ def roofline_block(meas, names, st_ms, ms_per_step, n_cand, n_keep):
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ab[dom], "pages_per_launch": b,
             "step": {"algorithmic_bytes": total_ab, "gbs": step_gbs, "frac": step_gbs / peak},
-            "stages": {n: {"ms": st_ms[n], "algorithmic_bytes": ab.get(n),
-                           "gbs": (ab[n] / (st_ms[n] * 1e-3) / 1e9) if ab.get(n) else None,
-                           "frac": (ab[n] / (st_ms[n] * 1e-3) / 1e9 / peak) if ab.get(n) else None} for n in names},
+            "stages": {n: stage_entry(n, st_ms[n], ab.get(n), peak, meas.fuse_filter) for n in names},
             "stage_note": "stage ms = device time of that stage's kernels on one micro-batch (own CUDA graph; L2 flushed "
                           "before each replay by writing 256 MB and then reading 256 MB, so no dirty lines are left for "
                           "the stage to evict; CUDA events); the timed region replays all stages as one graph"}
@@ -696,6 +713,23 @@ def measure_workload(kzd, kdist, synth, cfg, m, dev, rank, world, steps, warmup,
     return res
 
 
+def context_stages(kzd, synth, cfg, dev, fuse, fuse_filter, only=None):
+    """Stage times + roofline fractions of one more BASELINE config (one pipeline, one micro-batch; no step timing)."""
+    meas = Measure(kzd, synth, cfg, 1, dev, seed0=0, fuse=fuse, fuse_filter=fuse_filter, n_pipes=1)
+    pipe = meas.pipes[0]
+    pipe.step()
+    _, n_keep = pipe.results()
+    n_cand = int(sum(pipe.candidate_counts()))
+    names, st_ms = meas.stage_times()
+    rb = roofline_block(meas, names, st_ms, sum(st_ms.values()), n_cand, int(sum(n_keep)))
+    stages = {n: v for n, v in rb["stages"].items() if only is None or n in only}
+    out = {"config": dict(workload_config(cfg, 1), max_det=cfg["max_det"]), "pages_per_launch": cfg["micro"], "stages": stages,
+           "nms_candidates": n_cand, "kept_boxes": int(sum(n_keep)), "note": rb["stage_note"]}
+    del meas, pipe
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_kzd(args, rank, local_rank, world):
     import kuzushiji_vision_b200 as kzd
     from kuzushiji_vision_b200 import dist as kdist
@@ -746,6 +780,13 @@ def run_kzd(args, rank, local_rank, world):
         r1.pop("_meas")
         extra["config1"] = dict(r1, config=workload_config(CFG1, world), unit="pages/s", metric=METRIC)
         torch.cuda.empty_cache()
+        # ---- stage lines of BASELINE configs[2] (nc = 4300) and configs[3] (inference path, 1536^2, batch 32) ----
+        for key, c_, only in (("config3_stages", CFG3, None), ("config4_stages", CFG4, ("decode_dual", "decode_infer", "nms"))):
+            try:
+                extra[key] = context_stages(kzd, synth, c_, dev, fuse, fuse_filter, only)
+            except Exception as exc:  # context only: never costs the headline line
+                extra[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                torch.cuda.empty_cache()
     if rank != 0:
         return
 
@@ -788,18 +829,17 @@ def run_kzd(args, rank, local_rank, world):
         "metric": METRIC, "value": res["value"], "unit": "pages/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(cfg, world), pages_per_gpu=m * cfg["micro"], anchors_per_page=synth.num_anchors(cfg["imgsz"], cfg["strides"]),
-                       l2_policy="inputs larger than L2 (0.6-1.2 GB read per micro-batch vs 126 MB L2)",
-                       decodes=("fused: one kernel reads the head maps once and emits y + the training-side boxes"
-                                if fuse else "separate decode_train (b,A,64) and decode_infer (NCHW maps) kernels"),
-                       nms_filter=("inside the inference decode kernel (no second pass over y); the kernel's roofline "
-                                   "figure counts the decode's algorithmic bytes only" if fuse_filter else
-                                   "separate nms_filter_kernel pass over y"),
-                       step="PagePipeline: one CUDA-graph replay of decode_train+assign+decode_infer+NMS per micro-batch; " + depth_note,
-                       timing=f"median of {N_WINDOWS} windows of exactly {args.steps} steps; ranks aligned by a device-side "
-                              "all-reduce before each window; CUDA events per rank, max over ranks",
-                       ms_per_step_single_stream=res["ms_per_step_single_stream"],
-                       parallelism=f"image-sharded x{world}", numa_node_rank0=numa_node),
+        "config": workload_config(cfg, world),  # the same object in both arms
+        "config_detail": dict(anchors_per_page=synth.num_anchors(cfg["imgsz"], cfg["strides"]),
+                              decodes=("fused: one kernel reads the head maps once and emits y + the training-side boxes"
+                                       if fuse else "separate decode_train (b,A,64) and decode_infer (NCHW maps) kernels"),
+                              nms_filter=("inside the inference decode kernel (no second pass over y); the kernel's roofline "
+                                          "figure counts the decode's algorithmic bytes only" if fuse_filter else
+                                          "separate nms_filter_kernel pass over y"),
+                              step="PagePipeline: one CUDA-graph replay of decode_train+assign+decode_infer+NMS per micro-batch; " + depth_note,
+                              timing=f"median of {N_WINDOWS} windows of exactly {args.steps} steps; ranks aligned by a device-side "
+                                     "all-reduce before each window; CUDA events per rank, max over ranks",
+                              ms_per_step_single_stream=res["ms_per_step_single_stream"], numa_node_rank0=numa_node),
         "clocks": clk.summary(),
         "e2e": res["e2e"],
         "gpu_launches": res["launches_per_step"] * args.steps,

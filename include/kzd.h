@@ -119,7 +119,7 @@ size_t kzd_assign_report_offset(int b, int A);
  *     than topk positive candidates: 0 = padding never lands inside the GT (true whenever anchors
  *     0..topk-1 are outside every GT); 1 = emulate "lowest anchor indices first".
  *   score_dtype: dtype pd_scores had at the reference call site (0 fp32, 1 fp16, 2 bf16). The kernel
- *     reads fp32 values; under AMP the reference rounds pd_scores.pow(alpha) to that dtype
+ *     reads fp32 values (or the half-precision tensor itself: KZD_ASSIGN_NATIVE_SCORES); under AMP the reference rounds pd_scores.pow(alpha) to that dtype
  *     (utils/tal.py:137,150) and the kernel reproduces that one rounding.
  * Outputs (all written for every anchor):
  *   target_labels int64 (b,A), target_bboxes (b,A,4), target_scores (b,A,nc), fg_mask uint8 (b,A),
@@ -133,10 +133,14 @@ size_t kzd_assign_report_offset(int b, int A);
  *       bit the call zeroes the state itself first (one extra 8 B/anchor memset).
  *     KZD_ASSIGN_TRUSTED_ANCHORS the caller vouches that anc_points equals the grid described by h_levels
  *       bit for bit (e.g. it built both, or checked them once on the host); the per-call device check is
- *       skipped. */
+ *       skipped.
+ *     KZD_ASSIGN_NATIVE_SCORES   pd_scores points to elements of score_dtype (fp16 / bf16, the tensor the AMP
+ *       flow passes: utils/loss.py:233 under autocast) instead of fp32: the kernels read them as they are, so
+ *       the caller needs no up-cast pass over (b,A,nc). No effect with score_dtype 0. */
 #define KZD_ASSIGN_PERSISTENT 1
 #define KZD_ASSIGN_TRUSTED_ANCHORS 2
-int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
+#define KZD_ASSIGN_NATIVE_SCORES 4
+int kzd_tal_assign(const void* pd_scores, const float* pd_bboxes, const float* anc_points,
                    const float* gt_labels, const float* gt_bboxes, const float* mask_gt,
                    int b, int A, int G, int nc, int topk, float alpha, float beta, float eps,
                    const kzd_level* h_levels, int n_levels, int zero_fill, int score_dtype,

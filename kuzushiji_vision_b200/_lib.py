@@ -15,6 +15,7 @@ KZD_MAX_LEVELS = 8
 KZD_MAX_TOPK = 32
 KZD_ASSIGN_PERSISTENT = 1        # include/kzd.h: flags of kzd_tal_assign
 KZD_ASSIGN_TRUSTED_ANCHORS = 2
+KZD_ASSIGN_NATIVE_SCORES = 4
 
 
 class KzdError(RuntimeError):

@@ -54,7 +54,8 @@ struct AssignWs {
 };
 
 struct AssignParams {
-    const float *pd_scores, *pd_bboxes, *anc, *gt_labels, *gt_bboxes, *mask_gt;
+    const void* pd_scores;  // fp32, or score_dtype elements when scores_native
+    const float *pd_bboxes, *anc, *gt_labels, *gt_bboxes, *mask_gt;
     int b, A, G, nc, topk;
     float alpha, beta, eps;
     kzd_level lv[KZD_MAX_LEVELS];
@@ -63,6 +64,7 @@ struct AssignParams {
     int fill_vec;     // A % 16 == 0 and 16-byte aligned outputs: background targets are stored as 16 B words
     int fill_per;     // anchors whose background targets one GT's warp stores
     int score_dtype;  // dtype pd_scores had at the call site: 0 fp32, 1 fp16, 2 bf16 (AMP, utils/tal.py:137)
+    int scores_native;  // 0: pd_scores holds fp32; 1 / 2: it holds fp16 / bf16 elements (KZD_ASSIGN_NATIVE_SCORES), read as they are
     int strip_words;  // 32-bit words of one strip's GT mask in the patch kernel's index (0: index not used)
     float inv_strip;  // strips per pixel
     long long* target_labels;
@@ -97,6 +99,14 @@ __device__ __forceinline__ float score_pow(float s, float alpha, int score_dtype
     if (score_dtype == 1) return __half2float(__float2half_rn(v));
     if (score_dtype == 2) return __bfloat162float(__float2bfloat16_rn(v));
     return v;
+}
+
+// pd_scores element i as fp32: the AMP flow hands the assigner half-precision scores (utils/loss.py:233 under
+// autocast), read here without an up-cast pass over the (b,A,nc) tensor
+__device__ __forceinline__ float load_score(const void* base, size_t i, int native) {
+    if (native == 1) return __half2float(__ldg(reinterpret_cast<const __half*>(base) + i));
+    if (native == 2) return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(base) + i));
+    return __ldg(reinterpret_cast<const float*>(base) + i);
 }
 
 struct GtBox {
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
     const bool grid_ok = p.n_levels > 0 && flag_mismatch == 0;  // warp-uniform
     const float2* __restrict__ anc = reinterpret_cast<const float2*>(p.anc);
     const float4* __restrict__ pdb = reinterpret_cast<const float4*>(p.pd_bboxes) + img;
-    const float* __restrict__ pds = p.pd_scores + img * p.nc + label;
+    const size_t pds = img * p.nc + label;  // element index of (image, anchor 0, this GT's class) in pd_scores
     const int topk = p.topk;
     uint32_t* bits = s_bits[wib] + grp * CAP;
     int* ancs = s_anc[wib] + grp * CAP;
@@ -365,7 +375,7 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
             if (t < n) {
                 a_nx = ancs[t];
                 pb_nx = __ldg(pdb + a_nx);
-                sc_nx = __ldg(pds + (size_t)a_nx * p.nc);
+                sc_nx = load_score(p.pd_scores, pds + (size_t)a_nx * p.nc, p.scores_native);
             }
         };
         const int trips = wmax((n - n_eval + GW - 1) / GW);
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
                 ap = __ldg(anc + a);
                 pb = __ldg(reinterpret_cast<const float4*>(p.pd_bboxes) + idx);
                 gb = gtb[g_own], glab = gtl[g_own], gmsk = gtm[g_own];
-                if (p.nc == 1) sc_pre = __ldg(p.pd_scores + idx);  // single class: the score's address does not wait for the label
+                if (p.nc == 1) sc_pre = load_score(p.pd_scores, idx, p.scores_native);  // single class: the score's address does not wait for the label
                 rep = sel != 0ull;  // the other entries of this anchor find zero
                 const uint32_t g_min = 0xffffffffu - (uint32_t)sel, g_max = (uint32_t)(sel >> 32) - 1u;
                 contested = rep && g_min != g_max;
@@ -750,7 +760,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
             if (gmsk != 0.f) {
                 const GtBox gt = make_gt(gb);
                 if (anchor_in_gt(ap.x, ap.y, gt)) {
-                    const float sc = p.nc == 1 ? sc_pre : __ldg(p.pd_scores + idx * p.nc + lab);
+                    const float sc = p.nc == 1 ? sc_pre : load_score(p.pd_scores, idx * p.nc + lab, p.scores_native);
                     const float o = overlap_ciou(gt, pb);
                     al = __fmul_rn(score_pow(sc, p.alpha, p.score_dtype), pow_scalar(o, p.beta));
                     atomicMax(p.ws.pos_ov + gslot, __float_as_uint(o));
@@ -896,7 +906,7 @@ extern "C" __attribute__((visibility("default"))) size_t kzd_assign_report_offse
     return align_up((size_t)b * A * 8, 256) + 2 * sizeof(int32_t);
 }
 
-extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points,
+extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const void* pd_scores, const float* pd_bboxes, const float* anc_points,
                               const float* gt_labels, const float* gt_bboxes, const float* mask_gt, int b, int A,
                               int G, int nc, int topk, float alpha, float beta, float eps, const kzd_level* h_levels,
                               int n_levels, int zero_fill, int score_dtype, int64_t* target_labels, float* target_bboxes,
@@ -912,7 +922,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
                   "kzd_tal_assign: bad level table");
     KZD_CHECK_ARG(b <= 65535, "kzd_tal_assign: b=%d > 65535", b);
     KZD_CHECK_ARG(score_dtype >= 0 && score_dtype <= 2, "kzd_tal_assign: score_dtype=%d not in {0,1,2}", score_dtype);
-    KZD_CHECK_ARG((flags & ~(KZD_ASSIGN_PERSISTENT | KZD_ASSIGN_TRUSTED_ANCHORS)) == 0, "kzd_tal_assign: unknown flags 0x%x", flags);
+    KZD_CHECK_ARG((flags & ~(KZD_ASSIGN_PERSISTENT | KZD_ASSIGN_TRUSTED_ANCHORS | KZD_ASSIGN_NATIVE_SCORES)) == 0, "kzd_tal_assign: unknown flags 0x%x", flags);
     KZD_CHECK_ARG((double)b * A < 4294967295.0 && G < (1 << 24) - 2, "kzd_tal_assign: b*A or G too large");
     KZD_CHECK_ARG((double)b * G < 4294967295.0, "kzd_tal_assign: b*G too large");
     KZD_CHECK_ARG(((uintptr_t)gt_bboxes) % 16 == 0 && ((uintptr_t)pd_bboxes) % 16 == 0 &&
@@ -941,6 +951,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const float
     p.b = b, p.A = A, p.G = G, p.nc = nc, p.topk = topk;
     p.alpha = alpha, p.beta = beta, p.eps = eps;
     p.n_levels = n_levels, p.zero_fill = zero_fill, p.score_dtype = score_dtype;
+    p.scores_native = (flags & KZD_ASSIGN_NATIVE_SCORES) ? score_dtype : 0;
     p.fill_vec = A % 16 == 0 && ((uintptr_t)target_labels | (uintptr_t)target_gt_idx | (uintptr_t)fg_mask |
                                  (uintptr_t)target_scores | (uintptr_t)target_bboxes) % 16 == 0;
     p.fill_per = (A + G - 1) / G;

@@ -210,6 +210,7 @@ struct SuppressWs {
     int32_t* state;     // (b, 4)       scan state carried between phases: done, kept, chunks walked
     u64* keepmask;      // (b, T_cap)   keep mask of every walked chunk
     int32_t* kept_before;  // (b, T_cap)
+    int32_t* pending;      // [1] images whose walk is not over after the first phase (0: later phases return at once)
     int T_cap, C_cap;
 };
 
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS) nms_chunk_sort_kernel(const u64
     const int n = count < max_nms ? count : max_nms;
     const bool overflow = count > cand_cap || n > n_cap;  // pool or suppression stage too small
     if (chunk == 0 && threadIdx.x == 0) ws.n_sorted[bi] = overflow ? -1 : n;
+    if (chunk == 0 && bi == 0 && threadIdx.x == 0) *ws.pending = 0;
     if (overflow || chunk * CHUNK >= count) return;
     const u64* __restrict__ src = cand_keys + (size_t)bi * cand_cap;
     const int t = threadIdx.x;
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(BR_THREADS) nms_order_bucket_kernel(const u64*
     const int n = count < max_nms ? count : max_nms;
     const bool overflow = count > cand_cap || n > n_cap;  // pool or suppression stage too small
     if (t == 0) ws.n_sorted[bi] = overflow ? -1 : n;
+    if (bi == 0 && t == 0) *ws.pending = 0;
     if (overflow || count <= 0) return;
     const u64* __restrict__ src = cand_keys + (size_t)bi * cand_cap;
     u64 kreg[BR_REG];
@@ -520,6 +523,7 @@ __global__ void __cluster_dims__(ORDER_CL, 1, 1) __launch_bounds__(CHUNK_THREADS
     const int n = count < max_nms ? count : max_nms;
     const bool overflow = count > cand_cap || n > n_cap;  // pool or suppression stage too small
     if (chunk == 0 && t == 0) ws.n_sorted[bi] = overflow ? -1 : n;
+    if (chunk == 0 && bi == 0 && t == 0) *ws.pending = 0;
     if (overflow || count <= 0) return;  // uniform over the cluster
     const bool active = chunk * CHUNK < count;
     const int i0 = t, i1 = t + CHUNK_THREADS;
@@ -631,6 +635,7 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(int b, int n_cap
                                                                 int g_lo, int g_hi, SuppressWs ws) {
     extern __shared__ int pre[];  // (b+1) prefix of item counts
     __shared__ float4 colbox[MASK_CG * 64];
+    if (phase > 0 && *ws.pending == 0) return;  // every image's walk ended in the first phase (the usual case)
     for (int i = threadIdx.x; i < b; i += MASK_THREADS) {  // item counts: the loads of all images in flight together
         const int n = ws.n_sorted[i];
         const int done = phase > 0 ? ws.state[i * 4] : 0;
@@ -753,6 +758,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
     u64* keep_s = scan_smem + ws.T_cap;                                     // T_cap: keep mask of every chunk walked here
     int* kb_s = reinterpret_cast<int*>(scan_smem + 2 * (size_t)ws.T_cap);   // T_cap: boxes kept before the chunk
     const int bi = blockIdx.x;
+    if (phase > 0 && *ws.pending == 0) return;  // every image's walk ended in the first phase (the usual case)
     const int n = ws.n_sorted[bi];
     int32_t* state = ws.state + bi * 4;  // [0] done, [1] kept, [2] chunks walked
     if (n < 0) {
@@ -905,7 +911,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const float* __r
     }
     if (n == 0) finished = true;
     if (!finished) {  // more columns are needed: the next phase continues from here
-        if (threadIdx.x == 0) state[0] = 0, state[1] = kept, state[2] = chunks;
+        if (threadIdx.x == 0) {
+            state[0] = 0, state[1] = kept, state[2] = chunks;
+            if (phase == 0) atomicAdd(ws.pending, 1);
+        }
         return;
     }
     // gather the kept rows in score order, all threads
@@ -946,6 +955,7 @@ static int split_ws(void* workspace, int b, int cand_cap, int n_cap, SuppressWs&
     ws.state = (int32_t*)take((size_t)b * 4 * sizeof(int32_t));
     ws.keepmask = (u64*)take((size_t)b * T_cap * sizeof(u64));
     ws.kept_before = (int32_t*)take((size_t)b * T_cap * sizeof(int32_t));
+    ws.pending = (int32_t*)take(sizeof(int32_t));
     ws.T_cap = T_cap;
     ws.C_cap = C_cap;
     total = o;

@@ -143,10 +143,11 @@ class TaskAlignedAssigner(nn.Module):
         b, A, nc = pd_scores.shape
         G = self.n_max_boxes
         f32 = torch.float32
-        # AMP: the reference keeps bbox_scores in pd_scores' dtype (utils/tal.py:137); libkzd reads fp32
-        # values and reproduces that one rounding
+        # AMP: the reference keeps bbox_scores in pd_scores' dtype (utils/tal.py:137); libkzd reproduces that one
+        # rounding of pd_scores.pow(alpha)
         score_dtype = _lib.dtype_code(pd_scores.dtype)
-        pd_scores_c = pd_scores.to(f32).contiguous()
+        native = score_dtype != 0  # fp16 / bf16 scores are read by the kernels as they are: no up-cast pass over (b,A,nc)
+        pd_scores_c = pd_scores.contiguous() if native else pd_scores.to(f32).contiguous()
         pd_bboxes_c = pd_bboxes.to(f32).contiguous()
         anc_c = anc_points if (anc_points.dtype == f32 and anc_points.is_contiguous()) else anc_points.to(f32).contiguous()
         gl = gt_labels.reshape(b, G).to(f32).contiguous()
@@ -167,7 +168,8 @@ class TaskAlignedAssigner(nn.Module):
             ws = torch.empty(_lib.lib.kzd_assign_workspace_bytes(b, A, G), dtype=torch.uint8, device=dev)
         else:
             ws = self._workspace(b, A, G, dev, stream.cuda_stream)
-        flags = (0 if self.stateless else _lib.KZD_ASSIGN_PERSISTENT) | (_lib.KZD_ASSIGN_TRUSTED_ANCHORS if trusted else 0)
+        flags = ((0 if self.stateless else _lib.KZD_ASSIGN_PERSISTENT) | (_lib.KZD_ASSIGN_TRUSTED_ANCHORS if trusted else 0)
+                 | (_lib.KZD_ASSIGN_NATIVE_SCORES if native else 0))
         with torch.cuda.device(dev):
             rc = _lib.lib.kzd_tal_assign(
                 pd_scores_c.data_ptr(), pd_bboxes_c.data_ptr(), anc_c.data_ptr(), gl.data_ptr(), gb.data_ptr(),

@@ -48,6 +48,8 @@ def _check_assign(mine, ref):
     (2, 300, 1280, 3, synth.P2_P5, "columns", 10, 0.5),
     (3, 64, 320, 2, synth.P2_P5, "uniform", 13, 1.0),    # the class defaults topk=13, alpha=1
     (1, 7, 256, 1, synth.P2_P5, "columns", 1, 0.5),      # one-to-one (topk=1)
+    (4, 300, 640, 3, synth.P2_P5, "uniform", 1, 0.5),    # one-to-one head (E2EDetectLoss, utils/loss.py:728-743) at page scale
+    (2, 700, 320, 2, synth.P2_P5, "uniform", 10, 0.5),   # hundreds of contested anchors per CTA: the patch kernel's strip index
     (2, 33, 200, 4, synth.P3_P5, "uniform", 10, 0.5),    # grid 25/12/6: odd sizes
 ])
 def test_assign_matches_oracle(cfg):
@@ -213,6 +215,44 @@ def test_assign_amp_score_dtype(dt):
     assert torch.equal(mine[3], ref[3]) and torch.equal(mine[4], ref[4]) and torch.equal(mine[0], ref[0])
     assert torch.equal(mine[1], ref[1])
     torch.testing.assert_close(mine[2], ref[2].float(), rtol=RTOL, atol=1e-9)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_assign_reads_half_scores_natively(dt):
+    """fp16 / bf16 pd_scores go to libkzd as they are (KZD_ASSIGN_NATIVE_SCORES): same bits as handing it the
+    up-cast copy together with score_dtype, for a contiguous tensor and for a strided view."""
+    import ctypes as C
+
+    from kuzushiji_vision_b200 import _lib
+
+    b, G, nc = 2, 90, 4
+    d = synth.assigner_inputs(b, G, 640, nc, synth.P2_P5, seed=23, device=DEV, layout="uniform")
+    half = d["pd_scores"].to(dt)
+    asg = kzd.TaskAlignedAssigner(10, nc, 0.5, 6.0)
+    rest = (d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+    native = asg(half, *rest)
+    wide = torch.zeros((b, half.shape[1], 2 * nc), dtype=dt, device=DEV)
+    wide[..., ::2] = half
+    strided = asg(wide[..., ::2], *rest)
+    # the up-cast route, through the C ABI directly: fp32 copy of the scores + score_dtype, no NATIVE flag
+    A = half.shape[1]
+    f32 = torch.float32
+    out = [torch.empty((b, A), dtype=torch.int64, device=DEV), torch.empty((b, A, 4), dtype=f32, device=DEV),
+           torch.empty((b, A, nc), dtype=f32, device=DEV), torch.empty((b, A), dtype=torch.uint8, device=DEV),
+           torch.empty((b, A), dtype=torch.int64, device=DEV)]
+    ws = torch.zeros(_lib.lib.kzd_assign_workspace_bytes(b, A, G), dtype=torch.uint8, device=DEV)
+    up = half.to(f32).contiguous()
+    levels, n_levels, _ = asg._level_table(d["anc_points"])
+    rc = _lib.lib.kzd_tal_assign(up.data_ptr(), d["pd_bboxes"].data_ptr(), d["anc_points"].data_ptr(),
+                                 d["gt_labels"].reshape(b, G).contiguous().data_ptr(), d["gt_bboxes"].data_ptr(),
+                                 d["mask_gt"].reshape(b, G).contiguous().data_ptr(), b, A, G, nc, 10, 0.5, 6.0, 1e-9, levels,
+                                 n_levels, 1, _lib.dtype_code(dt), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                 out[3].data_ptr(), out[4].data_ptr(), None, ws.data_ptr(), ws.numel(), 0,
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "kzd_tal_assign")
+    torch.cuda.synchronize()
+    for n_, s_, o_ in zip(native, strided, out):
+        assert torch.equal(n_, s_) and torch.equal(n_.view(o_.dtype) if n_.dtype == torch.bool else n_, o_)
 
 
 def test_assign_tie_heavy_micro_case():

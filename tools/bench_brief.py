@@ -5,4 +5,4 @@ r = d.get("roofline", {})
 print("value", round(d["value"]), "pages/s  ms/step", round(d["ms_per_step"], 4), " stages(us)",
       {k: round(v["ms"] * 1e3, 1) for k, v in r.get("stages", {}).items()}, " dom frac", round(r.get("frac", 0), 3),
       " step frac", round(r.get("step", {}).get("frac", 0), 3), " e2e", round(d["e2e"]["value"]),
-      " single-stream ms", round(d["config"].get("ms_per_step_single_stream", 0), 4))
+      " single-stream ms", round(d.get("config_detail", d["config"]).get("ms_per_step_single_stream", 0), 4))

@@ -84,6 +84,21 @@ def loss_case(name, b, G, nc):
                     "fwd_gbs_on_bce_bytes": fwd_bytes / (f * 1e-6) / 1e9, "fwd_frac_of_peak": fwd_bytes / (f * 1e-6) / 1e9 / PEAK,
                     "bwd_gbs_on_bce_bytes": bwd_bytes / ((fb - f) * 1e-6) / 1e9,
                     "bwd_frac_of_peak": bwd_bytes / ((fb - f) * 1e-6) / 1e9 / PEAK}
+    # per-kernel device times of one sparse-target forward + backward (CUPTI): the eager figures above include the
+    # host side of the autograd Function and of the torch glue, which dominates at nc = 1
+    import collections
+
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            flush.zero_()
+            run(True, True)
+        torch.cuda.synchronize()
+    agg = collections.OrderedDict()
+    for e in prof.events():
+        if e.device_type.name == "CUDA" and "kzd::" in e.name:
+            agg.setdefault(e.name.replace("kzd::", "").split("(")[0][-40:], []).append(e.device_time if hasattr(e, "device_time") else e.cuda_time)
+    res["sparse_fwd_bwd_kernels_us"] = {k: round(sum(v) / len(v), 2) for k, v in agg.items()}
     a, bq = run(False, False), run(True, False)
     res["sparse_vs_dense_max_rel"] = float(((a - bq).abs() / a.abs().clamp(min=1e-6)).max())
     return res
@@ -107,6 +122,17 @@ scale = torch.tensor([1280.0, 1280.0, 1280.0, 1280.0], device=dev)
 out["gt_pack_16x600_us"] = timeit(lambda: kloss.preprocess(t, 16, scale), iters=10)
 det = torch.rand((16, 1000, 6), device=dev) * 1280
 out["scale_boxes_16x1000_us"] = timeit(lambda: kzd.scale_boxes_batched(det, [1000] * 16, (1280, 1280), [(2000, 1500)] * 16), iters=10)
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(3):
+        kloss.preprocess(t, 16, scale)
+        kzd.scale_boxes_batched(det, [1000] * 16, (1280, 1280), [(2000, 1500)] * 16)
+    torch.cuda.synchronize()
+kk = {}
+for e in prof.events():
+    if e.device_type.name == "CUDA" and "kzd::" in e.name:
+        kk.setdefault(e.name.replace("kzd::", "").split("(")[0][-40:], []).append(e.device_time if hasattr(e, "device_time") else e.cuda_time)
+out["gt_scale_kernels_us"] = {k: round(sum(v) / len(v), 2) for k, v in kk.items()}
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/r2_frow_times.json", "w"), indent=1)
 print(json.dumps(out, indent=1))
