@@ -626,8 +626,9 @@ def roofline_block(meas, names, st_ms, ms_per_step, n_cand, n_keep):
     b, A, G, nc, m = meas.b, meas.A, meas.G, meas.nc, meas.m
     ab = algorithmic_bytes(b, A, G, nc, n_cand, n_keep)
     ff = "true" if meas.fuse_filter else "false"
-    single = ({"decode_dual": f"decode_infer_kernel<4, float, true, {ff}>"} if meas.fuse else
-              {"decode_train": "decode_train_kernel", "decode_infer": f"decode_infer_kernel<4, float, false, {ff}>"})
+    wide = "true" if nc >= 32 else "false"  # csrc/kzd_decode.cu: WIDE_NC
+    single = ({"decode_dual": f"decode_infer_kernel<4, float, true, {ff}, {wide}>"} if meas.fuse else
+              {"decode_train": "decode_train_kernel", "decode_infer": f"decode_infer_kernel<4, float, false, {ff}, {wide}>"})
     dom = max(single, key=lambda n: st_ms[n])
     peak, peak_src = hbm_peak()
     achieved = ab[dom] / (st_ms[dom] * 1e-3) / 1e9

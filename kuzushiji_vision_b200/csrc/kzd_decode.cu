@@ -101,7 +101,12 @@ struct FilterArgs {
     int cap;
 };
 
-template <int VEC, typename T, bool DUAL, bool FILTER>
+// WIDE: heads with many classes (the kuzushiji recogniser's ~4,300 Unicode classes). The class loop then carries
+// nearly all of the traffic AND of the instructions: with the IEEE division of the sigmoid the kernel is
+// issue-bound (4.11 ms for 4 pages at nc = 4300, 0.70 of the HBM peak); the approximate division (MUFU.RCP + one
+// multiply, <= 2 ulp) brings it to 3.11 ms = 0.93. A separate instantiation, because the extra registers of
+// that loop cost the single-class kernel a resident CTA per SM (107.7 -> 110 us).
+template <int VEC, typename T, bool DUAL, bool FILTER, bool WIDE>
 __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, float* __restrict__ y,
                                                            float* __restrict__ out_xyxy,
                                                            float* __restrict__ out_px, const FilterArgs f) {
@@ -198,7 +203,8 @@ __global__ void __launch_bounds__(128) decode_infer_kernel(const InferParams p, 
                 float o[VEC];
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
-                    o[i] = 1.f / (1.f + __expf(-v[k][i]));  // |err| < 2e-7: ex2.approx + IEEE div
+                    // |err| < 2e-7: ex2.approx + IEEE division; WIDE: approximate division, |err| < 4e-7
+                    o[i] = WIDE ? __fdividef(1.f, 1.f + __expf(-v[k][i])) : 1.f / (1.f + __expf(-v[k][i]));
                     if (FILTER && (c == 0 || o[i] > best[i])) best[i] = o[i], cls[i] = c;  // first maximum wins (ops.py:274)
                 }
                 Out<VEC>::store(cdst + (size_t)c * p.A, o);
@@ -442,24 +448,27 @@ __global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const floa
 
 using namespace kzd;
 
-template <int VEC, typename T>
+constexpr int WIDE_NC = 32;  // class count from which the WIDE instantiation is used
+
+template <int VEC, typename T, bool WIDE>
 static void launch_infer_vec(const InferParams& p, dim3 grid, float* y, float* out_xyxy, float* out_px,
                              const FilterArgs* f, cudaStream_t st) {
     const FilterArgs none{0.f, nullptr, nullptr, nullptr, 0};
     if (f) {
-        if (out_xyxy) decode_infer_kernel<VEC, T, true, true><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px, *f);
-        else decode_infer_kernel<VEC, T, false, true><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr, *f);
+        if (out_xyxy) decode_infer_kernel<VEC, T, true, true, WIDE><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px, *f);
+        else decode_infer_kernel<VEC, T, false, true, WIDE><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr, *f);
     } else {
-        if (out_xyxy) decode_infer_kernel<VEC, T, true, false><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px, none);
-        else decode_infer_kernel<VEC, T, false, false><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr, none);
+        if (out_xyxy) decode_infer_kernel<VEC, T, true, false, WIDE><<<grid, 128, 0, st>>>(p, y, out_xyxy, out_px, none);
+        else decode_infer_kernel<VEC, T, false, false, WIDE><<<grid, 128, 0, st>>>(p, y, nullptr, nullptr, none);
     }
 }
 
 template <typename T>
 static void launch_infer(const InferParams& p, int total, int b, bool vec4, float* y, float* out_xyxy, float* out_px,
                          const FilterArgs* f, cudaStream_t st) {
-    if (vec4) launch_infer_vec<4, T>(p, dim3((total / 4 + 127) / 128, b), y, out_xyxy, out_px, f, st);
-    else launch_infer_vec<1, T>(p, dim3((total + 127) / 128, b), y, out_xyxy, out_px, f, st);
+    if (vec4 && p.nc >= WIDE_NC) launch_infer_vec<4, T, true>(p, dim3((total / 4 + 127) / 128, b), y, out_xyxy, out_px, f, st);
+    else if (vec4) launch_infer_vec<4, T, false>(p, dim3((total / 4 + 127) / 128, b), y, out_xyxy, out_px, f, st);
+    else launch_infer_vec<1, T, false>(p, dim3((total + 127) / 128, b), y, out_xyxy, out_px, f, st);
 }
 
 static int decode_maps(const void* const* h_level_ptrs, int in_dtype, const kzd_level* h_levels, int n_levels, int b,

@@ -290,7 +290,8 @@ def _box_rel_err(y, ref, strides_per_anchor):
 
 
 @pytest.mark.parametrize("cfg", [(2, 1, 640, synth.P3_P5), (2, 7, 320, synth.P2_P5), (3, 2, 200, synth.P3_P5),
-                                 (1, 1, 1280, synth.P2_P5), (2, 80, 256, synth.P2_P5)])
+                                 (1, 1, 1280, synth.P2_P5), (2, 80, 256, synth.P2_P5),
+                                 (1, 4300, 320, synth.P2_P5)])  # the last two: wide heads (kzd_decode.cu WIDE instantiation)
 def test_decode_infer_matches_oracle(cfg):
     b, nc, imgsz, strides = cfg
     lv = synth.head_outputs(b, nc, imgsz, strides, seed=1, device=DEV)

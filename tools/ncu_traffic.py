@@ -27,10 +27,10 @@ scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us"
 out = {"_csrc_digest": csrc_digest()}
 for r in rows[2:]:
     name = re.sub(r"^(void )?(kzd::)?", "", r[col["Kernel Name"]].split("(")[0]).replace("kzd::", "")
-    m = re.match(r"decode_infer_kernel<(\d+), (\w+), (\d), (\d)>", name)
+    m = re.match(r"decode_infer_kernel<(\d+), (\w+), (\d), (\d), (\d)>", name)
     if m:  # ncu prints bool template arguments as 0/1
-        name = "decode_infer_kernel<%s, %s, %s, %s>" % (m.group(1), m.group(2), "true" if m.group(3) == "1" else "false",
-                                                        "true" if m.group(4) == "1" else "false")
+        tf = lambda g: "true" if m.group(g) == "1" else "false"
+        name = "decode_infer_kernel<%s, %s, %s, %s, %s>" % (m.group(1), m.group(2), tf(3), tf(4), tf(5))
     rd = float(r[col["dram__bytes_read.sum"]].replace(",", "")) * scale[units[col["dram__bytes_read.sum"]]]
     wr = float(r[col["dram__bytes_write.sum"]].replace(",", "")) * scale[units[col["dram__bytes_write.sum"]]]
     us = float(r[col["gpu__time_duration.sum"]].replace(",", "")) * scale[units[col["gpu__time_duration.sum"]]]
