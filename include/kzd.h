@@ -128,8 +128,8 @@ size_t kzd_assign_report_offset(int b, int A);
  *   flags: bit mask.
  *     KZD_ASSIGN_PERSISTENT      the caller keeps ONE workspace per (b, A) - sized for the largest G it
  *       will pass - zeroed ONCE after allocation, and passes it unchanged on every call (one call at a time
- *       per workspace). Every call leaves the per-anchor state all-zero again (the last CTA of each image
- *       clears what the call set), so no per-call memset is needed (CUDA-graph friendly). Without this
+ *       per workspace). Every call leaves the per-anchor state all-zero again (the patch kernel swaps the words
+ *       it reads for zero, the last CTA of each image clears the counters), so no per-call memset is needed (CUDA-graph friendly). Without this
  *       bit the call zeroes the state itself first (one extra 8 B/anchor memset).
  *     KZD_ASSIGN_TRUSTED_ANCHORS the caller vouches that anc_points equals the grid described by h_levels
  *       bit for bit (e.g. it built both, or checked them once on the host); the per-call device check is

@@ -4,25 +4,25 @@
 // :132-151, select_topk_candidates :157-190, get_targets :192-238, select_candidates_in_gts :241-262,
 // select_highest_overlaps :264-295) and CIoU utils/metrics.py:96-130.
 //
-// Kernels (one stream, no host sync; two launches in the steady state):
+// Kernels (one stream, no host sync; three launches in the steady state):
 //   assign_verify_kernel      only when the caller does not vouch for anc_points: checks them against the
 //                             level table bit for bit (the grid accelerator is used only when every anchor
 //                             matches)
-//   assign_candidates_kernel  one half warp (topk <= 16) or warp per (image, GT): the anchors inside the GT are an exact
-//                             rectangle per level (separable x / y tests); CIoU + alignment metric 32
-//                             pairs at a time, top-k by warp-wide redux max, selecting GTs recorded with two
-//                             atomicMax words per picked anchor and in a pick list; each warp also stores the
-//                             background targets of a slice of the image's anchors (no dense pass over the
-//                             anchors remains)
+//   assign_candidates_kernel  one half warp (topk <= 16) or warp per (image, GT), the groups of a warp in
+//                             lockstep: the anchors inside the GT are an exact rectangle per level (separable
+//                             x / y tests); CIoU + alignment metric a batch of pairs at a time, top-k by
+//                             group-wide max, selecting GTs recorded with two atomicMax words per picked anchor
+//                             and in a pick list; each group also stores the background targets of a slice of
+//                             the image's anchors (no dense pass over the anchors remains)
 //   assign_patch_kernel       pick list (~10 per GT): resolve each picked anchor's owner GT (a contested
 //                             anchor - picked by several GTs - takes the first-max argmax of overlaps over
-//                             ALL GTs of the image, found by one warp scanning the image's GT rows), overwrite
-//                             its targets, owner pair's metric + per-GT maxima; the entry that swaps the
-//                             anchor's selection words for zero represents it, so the persistent state is
-//                             all-zero again when the call ends: no begin kernel, no epoch, no per-call
-//                             memset. The LAST CTA of every image (ticket) then normalises that image's
-//                             foreground scores (target_scores = align * pos_ov / (pos_align + eps)), one
-//                             thread per pick slot.
+//                             ALL GTs of the image: a scan of the GT rows, or a strip index of the page when a
+//                             CTA meets many of them), overwrite its targets, owner pair's metric + per-GT
+//                             maxima; the entry that swaps the anchor's selection words for zero represents
+//                             it, so the persistent state is all-zero again when the call ends: no begin
+//                             kernel, no epoch, no per-call memset
+//   assign_normalize_kernel   one thread per pick slot: target_scores = align * pos_ov / (pos_align + eps),
+//                             the counters; the last CTA of an image to leave clears the image's state words
 //
 // Bit-exactness: every fp32 operation of the eager reference rounds separately, so the pair
 // arithmetic below uses __fadd_rn/__fmul_rn/__fdiv_rn (never contracted into FMAs) and the same
