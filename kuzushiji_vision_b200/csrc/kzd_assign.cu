@@ -1017,11 +1017,8 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const void*
 #endif
         if (!KZD_NO_STRIPS && extent > 0.f && index_bytes <= PATCH_INDEX_MAX) {
             p.strip_words = (G + 31) / 32, p.inv_strip = (float)PATCH_STRIPS / extent;
-            static thread_local bool raised = false;
-            if (!raised) {
-                KZD_CUDA(cudaFuncSetAttribute(assign_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATCH_INDEX_MAX));
-                raised = true;
-            }
+            // (per call: the attribute belongs to the current device's copy of the kernel)
+            KZD_CUDA(cudaFuncSetAttribute(assign_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PATCH_INDEX_MAX));
         }
         assign_patch_kernel<<<dim3((unsigned)per_img, (unsigned)b), PATCH_THREADS, p.strip_words ? index_bytes : 0, st>>>(p);
         KZD_LAUNCH_CHECK("assign_patch_kernel");

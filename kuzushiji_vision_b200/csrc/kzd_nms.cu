@@ -1053,11 +1053,8 @@ extern "C" __attribute__((visibility("default"))) int kzd_nms_suppress(const uin
 #define KZD_NO_BUCKET 0
 #endif
     if (!KZD_NO_BUCKET && n_cap <= 4096 && cand_cap <= 65535) {  // the usual capacity: one CTA per image ranks by buckets
-        static thread_local bool raised = false;
-        if (!raised) {
-            KZD_CUDA(cudaFuncSetAttribute(nms_order_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BR_SMEM));
-            raised = true;
-        }
+        // (per call: the attribute belongs to the current device's copy of the kernel)
+        KZD_CUDA(cudaFuncSetAttribute(nms_order_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BR_SMEM));
         nms_order_bucket_kernel<<<b, BR_THREADS, BR_SMEM, st>>>((const u64*)cand_keys, cand_rows, cand_counts, cand_cap, n_cap,
                                                                max_nms, agnostic, max_wh, ws);
         KZD_LAUNCH_CHECK("nms_order_bucket_kernel");

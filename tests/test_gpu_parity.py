@@ -50,6 +50,7 @@ def _check_assign(mine, ref):
     (1, 7, 256, 1, synth.P2_P5, "columns", 1, 0.5),      # one-to-one (topk=1)
     (4, 300, 640, 3, synth.P2_P5, "uniform", 1, 0.5),    # one-to-one head (E2EDetectLoss, utils/loss.py:728-743) at page scale
     (2, 700, 320, 2, synth.P2_P5, "uniform", 10, 0.5),   # hundreds of contested anchors per CTA: the patch kernel's strip index
+    (3, 45, 320, 2, synth.P2_P5, "uniform", 20, 0.5),    # topk > 16: a whole warp per GT (the <32> instantiation), odd GT count
     (2, 33, 200, 4, synth.P3_P5, "uniform", 10, 0.5),    # grid 25/12/6: odd sizes
 ])
 def test_assign_matches_oracle(cfg):
