@@ -166,8 +166,9 @@ def algorithmic_bytes(b, A, G, nc, n_cand, n_keep):
         # 272*A for the decode + 16*A for the pixel-space copy (x stride, utils/loss.py:236) that the
         # same kernel writes (the reference's separate elementwise pass would read 16*A more)
         "decode_train": (272 + 16) * A * b,
-        # nc > 1: target_scores is a dense (b,A,nc) tensor the call has to write (4*nc instead of 4 bytes per anchor)
-        "assign": int((53 + 4 * nc + 8 / b) * A + 24 * G) * b,
+        # nc = 1: (57 + 8/b) A + 24 G; nc > 1: (49 + 4 nc + 8/b) A + 4 P + 24 G - the dense (b,A,nc)
+        # target_scores has to be written; P = in-GT pairs whose score is gathered, ~90 per GT on these pages
+        "assign": int((57 + 8 / b) * A + 24 * G) * b if nc == 1 else int((49 + 4 * nc + 8 / b) * A + 4 * 90 * G + 24 * G) * b,
         "decode_infer": (272 + 8 * nc) * A * b,
         # fused: one read of the maps 4(64+nc)A, writes y 4(4+nc)A + grid-unit boxes 16A + pixel boxes 16A
         "decode_dual": (4 * (64 + nc) + 4 * (4 + nc) + 32) * A * b,
