@@ -130,7 +130,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 kk = {}
 for e in prof.events():
-    if e.device_type.name == "CUDA" and "kzd::" in e.name:
+    if e.device_type.name == "CUDA" and "at::" not in e.name and "Memcpy" not in e.name and "Memset" not in e.name:
         kk.setdefault(e.name.replace("kzd::", "").split("(")[0][-40:], []).append(e.device_time if hasattr(e, "device_time") else e.cuda_time)
 out["gt_scale_kernels_us"] = {k: round(sum(v) / len(v), 2) for k, v in kk.items()}
 os.makedirs("gpurun_out", exist_ok=True)
