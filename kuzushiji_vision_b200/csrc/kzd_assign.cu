@@ -566,9 +566,9 @@ __global__ void __launch_bounds__(CAND_THREADS, KZD_CAND_MINB) assign_candidates
 constexpr int PATCH_THREADS = 512;
 constexpr int PATCH_STRIPS = 64;               // vertical page strips of the contested-anchor index
 #ifndef KZD_PATCH_STRIP_MIN
-#define KZD_PATCH_STRIP_MIN 128
+#define KZD_PATCH_STRIP_MIN 48
 #endif
-constexpr int PATCH_STRIP_MIN = KZD_PATCH_STRIP_MIN;  // contested anchors in a round from which the index pays
+constexpr int PATCH_STRIP_MIN = KZD_PATCH_STRIP_MIN;  // (contested anchors) x (GT rows per thread) from which the index pays
 constexpr size_t PATCH_INDEX_MAX = 64 * 1024;  // bytes of shared memory the index may take (GT boxes + strip masks)
 
 __device__ __forceinline__ int strip_of(float x, float inv_strip) {
@@ -647,16 +647,16 @@ __global__ void __launch_bounds__(PATCH_THREADS, 2) assign_patch_kernel(const As
         }
         __syncthreads();
         const int n_c = c_n;  // CTA-uniform
-        if (n_c >= PATCH_STRIP_MIN && p.strip_words > 0) {
+        if (n_c * ((p.G + PATCH_THREADS - 1) / PATCH_THREADS) >= PATCH_STRIP_MIN && p.strip_words > 0) {
             // Strip index: the page is cut into PATCH_STRIPS vertical strips; strip s holds a G-bit mask of the valid
             // GTs whose x-range reaches into it. strip(x) = clamp(floor(x * inv_strip)) is monotone in x, so a GT
             // that contains an anchor (x1 < ax < x2) is always listed in the anchor's strip: the argmax below tests
             // ~G * (box width + strip width) / page width GTs per anchor instead of all G (scanning every GT row
             // for every contested anchor, a CTA with 300 of them took 19 us at G = 1000 and set the kernel's
             // duration). Masks and a copy of the image's GT boxes live in shared memory; built once per CTA, the
-            // first time a round lists at least PATCH_STRIP_MIN contested anchors (building costs ~4 us: below
-            // that the plain scan of the GT rows is faster - measured 13.3 vs 17.2 us per call at G = 600, where
-            // a CTA lists a few dozen, and 28.6 vs 23.6 us at G = 1000, where it lists hundreds).
+            // first time a round's scan would cost more than building it (~4 us): the scan runs (contested anchors)
+            // x (GT rows per thread) tests per thread. Measured per call, index always / never / from 48 tests:
+            // 17.2 / 13.3 / 14.4 us at G = 600 (a CTA lists a dozen or two), 23.6 / 28.6 / 24.2 us at G = 1000.
             const int W = p.strip_words;
             float4* s_box = reinterpret_cast<float4*>(patch_dyn);
             uint32_t* strips = reinterpret_cast<uint32_t*>(s_box + p.G);

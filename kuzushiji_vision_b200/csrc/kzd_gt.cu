@@ -13,16 +13,24 @@ namespace kzd {
 // flags[0] != 0 when the image indices are not non-decreasing (the pack kernel needs them grouped).
 __global__ void gt_count_kernel(const float* __restrict__ targets, int n, int b, int32_t* __restrict__ counts,
                                 int32_t* __restrict__ first, int32_t* __restrict__ flags) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int j = (int)targets[(size_t)t * 6];
-    if (j < 0 || j >= b) {
-        atomicOr(flags, 2);
-        return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive for the match
+    int j = -1;
+    if (t < n) {
+        j = (int)targets[(size_t)t * 6];
+        if (j < 0 || j >= b) {
+            atomicOr(flags, 2);
+            j = -1;
+        } else if (t > 0 && targets[(size_t)(t - 1) * 6] > targets[(size_t)t * 6]) {
+            atomicOr(flags, 1);
+        }
     }
-    atomicAdd(counts + j, 1);
-    atomicMin(first + j, t);
-    if (t > 0 && targets[(size_t)(t - 1) * 6] > targets[(size_t)t * 6]) atomicOr(flags, 1);
+    // rows of one image sit next to each other, so a warp holds one or two images: the lowest lane of each takes
+    // the image's two atomics for all of them (hundreds of rows per image would otherwise queue on one address)
+    const unsigned peers = __match_any_sync(0xffffffffu, j);
+    if (j >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        atomicAdd(counts + j, __popc(peers));
+        atomicMin(first + j, t);  // the lowest lane of the group holds its smallest row index
+    }
 }
 
 // One thread per output row (image j, slot s): row first[j]+s of the (grouped) targets, or zeros.
