@@ -1165,3 +1165,16 @@ def test_nms_validation_scale_full_size():
     ref = O.non_max_suppression(y.clone(), conf_thres=0.001, iou_thres=0.7, multi_label=True, max_det=300)
     _check_nms(mine, ref)
     assert all(int(t.shape[0]) == 300 for t in ref)
+
+
+def test_every_kernel_variant_runs():
+    """tools/sanitize_target.py launches every libkzd kernel and every dispatch variant once on small inputs (all decode
+    forms, the assigner's warp-per-GT / contested / off-grid / half-score paths, the three NMS orderings, the two-phase walk,
+    the graph pipeline, both loss-tail forms forward and backward, GT packing, scale/clip, validator matching): it has to
+    come through without a CUDA error. (The value checks are the parity tests above.)"""
+    import os
+    import runpy
+
+    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "sanitize_target.py"),
+                   run_name="__main__")
+    torch.cuda.synchronize()
