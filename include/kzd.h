@@ -260,16 +260,21 @@ int kzd_loss_tail_bwd(const float* pred_scores, const float* pred_dist, const fl
  * reference takes as target_scores.sum(-1), utils/loss.py:93); target_labels int64 (b,A) is kzd_tal_assign's
  * first output. score_dtype (0 fp32, 1 fp16, 2 bf16): dtype the reference rounds the BCE target to under AMP
  * (target_scores.to(dtype), utils/loss.py:247) - the weight keeps the fp32 value. The backward writes
- * sigmoid(x)*scale everywhere (reads pred_scores only) and subtracts t*scale at the foreground elements. */
-int kzd_loss_tail_sparse_fwd(const float* pred_scores, const float* pred_dist, const float* anchor_points,
+ * sigmoid(x)*scale everywhere (reads pred_scores only) and subtracts t*scale at the foreground elements.
+ * logits_dtype / dist_dtype (0 fp32, 1 fp16, 2 bf16): element type of pred_scores + grad_pred_scores and of
+ * pred_dist + grad_pred_dist. Under AMP the head outputs are half precision (engine/trainer.py:379): the kernels
+ * read them as they are, compute in fp32 and round the gradients once into the same dtype (what autograd does
+ * behind the reference's fp32-autocast BCE / softmax) - no up-cast copies of the (b,A,nc) and (b,A,64) tensors. */
+int kzd_loss_tail_sparse_fwd(const void* pred_scores, const void* pred_dist, const float* anchor_points,
                              const float* stride_tensor, const float* target_bboxes, const float* target_scores,
                              const int64_t* target_labels, const uint8_t* fg_mask, const float* target_scores_sum,
-                             int b, int A, int nc, int score_dtype, double* sums_ws, float* loss3, void* stream);
-int kzd_loss_tail_sparse_bwd(const float* pred_scores, const float* pred_dist, const float* anchor_points,
+                             int b, int A, int nc, int score_dtype, int logits_dtype, int dist_dtype,
+                             double* sums_ws, float* loss3, void* stream);
+int kzd_loss_tail_sparse_bwd(const void* pred_scores, const void* pred_dist, const float* anchor_points,
                              const float* stride_tensor, const float* target_bboxes, const float* target_scores,
                              const int64_t* target_labels, const uint8_t* fg_mask, const float* target_scores_sum,
-                             int b, int A, int nc, int score_dtype, const float* grad_loss3,
-                             float* grad_pred_scores, float* grad_pred_dist, void* stream);
+                             int b, int A, int nc, int score_dtype, int logits_dtype, int dist_dtype,
+                             const float* grad_loss3, void* grad_pred_scores, void* grad_pred_dist, void* stream);
 
 #ifdef __cplusplus
 }

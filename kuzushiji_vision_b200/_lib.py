@@ -56,8 +56,8 @@ def _load():
         "kzd_gt_pack": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
         "kzd_loss_tail_fwd": (C.c_int, [vp] * 8 + [i32] * 3 + [vp, vp, vp]),
         "kzd_loss_tail_bwd": (C.c_int, [vp] * 8 + [i32] * 3 + [vp, vp, vp, vp]),
-        "kzd_loss_tail_sparse_fwd": (C.c_int, [vp] * 9 + [i32] * 4 + [vp, vp, vp]),
-        "kzd_loss_tail_sparse_bwd": (C.c_int, [vp] * 9 + [i32] * 4 + [vp, vp, vp, vp]),
+        "kzd_loss_tail_sparse_fwd": (C.c_int, [vp] * 9 + [i32] * 6 + [vp, vp, vp]),
+        "kzd_loss_tail_sparse_bwd": (C.c_int, [vp] * 9 + [i32] * 6 + [vp, vp, vp, vp]),
         "kzd_scale_boxes": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
         "kzd_match_workspace_bytes": (sz, [i32, i32, i32, i32]),
         "kzd_match_predictions": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, i32, vp, i32, vp, vp, sz, vp]),

@@ -22,7 +22,8 @@
 namespace kzd {
 
 struct LossParams {
-    const float *pred_scores, *pred_dist, *anchor_points, *stride, *target_bboxes, *target_scores;
+    const void *pred_scores, *pred_dist;  // fp32, or the AMP flow's fp16 / bf16 tensors themselves (logits_dtype, dist_dtype)
+    const float *anchor_points, *stride, *target_bboxes, *target_scores;
     const uint8_t* fg_mask;
     const float* tss;  // device scalar: target_scores.sum() (max(., 1) is applied here)
     int b, A, nc;
@@ -31,7 +32,50 @@ struct LossParams {
     // only read at those (anchor, label) elements
     const long long* target_labels;  // nullptr: dense form
     int score_dtype;                 // dtype the BCE target is rounded to (utils/loss.py:247 under AMP): 0 fp32, 1 fp16, 2 bf16
+    int logits_dtype;                // element type of pred_scores and grad_pred_scores: 0 fp32, 1 fp16, 2 bf16
+    int dist_dtype;                  // element type of pred_dist and grad_pred_dist
 };
+
+// element i of a tensor of the given dtype code, as fp32 / fp32 value v rounded into element i
+__device__ __forceinline__ float load_elem(const void* base, size_t i, int dtype) {
+    if (dtype == 1) return __half2float(reinterpret_cast<const __half*>(base)[i]);
+    if (dtype == 2) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
+    return reinterpret_cast<const float*>(base)[i];
+}
+__device__ __forceinline__ void store_elem(void* base, size_t i, int dtype, float v) {
+    if (dtype == 1) reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
+    else if (dtype == 2) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(base)[i] = v;
+}
+// eight consecutive half-precision elements (one 16-byte word) <-> fp32
+template <int DT>
+__device__ __forceinline__ void unpack8(const uint4 w, float (&v)[8]) {
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (DT == 1) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
+            v[2 * k] = f.x, v[2 * k + 1] = f.y;
+        } else {
+            v[2 * k] = __uint_as_float(u[k] << 16), v[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
+        }
+    }
+}
+template <int DT>
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint32_t u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (DT == 1) {
+            const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+            u[k] = *reinterpret_cast<const uint32_t*>(&h);
+        } else {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+            u[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+    }
+    return make_uint4(u[0], u[1], u[2], u[3]);
+}
 
 __device__ __forceinline__ float round_to(float v, int dtype) {
     if (dtype == 1) return __half2float(__float2half_rn(v));
@@ -120,6 +164,49 @@ __global__ void __launch_bounds__(256) sigmoid_grad_kernel(const float* __restri
         __stcs(gx + i, sg(__ldcs(x + i)));
 }
 
+// The same two passes on the AMP flow's half-precision logits, read (and the gradient written) as they are: 16-byte
+// words of eight elements, fp32 arithmetic, one rounding of the gradient into the logits' dtype - what autograd
+// does behind the reference's fp32-autocast BCE (the gradient comes back through the cast of pred_scores).
+template <int DT>
+__global__ void __launch_bounds__(256) softplus_sum_half_kernel(const void* __restrict__ x, size_t n, size_t n8,
+                                                                double* __restrict__ sums) {
+    __shared__ double s_red[8];
+    float acc = 0.f;
+    double total = 0.0;
+    int k = 0;
+    const uint4* __restrict__ x8 = reinterpret_cast<const uint4*>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float v[8];
+        unpack8<DT>(__ldcs(x8 + i), v);
+        acc += ((softplus_fast(v[0]) + softplus_fast(v[1])) + (softplus_fast(v[2]) + softplus_fast(v[3]))) +
+               ((softplus_fast(v[4]) + softplus_fast(v[5])) + (softplus_fast(v[6]) + softplus_fast(v[7])));
+        if (++k == 8) total += (double)acc, acc = 0.f, k = 0;  // bound the fp32 partial
+    }
+    for (size_t i = n8 * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        acc += softplus_fast(load_elem(x, i, DT));
+    total += (double)acc;
+    block_add(total, sums + 1, s_red);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) sigmoid_grad_half_kernel(const void* __restrict__ x, size_t n, size_t n8,
+                                                                const float* __restrict__ tss, const float* __restrict__ gout,
+                                                                void* __restrict__ gx) {
+    const float scale = gout[1] / fmaxf(*tss, 1.f);
+    const uint4* __restrict__ x8 = reinterpret_cast<const uint4*>(x);
+    uint4* __restrict__ g8 = reinterpret_cast<uint4*>(gx);
+    auto sg = [&](float v) { return __fdividef(scale, 1.f + __expf(-v)); };
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float v[8];
+        unpack8<DT>(__ldcs(x8 + i), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = sg(v[k]);
+        __stcs(g8 + i, pack8<DT>(v));
+    }
+    for (size_t i = n8 * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        store_elem(gx, i, DT, sg(load_elem(x, i, DT)));
+}
+
 __global__ void __launch_bounds__(256) bce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                                       size_t n, const float* __restrict__ tss,
                                                       const float* __restrict__ gout, float* __restrict__ gx) {
@@ -166,15 +253,25 @@ template <bool GRAD>
 __device__ __forceinline__ FgTerms fg_anchor(const LossParams& p, bool live, size_t idx, int a, int side, float (&x)[16]) {
     FgTerms r;
     r.box = r.dfl = r.gd = r.d = r.wl = r.wr = r.w = r.m = 0.f, r.inv_sum = 1.f, r.tl = 0, r.lab = 0;
-    const float4* __restrict__ row = reinterpret_cast<const float4*>(p.pred_dist + idx * 64 + side * 16);
+    const size_t row0 = idx * 64 + side * 16;  // this lane's 16 bins inside pred_dist
     float ax = 0.f, ay = 0.f, st = 1.f;
     float4 tbp = make_float4(0.f, 0.f, 1.f, 1.f);
     float w = 0.f;
     if (live) {
+        if (p.dist_dtype == 0) {
+            const float4* __restrict__ row = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.pred_dist) + row0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float4 t = __ldg(row + k);
-            x[4 * k] = t.x, x[4 * k + 1] = t.y, x[4 * k + 2] = t.z, x[4 * k + 3] = t.w;
+            for (int k = 0; k < 4; ++k) {
+                const float4 t = __ldg(row + k);
+                x[4 * k] = t.x, x[4 * k + 1] = t.y, x[4 * k + 2] = t.z, x[4 * k + 3] = t.w;
+            }
+        } else {  // 16 half-precision bins = two 16-byte words
+            const uint4* __restrict__ row = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.pred_dist) + row0);
+            float lo[8], hi[8];
+            if (p.dist_dtype == 1) unpack8<1>(__ldg(row), lo), unpack8<1>(__ldg(row + 1), hi);
+            else unpack8<2>(__ldg(row), lo), unpack8<2>(__ldg(row + 1), hi);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = lo[k], x[8 + k] = hi[k];
         }
         ax = p.anchor_points[2 * a], ay = p.anchor_points[2 * a + 1], st = p.stride[a];
         tbp = *reinterpret_cast<const float4*>(p.target_bboxes + idx * 4);
@@ -318,7 +415,8 @@ __global__ void __launch_bounds__(FG_THREADS) fg_fwd_kernel(const LossParams p, 
         if (live && side == 0) {
             box += (double)t.box, dfl += (double)t.dfl;
             // sparse-target BCE: BCE(x, t) - BCE(x, 0) = -t x at the row's only non-zero target
-            if (p.target_labels) cls -= (double)(round_to(t.w, p.score_dtype) * p.pred_scores[idx * p.nc + t.lab]);
+            if (p.target_labels)
+                cls -= (double)(round_to(t.w, p.score_dtype) * load_elem(p.pred_scores, idx * p.nc + t.lab, p.logits_dtype));
         }
     }
     block_add(box, sums + 0, s_red);
@@ -329,7 +427,7 @@ __global__ void __launch_bounds__(FG_THREADS) fg_fwd_kernel(const LossParams p, 
 // grad_pred_dist for every anchor of the span: zeros for the background rows (streamed, the bulk of the
 // kernel's traffic: 256 B per anchor), decode + CIoU + DFL chain for the foreground rows.
 __global__ void __launch_bounds__(FG_THREADS) fg_bwd_kernel(const LossParams p, const float* __restrict__ gout,
-                                                            float* __restrict__ gdist, float* gscores) {
+                                                            void* __restrict__ gdist, void* gscores) {
     __shared__ uint16_t s_list[FG_SPAN];
     __shared__ uint8_t s_flag[FG_SPAN];
     __shared__ int s_n;
@@ -338,10 +436,11 @@ __global__ void __launch_bounds__(FG_THREADS) fg_bwd_kernel(const LossParams p, 
     const int span = (int)min((long long)FG_SPAN, n - first);
     const int n_fg = fg_compact(p, first, span, s_list, &s_n, s_flag);
     // background rows: 16 float4 per row, consecutive threads write consecutive float4
-    float4* __restrict__ g4 = reinterpret_cast<float4*>(gdist + (size_t)first * 64);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = threadIdx.x; i < span * 16; i += FG_THREADS)
-        if (!s_flag[i >> 4]) __stcs(g4 + i, z);
+    const int w_row = p.dist_dtype == 0 ? 16 : 8;  // 16-byte words per row of grad_pred_dist (64 fp32 / 64 half elements)
+    uint4* __restrict__ g4 = reinterpret_cast<uint4*>(gdist) + (size_t)first * w_row;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < span * w_row; i += FG_THREADS)
+        if (!s_flag[p.dist_dtype == 0 ? i >> 4 : i >> 3]) __stcs(g4 + i, z);
     const float inv_tss = 1.f / fmaxf(*p.tss, 1.f);
     const float g_box = gout[0] * inv_tss, g_dfl = gout[2] * inv_tss, g_cls = gout[1] * inv_tss;
     const int quad = threadIdx.x >> 2, side = threadIdx.x & 3;
@@ -354,20 +453,35 @@ __global__ void __launch_bounds__(FG_THREADS) fg_bwd_kernel(const LossParams p, 
         if (!live) continue;  // (no collective below)
         const float gd = g_box * t.gd;          // through the expectation d = sum_k k p_k
         const float gc = g_dfl * 0.25f * t.w;   // through the two cross entropies
-        float4* __restrict__ dst = reinterpret_cast<float4*>(gdist + idx * 64 + side * 16);
+        float g[16];
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-            float g[4];
+        for (int k = 0; k < 16; ++k) {
+            const float pk = expf(x[k] - t.m) * t.inv_sum;
+            g[k] = gd * pk * ((float)k - t.d) + gc * (pk - (k == t.tl ? t.wl : 0.f) - (k == t.tl + 1 ? t.wr : 0.f));
+        }
+        if (p.dist_dtype == 0) {
+            float4* __restrict__ dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(gdist) + idx * 64 + side * 16);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = 4 * k4 + j;
-                const float pk = expf(x[k] - t.m) * t.inv_sum;
-                g[j] = gd * pk * ((float)k - t.d) + gc * (pk - (k == t.tl ? t.wl : 0.f) - (k == t.tl + 1 ? t.wr : 0.f));
-            }
-            __stcs(dst + k4, make_float4(g[0], g[1], g[2], g[3]));
+            for (int k4 = 0; k4 < 4; ++k4) __stcs(dst + k4, make_float4(g[4 * k4], g[4 * k4 + 1], g[4 * k4 + 2], g[4 * k4 + 3]));
+        } else {
+            uint4* __restrict__ dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(gdist) + idx * 64 + side * 16);
+            float lo[8], hi[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) lo[k] = g[k], hi[k] = g[8 + k];
+            if (p.dist_dtype == 1) __stcs(dst, pack8<1>(lo)), __stcs(dst + 1, pack8<1>(hi));
+            else __stcs(dst, pack8<2>(lo)), __stcs(dst + 1, pack8<2>(hi));
         }
         // sparse-target BCE: the dense pass wrote sigmoid(x) * scale; the target's share goes in here
-        if (gscores && side == 0) gscores[idx * p.nc + t.lab] -= round_to(t.w, p.score_dtype) * g_cls;
+        if (gscores && side == 0) {
+            const size_t gi = idx * p.nc + t.lab;
+            const float share = round_to(t.w, p.score_dtype) * g_cls;
+            if (p.logits_dtype == 0) {
+                reinterpret_cast<float*>(gscores)[gi] -= share;
+            } else {  // half-precision gradient: recomputed in fp32 and rounded once, not the stored rounded value minus the share
+                const float xv = load_elem(p.pred_scores, gi, p.logits_dtype);
+                store_elem(gscores, gi, p.logits_dtype, __fdividef(gout[1] / fmaxf(*p.tss, 1.f), 1.f + __expf(-xv)) - share);
+            }
+        }
     }
 }
 
@@ -395,15 +509,22 @@ static int loss_fwd(const LossParams& p, double* sums_ws, float* loss3, cudaStre
     KZD_CUDA(cudaMemsetAsync(sums_ws, 0, 3 * sizeof(double), st));
     const size_t n = (size_t)p.b * p.A * p.nc;
     const int cap = sm_count() * 8;
-    if (p.target_labels) {
+    if (p.target_labels && p.logits_dtype != 0) {
+        const size_t n8 = ((uintptr_t)p.pred_scores) % 16 == 0 ? n / 8 : 0;
+        const size_t work = n8 ? n8 : n;
+        const unsigned grid = (unsigned)((work + 255) / 256 < (size_t)cap ? (work + 255) / 256 : cap);
+        if (p.logits_dtype == 1) softplus_sum_half_kernel<1><<<grid, 256, 0, st>>>(p.pred_scores, n, n8, sums_ws);
+        else softplus_sum_half_kernel<2><<<grid, 256, 0, st>>>(p.pred_scores, n, n8, sums_ws);
+        KZD_LAUNCH_CHECK("softplus_sum_half_kernel");
+    } else if (p.target_labels) {
         const size_t n4 = ((uintptr_t)p.pred_scores) % 16 == 0 ? n / 4 : 0;
         const size_t work = n4 ? n4 : n;
         softplus_sum_kernel<<<(unsigned)((work + 255) / 256 < (size_t)cap ? (work + 255) / 256 : cap), 256, 0, st>>>(
-            p.pred_scores, n, n4, sums_ws);
+            reinterpret_cast<const float*>(p.pred_scores), n, n4, sums_ws);
         KZD_LAUNCH_CHECK("softplus_sum_kernel");
     } else {
         bce_fwd_kernel<<<(unsigned)((n + 255) / 256 < (size_t)cap ? (n + 255) / 256 : cap), 256, 0, st>>>(
-            p.pred_scores, p.target_scores, n, sums_ws);
+            reinterpret_cast<const float*>(p.pred_scores), p.target_scores, n, sums_ws);
         KZD_LAUNCH_CHECK("bce_fwd_kernel");
     }
     const long long spans = ((long long)p.b * p.A + FG_SPAN - 1) / FG_SPAN;
@@ -414,19 +535,27 @@ static int loss_fwd(const LossParams& p, double* sums_ws, float* loss3, cudaStre
     return 0;
 }
 
-static int loss_bwd(const LossParams& p, const float* grad_loss3, float* grad_pred_scores, float* grad_pred_dist,
+static int loss_bwd(const LossParams& p, const float* grad_loss3, void* grad_pred_scores, void* grad_pred_dist,
                     cudaStream_t st) {
     const size_t n = (size_t)p.b * p.A * p.nc;
     const int cap = sm_count() * 8;
-    if (p.target_labels) {
+    if (p.target_labels && p.logits_dtype != 0) {
+        const size_t n8 = (((uintptr_t)p.pred_scores) | ((uintptr_t)grad_pred_scores)) % 16 == 0 ? n / 8 : 0;
+        const size_t work = n8 ? n8 : n;
+        const unsigned grid = (unsigned)((work + 255) / 256 < (size_t)cap ? (work + 255) / 256 : cap);
+        if (p.logits_dtype == 1) sigmoid_grad_half_kernel<1><<<grid, 256, 0, st>>>(p.pred_scores, n, n8, p.tss, grad_loss3, grad_pred_scores);
+        else sigmoid_grad_half_kernel<2><<<grid, 256, 0, st>>>(p.pred_scores, n, n8, p.tss, grad_loss3, grad_pred_scores);
+        KZD_LAUNCH_CHECK("sigmoid_grad_half_kernel");
+    } else if (p.target_labels) {
         const size_t n4 = (((uintptr_t)p.pred_scores) | ((uintptr_t)grad_pred_scores)) % 16 == 0 ? n / 4 : 0;
         const size_t work = n4 ? n4 : n;
         sigmoid_grad_kernel<<<(unsigned)((work + 255) / 256 < (size_t)cap ? (work + 255) / 256 : cap), 256, 0, st>>>(
-            p.pred_scores, n, n4, p.tss, grad_loss3, grad_pred_scores);
+            reinterpret_cast<const float*>(p.pred_scores), n, n4, p.tss, grad_loss3, reinterpret_cast<float*>(grad_pred_scores));
         KZD_LAUNCH_CHECK("sigmoid_grad_kernel");
     } else {
         bce_bwd_kernel<<<(unsigned)((n + 255) / 256 < (size_t)cap ? (n + 255) / 256 : cap), 256, 0, st>>>(
-            p.pred_scores, p.target_scores, n, p.tss, grad_loss3, grad_pred_scores);
+            reinterpret_cast<const float*>(p.pred_scores), p.target_scores, n, p.tss, grad_loss3,
+            reinterpret_cast<float*>(grad_pred_scores));
         KZD_LAUNCH_CHECK("bce_bwd_kernel");
     }
     const long long spans = ((long long)p.b * p.A + FG_SPAN - 1) / FG_SPAN;
@@ -440,7 +569,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_fwd(
     const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* target_scores_sum,
     int b, int A, int nc, double* sums_ws, float* loss3, void* stream) {
     LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
-                 target_scores_sum, b, A, nc, nullptr, 0};
+                 target_scores_sum, b, A, nc, nullptr, 0, 0, 0};
     if (int rc = check_loss_args(p, "kzd_loss_tail_fwd")) return rc;
     KZD_CHECK_ARG(sums_ws && loss3, "kzd_loss_tail_fwd: null output");
     return loss_fwd(p, sums_ws, loss3, (cudaStream_t)stream);
@@ -451,19 +580,27 @@ extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_bwd(
     const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* target_scores_sum,
     int b, int A, int nc, const float* grad_loss3, float* grad_pred_scores, float* grad_pred_dist, void* stream) {
     LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
-                 target_scores_sum, b, A, nc, nullptr, 0};
+                 target_scores_sum, b, A, nc, nullptr, 0, 0, 0};
     if (int rc = check_loss_args(p, "kzd_loss_tail_bwd")) return rc;
     KZD_CHECK_ARG(grad_loss3 && grad_pred_scores && grad_pred_dist, "kzd_loss_tail_bwd: null pointer");
     KZD_CHECK_ARG(((uintptr_t)grad_pred_dist) % 16 == 0, "kzd_loss_tail_bwd: misaligned grad_pred_dist");
     return loss_bwd(p, grad_loss3, grad_pred_scores, grad_pred_dist, (cudaStream_t)stream);
 }
 
+static int check_native(int logits_dtype, int dist_dtype, const char* who) {
+    KZD_CHECK_ARG(logits_dtype >= 0 && logits_dtype <= 2 && dist_dtype >= 0 && dist_dtype <= 2,
+                  "%s: logits_dtype=%d / dist_dtype=%d not in {0 fp32, 1 fp16, 2 bf16}", who, logits_dtype, dist_dtype);
+    return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_sparse_fwd(
-    const float* pred_scores, const float* pred_dist, const float* anchor_points, const float* stride_tensor,
+    const void* pred_scores, const void* pred_dist, const float* anchor_points, const float* stride_tensor,
     const float* target_bboxes, const float* target_scores, const int64_t* target_labels, const uint8_t* fg_mask,
-    const float* target_scores_sum, int b, int A, int nc, int score_dtype, double* sums_ws, float* loss3, void* stream) {
+    const float* target_scores_sum, int b, int A, int nc, int score_dtype, int logits_dtype, int dist_dtype,
+    double* sums_ws, float* loss3, void* stream) {
+    if (int rc = check_native(logits_dtype, dist_dtype, "kzd_loss_tail_sparse_fwd")) return rc;
     LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
-                 target_scores_sum, b, A, nc, (const long long*)target_labels, score_dtype};
+                 target_scores_sum, b, A, nc, (const long long*)target_labels, score_dtype, logits_dtype, dist_dtype};
     if (int rc = check_loss_args(p, "kzd_loss_tail_sparse_fwd")) return rc;
     KZD_CHECK_ARG(target_labels && sums_ws && loss3, "kzd_loss_tail_sparse_fwd: null pointer");
     KZD_CHECK_ARG(score_dtype >= 0 && score_dtype <= 2, "kzd_loss_tail_sparse_fwd: score_dtype=%d not in {0,1,2}", score_dtype);
@@ -471,12 +608,13 @@ extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_sparse_fwd(
 }
 
 extern "C" __attribute__((visibility("default"))) int kzd_loss_tail_sparse_bwd(
-    const float* pred_scores, const float* pred_dist, const float* anchor_points, const float* stride_tensor,
+    const void* pred_scores, const void* pred_dist, const float* anchor_points, const float* stride_tensor,
     const float* target_bboxes, const float* target_scores, const int64_t* target_labels, const uint8_t* fg_mask,
-    const float* target_scores_sum, int b, int A, int nc, int score_dtype, const float* grad_loss3,
-    float* grad_pred_scores, float* grad_pred_dist, void* stream) {
+    const float* target_scores_sum, int b, int A, int nc, int score_dtype, int logits_dtype, int dist_dtype,
+    const float* grad_loss3, void* grad_pred_scores, void* grad_pred_dist, void* stream) {
+    if (int rc = check_native(logits_dtype, dist_dtype, "kzd_loss_tail_sparse_bwd")) return rc;
     LossParams p{pred_scores, pred_dist, anchor_points, stride_tensor, target_bboxes, target_scores, fg_mask,
-                 target_scores_sum, b, A, nc, (const long long*)target_labels, score_dtype};
+                 target_scores_sum, b, A, nc, (const long long*)target_labels, score_dtype, logits_dtype, dist_dtype};
     if (int rc = check_loss_args(p, "kzd_loss_tail_sparse_bwd")) return rc;
     KZD_CHECK_ARG(target_labels && grad_loss3 && grad_pred_scores && grad_pred_dist, "kzd_loss_tail_sparse_bwd: null pointer");
     KZD_CHECK_ARG(((uintptr_t)grad_pred_dist) % 16 == 0, "kzd_loss_tail_sparse_bwd: misaligned grad_pred_dist");

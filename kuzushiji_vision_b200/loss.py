@@ -68,15 +68,19 @@ class _LossTailFn(torch.autograd.Function):
         b, A, nc = pred_scores.shape
         dev = pred_scores.device
         f32 = torch.float32
-        ps = pred_scores.to(f32).contiguous()
-        pd = pred_distri.to(f32).contiguous()
+        tl = None if target_labels is None else target_labels.to(torch.int64).contiguous()
+        # sparse form: half-precision head outputs (AMP) go to libkzd as they are - no up-cast copies of (b,A,nc) / (b,A,64)
+        native = tl is not None
+        ps_code = _lib.dtype_code(pred_scores.dtype) if native else 0
+        pd_code = _lib.dtype_code(pred_distri.dtype) if native else 0
+        ps = pred_scores.contiguous() if ps_code else pred_scores.to(f32).contiguous()
+        pd = pred_distri.contiguous() if pd_code else pred_distri.to(f32).contiguous()
         anc = anchor_points.to(f32).contiguous()
         st = stride_tensor.to(f32).reshape(-1).contiguous()
         tb = target_bboxes.to(f32).contiguous()
         ts = target_scores.to(f32).contiguous()
         fg = fg_mask.contiguous().view(torch.uint8)
         tss = target_scores_sum.to(f32).reshape(1).contiguous()
-        tl = None if target_labels is None else target_labels.to(torch.int64).contiguous()
         sums = torch.empty(3, dtype=torch.float64, device=dev)
         loss3 = torch.empty(3, dtype=f32, device=dev)
         with torch.cuda.device(dev):
@@ -87,11 +91,13 @@ class _LossTailFn(torch.autograd.Function):
             else:
                 _lib.check(_lib.lib.kzd_loss_tail_sparse_fwd(ps.data_ptr(), pd.data_ptr(), anc.data_ptr(), st.data_ptr(),
                                                              tb.data_ptr(), ts.data_ptr(), tl.data_ptr(), fg.data_ptr(),
-                                                             tss.data_ptr(), b, A, nc, int(score_dtype), sums.data_ptr(),
-                                                             loss3.data_ptr(), _stream(dev)), "kzd_loss_tail_sparse_fwd")
+                                                             tss.data_ptr(), b, A, nc, int(score_dtype), ps_code, pd_code,
+                                                             sums.data_ptr(), loss3.data_ptr(), _stream(dev)),
+                           "kzd_loss_tail_sparse_fwd")
         ctx.save_for_backward(ps, pd, anc, st, tb, ts, fg, tss, *(() if tl is None else (tl,)))
         ctx.dtypes = (pred_scores.dtype, pred_distri.dtype)
         ctx.score_dtype = int(score_dtype)
+        ctx.codes = (ps_code, pd_code)
         return loss3
 
     @staticmethod
@@ -110,8 +116,9 @@ class _LossTailFn(torch.autograd.Function):
             else:
                 _lib.check(_lib.lib.kzd_loss_tail_sparse_bwd(ps.data_ptr(), pd.data_ptr(), anc.data_ptr(), st.data_ptr(),
                                                              tb.data_ptr(), ts.data_ptr(), rest[0].data_ptr(), fg.data_ptr(),
-                                                             tss.data_ptr(), b, A, nc, ctx.score_dtype, g.data_ptr(),
-                                                             g_ps.data_ptr(), g_pd.data_ptr(), _stream(dev)),
+                                                             tss.data_ptr(), b, A, nc, ctx.score_dtype, ctx.codes[0],
+                                                             ctx.codes[1], g.data_ptr(), g_ps.data_ptr(), g_pd.data_ptr(),
+                                                             _stream(dev)),
                            "kzd_loss_tail_sparse_bwd")
         return g_ps.to(ctx.dtypes[0]), g_pd.to(ctx.dtypes[1]), None, None, None, None, None, None, None, None
 

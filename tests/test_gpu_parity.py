@@ -1070,6 +1070,37 @@ def test_loss_tail_sparse_target_bce_matches_oracle(cfg):
         torch.testing.assert_close(mine.detach(), dense, rtol=2e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("nc", [1, 5])
+def test_loss_tail_reads_half_precision_head_outputs_natively(dt, nc):
+    """AMP (engine/trainer.py:379): pred_scores and pred_distri arrive in half precision. The sparse-target loss tail reads
+    them as they are (no fp32 copies), computes in fp32 and writes the gradients in the same dtype: the losses equal the
+    oracle's on the up-cast values, the gradients equal the oracle's fp32 gradients rounded once."""
+    from kuzushiji_vision_b200 import loss as kloss
+
+    b, G, imgsz = 2, 80, 320
+    d = synth.assigner_inputs(b, G, imgsz, nc, synth.P2_P5, seed=19, device=DEV, layout="uniform")
+    logits = torch.cat([l.view(b, 64 + nc, -1) for l in d["levels"]], 2)[:, 64:].permute(0, 2, 1).contiguous()
+    tl, tb, ts, fg, gi = kzd.TaskAlignedAssigner(10, nc, 0.5, 6.0)(d["pd_scores"], d["pd_bboxes"], d["anc_points"],
+                                                                    d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
+    x1, p1 = logits.to(dt).requires_grad_(True), d["pred_distri"].to(dt).requires_grad_(True)
+    x2, p2 = logits.to(dt).float().requires_grad_(True), d["pred_distri"].to(dt).float().requires_grad_(True)
+    gains = torch.tensor([7.5, 0.5, 1.5], device=DEV)
+    mine = kloss.loss_tail(x1, p1, d["anchor_points"], d["stride_tensor"], tb, ts, fg, target_labels=tl)
+    assert mine.dtype == torch.float32
+    ref_cls = O.loss_tail(x2, p2, d["anchor_points"], d["stride_tensor"], tb, ts.to(dt).float(), fg, ts.sum())
+    ref_box = O.loss_tail(x2, p2, d["anchor_points"], d["stride_tensor"], tb, ts, fg, ts.sum())
+    ref = torch.stack((ref_box[0], ref_cls[1], ref_box[2]))
+    torch.testing.assert_close(mine, ref, rtol=2e-5, atol=1e-6)
+    ((mine * gains).sum() * b).backward()
+    ((ref * gains).sum() * b).backward()
+    assert x1.grad.dtype == dt and p1.grad.dtype == dt
+    ulp = 2.0 ** -9 if dt == torch.float16 else 2.0 ** -6  # one rounding into the dtype (+ fp32 noise near a tie)
+    torch.testing.assert_close(x1.grad.float(), x2.grad.to(dt).float(), rtol=ulp, atol=2e-7)
+    torch.testing.assert_close(p1.grad.float(), p2.grad.to(dt).float(), rtol=ulp, atol=2e-7)
+    assert (p1.grad[~fg] == 0).all()
+
+
 # ---------------------------------------------------------------------------------------------
 # validator matching (SURVEY.md 8f-3: models/yolo/detect/val.py:209-228, engine/validator.py:222-260)
 # ---------------------------------------------------------------------------------------------

@@ -44,6 +44,11 @@ def timeit(fn, iters=10):
     return tot / iters * 1e3  # us
 
 
+import collections  # noqa: E402
+
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+
 def loss_case(name, b, G, nc):
     imgsz, strides = 1280, synth.P2_P5
     A = synth.num_anchors(imgsz, strides)
@@ -84,11 +89,34 @@ def loss_case(name, b, G, nc):
                     "fwd_gbs_on_bce_bytes": fwd_bytes / (f * 1e-6) / 1e9, "fwd_frac_of_peak": fwd_bytes / (f * 1e-6) / 1e9 / PEAK,
                     "bwd_gbs_on_bce_bytes": bwd_bytes / ((fb - f) * 1e-6) / 1e9,
                     "bwd_frac_of_peak": bwd_bytes / ((fb - f) * 1e-6) / 1e9 / PEAK}
+    # AMP flow: fp16 logits and distances read natively by the sparse form (no fp32 copies)
+    lh, ph = logits.half(), pred_distri.half()
+
+    def run_half(backward):
+        x = lh.detach().requires_grad_(backward)
+        pp = ph.detach().requires_grad_(backward)
+        out = kloss.loss_tail(x, pp, anchor_points, stride_tensor, tb, ts, fg, tss, target_labels=tl)
+        if backward:
+            out.backward(gout)
+        return out
+
+    fh = timeit(lambda: run_half(False), iters=5)
+    fbh = timeit(lambda: run_half(True), iters=5)
+    res["sparse_fp16"] = {"fwd_us": fh, "fwd_bwd_us": fbh, "bce_fwd_bytes": n * 2, "bce_bwd_bytes": n * 4,
+                          "fwd_gbs_on_bce_bytes": n * 2 / (fh * 1e-6) / 1e9, "bwd_gbs_on_bce_bytes": n * 4 / ((fbh - fh) * 1e-6) / 1e9}
+    with profile(activities=[ProfilerActivity.CUDA]) as prof_h:
+        for _ in range(3):
+            flush.zero_()
+            run_half(True)
+        torch.cuda.synchronize()
+    aggh = collections.OrderedDict()
+    for e in prof_h.events():
+        if e.device_type.name == "CUDA" and "kzd::" in e.name:
+            aggh.setdefault(e.name.replace("kzd::", "").split("(")[0][-40:], []).append(e.device_time if hasattr(e, "device_time") else e.cuda_time)
+    res["sparse_fp16_kernels_us"] = {k: round(sum(v) / len(v), 2) for k, v in aggh.items()}
+    del lh, ph
     # per-kernel device times of one sparse-target forward + backward (CUPTI): the eager figures above include the
     # host side of the autograd Function and of the torch glue, which dominates at nc = 1
-    import collections
-
-    from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(3):
             flush.zero_()
