@@ -95,9 +95,11 @@ int kzd_decode_train(const void* pred_dist, int in_dtype, const float* anchor_po
                      void* stream);
 
 /* Backward of kzd_decode_train wrt pred_dist (the CIoU/DFL losses back-propagate through the
- * decoded boxes, utils/loss.py:252-254): grad_pred_dist (b,A,64) from grad_xyxy (b,A,4). */
-int kzd_decode_train_bwd(const float* pred_dist, const float* grad_xyxy, int b, int A,
-                         float* grad_pred_dist, void* stream);
+ * decoded boxes, utils/loss.py:252-254): grad_pred_dist (b,A,64) from grad_xyxy (b,A,4) fp32. pred_dist and
+ * grad_pred_dist are elements of in_dtype (0 fp32, 1 fp16, 2 bf16: the AMP flow's tensor is read as it is and
+ * the gradient is rounded once into the same dtype). */
+int kzd_decode_train_bwd(const void* pred_dist, int in_dtype, const float* grad_xyxy, int b, int A,
+                         void* grad_pred_dist, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * assign

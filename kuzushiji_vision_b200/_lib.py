@@ -45,7 +45,7 @@ def _load():
         "kzd_decode_filter": (C.c_int, [C.POINTER(vp), i32, C.POINTER(Level), i32, i32, i32, vp, vp, vp, f32, vp, vp, vp,
                                         i32, vp]),
         "kzd_decode_train": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp, vp]),
-        "kzd_decode_train_bwd": (C.c_int, [vp, vp, i32, i32, vp, vp]),
+        "kzd_decode_train_bwd": (C.c_int, [vp, i32, vp, i32, i32, vp, vp]),
         "kzd_assign_workspace_bytes": (sz, [i32, i32, i32]),
         "kzd_assign_report_offset": (sz, [i32, i32]),
         "kzd_tal_assign": (C.c_int, [vp] * 6 + [i32] * 5 + [f32] * 3 + [C.POINTER(Level), i32, i32, i32] + [vp] * 6 + [vp, sz, i32, vp]),

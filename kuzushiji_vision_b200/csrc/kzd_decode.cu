@@ -383,11 +383,13 @@ __global__ void __launch_bounds__(ANCH * 4) decode_train_kernel(const T* __restr
 }
 
 // Backward: d = sum_j j p_j  =>  dd/dx_j = p_j (j - d); x1y1 = a - lt, x2y2 = a + rb.
-__global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const float* __restrict__ pred,
+// T = float, or the AMP flow's fp16 / bf16 pred_dist: read natively, the gradient rounded once into the same dtype.
+template <typename T>
+__global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const T* __restrict__ pred,
                                                                       const float* __restrict__ gout,
-                                                                      long long N, float* __restrict__ gin) {
+                                                                      long long N, T* __restrict__ gin) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* buf = reinterpret_cast<float*>(smem_raw);
+    T* buf = reinterpret_cast<T*>(smem_raw);
     __shared__ uint64_t full[TR_STAGES];
     const int tid = threadIdx.x;
     const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const floa
     auto issue = [&](long long tile, int stage) {
         const long long first = tile * TR_ANCH;
         const long long cnt = (N - first < TR_ANCH) ? (N - first) : TR_ANCH;
-        const uint32_t bytes = (uint32_t)cnt * 256u;
+        const uint32_t bytes = (uint32_t)cnt * (uint32_t)(64 * sizeof(T));
         mbar_expect_tx(&full[stage], bytes);
         tma_load_1d(buf + stage * TR_FLOATS, pred + first * 64, bytes, &full[stage]);
     };
@@ -417,23 +419,36 @@ __global__ void __launch_bounds__(TR_THREADS) decode_train_bwd_kernel(const floa
         mbar_wait(&full[stage], (uint32_t)((it / TR_STAGES) & 1));
         const long long n = tile * TR_ANCH + a_local;
         if (n < N) {
-            const float* row = buf + stage * TR_FLOATS + tid * 16;
+            const T* tile_ptr = buf + stage * TR_FLOATS;
             float d, m, s;
-            side_stats<float>(buf + stage * TR_FLOATS, tid, d, m, s);
+            side_stats<T>(tile_ptr, tid, d, m, s);
             float g = gout[n * 4 + side];
             g = (side < 2) ? -g : g;
             const float inv = g / s;
-            float* dst = gin + n * 64 + side * 16;
+            // the row again, in the registers' (rotated) order: first[j] = bin of register 4 j
+            float v[16];
+            int first[4];
+            Bins<T>::load(tile_ptr, tid, v, first);
+            float o[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int q = (j + (tid >> 1)) & 3;
-                const float4 t = *reinterpret_cast<const float4*>(row + q * 4);
-                float4 o;
-                o.x = inv * __expf(t.x - m) * ((float)(q * 4 + 0) - d);
-                o.y = inv * __expf(t.y - m) * ((float)(q * 4 + 1) - d);
-                o.z = inv * __expf(t.z - m) * ((float)(q * 4 + 2) - d);
-                o.w = inv * __expf(t.w - m) * ((float)(q * 4 + 3) - d);
-                *reinterpret_cast<float4*>(dst + q * 4) = o;
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[4 * j + k] = inv * __expf(v[4 * j + k] - m) * ((float)(first[j] + k) - d);
+            T* dst = gin + n * 64 + side * 16;
+            if (std::is_same<T, float>::value) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + first[j]) =
+                        make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            } else {  // registers 8 jj .. 8 jj + 7 hold eight consecutive bins starting at first[2 jj]
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    float w8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) w8[k] = o[8 * jj + k];
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dst) + first[2 * jj]) =
+                        std::is_same<T, __half>::value ? pack8<1>(w8) : pack8<2>(w8);
+                }
             }
         }
         __syncthreads();
@@ -595,19 +610,28 @@ extern "C" __attribute__((visibility("default"))) int kzd_decode_train(const voi
     return launch_train_idx<float>(pred_dist, anchor_points, stride_tensor, A, N, out_xyxy, out_xyxy_px, st);
 }
 
-extern "C" __attribute__((visibility("default"))) int kzd_decode_train_bwd(const float* pred_dist, const float* grad_xyxy, int b, int A,
-                                    float* grad_pred_dist, void* stream) {
+template <typename T>
+static int launch_train_bwd(const void* pred_dist, const float* grad_xyxy, long long N, void* grad_pred_dist, cudaStream_t st) {
+    auto fn = decode_train_bwd_kernel<T>;
+    KZD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+    const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
+    const int grid = train_grid(n_tiles, (const void*)fn, TR_THREADS, TR_SMEM);
+    fn<<<grid, TR_THREADS, TR_SMEM, st>>>(reinterpret_cast<const T*>(pred_dist), grad_xyxy, N, reinterpret_cast<T*>(grad_pred_dist));
+    KZD_LAUNCH_CHECK("decode_train_bwd_kernel");
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int kzd_decode_train_bwd(const void* pred_dist, int in_dtype, const float* grad_xyxy, int b,
+                                    int A, void* grad_pred_dist, void* stream) {
     KZD_CHECK_ARG(pred_dist && grad_xyxy && grad_pred_dist, "kzd_decode_train_bwd: null pointer");
     KZD_CHECK_ARG(b >= 0 && A >= 0, "kzd_decode_train_bwd: negative size");
+    KZD_CHECK_ARG(in_dtype >= 0 && in_dtype <= 2, "kzd_decode_train_bwd: in_dtype=%d not in {0 fp32, 1 fp16, 2 bf16}", in_dtype);
     KZD_CHECK_ARG(((uintptr_t)pred_dist) % 16 == 0 && ((uintptr_t)grad_pred_dist) % 16 == 0,
                   "kzd_decode_train_bwd: tensors must be 16-byte aligned");
     const long long N = (long long)b * A;
     if (N == 0) return 0;
-    KZD_CUDA(cudaFuncSetAttribute(decode_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
-    const long long n_tiles = (N + TR_ANCH - 1) / TR_ANCH;
-    const int grid = train_grid(n_tiles, (const void*)decode_train_bwd_kernel, TR_THREADS, TR_SMEM);
-    decode_train_bwd_kernel<<<grid, TR_THREADS, TR_SMEM, (cudaStream_t)stream>>>(pred_dist, grad_xyxy, N,
-                                                                                grad_pred_dist);
-    KZD_LAUNCH_CHECK("decode_train_bwd_kernel");
-    return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_dtype == 1) return launch_train_bwd<__half>(pred_dist, grad_xyxy, N, grad_pred_dist, st);
+    if (in_dtype == 2) return launch_train_bwd<__nv_bfloat16>(pred_dist, grad_xyxy, N, grad_pred_dist, st);
+    return launch_train_bwd<float>(pred_dist, grad_xyxy, N, grad_pred_dist, st);
 }

@@ -47,35 +47,7 @@ __device__ __forceinline__ void store_elem(void* base, size_t i, int dtype, floa
     else if (dtype == 2) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
     else reinterpret_cast<float*>(base)[i] = v;
 }
-// eight consecutive half-precision elements (one 16-byte word) <-> fp32
-template <int DT>
-__device__ __forceinline__ void unpack8(const uint4 w, float (&v)[8]) {
-    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (DT == 1) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
-            v[2 * k] = f.x, v[2 * k + 1] = f.y;
-        } else {
-            v[2 * k] = __uint_as_float(u[k] << 16), v[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
-        }
-    }
-}
-template <int DT>
-__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
-    uint32_t u[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (DT == 1) {
-            const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-            u[k] = *reinterpret_cast<const uint32_t*>(&h);
-        } else {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-            u[k] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-    }
-    return make_uint4(u[0], u[1], u[2], u[3]);
-}
+
 
 __device__ __forceinline__ float round_to(float v, int dtype) {
     if (dtype == 1) return __half2float(__float2half_rn(v));

@@ -124,13 +124,13 @@ class _BboxDecodeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out, *unused):
-        (pd,) = ctx.saved_tensors
-        pd = pd.to(torch.float32)
+        (pd,) = ctx.saved_tensors  # fp32, or the half-precision tensor itself: its gradient is written in the same dtype
         b, A, _ = pd.shape
         g = grad_out.to(torch.float32).contiguous()
         gin = torch.empty_like(pd)
         with torch.cuda.device(pd.device):
-            rc = _lib.lib.kzd_decode_train_bwd(pd.data_ptr(), g.data_ptr(), b, A, gin.data_ptr(), _stream(pd.device))
+            rc = _lib.lib.kzd_decode_train_bwd(pd.data_ptr(), _lib.dtype_code(pd.dtype), g.data_ptr(), b, A, gin.data_ptr(),
+                                               _stream(pd.device))
         _lib.check(rc, "kzd_decode_train_bwd")
         return gin.to(ctx.in_dtype), None, None
 

@@ -724,8 +724,15 @@ def test_decodes_read_half_precision_inputs_natively(dt):
     assert torch.equal(kzd.decode_inference(lv2, synth.P3_P5, 1), kzd.decode_inference([l.float() for l in lv2], synth.P3_P5, 1))
     # gradients flow back in the input dtype
     x = pdh.clone().requires_grad_(True)
-    kzd.bbox_decode(d["anchor_points"], x).sum().backward()
+    w = torch.randn((b, d["anchor_points"].shape[0], 4), generator=torch.Generator().manual_seed(3)).to(DEV)
+    (kzd.bbox_decode(d["anchor_points"], x) * w).sum().backward()
     assert x.grad.dtype == dt and torch.isfinite(x.grad.float()).all()
+    # ... computed from the half-precision tensor itself (kzd_decode_train_bwd in_dtype): the oracle's fp32 gradient
+    # of the up-cast values, rounded once
+    x32 = pdh.float().requires_grad_(True)
+    (O.decode_train(x32, d["anchor_points"]) * w).sum().backward()
+    ulp = 2.0 ** -9 if dt == torch.float16 else 2.0 ** -6
+    torch.testing.assert_close(x.grad.float(), x32.grad.to(dt).float(), rtol=ulp, atol=2e-7)
 
 
 def test_install_routes_reference_call_sites_to_libkzd():
