@@ -170,3 +170,39 @@ def test_install_patches_and_restores_reference_attributes():
         kzd.uninstall()
     assert (u_tal.TaskAlignedAssigner, u_loss.TaskAlignedAssigner, u_ops.non_max_suppression, u_head.Detect._inference,
             u_loss.v8DetectionLoss.bbox_decode, u_loss.v8DetectionLoss.preprocess) == orig
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the kzd arm): one JSON line with the contract's
+    keys, the same `config` object the kzd arm prints for this world size, the reference package (or the oracle port)
+    named in `cpu_baseline`, no device copies and no kernel launches claimed."""
+    import importlib.util
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "2"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert p.returncode == 0, p.stderr[-500:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "pages/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["steps"] == 1 and d["n_gpus"] == 1 and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    spec = importlib.util.spec_from_file_location("kzd_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    assert d["config"] == bench.workload_config(bench.CFG5, 1)  # what the kzd arm prints as `config`
+    assert "configs[4]" in d["config"]["workload"] and d["scaling"] == bench.CFG5["scaling"]
