@@ -1,6 +1,8 @@
 """Randomised parity sweep against the same-device oracle (not part of the test suite: minutes, not seconds).
 Assigner: random batch / GT count / page size / level set / class count / topk / alpha / beta / layout / score dtype;
 NMS: random conf / iou / max_det / agnostic / multi_label / class filter. Every mismatch is printed with its configuration.
+With KZD_FUZZ_REF=1 the checker is the UNMODIFIED reference package on CUDA (oracle/_ref, staged by build()) instead of the
+oracle restatement.
 usage: python tools/fuzz_parity.py [n_assign] [n_nms] [seed]"""
 import os
 import random
@@ -14,6 +16,11 @@ import kuzushiji_vision_b200 as kzd  # noqa: E402
 from kuzushiji_vision_b200 import synth  # noqa: E402
 from oracle import torch_oracle as O  # noqa: E402
 
+USE_REF = os.environ.get("KZD_FUZZ_REF", "0") == "1"
+if USE_REF:
+    from oracle import ref_loader  # noqa: E402
+
+    R = ref_loader.load()
 dev = "cuda:0"
 n_assign = int(sys.argv[1]) if len(sys.argv) > 1 else 150
 n_nms = int(sys.argv[2]) if len(sys.argv) > 2 else 60
@@ -40,7 +47,11 @@ for it in range(n_assign):
     args = (ps, d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
     asg = kzd.TaskAlignedAssigner(topk, nc, alpha, beta)
     mine = asg(*args)
-    ref = O.tal_assign(*args, topk, nc, alpha, beta)
+    if USE_REF:
+        with torch.no_grad():
+            ref = R.TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=alpha, beta=beta).to(dev)(*args)
+    else:
+        ref = O.tal_assign(*args, topk, nc, alpha, beta)
     ok = all(torch.equal(mine[i], ref[i]) for i in (0, 1, 3, 4))
     try:
         torch.testing.assert_close(mine[2], ref[2].float(), rtol=1e-5, atol=1e-9)
@@ -49,6 +60,7 @@ for it in range(n_assign):
     if not ok:
         bad += 1
         print("ASSIGN MISMATCH", cfg, "fg diff", int((mine[3] != ref[3]).sum()), "idx diff", int((mine[4] != ref[4]).sum()), flush=True)
+print("checker:", "unmodified reference package (oracle/_ref) on CUDA" if USE_REF else "oracle/torch_oracle on CUDA", flush=True)
 print(f"assign: {n_assign} cases, {bad} mismatches, {time.time() - t0:.0f} s", flush=True)
 bad_nms = 0
 for it in range(n_nms):
@@ -64,7 +76,7 @@ for it in range(n_nms):
     if nc > 1 and rng.random() < 0.3:
         kw["classes"] = [0, nc - 1]
     mine = kzd.non_max_suppression(y.clone(), **kw)
-    ref = O.non_max_suppression(y.clone(), **kw)
+    ref = R.non_max_suppression(y.clone(), **kw) if USE_REF else O.non_max_suppression(y.clone(), **kw)
     ok = len(mine) == len(ref) and all(m.shape == r.shape and torch.equal(m, r) for m, r in zip(mine, ref))
     if not ok:
         bad_nms += 1
