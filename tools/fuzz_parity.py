@@ -3,7 +3,7 @@ Assigner: random batch / GT count / page size / level set / class count / topk /
 NMS: random conf / iou / max_det / agnostic / multi_label / class filter. Every mismatch is printed with its configuration.
 With KZD_FUZZ_REF=1 the checker is the UNMODIFIED reference package on CUDA (oracle/_ref, staged by build()) instead of the
 oracle restatement.
-usage: python tools/fuzz_parity.py [n_assign] [n_nms] [seed]"""
+usage: python tools/fuzz_parity.py [n_assign] [n_nms] [seed] [n_decode_loss]"""
 import os
 import random
 import sys
@@ -82,4 +82,47 @@ for it in range(n_nms):
         bad_nms += 1
         print("NMS MISMATCH", dict(b=b, nc=nc, imgsz=imgsz, n_obj=n_obj, **kw), [tuple(m.shape) for m in mine], [tuple(r.shape) for r in ref], flush=True)
 print(f"nms: {n_nms} cases, {bad_nms} mismatches, {time.time() - t0:.0f} s total", flush=True)
-sys.exit(1 if bad or bad_nms else 0)
+# ---- decodes and loss tail (oracle only: floating-point tolerances of the tests) ----
+from kuzushiji_vision_b200 import loss as kloss  # noqa: E402
+
+n_dec = int(sys.argv[4]) if len(sys.argv) > 4 else 60
+bad_dec = 0
+for it in range(n_dec):
+    b = rng.choice([1, 2, 3])
+    nc = rng.choice([1, 1, 3, 40])
+    imgsz = rng.choice([160, 200, 256, 320, 416])
+    strides = rng.choice([synth.P2_P5, synth.P3_P5])
+    dt = rng.choice([torch.float32, torch.float32, torch.float16, torch.bfloat16])
+    lv = [x.to(dt) for x in synth.head_outputs(b, nc, imgsz, strides, seed=9000 + it, device=dev)]
+    lv32 = [x.float() for x in lv]
+    y = kzd.decode_inference(lv, strides, nc)
+    ref = O.decode_infer(lv32, strides, nc)
+    _, st = O.make_anchors([x.shape[2:] for x in lv], strides, device=dev)
+    e_box = ((y[:, :4] - ref[:, :4]).abs() / torch.maximum(ref[:, :4].abs(), st.view(1, 1, -1))).max().item()
+    e_cls = (y[:, 4:] - ref[:, 4:]).abs().max().item()
+    d = synth.assigner_inputs(b, rng.choice([5, 40, 120]), imgsz, nc, strides, seed=9500 + it, device=dev, layout="uniform")
+    pdt = d["pred_distri"].to(dt)
+    out = kzd.bbox_decode(d["anchor_points"], pdt)
+    rt = O.decode_train(pdt.float(), d["anchor_points"])
+    e_tr = ((out - rt).abs() / rt.abs().clamp(min=1.0)).max().item()
+    # loss tail (sparse form) on the assigner's targets, forward and both gradients
+    logits = torch.cat([x.view(b, 64 + nc, -1) for x in d["levels"]], 2)[:, 64:].permute(0, 2, 1).contiguous()
+    tl, tb, ts, fg, gi = kzd.TaskAlignedAssigner(10, nc, 0.5, 6.0)(d["pd_scores"], d["pd_bboxes"], d["anc_points"], d["gt_labels"],
+                                                                    d["gt_bboxes"], d["mask_gt"])
+    x1, p1 = logits.clone().requires_grad_(True), d["pred_distri"].clone().requires_grad_(True)
+    x2, p2 = logits.clone().requires_grad_(True), d["pred_distri"].clone().requires_grad_(True)
+    mine = kloss.loss_tail(x1, p1, d["anchor_points"], d["stride_tensor"], tb, ts, fg, target_labels=tl)
+    refl = O.loss_tail(x2, p2, d["anchor_points"], d["stride_tensor"], tb, ts, fg)
+    mine.sum().backward()
+    refl.sum().backward()
+    e_loss = ((mine - refl).abs() / refl.abs().clamp(min=1e-6)).max().item()
+    if p2.grad is None:  # no foreground anchor on this batch: the oracle's loss does not touch pred_distri
+        p2.grad = torch.zeros_like(p2)
+    gs = max(p2.grad.abs().max().item(), 1e-12)
+    e_gx = ((x1.grad - x2.grad).abs() / x2.grad.abs().clamp(min=1e-7)).max().item()
+    e_gp = ((p1.grad - p2.grad).abs().max().item()) / gs
+    if e_box > 1e-5 or e_cls > 1e-6 or e_tr > 1e-5 or e_loss > 5e-5 or e_gx > 2e-4 or e_gp > 5e-5:
+        bad_dec += 1
+        print("DECODE/LOSS MISMATCH", dict(b=b, nc=nc, imgsz=imgsz, strides=strides, dt=dt), e_box, e_cls, e_tr, e_loss, e_gx, e_gp, flush=True)
+print(f"decode + loss: {n_dec} cases, {bad_dec} out of tolerance, {time.time() - t0:.0f} s total", flush=True)
+sys.exit(1 if bad or bad_nms or bad_dec else 0)
