@@ -468,6 +468,40 @@ def test_nms_full_size_config4():
         assert 2000 <= m.shape[0] + 1000 and m.shape[0] <= 2000
 
 
+def test_nms_greedy_properties_at_page_scale():
+    """Size-independent properties of greedy NMS on full pages (1280x1280 P2-P5, ~3,000 candidates/page, a low IoU
+    threshold so that a third of them is suppressed), checked without the oracle: rows sorted by score; kept boxes
+    of one class pairwise at or below the threshold; every candidate that was dropped before the max_det cut has a
+    kept box of its class with a higher (or equal, earlier) score and IoU above the threshold; a second pass over the
+    kept rows keeps them all (idempotence)."""
+    import torchvision
+
+    b, nc, imgsz, iou_t, conf, max_det = 4, 3, 1280, 0.3, 0.25, 3000
+    lv = synth.head_outputs(b, nc, imgsz, synth.P2_P5, seed=77, device=DEV, sparse_cls=3000)
+    y = kzd.decode_inference(lv, synth.P2_P5, nc)
+    rows, n_keep = kzd.nms_batched(y.clone(), conf, iou_t, max_det=max_det, in_place=False)
+    xyxy = kzd.xywh2xyxy(y[:, :4].permute(0, 2, 1))
+    for i in range(b):
+        kept = rows[i, :n_keep[i]]
+        assert (kept[:-1, 4] >= kept[1:, 4]).all() and (kept[:, 4] > conf).all()
+        off = kept[:, 5:6] * 7680.0  # the reference's class offset: boxes of different classes never meet
+        iou_kk = torchvision.ops.box_iou(kept[:, :4] + off, kept[:, :4] + off)
+        iou_kk.fill_diagonal_(0)
+        assert iou_kk.max() <= iou_t
+        sc, cls = y[i, 4:].max(0)
+        cand = (sc > conf).nonzero().squeeze(1)
+        assert n_keep[i] < cand.numel() * 0.9, "the inputs must exercise suppression"
+        cb = xyxy[i, cand] + cls[cand].float().unsqueeze(1) * 7680.0
+        iou_ck = torchvision.ops.box_iou(cb, kept[:, :4] + off)                 # (candidates, kept)
+        earlier = kept[:, 4].unsqueeze(0) >= sc[cand].unsqueeze(1)               # kept box ranks at or before the candidate
+        is_kept = (iou_ck > 0.999999).any(1) & (sc[cand].unsqueeze(1) == kept[:, 4].unsqueeze(0)).any(1)
+        covered = ((iou_ck > iou_t) & earlier).any(1)
+        assert (is_kept | covered).all(), f"image {i}: {int((~(is_kept | covered)).sum())} dropped candidates without a suppressor"
+        # idempotence: the kept rows survive a second pass unchanged
+        again = torchvision.ops.nms(kept[:, :4] + off, kept[:, 4], iou_t)
+        assert again.numel() == kept.shape[0]
+
+
 @pytest.mark.parametrize("name", ["nms_nc1", "nms_nc5", "nms_nc5_agnostic", "nms_nc5_multilabel", "nms_nc5_classes"])
 def test_nms_against_reference_golden(name):
     g = load_golden(name)
