@@ -31,6 +31,9 @@ for e in prof.events():
         continue
     name = e.name.replace("kzd::", "").split("(")[0]
     agg.setdefault(name, []).append(e.device_time if hasattr(e, "device_time") else e.cuda_time)
+print("Per-kernel device times inside ONE PagePipeline graph replay (CUPTI). The two branches of the graph run concurrently: a\n"
+      "kernel's duration includes the time its CTAs wait for SM slots behind the other branch (the persistent candidates kernel\n"
+      "holds every SM's register file while it runs); stages alone: tools/time_assign.py, tools/time_nms.py.\n")
 print("| kernel (inside the graph) | launches per step | mean us | us per step |\n|---|---|---|---|")
 tot = 0.0
 for k, v in agg.items():
