@@ -138,10 +138,14 @@ size_t kzd_assign_report_offset(int b, int A);
  *       skipped.
  *     KZD_ASSIGN_NATIVE_SCORES   pd_scores points to elements of score_dtype (fp16 / bf16, the tensor the AMP
  *       flow passes: utils/loss.py:233 under autocast) instead of fp32: the kernels read them as they are, so
- *       the caller needs no up-cast pass over (b,A,nc). No effect with score_dtype 0. */
+ *       the caller needs no up-cast pass over (b,A,nc). No effect with score_dtype 0.
+ *     KZD_ASSIGN_WARP_PER_GT     scheduling hint, same results: a whole warp per GT instead of two GTs per warp -
+ *       faster when the call has the GPU to itself (an eager training step), slower when other kernels share the
+ *       SMs with it (several graph pipelines in flight). */
 #define KZD_ASSIGN_PERSISTENT 1
 #define KZD_ASSIGN_TRUSTED_ANCHORS 2
 #define KZD_ASSIGN_NATIVE_SCORES 4
+#define KZD_ASSIGN_WARP_PER_GT 8
 int kzd_tal_assign(const void* pd_scores, const float* pd_bboxes, const float* anc_points,
                    const float* gt_labels, const float* gt_bboxes, const float* mask_gt,
                    int b, int A, int G, int nc, int topk, float alpha, float beta, float eps,

@@ -16,6 +16,7 @@ KZD_MAX_TOPK = 32
 KZD_ASSIGN_PERSISTENT = 1        # include/kzd.h: flags of kzd_tal_assign
 KZD_ASSIGN_TRUSTED_ANCHORS = 2
 KZD_ASSIGN_NATIVE_SCORES = 4
+KZD_ASSIGN_WARP_PER_GT = 8
 
 
 class KzdError(RuntimeError):

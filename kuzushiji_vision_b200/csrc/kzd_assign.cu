@@ -922,7 +922,7 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const void*
                   "kzd_tal_assign: bad level table");
     KZD_CHECK_ARG(b <= 65535, "kzd_tal_assign: b=%d > 65535", b);
     KZD_CHECK_ARG(score_dtype >= 0 && score_dtype <= 2, "kzd_tal_assign: score_dtype=%d not in {0,1,2}", score_dtype);
-    KZD_CHECK_ARG((flags & ~(KZD_ASSIGN_PERSISTENT | KZD_ASSIGN_TRUSTED_ANCHORS | KZD_ASSIGN_NATIVE_SCORES)) == 0, "kzd_tal_assign: unknown flags 0x%x", flags);
+    KZD_CHECK_ARG((flags & ~(KZD_ASSIGN_PERSISTENT | KZD_ASSIGN_TRUSTED_ANCHORS | KZD_ASSIGN_NATIVE_SCORES | KZD_ASSIGN_WARP_PER_GT)) == 0, "kzd_tal_assign: unknown flags 0x%x", flags);
     KZD_CHECK_ARG((double)b * A < 4294967295.0 && G < (1 << 24) - 2, "kzd_tal_assign: b*A or G too large");
     KZD_CHECK_ARG((double)b * G < 4294967295.0, "kzd_tal_assign: b*G too large");
     KZD_CHECK_ARG(((uintptr_t)gt_bboxes) % 16 == 0 && ((uintptr_t)pd_bboxes) % 16 == 0 &&
@@ -986,7 +986,9 @@ extern "C" __attribute__((visibility("default"))) int kzd_tal_assign(const void*
 #ifndef KZD_CAND_GW
 #define KZD_CAND_GW 16
 #endif
-        const int gw = (topk <= 16 && KZD_CAND_GW == 16) ? 16 : 32;
+        // a warp per GT is the faster form when the call has the machine to itself (36.8 vs 43.5 us at G = 600, 53 vs 63 us at
+        // G = 1000); two GTs per warp when other kernels run next to it (the graph pipelines: 153.2 vs 156.8 us per step)
+        const int gw = (topk <= 16 && KZD_CAND_GW == 16 && !(flags & KZD_ASSIGN_WARP_PER_GT)) ? 16 : 32;
         const long long warps = ((long long)b * G + (32 / gw) - 1) / (32 / gw);
         long long blocks = (warps + CAND_WARPS - 1) / CAND_WARPS;
         if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;  // the kernel strides over the rest

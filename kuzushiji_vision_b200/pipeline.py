@@ -55,6 +55,7 @@ class PagePipeline:
         self.anc_points = self.anchor_points * self.stride_tensor
         self.assigner = TaskAlignedAssigner(topk, nc, alpha, beta)
         self.assigner.per_stream = False  # one graph = one call in flight: warm-up and capture share the workspace
+        self.assigner.overlapped = True   # the NMS chain and other pipelines' decodes run next to the assigner
         # NMS buffers (fixed capacities; an overflow is reported by results())
         self.pool = min(A, int(pool))
         self.n_cap = max(64, (min(int(n_cap), self.max_nms, self.pool) + 63) // 64 * 64)

@@ -68,6 +68,9 @@ class TaskAlignedAssigner(nn.Module):
         reference's ``G`` is the batch's largest label count (utils/loss.py:188) and changes every
         iteration. Calls on different streams get different workspaces, so one instance may be used from
         several streams; calls on ONE stream are ordered by the stream.
+      * ``overlapped``: a scheduling hint. A lone call (the eager drop-in in a training step) gives every GT a whole
+        warp; ``PagePipeline`` sets it, because two GTs per warp leave more of the machine to the kernels running
+        next to the assigner. Same results either way.
       * the level table of the anchor grid, inferred on the host from ``anc_points`` once per anchor tensor.
         The same tensor object (same storage, same version counter) is vouched for on later calls, so the
         device-side check is skipped; any other tensor is checked on the device against the cached table and,
@@ -85,6 +88,7 @@ class TaskAlignedAssigner(nn.Module):
         self.zero_fill = ZERO_FILL_DEFAULT
         self.stateless = False  # True: libkzd zeroes the per-anchor state on every call (no persistent workspace)
         self.per_stream = True  # False: one workspace per (b, A, device) whatever the stream (PagePipeline: one graph)
+        self.overlapped = False  # True: other kernels share the SMs with the call (PagePipeline): two GTs per warp (same results)
         self.counters = None
         self._levels = {}    # (A, device) -> (ctypes level array, n_levels)
         self._vouched = {}   # (A, device) -> (anchor tensor, its version): verified against the table on the host
@@ -169,7 +173,7 @@ class TaskAlignedAssigner(nn.Module):
         else:
             ws = self._workspace(b, A, G, dev, stream.cuda_stream)
         flags = ((0 if self.stateless else _lib.KZD_ASSIGN_PERSISTENT) | (_lib.KZD_ASSIGN_TRUSTED_ANCHORS if trusted else 0)
-                 | (_lib.KZD_ASSIGN_NATIVE_SCORES if native else 0))
+                 | (_lib.KZD_ASSIGN_NATIVE_SCORES if native else 0) | (0 if self.overlapped else _lib.KZD_ASSIGN_WARP_PER_GT))
         with torch.cuda.device(dev):
             rc = _lib.lib.kzd_tal_assign(
                 pd_scores_c.data_ptr(), pd_bboxes_c.data_ptr(), anc_c.data_ptr(), gl.data_ptr(), gb.data_ptr(),

@@ -26,6 +26,13 @@ def _assign_both(d, nc, topk=10, alpha=0.5, beta=6.0, zero_fill=None):
         asg.zero_fill = zero_fill
     mine = asg(*args)
     ref = O.tal_assign(*args, topk, nc, alpha, beta)
+    # the other scheduling form (two GTs per warp, what PagePipeline uses): the same bits
+    asg2 = kzd.TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=alpha, beta=beta)
+    asg2.overlapped = True
+    if zero_fill is not None:
+        asg2.zero_fill = zero_fill
+    for m_, o_ in zip(mine, asg2(*args)):
+        assert torch.equal(m_, o_)
     torch.cuda.synchronize()
     return mine, ref, asg
 

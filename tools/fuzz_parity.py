@@ -46,6 +46,7 @@ for it in range(n_assign):
     ps = d["pd_scores"] if dt is None else d["pd_scores"].to(dt)
     args = (ps, d["pd_bboxes"], d["anc_points"], d["gt_labels"], d["gt_bboxes"], d["mask_gt"])
     asg = kzd.TaskAlignedAssigner(topk, nc, alpha, beta)
+    asg.overlapped = rng.random() < 0.5  # two GTs per warp / a warp per GT
     mine = asg(*args)
     if USE_REF:
         with torch.no_grad():
