@@ -186,10 +186,13 @@ class DetectionLoss:
         feats = preds[1] if isinstance(preds, tuple) else preds
         dev = feats[0].device
         bs = feats[0].shape[0]
-        cat = torch.cat([xi.view(bs, self.no, -1) for xi in feats], 2)
-        pred_distri, pred_scores = cat.split((self.reg_max * 4, self.nc), 1)
-        pred_scores = pred_scores.permute(0, 2, 1).contiguous()
-        pred_distri = pred_distri.permute(0, 2, 1).contiguous()
+        # utils/loss.py:210-215 in one pass per tensor: the per-level channel slices are permuted views and the cat
+        # writes them straight into the anchor-major layout (the reference's cat -> split -> permute -> contiguous
+        # moves the head outputs twice; same values, same autograd graph shape)
+        c4 = self.reg_max * 4
+        views = [xi.view(bs, self.no, -1) for xi in feats]
+        pred_distri = torch.cat([v[:, :c4].permute(0, 2, 1) for v in views], 1)
+        pred_scores = torch.cat([v[:, c4:].permute(0, 2, 1) for v in views], 1)
         dtype = pred_scores.dtype
         imgsz = torch.tensor(feats[0].shape[2:], device=dev, dtype=dtype) * self.stride[0]
         anchor_points, stride_tensor, anc_px = self._anchor_cache(feats)
