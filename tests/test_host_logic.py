@@ -206,3 +206,36 @@ def test_bench_reference_arm_contract():
         sys.argv = argv
     assert d["config"] == bench.workload_config(bench.CFG5, 1)  # what the kzd arm prints as `config`
     assert "configs[4]" in d["config"]["workload"] and d["scaling"] == bench.CFG5["scaling"]
+
+
+def test_bench_algorithmic_bytes_match_survey_8d():
+    """bench.py's roofline numerators are SURVEY.md 8(d)'s per-page formulas times the pages of one launch: pinned against the
+    survey's own config values (config 2: assign 125 MB / batch, train decode 592 MB; config 4: inference decode 1.754 GB,
+    NMS 230 MB), and the fused-filter NMS stage drops a meaningless fraction instead of printing it."""
+    import importlib.util
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("kzd_bench2", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    ab = bench.algorithmic_bytes(16, 136000, 600, 1, 16 * 2940, 16 * 1000)
+    assert abs(ab["assign"] / 1e6 - 125.3) < 0.5
+    assert ab["decode_train"] == (272 + 16) * 136000 * 16 and abs(272 * 136000 * 16 / 1e6 - 591.9) < 0.1
+    assert ab["decode_infer"] == 280 * 136000 * 16
+    assert ab["decode_dual"] == (4 * 65 + 4 * 5 + 32) * 136000 * 16
+    ab4 = bench.algorithmic_bytes(32, 195840, 600, 1, 32 * 2940, 32 * 2000)
+    assert abs(ab4["decode_infer"] / 1e9 - 1.754) < 0.002 and abs(ab4["nms"] / 1e6 - 229.4) < 1.0
+    ab3 = bench.algorithmic_bytes(16, 136000, 600, 4300, 0, 0)
+    assert abs(ab3["assign"] / 1e9 - 37.5) < 0.1  # survey: 2.35 GB / page
+    e = bench.stage_entry("nms", 0.036, 9_374_586_360, 6524.9, True)
+    assert e["frac"] is None and "note" in e
+    e = bench.stage_entry("assign", 0.0675, 125_350_400, 6524.9, True)
+    assert abs(e["frac"] - 0.2846) < 0.002
+    w1, w8 = bench.workload_config(bench.CFG5, 1), bench.workload_config(bench.CFG5, 8)
+    assert w1["pages_per_gpu"] == 128 and w8["pages_per_gpu"] == 16 and w1["global_pages"] == w8["global_pages"] == 128
